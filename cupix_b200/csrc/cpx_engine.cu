@@ -1,0 +1,751 @@
+// cupix_b200 host engine + C ABI (include/cupix_b200.h).  Compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is deliberately no CPU fallback: every entry point that computes needs a CUDA device.
+#include "../../include/cupix_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cpx_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CPX_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(CPX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+template <typename T>
+int upload(const std::vector<T>& h, T** d, size_t* bytes_total) {
+  *d = nullptr;
+  if (h.empty()) return CPX_OK;
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(d), h.size() * sizeof(T)));
+  CPX_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *bytes_total += h.size() * sizeof(T);
+  return CPX_OK;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct ZHost {
+  cpx::ZDev dev;                 // device pointers + dims (mirrored into the device table)
+  std::vector<double> Linv;      // [n_A][n_M][n_M] inverse Cholesky factors (kept for cpx_set_data)
+  std::vector<void*> owned;      // device allocations of this z
+};
+
+}  // namespace
+
+struct cpx_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<ZHost> z;
+  cpx::ZDev* d_ztab = nullptr;       // table of the z bins selected for the current launch
+  int* d_zlist = nullptr;
+  int* d_nA_of_z = nullptr;
+  int na_blk = 0;                    // a-block width shared by all z (template NA)
+  int max_na = 0, max_nm = 0, max_nA = 0, max_nM = 0, max_nq = 0;
+  int chunk = 0;                     // points per chunk
+  size_t device_bytes = 0;
+  long long launches = 0;
+  // per-chunk scratch
+  double* d_points = nullptr;        // [chunk][16]
+  int* d_data_idx = nullptr;         // [chunk]
+  double* d_chi2 = nullptr;          // [chunk]
+  double* d_chi2_zA = nullptr;       // [chunk][n_z][max_nA]
+  double* d_model = nullptr;         // [chunk][n_z][max_nA][max_nM]  (lazy)
+  double* d_pxout = nullptr;         // [chunk][n_z][max_na][max_nm]  (lazy)
+  std::vector<void*> owned;
+};
+
+namespace {
+
+// ---- dense helpers (float64, tiny sizes) ---------------------------------------------------
+bool cholesky_lower(const double* C, int n, std::vector<double>& L) {
+  L.assign(static_cast<size_t>(n) * n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double s = C[j * n + j];
+    for (int k = 0; k < j; ++k) s -= L[j * n + k] * L[j * n + k];
+    if (!(s > 0.0)) return false;
+    const double d = std::sqrt(s);
+    L[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double t = C[i * n + j];
+      for (int k = 0; k < j; ++k) t -= L[i * n + k] * L[j * n + k];
+      L[i * n + j] = t / d;
+    }
+  }
+  return true;
+}
+
+void invert_lower(const std::vector<double>& L, int n, double* Li) {
+  std::fill(Li, Li + static_cast<size_t>(n) * n, 0.0);
+  for (int c = 0; c < n; ++c) {
+    Li[c * n + c] = 1.0 / L[c * n + c];
+    for (int r = c + 1; r < n; ++r) {
+      double s = 0.0;
+      for (int k = c; k < r; ++k) s += L[r * n + k] * Li[k * n + c];
+      Li[r * n + c] = -s / L[r * n + r];
+    }
+  }
+}
+
+int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
+  using namespace cpx;
+  ZDev& Z = zh.dev;
+  std::memset(&Z, 0, sizeof(Z));
+  Z.n_a = d.n_a;
+  Z.n_m = d.n_m;
+  Z.n_q = d.n_q;
+  Z.n_tiles = (d.n_m + kTileRows - 1) / kTileRows;
+  Z.n_m_pad = Z.n_tiles * kTileRows;
+  Z.na_blk = na_blk;
+  Z.n_ablk = (d.n_a + na_blk - 1) / na_blk;
+  Z.flags = d.flags;
+  Z.dAA = d.dAA_dMpc;
+  std::memcpy(Z.defaults, d.defaults, sizeof(Z.defaults));
+  size_t& bytes = h->device_bytes;
+  auto keep = [&](void* p) { if (p) zh.owned.push_back(p); };
+
+  // cell constants [tile][q][6][32]
+  {
+    std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * d.n_q * kCellConsts * kTileRows, 0.0f);
+    const double two_pi2 = 2.0 * M_PI * M_PI;
+    for (int m = 0; m < d.n_m; ++m) {
+      const int tile = m / kTileRows, r = m % kTileRows;
+      const double kp = d.kpar_Mpc[m];
+      for (int q = 0; q < d.n_q; ++q) {
+        const double kt = d.kperp_Mpc[q];
+        const double k2 = kp * kp + kt * kt;
+        float* c = &cell[((static_cast<size_t>(tile) * d.n_q + q) * kCellConsts) * kTileRows + r];
+        if (!(k2 > 0.0)) continue;   // k == 0: P_L(0) = 0, cell contributes nothing
+        const double k = std::sqrt(k2);
+        const double mu = kp / k;
+        const double PL = d.linP_cell[static_cast<size_t>(m) * d.n_q + q];
+        c[0 * kTileRows] = static_cast<float>(k * k2 * PL / two_pi2);            // Delta^2(k)
+        c[1 * kTileRows] = static_cast<float>(std::log2(k));
+        c[2 * kTileRows] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;   // mu = 0: mu^bv -> 0 (bv>0) or 1 (bv=0)
+        c[3 * kTileRows] = static_cast<float>(mu * mu);
+        c[4 * kTileRows] = static_cast<float>(k2);
+        c[5 * kTileRows] = static_cast<float>(PL);
+      }
+    }
+    float* dptr;
+    int rc = upload(cell, &dptr, &bytes);
+    if (rc) return rc;
+    Z.cellc = dptr;
+    keep(dptr);
+  }
+  // Hankel weights [ablk][q][na_blk]
+  {
+    std::vector<double> W(static_cast<size_t>(Z.n_ablk) * d.n_q * na_blk, 0.0);
+    for (int a = 0; a < d.n_a; ++a)
+      for (int q = 0; q < d.n_q; ++q)
+        W[(static_cast<size_t>(a / na_blk) * d.n_q + q) * na_blk + a % na_blk] = d.hankel_w[static_cast<size_t>(a) * d.n_q + q];
+    double* dptr;
+    int rc = upload(W, &dptr, &bytes);
+    if (rc) return rc;
+    Z.Wd = dptr;
+    keep(dptr);
+  }
+  auto up_copy = [&](const double* src, size_t n, const double** dst) -> int {
+    *dst = nullptr;
+    if (!src) return CPX_OK;
+    std::vector<double> v(src, src + n);
+    double* dptr;
+    int rc = upload(v, &dptr, &bytes);
+    if (rc) return rc;
+    *dst = dptr;
+    keep(dptr);
+    return CPX_OK;
+  };
+  {
+    std::vector<double> kp(Z.n_m_pad, 0.0);
+    std::copy(d.kpar_Mpc, d.kpar_Mpc + d.n_m, kp.begin());
+    double* dptr;
+    int rc = upload(kp, &dptr, &bytes);
+    if (rc) return rc;
+    Z.kpar = dptr;
+    keep(dptr);
+  }
+  int rc;
+  if (d.flags & CPX_INCLUDE_METAL) {
+    if (!d.metal_auto || !d.metal_cross) return fail(CPX_ERR_ARG, "include_metal set but metal tables are NULL");
+    if ((rc = up_copy(d.metal_auto, 3ull * d.n_a * d.n_m, &Z.metal_auto))) return rc;
+    if ((rc = up_copy(d.metal_cross, 3ull * d.n_a * d.n_m, &Z.metal_cross))) return rc;
+  }
+  if (d.flags & CPX_INCLUDE_SKY) {
+    if (!d.sky_xi_a || !d.sky_smooth_m) return fail(CPX_ERR_ARG, "include_sky set but sky tables are NULL");
+    if ((rc = up_copy(d.sky_xi_a, d.n_a, &Z.sky_xi))) return rc;
+    if ((rc = up_copy(d.sky_smooth_m, d.n_m, &Z.sky_smooth))) return rc;
+  }
+
+  // ---- window / covariance operators ----
+  Z.n_A = d.n_A;
+  if (d.n_A > 0) {
+    if (!d.B_A_a || !d.U_aMn || !d.V_aM || !d.Px_AM || !d.cov_AMM || d.n_M <= 0 || d.n_data <= 0)
+      return fail(CPX_ERR_ARG, "measurement arrays missing for a z bin with n_A > 0");
+    if (d.n_M > 64) return fail(CPX_ERR_UNSUPPORTED, "n_M > 64 coarse k bins is not supported yet");
+    const int nA = d.n_A, nM = d.n_M, na = d.n_a, nm = d.n_m;
+    Z.n_M = nM;
+    Z.n_M_pad = round_up(nM, 8);
+    Z.n_data = d.n_data;
+    std::vector<int> pair_start(nA + 1, 0), pair_a;
+    for (int A = 0; A < nA; ++A) {
+      for (int a = 0; a < na; ++a)
+        if (d.B_A_a[static_cast<size_t>(A) * na + a] != 0.0) pair_a.push_back(a);
+      pair_start[A + 1] = static_cast<int>(pair_a.size());
+      if (pair_start[A + 1] == pair_start[A])
+        return fail(CPX_ERR_ARG, "coarse theta bin without fine bins in B_A_a");
+    }
+    Z.n_pairs = static_cast<int>(pair_a.size());
+    const size_t tstride = static_cast<size_t>(Z.n_M_pad) * Z.n_m_pad;
+    std::vector<double> Tm(Z.n_pairs * tstride, 0.0), Tc(Z.n_pairs * tstride, 0.0);
+    zh.Linv.assign(static_cast<size_t>(nA) * nM * nM, 0.0);
+    std::vector<double> L, vsum(nM);
+    for (int A = 0; A < nA; ++A) {
+      if (!cholesky_lower(d.cov_AMM + static_cast<size_t>(A) * nM * nM, nM, L)) {
+        char buf[128];
+        std::snprintf(buf, sizeof buf, "covariance block of coarse theta bin %d is not positive definite", A);
+        return fail(CPX_ERR_COV, buf);
+      }
+      double* Li = &zh.Linv[static_cast<size_t>(A) * nM * nM];
+      invert_lower(L, nM, Li);
+      std::fill(vsum.begin(), vsum.end(), 0.0);
+      for (int p = pair_start[A]; p < pair_start[A + 1]; ++p)
+        for (int M = 0; M < nM; ++M) vsum[M] += d.V_aM[static_cast<size_t>(pair_a[p]) * nM + M];
+      for (int p = pair_start[A]; p < pair_start[A + 1]; ++p) {
+        const int a = pair_a[p];
+        double* tm = &Tm[p * tstride];
+        double* tc = &Tc[p * tstride];
+        for (int M = 0; M < nM; ++M) {
+          const double wgt = d.V_aM[static_cast<size_t>(a) * nM + M] / vsum[M];
+          const double* u = d.U_aMn + (static_cast<size_t>(a) * nM + M) * nm;
+          for (int m = 0; m < nm; ++m) tm[static_cast<size_t>(M) * Z.n_m_pad + m] = wgt * u[m];
+        }
+        for (int M = 0; M < nM; ++M)
+          for (int Mp = 0; Mp <= M; ++Mp) {
+            const double l = Li[M * nM + Mp];
+            const double* src = &tm[static_cast<size_t>(Mp) * Z.n_m_pad];
+            double* dst = &tc[static_cast<size_t>(M) * Z.n_m_pad];
+            for (int m = 0; m < nm; ++m) dst[m] += l * src[m];
+          }
+      }
+    }
+    int* dps;
+    int* dpa;
+    double *dTm, *dTc;
+    if ((rc = upload(pair_start, &dps, &bytes))) return rc;
+    if ((rc = upload(pair_a, &dpa, &bytes))) return rc;
+    if ((rc = upload(Tm, &dTm, &bytes))) return rc;
+    if ((rc = upload(Tc, &dTc, &bytes))) return rc;
+    Z.pair_start = dps;
+    Z.pair_a = dpa;
+    Z.T_model = dTm;
+    Z.T_chi = dTc;
+    keep(dps);
+    keep(dpa);
+    keep(dTm);
+    keep(dTc);
+  }
+  return CPX_OK;
+}
+
+// whitened data vectors yd[d][A][M_pad] = L_A^-1 d_A
+int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
+  cpx::ZDev& Z = zh.dev;
+  const int nA = Z.n_A, nM = Z.n_M;
+  std::vector<double> yd(static_cast<size_t>(n_data) * nA * Z.n_M_pad, 0.0);
+  for (int dd = 0; dd < n_data; ++dd)
+    for (int A = 0; A < nA; ++A) {
+      const double* Li = &zh.Linv[static_cast<size_t>(A) * nM * nM];
+      const double* x = Px_AM + (static_cast<size_t>(dd) * nA + A) * nM;
+      double* y = &yd[(static_cast<size_t>(dd) * nA + A) * Z.n_M_pad];
+      for (int M = 0; M < nM; ++M) {
+        double s = 0.0;
+        for (int Mp = 0; Mp <= M; ++Mp) s += Li[M * nM + Mp] * x[Mp];
+        y[M] = s;
+      }
+    }
+  if (Z.yd) {
+    cudaFree(const_cast<double*>(Z.yd));
+    zh.owned.erase(std::remove(zh.owned.begin(), zh.owned.end(), (void*)Z.yd), zh.owned.end());
+  }
+  double* dptr;
+  int rc = upload(yd, &dptr, &h->device_bytes);
+  if (rc) return rc;
+  Z.yd = dptr;
+  Z.n_data = n_data;
+  zh.owned.push_back(dptr);
+  return CPX_OK;
+}
+
+// ---- kernel dispatch -----------------------------------------------------------------------
+typedef void (*K1Fn)(const cpx::ZDev*, int, int, long long);
+
+template <int PP>
+K1Fn k1_for_na(int na) {
+  switch (na) {
+    case 4: return cpx::k_p3d_hankel<PP, 4>;
+    case 8: return cpx::k_p3d_hankel<PP, 8>;
+    case 12: return cpx::k_p3d_hankel<PP, 12>;
+    case 16: return cpx::k_p3d_hankel<PP, 16>;
+    case 20: return cpx::k_p3d_hankel<PP, 20>;
+    case 24: return cpx::k_p3d_hankel<PP, 24>;
+  }
+  return nullptr;
+}
+K1Fn k1_select(int pp, int na) {
+  switch (pp) {
+    case 1: return k1_for_na<1>(na);
+    case 2: return k1_for_na<2>(na);
+    case 3: return k1_for_na<3>(na);
+    case 4: return k1_for_na<4>(na);
+  }
+  return nullptr;
+}
+
+typedef void (*K2Fn)(const cpx::ZDev*, int, cpx::WindowArgs);
+template <bool CHI2>
+K2Fn k2_select(int mt) {
+  switch (mt) {
+    case 1: return cpx::k_window<1, CHI2>;
+    case 2: return cpx::k_window<2, CHI2>;
+    case 3: return cpx::k_window<3, CHI2>;
+    case 4: return cpx::k_window<4, CHI2>;
+    case 5: return cpx::k_window<5, CHI2>;
+    case 6: return cpx::k_window<6, CHI2>;
+    case 7: return cpx::k_window<7, CHI2>;
+    case 8: return cpx::k_window<8, CHI2>;
+  }
+  return nullptr;
+}
+
+int choose_na_blk(int max_na) {
+  if (max_na <= 24) return round_up(max_na, 4);
+  const int nblk = (max_na + 23) / 24;
+  return round_up((max_na + nblk - 1) / nblk, 4);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : dflt;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+const char* cpx_last_error(void) { return g_err.c_str(); }
+int cpx_version(void) { return 100; }
+
+void cpx_destroy(cpx_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& zh : h->z)
+    for (void* p : zh.owned) cudaFree(p);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_handle** out) {
+  if (!zbins || n_zbins <= 0 || n_zbins > cpx::kMaxZ || !out) return fail(CPX_ERR_ARG, "cpx_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(CPX_ERR_CUDA, std::string("cpx_create: no CUDA device (") + cudaGetErrorString(e) +
+                                  "); cupix_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CPX_ERR_ARG, "cpx_create: device index out of range");
+  CPX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CPX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(CPX_ERR_UNSUPPORTED, "cpx_create: kernels are built for sm_100a (Blackwell) only");
+
+  cpx_handle* h = new cpx_handle;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int rc) { cpx_destroy(h); return rc; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(CPX_ERR_CUDA, "cudaStreamCreate failed"));
+
+  for (int i = 0; i < n_zbins; ++i) {
+    const cpx_zbin_desc& d = zbins[i];
+    if (d.n_a <= 0 || d.n_m <= 0 || d.n_q <= 0 || !d.kpar_Mpc || !d.kperp_Mpc || !d.hankel_w || !d.linP_cell)
+      return bail(fail(CPX_ERR_ARG, "cpx_create: z bin with missing theory arrays"));
+    h->max_na = std::max(h->max_na, d.n_a);
+    h->max_nm = std::max(h->max_nm, d.n_m);
+    h->max_nA = std::max(h->max_nA, d.n_A);
+    h->max_nM = std::max(h->max_nM, d.n_M);
+    h->max_nq = std::max(h->max_nq, d.n_q);
+  }
+  h->na_blk = choose_na_blk(h->max_na);
+  const size_t smem_need = static_cast<size_t>(h->max_nq) * (cpx::kCellConsts * cpx::kTileRows * 4 + h->na_blk * 8);
+  if (smem_need > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
+    return bail(fail(CPX_ERR_UNSUPPORTED, "cpx_create: n_q too large for the shared-memory-resident grid"));
+
+  h->z.resize(n_zbins);
+  size_t per_point_bytes = 0;
+  for (int i = 0; i < n_zbins; ++i) {
+    int rc = build_zbin(h, zbins[i], h->na_blk, h->z[i]);
+    if (rc) return bail(rc);
+    if (zbins[i].n_A > 0) {
+      rc = upload_yd(h, h->z[i], zbins[i].Px_AM, zbins[i].n_data);
+      if (rc) return bail(rc);
+    }
+    per_point_bytes += static_cast<size_t>(h->z[i].dev.n_a) * h->z[i].dev.n_m_pad * 8 + sizeof(cpx::PtPar);
+  }
+  // chunk: Px_Zam scratch of all z within the budget (default 4 GiB), multiple of 256 points
+  const size_t budget = static_cast<size_t>(env_int("CPX_SCRATCH_MB", 4096)) << 20;
+  long long chunk = static_cast<long long>(budget / std::max<size_t>(per_point_bytes, 1));
+  chunk = std::max(256LL, std::min(chunk, 65536LL)) / 256 * 256;
+  h->chunk = static_cast<int>(chunk);
+
+  auto dmalloc = [&](void** p, size_t bytes) -> int {
+    CPX_CUDA(cudaMalloc(p, bytes));
+    h->owned.push_back(*p);
+    h->device_bytes += bytes;
+    return CPX_OK;
+  };
+  int rc;
+  for (int i = 0; i < n_zbins; ++i) {
+    cpx::ZDev& Z = h->z[i].dev;
+    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.ptpar), sizeof(cpx::PtPar) * h->chunk))) return bail(rc);
+    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.pxzam),
+                      static_cast<size_t>(h->chunk) * Z.n_a * Z.n_m_pad * 8 + 256)))
+      return bail(rc);
+  }
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_ztab), sizeof(cpx::ZDev) * n_zbins))) return bail(rc);
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_zlist), sizeof(int) * n_zbins))) return bail(rc);
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_nA_of_z), sizeof(int) * n_zbins))) return bail(rc);
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_points), sizeof(double) * 16 * h->chunk))) return bail(rc);
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_data_idx), sizeof(int) * h->chunk))) return bail(rc);
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2), sizeof(double) * h->chunk))) return bail(rc);
+  if (h->max_nA > 0)
+    if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2_zA),
+                      sizeof(double) * static_cast<size_t>(h->chunk) * n_zbins * h->max_nA)))
+      return bail(rc);
+
+  // opt in to the large dynamic shared memory for every k_p3d_hankel instantiation we may launch
+  for (int pp = 1; pp <= 4; ++pp) {
+    K1Fn fn = k1_select(pp, h->na_blk);
+    if (!fn) return bail(fail(CPX_ERR_UNSUPPORTED, "no k_p3d_hankel instantiation for this theta-bin count"));
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
+      return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
+  }
+  *out = h;
+  return CPX_OK;
+}
+
+int cpx_set_data(cpx_handle* h, int32_t iz, const double* Px_AM, int32_t n_data) {
+  if (!h || iz < 0 || iz >= static_cast<int>(h->z.size()) || !Px_AM || n_data <= 0)
+    return fail(CPX_ERR_ARG, "cpx_set_data: bad arguments");
+  if (h->z[iz].dev.n_A <= 0) return fail(CPX_ERR_ARG, "cpx_set_data: z bin has no measurement");
+  CPX_CUDA(cudaSetDevice(h->device));
+  CPX_CUDA(cudaStreamSynchronize(h->stream));
+  return upload_yd(h, h->z[iz], Px_AM, n_data);
+}
+
+int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
+  if (!h || !value) return fail(CPX_ERR_ARG, "cpx_get_info: bad arguments");
+  switch (what) {
+    case CPX_INFO_N_ZBINS: *value = static_cast<int64_t>(h->z.size()); break;
+    case CPX_INFO_MAX_NA: *value = h->max_na; break;
+    case CPX_INFO_MAX_NM: *value = h->max_nm; break;
+    case CPX_INFO_MAX_N_A: *value = h->max_nA; break;
+    case CPX_INFO_MAX_N_M: *value = h->max_nM; break;
+    case CPX_INFO_CHUNK: *value = h->chunk; break;
+    case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
+    case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
+    case CPX_INFO_SM_COUNT: *value = h->sm_count; break;
+    default: return fail(CPX_ERR_ARG, "cpx_get_info: unknown item");
+  }
+  return CPX_OK;
+}
+
+int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
+  using namespace cpx;
+  if (!h || !a) return fail(CPX_ERR_ARG, "cpx_eval: null handle or args");
+  if (a->B < 0 || a->P < 0 || a->P > 16) return fail(CPX_ERR_ARG, "cpx_eval: B < 0 or P outside 0..16");
+  if (a->P > 0 && !a->slot) return fail(CPX_ERR_ARG, "cpx_eval: slot is NULL");
+  if (a->P > 0 && !a->points && !a->grid_n) return fail(CPX_ERR_ARG, "cpx_eval: neither points nor a grid given");
+  for (int j = 0; j < a->P; ++j) {
+    if (a->slot[j] < 0 || a->slot[j] >= CPX_NSLOTS) return fail(CPX_ERR_ARG, "cpx_eval: slot out of range");
+    if (a->grid_n && a->grid_n[j] < 1) return fail(CPX_ERR_ARG, "cpx_eval: grid_n < 1");
+  }
+  if (a->B == 0) return CPX_OK;
+  CPX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : h->stream;
+  const bool dev_io = (a->flags & CPX_DEVICE_IO) != 0;
+
+  // ---- z selection ----
+  std::vector<int> zl;
+  if (a->z_list) {
+    if (a->n_z_list <= 0) return fail(CPX_ERR_ARG, "cpx_eval: empty z_list");
+    for (int i = 0; i < a->n_z_list; ++i) {
+      if (a->z_list[i] < 0 || a->z_list[i] >= static_cast<int>(h->z.size()))
+        return fail(CPX_ERR_ARG, "cpx_eval: z_list entry out of range");
+      zl.push_back(a->z_list[i]);
+    }
+  } else {
+    for (size_t i = 0; i < h->z.size(); ++i) zl.push_back(static_cast<int>(i));
+  }
+  const int n_zl = static_cast<int>(zl.size());
+  const bool want_chi2 = a->chi2 || a->chi2_zA;
+  const bool want_model = a->model_zAM != nullptr;
+  const bool want_px = a->px_zam != nullptr;
+  if (want_chi2 || want_model)
+    for (int zi : zl)
+      if (h->z[zi].dev.n_A <= 0) return fail(CPX_ERR_ARG, "cpx_eval: chi2/model requested for a theory-only z bin");
+  if (a->data_idx && dev_io == false) {
+    // validated on the host when available
+    for (int64_t i = 0; i < a->B; ++i)
+      for (int zi : zl)
+        if (a->data_idx[i] < 0 || a->data_idx[i] >= h->z[zi].dev.n_data)
+          return fail(CPX_ERR_ARG, "cpx_eval: data_idx out of range");
+  }
+
+  // lazy scratch for the bulky optional outputs
+  auto lazy = [&](double** p, size_t n) -> int {
+    if (*p) return CPX_OK;
+    CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(double)));
+    h->owned.push_back(*p);
+    h->device_bytes += n * sizeof(double);
+    return CPX_OK;
+  };
+  int rc;
+  const size_t nz_all = h->z.size();
+  if (want_model && !dev_io)
+    if ((rc = lazy(&h->d_model, static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM))) return rc;
+  if (want_px && !dev_io)
+    if ((rc = lazy(&h->d_pxout, static_cast<size_t>(h->chunk) * nz_all * h->max_na * h->max_nm))) return rc;
+
+  // ---- device table for this launch ----
+  std::vector<ZDev> tab(n_zl);
+  std::vector<int> nA_of_z(n_zl);
+  const int pp_env = env_int("CPX_PP", 0);
+  // output strides follow the evaluated list
+  int na_max = 0, nm_max = 0, nA_max = 0, nM_max = 0;
+  for (int zi : zl) {
+    na_max = std::max(na_max, h->z[zi].dev.n_a);
+    nm_max = std::max(nm_max, h->z[zi].dev.n_m);
+    nA_max = std::max(nA_max, h->z[zi].dev.n_A);
+    nM_max = std::max(nM_max, h->z[zi].dev.n_M);
+  }
+
+  ParamsArgs pa;
+  std::memset(&pa, 0, sizeof(pa));
+  pa.P = a->P;
+  pa.n_z = n_zl;
+  pa.grid_mode = a->grid_n ? 1 : 0;
+  pa.grid_first = a->grid_first;
+  for (int j = 0; j < a->P; ++j) {
+    pa.slot[j] = a->slot[j];
+    pa.zsel[j] = a->zsel ? a->zsel[j] : -1;
+    if (a->grid_n) {
+      pa.grid_n[j] = a->grid_n[j];
+      pa.grid_lo[j] = a->grid_lo[j];
+      pa.grid_step[j] = a->grid_n[j] > 1 ? (a->grid_hi[j] - a->grid_lo[j]) / (a->grid_n[j] - 1) : 0.0;
+    }
+  }
+
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() -> int {
+    if (!a->stage_ms) return CPX_OK;
+    cudaEvent_t ev;
+    CPX_CUDA(cudaEventCreate(&ev));
+    CPX_CUDA(cudaEventRecord(ev, st));
+    evs.push_back(ev);
+    return CPX_OK;
+  };
+
+  CPX_CUDA(cudaMemcpyAsync(h->d_zlist, zl.data(), sizeof(int) * n_zl, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < n_zl; ++i) nA_of_z[i] = h->z[zl[i]].dev.n_A;
+  CPX_CUDA(cudaMemcpyAsync(h->d_nA_of_z, nA_of_z.data(), sizeof(int) * n_zl, cudaMemcpyHostToDevice, st));
+
+  int last_table_count = -1, last_pp = -1;
+  for (int64_t first = 0; first < a->B; first += h->chunk) {
+    const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
+    int pp = pp_env > 0 ? std::min(pp_env, 4) : (count > 2048 ? 4 : (count > 256 ? 2 : 1));
+    const int n_pg = (count + kK1Warps * pp - 1) / (kK1Warps * pp);
+    if (count != last_table_count || pp != last_pp) {
+      long long items = 0;
+      for (int i = 0; i < n_zl; ++i) {
+        tab[i] = h->z[zl[i]].dev;
+        tab[i].item_start = items;
+        items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * n_pg;
+      }
+      // stream-ordered: the previous chunk's kernels have been enqueued before this copy
+      CPX_CUDA(cudaMemcpyAsync(h->d_ztab, tab.data(), sizeof(ZDev) * n_zl, cudaMemcpyHostToDevice, st));
+      last_table_count = count;
+      last_pp = pp;
+    }
+    long long n_items = 0;
+    for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * n_pg;
+
+    // ---- stage 0: parameters ----
+    if ((rc = mark())) return rc;
+    pa.first = 0;
+    pa.count = count;
+    if (!pa.grid_mode) {
+      if (dev_io) {
+        pa.points = a->points + first * a->P;
+      } else if (a->P > 0) {
+        CPX_CUDA(cudaMemcpyAsync(h->d_points, a->points + first * a->P, sizeof(double) * count * a->P,
+                                 cudaMemcpyHostToDevice, st));
+        pa.points = h->d_points;
+      }
+    } else {
+      pa.first = first;
+    }
+    const int* d_didx = nullptr;
+    if (a->data_idx) {
+      if (dev_io) {
+        d_didx = a->data_idx + first;
+      } else {
+        CPX_CUDA(cudaMemcpyAsync(h->d_data_idx, a->data_idx + first, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+        d_didx = h->d_data_idx;
+      }
+    }
+    {
+      dim3 grid((count + 127) / 128, n_zl);
+      k_params<<<grid, 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
+      ++h->launches;
+    }
+    // ---- stage 1: P3D + Hankel ----
+    if ((rc = mark())) return rc;
+    {
+      K1Fn fn = k1_select(pp, h->na_blk);
+      const size_t smem = static_cast<size_t>(h->max_nq) * (kCellConsts * kTileRows * 4 + h->na_blk * 8);
+      const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));
+      fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);
+      ++h->launches;
+    }
+    // ---- stage 2: window (+ whitening, chi2) ----
+    if ((rc = mark())) return rc;
+    double* chi2_zA_dst = nullptr;
+    if (want_chi2) chi2_zA_dst = (dev_io && a->chi2_zA) ? a->chi2_zA + first * n_zl * nA_max : h->d_chi2_zA;
+    double* model_dst = nullptr;
+    if (want_model) model_dst = dev_io ? a->model_zAM + first * n_zl * nA_max * nM_max : h->d_model;
+    double* px_dst = nullptr;
+    if (want_px) px_dst = dev_io ? a->px_zam + first * n_zl * na_max * nm_max : h->d_pxout;
+    for (int i = 0; i < n_zl; ++i) {
+      const ZDev& Z = tab[i];
+      WindowArgs w;
+      w.count = count;
+      w.zslot = i;
+      w.n_zl = n_zl;
+      w.nA_max = nA_max;
+      w.nM_max = nM_max;
+      w.data_idx = d_didx;
+      w.chi2_zA = chi2_zA_dst;
+      w.model = model_dst;
+      dim3 grid((count + kWinPts - 1) / kWinPts, std::max(Z.n_A, 1));
+      if (want_chi2) {
+        k2_select<true>(Z.n_M_pad / 8)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        ++h->launches;
+      }
+      if (want_model) {
+        k2_select<false>(Z.n_M_pad / 8)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        ++h->launches;
+      }
+      if (want_px) {
+        k_unpad_pxzam<<<std::min(4 * h->sm_count, 1024), 256, 0, st>>>(h->d_ztab, i, i, n_zl, na_max, nm_max, count, px_dst);
+        ++h->launches;
+      }
+    }
+    // ---- stage 3: reduce ----
+    if ((rc = mark())) return rc;
+    if (a->chi2) {
+      double* dst = dev_io ? a->chi2 + first : h->d_chi2;
+      k_reduce<<<(count + 255) / 256, 256, 0, st>>>(chi2_zA_dst, dst, count, n_zl, nA_max, h->d_nA_of_z);
+      ++h->launches;
+    }
+    if ((rc = mark())) return rc;
+    CPX_CUDA(cudaGetLastError());
+    if (!dev_io) {
+      if (a->chi2)
+        CPX_CUDA(cudaMemcpyAsync(a->chi2 + first, h->d_chi2, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+      if (a->chi2_zA)
+        CPX_CUDA(cudaMemcpyAsync(a->chi2_zA + first * n_zl * nA_max, h->d_chi2_zA,
+                                 sizeof(double) * count * n_zl * nA_max, cudaMemcpyDeviceToHost, st));
+      if (a->model_zAM)
+        CPX_CUDA(cudaMemcpyAsync(a->model_zAM + first * n_zl * nA_max * nM_max, h->d_model,
+                                 sizeof(double) * count * n_zl * nA_max * nM_max, cudaMemcpyDeviceToHost, st));
+      if (a->px_zam)
+        CPX_CUDA(cudaMemcpyAsync(a->px_zam + first * n_zl * na_max * nm_max, h->d_pxout,
+                                 sizeof(double) * count * n_zl * na_max * nm_max, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  if (!dev_io || a->stage_ms) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(CPX_ERR_CUDA, std::string("cpx_eval: ") + cudaGetErrorString(e));
+  }
+  if (a->stage_ms) {
+    for (int s = 0; s < 4; ++s) a->stage_ms[s] = 0.f;
+    for (size_t i = 0; i + 4 < evs.size(); i += 5)   // five marks per chunk
+      for (int s = 0; s < 4; ++s) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[i + s], evs[i + s + 1]);
+        a->stage_ms[s] += ms;
+      }
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  }
+  return CPX_OK;
+}
+
+int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(CPX_ERR_CUDA, "cpx_probe_peaks: no such CUDA device");
+  CPX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CPX_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* dbuf;
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 64));
+  cudaEvent_t e0, e1;
+  CPX_CUDA(cudaEventCreate(&e0));
+  CPX_CUDA(cudaEventCreate(&e1));
+  double* outs[3] = {dfma_per_s, ffma_per_s, mufu_per_s};
+  for (int which = 0; which < 3; ++which) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CPX_CUDA(cudaEventRecord(e0));
+      if (which == 0) cpx::k_probe_dfma<<<blocks, threads>>>(dbuf, iters, 1.0000001);
+      if (which == 1) cpx::k_probe_ffma<<<blocks, threads>>>(reinterpret_cast<float*>(dbuf), iters, 1.0000001f);
+      if (which == 2) cpx::k_probe_mufu<<<blocks, threads>>>(reinterpret_cast<float*>(dbuf), iters, -0.5f);
+      CPX_CUDA(cudaEventRecord(e1));
+      CPX_CUDA(cudaEventSynchronize(e1));
+      float ms;
+      CPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0) best = std::min(best, ms);
+    }
+    if (outs[which]) *outs[which] = 8.0 * iters * static_cast<double>(blocks) * threads / (best * 1e-3);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dbuf);
+  return CPX_OK;
+}
+
+}  // extern "C"

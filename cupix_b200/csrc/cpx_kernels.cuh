@@ -1,0 +1,544 @@
+// cupix_b200 device kernels (sm_100a).  See DESIGN.md section 3 for the data layout and section 4
+// for the roofline of each kernel.
+//
+//   k_params   per-(point, z) parameter expansion: defaults (+) overrides, derived scalars
+//              (model_lya.py:190-196, model_contaminants.py:103-144; grid generation of
+//              scripts/chi2_scan_mock.py:107-111)
+//   k_p3d_hankel  fused Arinyo P3D evaluation on the shared-memory-staged (k_par, k_perp) grid +
+//              J0 Hankel quadrature + contaminant epilogues  (theory.py:95-123,250-344; the theta
+//              average of likelihood.py:99-130 is inside the weights)
+//   k_window   window convolution + theta rebinning (+ Cholesky whitening and chi2) as a batched
+//              FP64 tensor-core (DMMA) contraction  (likelihood.py:53-88,170-194)
+//   k_reduce   chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpx {
+
+constexpr int kTileRows = 32;        // k_par rows per shared-memory tile (one per lane)
+constexpr int kCellConsts = 6;       // D, L2K, L2MU, MU2, K2, PL
+constexpr int kK1Warps = 8;
+constexpr int kK1Threads = kK1Warps * 32;
+constexpr int kMaxZ = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// per-(z, point) parameters written by k_params and read by k_p3d_hankel
+struct PtPar {
+  // cell evaluation (FP32 pipe)
+  float q1l, q2l;      // q1 * log2(e), q2 * log2(e)
+  float av, bv;
+  float nlkv;          // -av * log2(kv_Mpc)
+  float ikp2l;         // log2(e) / kp_Mpc^2
+  // epilogues (FP64)
+  double bias, beta;
+  double b_H, beta_H, L_H;
+  double b_X, beta_X;
+  double b_noise;
+  double kC, pC;
+};
+static_assert(sizeof(PtPar) == 104, "PtPar layout");
+
+// per-z device data for k_p3d_hankel / k_params
+struct ZDev {
+  int n_a, n_m, n_q, n_tiles;          // n_tiles = ceil(n_m / 32)
+  int n_m_pad;                          // 32 * n_tiles
+  int na_blk, n_ablk;                   // a-block width (template NA) and count
+  int flags;
+  double dAA;
+  const float* cellc;                   // [n_tiles][n_q][6][32]
+  const double* Wd;                     // [n_ablk][n_q][na_blk]
+  const double* kpar;                   // [n_m_pad]
+  const double* metal_auto;             // [3][n_a][n_m] or null
+  const double* metal_cross;            // [3][n_a][n_m] or null
+  const double* sky_xi;                 // [n_a] or null
+  const double* sky_smooth;             // [n_m] or null
+  double defaults[16];
+  // window part
+  int n_A, n_M, n_M_pad, n_pairs, n_data;
+  int pad0;
+  const int* pair_start;                // [n_A + 1] pairs of coarse bin A are pair_start[A] .. pair_start[A+1]
+  const int* pair_a;                    // [n_pairs] fine bin of each pair
+  const double* T_chi;                  // [n_pairs][n_M_pad][n_m_pad]  L^-1 diag(V/Vsum) U
+  const double* T_model;                // [n_pairs][n_M_pad][n_m_pad]  diag(V/Vsum) U
+  const double* yd;                     // [n_data][n_A][n_M_pad]       L^-1 d
+  // per-chunk buffers
+  PtPar* ptpar;                         // [chunk]
+  double* pxzam;                        // [chunk][n_a][n_m_pad]
+  long long item_start;                 // first k_p3d_hankel work item of this z in the launch
+};
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// FP64 tensor-core MMA, D(8x8) = A(8x4) * B(4x8) + C
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------
+// k_params
+// ------------------------------------------------------------------------------------------
+struct ParamsArgs {
+  const double* points;   // [B][P] or null (grid mode)
+  int P;
+  int n_z;                // number of z bins evaluated
+  long long first;        // chunk offset into points / grid
+  int count;              // points in this chunk
+  int grid_mode;
+  double grid_lo[16], grid_step[16];
+  int grid_n[16];
+  int slot[16], zsel[16];
+  long long grid_first;
+};
+
+__global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int* __restrict__ zlist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int zi = blockIdx.y;
+  if (i >= a.count) return;
+  const ZDev& Z = ztab[zi];
+  const int zglobal = zlist[zi];
+  double v[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) v[s] = Z.defaults[s];
+  if (a.grid_mode) {
+    long long idx = a.grid_first + a.first + i;
+    for (int j = a.P - 1; j >= 0; --j) {
+      const int n = a.grid_n[j];
+      const int ij = static_cast<int>(idx % n);
+      idx /= n;
+      const double x = a.grid_lo[j] + ij * a.grid_step[j];
+      if (a.zsel[j] < 0 || a.zsel[j] == zglobal) v[a.slot[j]] = x;
+    }
+  } else {
+    const double* p = a.points + (a.first + i) * a.P;
+    for (int j = 0; j < a.P; ++j)
+      if (a.zsel[j] < 0 || a.zsel[j] == zglobal) v[a.slot[j]] = p[j];
+  }
+  PtPar o;
+  const double l2e = 1.4426950408889634074;
+  o.q1l = static_cast<float>(v[2] * l2e);
+  o.q2l = static_cast<float>(v[3] * l2e);
+  o.av = static_cast<float>(v[5]);
+  o.bv = static_cast<float>(v[6]);
+  o.nlkv = static_cast<float>(-v[5] * log2(v[4]));
+  o.ikp2l = static_cast<float>(l2e / (v[7] * v[7]));
+  o.bias = v[0];
+  o.beta = v[1];
+  o.b_H = v[8];
+  o.beta_H = v[9];
+  o.L_H = v[10];
+  o.b_X = v[11];
+  o.beta_X = v[12];
+  o.b_noise = v[13];
+  o.kC = v[14];
+  o.pC = v[15];
+  Z.ptpar[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_p3d_hankel
+// ------------------------------------------------------------------------------------------
+// One CTA = 8 warps.  Lane = one k_par row of a 32-row tile; each warp carries PP parameter
+// points at a time through the whole k_perp loop, so a CTA pass covers 8*PP points.  The cell
+// constants of the tile ([n_q][6][32] floats) and the Hankel weights of the a-block ([n_q][NA]
+// doubles) are staged in shared memory with TMA bulk copies and stay resident while the CTA
+// walks its contiguous range of work items (z, tile, a-block, point-group).
+//
+// Per cell and point: 9 FP32 ops + 2 MUFU.EX2 (Arinyo P3D, theory.py:285-308) and NA FP64 FMAs
+// (Hankel accumulation).  The FP64 pipe is the bound: NA DFMA per (cell, point).
+template <int PP, int NA>
+__global__ void __launch_bounds__(kK1Threads, 1)
+    k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_pg = (count + kK1Warps * PP - 1) / (kK1Warps * PP);
+
+  // contiguous slice of the flattened item space for this CTA
+  const long long it0 = n_items * blockIdx.x / gridDim.x;
+  const long long it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+  if (it0 >= it1) return;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  int cur_z = -1, cur_tile = -1, cur_ablk = -1;
+  float* s_cell = reinterpret_cast<float*>(smem_raw);
+  double* s_w = nullptr;
+
+  for (long long it = it0; it < it1; ++it) {
+    // decode item -> (zi, tile, ablk, pg); z bins are few, linear scan
+    int zi = (cur_z >= 0) ? cur_z : 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
+    const ZDev& Z = ztab[zi];
+    long long r = it - Z.item_start;
+    const int pg = static_cast<int>(r % n_pg);
+    r /= n_pg;
+    const int ablk = static_cast<int>(r % Z.n_ablk);
+    const int tile = static_cast<int>(r / Z.n_ablk);
+    const int n_q = Z.n_q;
+
+    const bool new_tile = (zi != cur_z) || (tile != cur_tile);
+    const bool new_w = (zi != cur_z) || (ablk != cur_ablk);
+    if (new_tile || new_w) {
+      __syncthreads();   // every warp is done reading the previous tile / weights
+      const uint32_t cell_bytes = static_cast<uint32_t>(n_q) * kCellConsts * kTileRows * 4u;
+      const uint32_t w_bytes = static_cast<uint32_t>(n_q) * NA * 8u;
+      s_w = reinterpret_cast<double*>(smem_raw + cell_bytes);
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (new_tile ? cell_bytes : 0u) + (new_w ? w_bytes : 0u));
+        if (new_tile) {
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.cellc) + static_cast<size_t>(tile) * cell_bytes;
+          for (uint32_t off = 0; off < cell_bytes; off += 32768u)
+            bulk_g2s(smem_raw + off, src + off, min(32768u, cell_bytes - off), &bar);
+        }
+        if (new_w) {
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.Wd) + static_cast<size_t>(ablk) * w_bytes;
+          for (uint32_t off = 0; off < w_bytes; off += 32768u)
+            bulk_g2s(reinterpret_cast<unsigned char*>(s_w) + off, src + off, min(32768u, w_bytes - off), &bar);
+        }
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+      cur_z = zi;
+      cur_tile = tile;
+      cur_ablk = ablk;
+    }
+
+    const int pt0 = (pg * kK1Warps + warp) * PP;       // first point of this warp
+    if (pt0 >= count) continue;
+    const int m = tile * kTileRows + lane;
+    const bool row_ok = m < Z.n_m;
+    const double kpar = Z.kpar[m];                      // padded rows hold 0
+
+    // ---- per-point scalars ----
+    float q1l[PP], q2l[PP], av[PP], bv[PP], nlkv[PP], ikp2l[PP], betaT[PP];
+    double amp[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      const int pt = min(pt0 + p, count - 1);
+      const PtPar& pr = Z.ptpar[pt];
+      q1l[p] = pr.q1l;
+      q2l[p] = pr.q2l;
+      av[p] = pr.av;
+      bv[p] = pr.bv;
+      nlkv[p] = pr.nlkv;
+      ikp2l[p] = pr.ikp2l;
+      double bT = pr.bias, betaTd = pr.beta;
+      if (Z.flags & 1) {   // HCD: scale-dependent bias, theory.py:267-282
+        const double F = exp(-kpar * pr.L_H);
+        bT = pr.bias + pr.b_H * F;
+        betaTd = (pr.bias * pr.beta + pr.b_H * pr.beta_H * F) / bT;
+      }
+      betaT[p] = static_cast<float>(betaTd);
+      amp[p] = bT * bT * Z.dAA;
+    }
+
+    double acc[PP][NA];
+#pragma unroll
+    for (int p = 0; p < PP; ++p)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) acc[p][a] = 0.0;
+
+    // ---- k_perp loop: P3D cell -> Hankel accumulation ----
+    const float* c = s_cell + lane;
+    const double2* w2 = reinterpret_cast<const double2*>(s_w);
+#pragma unroll 2
+    for (int q = 0; q < n_q; ++q) {
+      const float D = c[0], L2K = c[32], L2MU = c[64], MU2 = c[96], K2 = c[128], PL = c[160];
+      c += kCellConsts * kTileRows;
+      double pd[PP];
+#pragma unroll
+      for (int p = 0; p < PP; ++p) {
+        const float nl = D * fmaf(q2l[p], D, q1l[p]);                       // Delta^2 (q1 + q2 Delta^2) log2e
+        const float v = ex2_approx(fmaf(av[p], L2K, fmaf(bv[p], L2MU, nlkv[p])));   // (k/kv)^av mu^bv
+        const float t = fmaf(-K2, ikp2l[p], nl);
+        const float e = ex2_approx(fmaf(-nl, v, t));                        // D_NL
+        const float ka = fmaf(betaT[p], MU2, 1.0f);
+        pd[p] = static_cast<double>((PL * ka) * (ka * e));
+      }
+#pragma unroll
+      for (int a2 = 0; a2 < NA / 2; ++a2) {
+        const double2 w = w2[a2];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+          acc[p][2 * a2] = fma(w.x, pd[p], acc[p][2 * a2]);
+          acc[p][2 * a2 + 1] = fma(w.y, pd[p], acc[p][2 * a2 + 1]);
+        }
+      }
+      w2 += NA / 2;
+    }
+
+    // ---- epilogue: amplitude, metals, sky, continuum; store Px_Zam[pt][a][m] ----
+    const int a0 = ablk * NA;
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      const int pt = pt0 + p;
+      if (pt >= count) break;
+      const PtPar& pr = Z.ptpar[pt];
+      double cont = 1.0;
+      if (Z.flags & 8) cont = tanh(pow(kpar / pr.kC, pr.pC));               // theory.py:525-535
+      double sky = 0.0;
+      if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];      // theory.py:476-506
+      double* out = Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a0) * Z.n_m_pad + m;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        if (a0 + a >= Z.n_a) break;
+        double px = 0.0;
+        if (row_ok) {
+          px = amp[p] * acc[p][a];
+          if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
+            const size_t o = static_cast<size_t>(a0 + a) * Z.n_m + m, st = static_cast<size_t>(Z.n_a) * Z.n_m;
+            const double bx = pr.b_X, btx = pr.beta_X;
+            px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+            px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                  pr.beta * btx * Z.metal_cross[o + 2 * st]);
+          }
+          if (Z.flags & 4) px += sky * Z.sky_xi[a0 + a];
+          px *= cont;
+        }
+        out[static_cast<size_t>(a) * Z.n_m_pad] = px;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_window: Y[pt][M] = sum_{pairs (A,a)} sum_m T[pair][M][m] * Px_Zam[pt][a][m]   (FP64 DMMA)
+//   MODE_CHI2 : T = L^-1 diag(V/Vsum) U, out chi2_zA[pt] = || yd[data_idx[pt]][A] - Y ||^2
+//   MODE_MODEL: T =      diag(V/Vsum) U, out model[pt][A][M] = Y
+// CTA = 4 warps, 64 points x (8*MT) coarse-k columns for one coarse theta bin A of one z.
+// ------------------------------------------------------------------------------------------
+constexpr int kWinPts = 64;
+constexpr int kWinKC = 16;
+constexpr int kWinLd = kWinKC + 4;   // padded row stride (doubles): conflict-free LDS.64 fragments
+
+struct WindowArgs {
+  int count;          // points in chunk
+  int zslot;          // index of this z in the evaluated list
+  int n_zl;           // number of evaluated z
+  int nA_max, nM_max; // output strides
+  const int* data_idx;   // [count] or null
+  double* chi2_zA;    // [count][n_zl][nA_max]
+  double* model;      // [count][n_zl][nA_max][nM_max] or null
+};
+
+template <int MT, bool CHI2>
+__global__ void __launch_bounds__(128) k_window(const ZDev* __restrict__ ztab, int zi, WindowArgs w) {
+  const ZDev& Z = ztab[zi];
+  const int A = blockIdx.y;
+  const int pt_base = blockIdx.x * kWinPts;
+  if (A >= Z.n_A) return;
+  __shared__ __align__(16) double sA[2][kWinPts][kWinLd];
+  __shared__ __align__(16) double sB[2][8 * MT][kWinLd];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
+  const int kchunks = Z.n_m_pad / kWinKC;
+  const int n_steps = (p1 - p0) * kchunks;
+  const double* Tbase = CHI2 ? Z.T_chi : Z.T_model;
+
+  double acc[2][MT][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_stage = [&](int step, int buf) {
+    const int pair = p0 + step / kchunks;
+    const int k0 = (step % kchunks) * kWinKC;
+    const int a = Z.pair_a[pair];
+    // A tile: 64 points x 16 doubles = 512 x 16B
+    for (int i = tid; i < kWinPts * (kWinKC / 2); i += 128) {
+      const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+      const int pt = min(pt_base + row, w.count - 1);
+      const double* src = Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + k0 + 2 * c2;
+      cp_async16(&sA[buf][row][2 * c2], src);
+    }
+    // B tile: (8*MT) coarse-k rows x 16 doubles
+    for (int i = tid; i < 8 * MT * (kWinKC / 2); i += 128) {
+      const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+      const double* src = Tbase + (static_cast<size_t>(pair) * Z.n_M_pad + row) * Z.n_m_pad + k0 + 2 * c2;
+      cp_async16(&sB[buf][row][2 * c2], src);
+    }
+    cp_async_commit();
+  };
+
+  load_stage(0, 0);
+  for (int step = 0; step < n_steps; ++step) {
+    const int buf = step & 1;
+    if (step + 1 < n_steps) {
+      load_stage(step + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kWinKC; kk += 4) {
+      double af[2];
+      af[0] = sA[buf][warp * 16 + g][kk + t];
+      af[1] = sA[buf][warp * 16 + 8 + g][kk + t];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const double bf = sB[buf][8 * j + g][kk + t];
+        dmma_884(acc[0][j][0], acc[0][j][1], af[0], bf);
+        dmma_884(acc[1][j][0], acc[1][j][1], af[1], bf);
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue.  C fragment: rows g (+8), columns 8j + 2t + {0,1}
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int pt = pt_base + warp * 16 + 8 * i + g;
+    if (CHI2) {
+      const int d = (w.data_idx != nullptr && pt < w.count) ? w.data_idx[pt] : 0;
+      const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int col = 8 * j + 2 * t;
+        const double y0 = yd[col] - acc[i][j][0];
+        const double y1 = yd[col + 1] - acc[i][j][1];
+        s = fma(y0, y0, s);
+        s = fma(y1, y1, s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (t == 0 && pt < w.count)
+        w.chi2_zA[(static_cast<size_t>(pt) * w.n_zl + w.zslot) * w.nA_max + A] = s;
+    } else {
+      if (pt < w.count) {
+        double* out = w.model + ((static_cast<size_t>(pt) * w.n_zl + w.zslot) * w.nA_max + A) * w.nM_max;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int col = 8 * j + 2 * t;
+          if (col < Z.n_M) out[col] = acc[i][j][0];
+          if (col + 1 < Z.n_M) out[col + 1] = acc[i][j][1];
+        }
+      }
+    }
+  }
+}
+
+// chi2 from an already computed model (used when both model and chi2 are requested is not needed:
+// the two window modes are launched separately).
+
+// ------------------------------------------------------------------------------------------
+// k_reduce: chi2[pt] = sum over (z, A) in fixed order
+// ------------------------------------------------------------------------------------------
+__global__ void k_reduce(const double* __restrict__ chi2_zA, double* __restrict__ chi2, int count, int n_zl,
+                         int nA_max, const int* __restrict__ nA_of_z) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= count) return;
+  double s = 0.0;
+  for (int z = 0; z < n_zl; ++z) {
+    const double* r = chi2_zA + (static_cast<size_t>(pt) * n_zl + z) * nA_max;
+    for (int A = 0; A < nA_of_z[z]; ++A) s += r[A];
+  }
+  chi2[pt] = s;
+}
+
+// copy Px_Zam out of the padded per-z buffer: dst[pt][zslot][a][m]
+__global__ void k_unpad_pxzam(const ZDev* __restrict__ ztab, int zi, int zslot, int n_zl, int na_max, int nm_max,
+                              int count, double* __restrict__ dst) {
+  const ZDev& Z = ztab[zi];
+  const size_t n = static_cast<size_t>(count) * Z.n_a * Z.n_m;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i % Z.n_m);
+    const size_t r = i / Z.n_m;
+    const int a = static_cast<int>(r % Z.n_a);
+    const size_t pt = r / Z.n_a;
+    dst[((pt * n_zl + zslot) * na_max + a) * nm_max + m] = Z.pxzam[(pt * Z.n_a + a) * Z.n_m_pad + m];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pipe-rate probes (roofline denominators)
+// ------------------------------------------------------------------------------------------
+__global__ void k_probe_dfma(double* out, int iters, double x) {
+  double a0 = threadIdx.x, a1 = 1, a2 = 2, a3 = 3, a4 = 4, a5 = 5, a6 = 6, a7 = 7;
+  const double y = x * 0.5;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+    a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+__global__ void k_probe_ffma(float* out, int iters, float x) {
+  float a0 = threadIdx.x, a1 = 1, a2 = 2, a3 = 3, a4 = 4, a5 = 5, a6 = 6, a7 = 7;
+  const float y = x * 0.5f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, x, y); a1 = fmaf(a1, x, y); a2 = fmaf(a2, x, y); a3 = fmaf(a3, x, y);
+    a4 = fmaf(a4, x, y); a5 = fmaf(a5, x, y); a6 = fmaf(a6, x, y); a7 = fmaf(a7, x, y);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+__global__ void k_probe_mufu(float* out, int iters, float x) {
+  float a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3, a4 = x + 4, a5 = x + 5, a6 = x + 6, a7 = x + 7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = ex2_approx(a0); a1 = ex2_approx(a1); a2 = ex2_approx(a2); a3 = ex2_approx(a3);
+    a4 = ex2_approx(a4); a5 = ex2_approx(a5); a6 = ex2_approx(a6); a7 = ex2_approx(a7);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+
+}  // namespace cpx

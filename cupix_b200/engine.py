@@ -1,0 +1,279 @@
+"""ctypes binding of the C ABI in include/cupix_b200.h (libcupix_b200.so, built in-tree by
+``__graft_entry__.build()``).  There is no CPU fallback: if the library or a CUDA device is
+missing, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from cupix_b200 import plan as _plan
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcupix_b200.so")
+
+NSLOTS = 16
+DEVICE_IO = 1
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class ZbinDesc(C.Structure):
+    _fields_ = [
+        ("n_a", C.c_int32), ("n_m", C.c_int32), ("n_q", C.c_int32), ("n_A", C.c_int32),
+        ("n_M", C.c_int32), ("n_data", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("dAA_dMpc", C.c_double),
+        ("kpar_Mpc", c_dp), ("kperp_Mpc", c_dp), ("hankel_w", c_dp), ("linP_cell", c_dp),
+        ("metal_auto", c_dp), ("metal_cross", c_dp), ("sky_xi_a", c_dp), ("sky_smooth_m", c_dp),
+        ("defaults", C.c_double * NSLOTS),
+        ("B_A_a", c_dp), ("U_aMn", c_dp), ("V_aM", c_dp), ("Px_AM", c_dp), ("cov_AMM", c_dp),
+    ]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("P", C.c_int32), ("flags", C.c_int32),
+        ("points", C.c_void_p), ("slot", c_ip), ("zsel", c_ip),
+        ("grid_lo", c_dp), ("grid_hi", c_dp), ("grid_n", c_ip), ("grid_first", C.c_int64),
+        ("data_idx", C.c_void_p), ("z_list", c_ip), ("n_z_list", C.c_int32), ("reserved", C.c_int32),
+        ("chi2", C.c_void_p), ("chi2_zA", C.c_void_p), ("model_zAM", C.c_void_p), ("px_zam", C.c_void_p),
+        ("stream", C.c_void_p), ("stage_ms", C.POINTER(C.c_float)),
+    ]
+
+
+class CpxError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the in-tree shared library; raises with build instructions if it is absent."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise CpxError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(cupix_b200 has no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    lib.cpx_create.argtypes = [C.POINTER(ZbinDesc), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.cpx_create.restype = C.c_int
+    lib.cpx_eval.argtypes = [C.c_void_p, C.POINTER(EvalArgs)]
+    lib.cpx_eval.restype = C.c_int
+    lib.cpx_set_data.argtypes = [C.c_void_p, C.c_int32, c_dp, C.c_int32]
+    lib.cpx_set_data.restype = C.c_int
+    lib.cpx_destroy.argtypes = [C.c_void_p]
+    lib.cpx_destroy.restype = None
+    lib.cpx_last_error.argtypes = []
+    lib.cpx_last_error.restype = C.c_char_p
+    lib.cpx_version.argtypes = []
+    lib.cpx_version.restype = C.c_int
+    lib.cpx_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
+    lib.cpx_get_info.restype = C.c_int
+    lib.cpx_probe_peaks.argtypes = [C.c_int32, c_dp, c_dp, c_dp]
+    lib.cpx_probe_peaks.restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def probe_peaks(device=0):
+    """Measured FP64-FMA, FP32-FMA and MUFU.EX2 rates of the GPU [ops/s]."""
+    lib = load_library()
+    d, f, m = C.c_double(), C.c_double(), C.c_double()
+    if lib.cpx_probe_peaks(device, C.byref(d), C.byref(f), C.byref(m)) != 0:
+        raise CpxError(lib.cpx_last_error().decode())
+    return {"dfma_per_s": d.value, "ffma_per_s": f.value, "mufu_per_s": m.value}
+
+
+class PxEngine(object):
+    """Device-resident Px likelihood for a list of redshift-bin plans (cupix_b200.plan.ZbinPlan)."""
+
+    INFO = {"n_zbins": 0, "max_na": 1, "max_nm": 2, "max_nA": 3, "max_nM": 4, "chunk": 5,
+            "device_bytes": 6, "kernel_launches": 7, "sm_count": 8}
+
+    def __init__(self, plans, device=0):
+        self.lib = load_library()
+        self.plans = list(plans)
+        self.device = int(device)
+        descs = (ZbinDesc * len(self.plans))()
+        self._keep = []
+        for d, p in zip(descs, self.plans):
+            arrs = {k: _f64(getattr(p, k)) for k in
+                    ("kpar_Mpc", "kperp_Mpc", "hankel_w", "linP_cell", "metal_auto", "metal_cross",
+                     "sky_xi_a", "sky_smooth_m", "B_A_a", "U_aMn", "V_aM", "Px_AM", "cov_AMM")}
+            self._keep.append(arrs)
+            d.n_a, d.n_m, d.n_q = p.n_a, p.n_m, p.n_q
+            d.n_A, d.n_M, d.n_data = p.n_A, p.n_M, p.n_data
+            d.flags = p.flags
+            d.dAA_dMpc = p.dAA_dMpc
+            for k, v in arrs.items():
+                setattr(d, k, _dp(v))
+            for i in range(NSLOTS):
+                d.defaults[i] = float(p.defaults[i])
+        h = C.c_void_p()
+        rc = self.lib.cpx_create(descs, len(self.plans), self.device, C.byref(h))
+        if rc != 0:
+            raise CpxError("cpx_create failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        self._h = h
+        self._keep = None           # host arrays were copied to the device
+        self.n_z = len(self.plans)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cpx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self, what):
+        v = C.c_int64()
+        if self.lib.cpx_get_info(self._h, self.INFO[what], C.byref(v)) != 0:
+            raise CpxError(self.lib.cpx_last_error().decode())
+        return v.value
+
+    def set_data(self, iz, Px_AM):
+        Px_AM = _f64(Px_AM)
+        if Px_AM.ndim == 2:
+            Px_AM = Px_AM[None]
+        rc = self.lib.cpx_set_data(self._h, iz, _dp(Px_AM), Px_AM.shape[0])
+        if rc != 0:
+            raise CpxError("cpx_set_data failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        self.plans[iz].n_data = Px_AM.shape[0]
+
+    # ----------------------------------------------------------------------------------------
+    def _dims(self, z_list):
+        zs = list(range(self.n_z)) if z_list is None else list(z_list)
+        pl = [self.plans[i] for i in zs]
+        return zs, max(p.n_a for p in pl), max(p.n_m for p in pl), max(p.n_A for p in pl), max(p.n_M for p in pl)
+
+    def eval(self, points=None, slots=(), zsel=None, grid=None, grid_first=0, B=None, data_idx=None,
+             z_list=None, want=("chi2",), stage_ms=False):
+        """Host-buffer evaluation.  ``points`` [B, P] float64 (or ``grid=(lo, hi, n)`` for on-device
+        meshgrid generation), ``slots`` [P] parameter slot per column.  Returns a dict of numpy
+        arrays for the requested outputs in ``want`` (chi2, chi2_zA, model, px_zam)."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        P = int(slots.size)
+        args = EvalArgs()
+        keep = [slots]
+        if grid is not None:
+            lo, hi, n = (np.ascontiguousarray(grid[0], dtype=np.float64), np.ascontiguousarray(grid[1], dtype=np.float64),
+                         np.ascontiguousarray(grid[2], dtype=np.int32))
+            assert lo.size == hi.size == n.size == P
+            total = int(np.prod(n.astype(np.int64)))
+            B = total - grid_first if B is None else B
+            args.grid_lo, args.grid_hi, args.grid_n = _dp(lo), _dp(hi), n.ctypes.data_as(c_ip)
+            args.grid_first = int(grid_first)
+            keep += [lo, hi, n]
+        else:
+            if points is None:
+                points = np.zeros((1 if B is None else B, 0))
+            points = np.ascontiguousarray(points, dtype=np.float64)
+            if points.ndim == 1:
+                points = points.reshape(1, -1)
+            assert points.shape[1] == P, "points must be [B, len(slots)]"
+            B = points.shape[0]
+            args.points = points.ctypes.data_as(C.c_void_p) if P > 0 else None
+            keep.append(points)
+        args.B, args.P, args.flags = int(B), P, 0
+        args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
+        if zsel is not None:
+            zsel = np.ascontiguousarray(zsel, dtype=np.int32)
+            args.zsel = zsel.ctypes.data_as(c_ip)
+            keep.append(zsel)
+        if data_idx is not None:
+            data_idx = np.ascontiguousarray(data_idx, dtype=np.int32)
+            assert data_idx.size == B
+            args.data_idx = data_idx.ctypes.data_as(C.c_void_p)
+            keep.append(data_idx)
+        zs, na, nm, nA, nM = self._dims(z_list)
+        if z_list is not None:
+            zl = np.ascontiguousarray(zs, dtype=np.int32)
+            args.z_list, args.n_z_list = zl.ctypes.data_as(c_ip), len(zs)
+            keep.append(zl)
+        out = {}
+        if "chi2" in want:
+            out["chi2"] = np.empty(B)
+            args.chi2 = out["chi2"].ctypes.data_as(C.c_void_p)
+        if "chi2_zA" in want:
+            out["chi2_zA"] = np.zeros((B, len(zs), nA))
+            args.chi2_zA = out["chi2_zA"].ctypes.data_as(C.c_void_p)
+        if "model" in want:
+            out["model"] = np.zeros((B, len(zs), nA, nM))
+            args.model_zAM = out["model"].ctypes.data_as(C.c_void_p)
+        if "px_zam" in want:
+            out["px_zam"] = np.zeros((B, len(zs), na, nm))
+            args.px_zam = out["px_zam"].ctypes.data_as(C.c_void_p)
+        ms = (C.c_float * 4)()
+        if stage_ms:
+            args.stage_ms = ms
+        rc = self.lib.cpx_eval(self._h, C.byref(args))
+        if rc != 0:
+            raise CpxError("cpx_eval failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        if stage_ms:
+            out["stage_ms"] = np.array(list(ms))
+        return out
+
+    def eval_device(self, B, P, slots, points_ptr=None, grid=None, grid_first=0, zsel=None,
+                    data_idx_ptr=None, z_list=None, chi2_ptr=None, chi2_zA_ptr=None, model_ptr=None,
+                    px_ptr=None, stream=None, stage_ms=False):
+        """Device-pointer evaluation (asynchronous on ``stream``): pointers are raw device addresses
+        (e.g. ``torch.Tensor.data_ptr()``).  Returns stage times if requested (this synchronises)."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        args = EvalArgs()
+        args.B, args.P, args.flags = int(B), int(P), DEVICE_IO
+        args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
+        args.points = points_ptr
+        keep = [slots]
+        if grid is not None:
+            lo, hi, n = (np.ascontiguousarray(grid[0], dtype=np.float64), np.ascontiguousarray(grid[1], dtype=np.float64),
+                         np.ascontiguousarray(grid[2], dtype=np.int32))
+            args.grid_lo, args.grid_hi, args.grid_n = _dp(lo), _dp(hi), n.ctypes.data_as(c_ip)
+            args.grid_first = int(grid_first)
+            keep += [lo, hi, n]
+        if zsel is not None:
+            zsel = np.ascontiguousarray(zsel, dtype=np.int32)
+            args.zsel = zsel.ctypes.data_as(c_ip)
+            keep.append(zsel)
+        if z_list is not None:
+            zl = np.ascontiguousarray(list(z_list), dtype=np.int32)
+            args.z_list, args.n_z_list = zl.ctypes.data_as(c_ip), zl.size
+            keep.append(zl)
+        args.data_idx = data_idx_ptr
+        args.chi2, args.chi2_zA, args.model_zAM, args.px_zam = chi2_ptr, chi2_zA_ptr, model_ptr, px_ptr
+        args.stream = stream
+        ms = (C.c_float * 4)()
+        if stage_ms:
+            args.stage_ms = ms
+        rc = self.lib.cpx_eval(self._h, C.byref(args))
+        if rc != 0:
+            raise CpxError("cpx_eval failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        return np.array(list(ms)) if stage_ms else None
+
+
+def slots_from_names(names, n_z=None):
+    """Parameter names -> (slots, zsel).  A trailing ``_<iz>`` restricts a parameter to one z bin
+    (the convention of the reference scan scripts, scripts/chi2_scan_mock.py:138).  Unknown names
+    raise here; the dict-based scalar API drops them silently like the reference does."""
+    slots, zsel = [], []
+    for name in names:
+        base, iz = name, -1
+        if name not in _plan.SLOT_INDEX:
+            head, _, tail = name.rpartition("_")
+            if head in _plan.SLOT_INDEX and tail.isdigit():
+                base, iz = head, int(tail)
+            else:
+                raise KeyError("unknown parameter name %r" % name)
+        slots.append(_plan.SLOT_INDEX[base])
+        zsel.append(iz)
+    return np.array(slots, dtype=np.int32), np.array(zsel, dtype=np.int32)

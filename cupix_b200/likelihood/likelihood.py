@@ -1,0 +1,162 @@
+"""``Likelihood``: Gaussian chi2 of a Px measurement, same interface as
+``cupix/likelihood/likelihood.py``, evaluated on the GPU for whole batches of parameter points.
+
+Scalar calls (``get_chi2(params)``, ``get_log_like``, ``get_convolved_px``) are the batch-of-one case
+of the ``*_batch`` / ``*_grid`` methods; all of them go through the C ABI (cupix_b200.engine).
+"""
+import numpy as np
+from scipy.stats.distributions import chi2 as chi2_scipy
+
+from cupix_b200 import plan as _plan
+from cupix_b200.engine import PxEngine, slots_from_names
+from cupix_b200.likelihood.likelihood_parameter import dict_from_likeparam
+
+
+class Likelihood(object):
+    """Likelihood class, holds data, theory, and knows about parameters"""
+
+    def __init__(self, data, theory, iz, config={}):
+        """Setup likelihood from theory and data (likelihood.py:10-34):
+        - data (required) is the data to model
+        - theory (required) instance of Theory
+        - iz (required) is the index of the redshift bin to use"""
+        self.data = data
+        self.theory = theory
+        self.iz = iz
+        assert self.data.z[iz] == self.theory.z, "inconsistent redshifts"
+        self.verbose = config.get('verbose', False)
+        self.N_theta_average = config.get('N_theta_average', 100)
+        self.device = config.get('device', getattr(theory, 'device', 0))
+        self._engines = {}
+        if self.verbose:
+            print("Likelihood will evaluate redshift bin", self.iz, "corresponds to z =", self.theory.z)
+
+    # ---- engine ------------------------------------------------------------------------------
+    def build_plan(self, cosmo=None):
+        cosmo = self.theory.fid_cosmo if cosmo is None else cosmo
+        return _plan.build_likelihood_plan(self.theory, cosmo, self.data, self.iz,
+                                           self.N_theta_average, self.theory.rule)
+
+    def engine(self, cosmo=None):
+        """Device engine for the current N_theta_average (callers toggle that attribute, e.g.
+        notebooks/examples/average_theory.py:267-271) and cosmology."""
+        key = (self.N_theta_average, 0 if cosmo is None or cosmo is self.theory.fid_cosmo else id(cosmo))
+        if key not in self._engines:
+            if len(self._engines) > 4:
+                self._engines.pop(next(iter(self._engines))).close()
+            self._engines[key] = PxEngine([self.build_plan(cosmo)], device=self.device)
+        return self._engines[key]
+
+    def _scalar_eval(self, params, want):
+        cosmo = self.theory.get_cosmology(params=params)
+        names, values = self.theory.split_params(params)
+        slots, _ = slots_from_names(names)
+        return self.engine(cosmo).eval(points=values, slots=slots, want=want)
+
+    # ---- reference API -----------------------------------------------------------------------
+    def generate_px_forecast(self, params={}, add_noise=False):
+        """Px data vector from the theory and the data window, optionally with noise drawn from the
+        data covariance (likelihood.py:37-50)."""
+        px_theory = self.get_convolved_px(params=params)
+        if add_noise:
+            for A in range(px_theory.shape[0]):
+                L = np.linalg.cholesky(self.data.cov_ZAM[self.iz, A, :, :])
+                px_theory[A] = px_theory[A] + np.dot(L, np.random.normal(size=px_theory[A].shape))
+        return px_theory
+
+    def get_convolved_px(self, params={}):
+        """Window-convolved, theta-rebinned model [N_A, N_M] (likelihood.py:53-88)."""
+        return self._scalar_eval(params, ("model",))["model"][0, 0]
+
+    def _compute_Px_Zam(self, params):
+        """Theory per fine bin (theta_a, k_m), theta-averaged [N_a, N_m] (likelihood.py:91-132)."""
+        return self._scalar_eval(params, ("px_zam",))["px_zam"][0, 0]
+
+    def _compute_log_like(self, params={}):
+        out = self._scalar_eval(params, ("chi2", "chi2_zA"))
+        log_like_all = -0.5 * out["chi2_zA"][0, 0]
+        return -0.5 * out["chi2"][0], {'log_like_all': log_like_all}
+
+    def get_chi2(self, params={}, return_info=False, like_params=None):
+        if like_params is not None:          # legacy keyword (old_likelihood.py:127-141)
+            params = dict_from_likeparam(like_params)
+        log_like, info = self._compute_log_like(params)
+        chi2 = -2.0 * log_like
+        return (chi2, info) if return_info else chi2
+
+    def get_log_like(self, params={}, return_info=False):
+        log_like, info = self._compute_log_like(params=params)
+        return (log_like, info) if return_info else log_like
+
+    def get_probability(self, params={}, n_free_p=0):
+        """Probability given the number of degrees of freedom (likelihood.py:152-161)."""
+        chi2 = self.get_chi2(params=params, return_info=False)
+        return chi2_scipy.sf(chi2, self.get_ndata() - n_free_p)
+
+    def get_ndata(self):
+        return self.data.Px_ZAM[self.iz].size
+
+    # ---- batched API (new) -------------------------------------------------------------------
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None):
+        """chi2 [B] for ``points`` [B, P] whose columns are the parameters ``names``."""
+        slots, _ = slots_from_names(names)
+        want = ("chi2", "chi2_zA") if return_info else ("chi2",)
+        out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx)
+        if return_info:
+            return out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"][:, 0]}
+        return out["chi2"]
+
+    def get_log_like_batch(self, points, names, data_idx=None):
+        return -0.5 * self.get_chi2_batch(points, names, data_idx=data_idx)
+
+    def get_convolved_px_batch(self, points, names):
+        slots, _ = slots_from_names(names)
+        return self.engine().eval(points=points, slots=slots, want=("model",))["model"][:, 0]
+
+    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None):
+        """chi2 on the meshgrid(indexing='ij') of linspace(lo[j], hi[j], n[j]); points are generated
+        on the device (scripts/chi2_scan_mock.py:107-111).  ``first``/``count`` select a flat slice."""
+        slots, _ = slots_from_names(names)
+        return self.engine().eval(slots=slots, grid=(lo, hi, n), grid_first=first, B=count)["chi2"]
+
+    def set_mock_data(self, Px_AM):
+        """Replace the data vector(s) [n_data, N_A, N_M] scored by ``data_idx`` (many-mock fits)."""
+        self.engine().set_data(0, Px_AM)
+
+
+class JointLikelihood(object):
+    """Several redshift bins scored in one device call: chi2 = sum over z (full-shape evaluation).
+    Parameter names may carry a ``_<iz>`` suffix to apply to one bin only."""
+
+    def __init__(self, likes, device=0):
+        self.likes = list(likes)
+        self.device = device
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = PxEngine([lk.build_plan() for lk in self.likes], device=self.device)
+        return self._engine
+
+    def get_ndata(self):
+        return sum(lk.get_ndata() for lk in self.likes)
+
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None):
+        slots, zsel = slots_from_names(names)
+        want = ("chi2", "chi2_zA") if return_info else ("chi2",)
+        out = self.engine().eval(points=points, slots=slots, zsel=zsel, want=want, data_idx=data_idx)
+        return (out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"]}) if return_info else out["chi2"]
+
+    def get_chi2(self, params={}, return_info=False):
+        names = [k for k in params]
+        pts = np.array([[params[k] for k in names]], dtype=np.float64).reshape(1, len(names))
+        r = self.get_chi2_batch(pts, names, return_info=return_info)
+        return (r[0][0], r[1]) if return_info else r[0]
+
+    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None):
+        slots, zsel = slots_from_names(names)
+        return self.engine().eval(slots=slots, zsel=zsel, grid=(lo, hi, n), grid_first=first, B=count)["chi2"]
+
+    def get_convolved_px_batch(self, points, names):
+        slots, zsel = slots_from_names(names)
+        return self.engine().eval(points=points, slots=slots, zsel=zsel, want=("model",))["model"]

@@ -1,0 +1,109 @@
+"""``Theory``: Px(k_par, theta) predictions, same interface as ``cupix/likelihood/theory.py``.
+
+The reference evaluates one parameter point per call in NumPy and delegates the Hankel transform to
+ForestFlow.  Here the object only prepares float64 constants (cupix_b200.plan) and hands batches
+of parameter points to the CUDA engine (cupix_b200.engine.PxEngine); ``get_px_obs`` is the
+batch-of-one special case.  No CPU evaluation path exists.
+"""
+import numpy as np
+
+from cupix_b200 import cosmology as _cosmology
+from cupix_b200 import plan as _plan
+from cupix_b200.engine import PxEngine, slots_from_names
+from cupix_b200.likelihood.likelihood_parameter import dict_from_likeparam
+from cupix_b200.likelihood.model_contaminants import ContaminantsModel
+from cupix_b200.likelihood.model_lya import LyaModel
+from cupix_b200.quadrature import DEFAULT_K0, DEFAULT_KMAX, DEFAULT_NQ, KperpRule
+
+COSMO_KEYS = ("H0", "omch2", "ombh2", "mnu", "omk", "As", "ns", "nrun", "w")
+
+
+class Theory(object):
+    """Likelihood will ask this object for Px predictions"""
+
+    def __init__(self, z, fid_cosmo=None, config={'verbose': False}):
+        """Inputs (theory.py:14-46):
+            - z: redshift of the Lya bin
+            - fid_cosmo: fiducial cosmology object (unit conversions, linear power)
+            - config: include_hcd / include_metal / include_sky / include_continuum, the LyaModel and
+              ContaminantsModel keys, plus engine settings n_q, k0_Mpc, kmax_Mpc, device."""
+        self.verbose = config.get('verbose', False)
+        self.z = z
+        self.zs = z
+        self.fid_cosmo = _cosmology.Cosmology() if fid_cosmo is None else fid_cosmo
+        self.lya_model = LyaModel(z, config)
+        self.cont_model = ContaminantsModel(z, config)
+        self.include_hcd = config.get('include_hcd', False)
+        self.include_metal = config.get('include_metal', False)
+        self.include_sky = config.get('include_sky', False)
+        self.include_continuum = config.get('include_continuum', False)
+        self.rule = KperpRule(config.get('n_q', DEFAULT_NQ), config.get('k0_Mpc', DEFAULT_K0),
+                              config.get('kmax_Mpc', DEFAULT_KMAX))
+        self.device = config.get('device', 0)
+        self._engines = {}
+
+    # -- cosmology (theory.py:49-64) ---------------------------------------------------------
+    def get_cosmology(self, cosmo=None, params={}):
+        if cosmo is not None:
+            return cosmo
+        if not any(k in params for k in COSMO_KEYS):
+            return self.fid_cosmo
+        if self.fid_cosmo.same_background(cosmo_params=params):
+            if isinstance(self.fid_cosmo, _cosmology.Cosmology):
+                return _cosmology.RescaledCosmology(self.fid_cosmo, params)
+            from lace.cosmo import rescale_cosmology
+            return rescale_cosmology.RescaledCosmology(fid_cosmo=self.fid_cosmo, new_params_dict=params)
+        if isinstance(self.fid_cosmo, _cosmology.Cosmology):
+            return _cosmology.Cosmology(cosmo_params_dict=params)
+        from lace.cosmo import cosmology
+        return cosmology.Cosmology(cosmo_params_dict=params)
+
+    def get_z_metal_auto(self):
+        """theory.py:168-180"""
+        return (1 + self.z) * self.lya_model.lr_lya / self.cont_model.lr_metal - 1
+
+    def get_z_metal_cross(self):
+        """theory.py:183-197"""
+        return np.sqrt((1 + self.z) * (1 + self.get_z_metal_auto())) - 1
+
+    # -- parameters ---------------------------------------------------------------------------
+    @staticmethod
+    def split_params(params):
+        """dict -> (names, values) of the keys the device path knows; the rest is dropped silently
+        (model_lya.py:193-196)."""
+        names = [k for k in params if k in _plan.SLOT_INDEX]
+        return names, np.array([[float(params[k]) for k in names]], dtype=np.float64).reshape(1, len(names))
+
+    # -- engine cache ---------------------------------------------------------------------------
+    def _theta_engine(self, theta_arc, k_AA, cosmo):
+        theta_arc = np.atleast_1d(np.asarray(theta_arc, dtype=np.float64))
+        k_AA = np.atleast_1d(np.asarray(k_AA, dtype=np.float64))
+        key = (theta_arc.tobytes(), k_AA.tobytes(), id(cosmo) if cosmo is not self.fid_cosmo else 0)
+        if key not in self._engines:
+            if len(self._engines) > 8:
+                self._engines.pop(next(iter(self._engines))).close()
+            p = _plan.build_theory_plan(self, cosmo, theta_arc, np.arange(theta_arc.size), k_AA, self.rule)
+            self._engines[key] = PxEngine([p], device=self.device)
+        return self._engines[key]
+
+    # -- predictions --------------------------------------------------------------------------
+    def get_px_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """Px [N_theta, N_k] in Angstrom (theory.py:95-123)."""
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        names, values = self.split_params(params)
+        eng = self._theta_engine(theta_arc, k_AA, cosmo)
+        slots, zsel = slots_from_names(names)
+        return eng.eval(points=values, slots=slots, want=("px_zam",))["px_zam"][0, 0]
+
+    def get_px_obs_batch(self, theta_arc, k_AA, points, names, cosmo=None):
+        """Px [B, N_theta, N_k] for B parameter points (columns named by ``names``)."""
+        cosmo = self.fid_cosmo if cosmo is None else cosmo
+        eng = self._theta_engine(theta_arc, k_AA, cosmo)
+        slots, zsel = slots_from_names(names)
+        return eng.eval(points=points, slots=slots, want=("px_zam",))["px_zam"][:, 0]
+
+    def get_px_AA(self, k_AA, theta_arcmin, zs=None, like_params={}, return_arinyo_coeffs=False, verbose=None):
+        """Legacy entry point kept for the old Likelihood class (theory.py:68-92)."""
+        params_dict = dict_from_likeparam(like_params)
+        assert zs == self.z, "Input redshift does not match one in theory"
+        return self.get_px_obs(theta_arc=theta_arcmin, k_AA=k_AA, params=params_dict)

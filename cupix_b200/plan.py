@@ -1,0 +1,150 @@
+"""Host-side (float64) construction of everything that is constant across the parameter batch.
+
+For one redshift bin this turns (Theory config, cosmology, theta binning, k_m, measurement) into
+the plain arrays of ``cpx_zbin_desc`` (include/cupix_b200.h):
+
+* the (k_par, k_perp) grid and the linear power sampled on it     (theory.py:300 does this per call)
+* the folded Hankel weights W[a, q]                               (theory.py:250-264 + likelihood.py:99-130)
+* Hankel moments of the SiIII auto / cross terms, which depend on the parameter point only through
+  b_X, beta_X, bias, beta *polynomially*  (theory.py:361-438), so they need no per-point quadrature
+* the theta-averaged xi_noise and the pixel smoothing of the sky term (theory.py:476-506)
+"""
+import numpy as np
+
+from cupix_b200.quadrature import KperpRule
+
+SLOT_NAMES = ("bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc",
+              "b_H", "beta_H", "L_H_Mpc", "b_X", "beta_X", "b_noise_Mpc", "kC_Mpc", "pC")
+SLOT_INDEX = {n: i for i, n in enumerate(SLOT_NAMES)}
+
+INCLUDE_HCD, INCLUDE_METAL, INCLUDE_SKY, INCLUDE_CONTINUUM = 1, 2, 4, 8
+METAL_KP_MPC = 10.0      # theory.py:378,421
+PIXEL_AA = 0.8           # theory.py:495
+
+
+class ZbinPlan(object):
+    """Plain-array description of one redshift bin (fields of cpx_zbin_desc)."""
+    n_A = 0
+    n_M = 0
+    n_data = 0
+    metal_auto = metal_cross = sky_xi_a = sky_smooth_m = None
+    B_A_a = U_aMn = V_aM = Px_AM = cov_AMM = None
+
+
+def fine_theta_grid(theta_min_a, theta_max_a, N):
+    """likelihood.py:99-116: bin centres for N == 1, else N mid-points per fine bin.
+    Returns (theta[n], group[n])."""
+    lo, hi = np.asarray(theta_min_a, dtype=np.float64), np.asarray(theta_max_a, dtype=np.float64)
+    if N == 1:
+        return 0.5 * (lo + hi), np.arange(lo.size)
+    th, grp = [], []
+    for i, (a, b) in enumerate(zip(lo, hi)):
+        d = (b - a) / N
+        th.append(np.linspace(a + 0.5 * d, b - 0.5 * d, N))
+        grp.append(np.full(N, i))
+    return np.concatenate(th), np.concatenate(grp)
+
+
+def _cells(kpar, kperp):
+    k2 = kpar[:, None] ** 2 + kperp[None, :] ** 2
+    k = np.sqrt(k2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mu = np.where(k > 0, kpar[:, None] / np.where(k > 0, k, 1.0), 0.0)
+    return k, mu
+
+
+def _linP_on_cells(cosmo, z, k):
+    P = np.zeros_like(k)
+    pos = k > 0
+    P[pos] = cosmo.get_linP_Mpc(z, k[pos])
+    return P
+
+
+def default_vector(theory, cosmo):
+    """The 16 per-z default parameter values in slot order."""
+    lya = theory.lya_model.get_lya_params(cosmo, {})
+    c = theory.cont_model
+    vals = dict(lya)
+    vals.update(c.get_hcd_params({}))
+    vals.update(c.get_metal_params({}))
+    vals.update(c.get_sky_params({}))
+    vals.update(c.get_continuum_params({}))
+    return np.array([float(vals[n]) for n in SLOT_NAMES])
+
+
+def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
+    """Theory part of a plan for separations ``theta_arc`` (arcmin) grouped into bins by
+    ``theta_group`` (theta-weighted average inside a group) and wavenumbers ``k_AA``."""
+    rule = rule or KperpRule()
+    p = ZbinPlan()
+    z = theory.z
+    theta_arc = np.asarray(theta_arc, dtype=np.float64)
+    theta_group = np.asarray(theta_group)
+    k_AA = np.asarray(k_AA, dtype=np.float64)
+    n_a = int(theta_group.max()) + 1
+    lr_lya, lr_metal = theory.lya_model.lr_lya, theory.cont_model.lr_metal
+
+    darc = cosmo.get_darc_dMpc(z)
+    dAA = cosmo.get_dAA_dMpc(z, lambda_rest_AA=lr_lya)
+    p.n_a, p.n_m, p.n_q = n_a, k_AA.size, rule.n_q
+    p.dAA_dMpc = float(dAA)
+    p.kpar_Mpc = k_AA * dAA
+    p.kperp_Mpc = rule.k.copy()
+    p.hankel_w = rule.weights(theta_arc / darc, theta_group, theta_arc, n_a)
+    k, _ = _cells(p.kpar_Mpc, p.kperp_Mpc)
+    p.linP_cell = _linP_on_cells(cosmo, z, k)
+    p.defaults = default_vector(theory, cosmo)
+    p.flags = (INCLUDE_HCD * bool(theory.include_hcd) | INCLUDE_METAL * bool(theory.include_metal)
+               | INCLUDE_SKY * bool(theory.include_sky) | INCLUDE_CONTINUUM * bool(theory.include_continuum))
+
+    if theory.include_metal:
+        # auto: z_X, lambda_X (theory.py:200-222, 361-381); cross: z_cross, sqrt(l_a l_X) (:225-247, 398-438)
+        z_auto = theory.get_z_metal_auto()
+        z_cross = theory.get_z_metal_cross()
+        lr_cross = np.sqrt(lr_metal * lr_lya)
+        tabs = []
+        for zz, lr, wiggle in ((z_auto, lr_metal, False), (z_cross, lr_cross, True)):
+            darc_x = cosmo.get_darc_dMpc(zz)
+            dAA_x = cosmo.get_dAA_dMpc(zz, lambda_rest_AA=lr)
+            kpar_x = k_AA * dAA_x
+            W_x = rule.weights(theta_arc / darc_x, theta_group, theta_arc, n_a)       # [n_a, n_q]
+            kx, mux = _cells(kpar_x, rule.k)
+            base = _linP_on_cells(cosmo, zz, kx) * np.exp(-(kx / METAL_KP_MPC) ** 2)  # [n_m, n_q]
+            mom = np.stack([W_x @ (base * mux ** (2 * j)).T for j in range(3)]) * dAA_x   # [3, n_a, n_m]
+            if wiggle:
+                dX_AA = np.log(lr_lya / lr_metal) * (1 + zz) * lr
+                drp_Mpc = dX_AA / dAA_x
+                mom = mom * (2.0 * np.cos(kpar_x * drp_Mpc))[None, None, :]
+            tabs.append(np.ascontiguousarray(mom))
+        p.metal_auto, p.metal_cross = tabs
+
+    if theory.include_sky:
+        xi = theory.cont_model.get_xi_noise(theta_arc)
+        wsum = np.bincount(theta_group, weights=theta_arc, minlength=n_a)
+        p.sky_xi_a = np.bincount(theta_group, weights=theta_arc * xi, minlength=n_a) / wsum
+        x = (PIXEL_AA / dAA) * p.kpar_Mpc / 2.0
+        smooth = np.ones_like(x)
+        pos = x > 0
+        smooth[pos] = (np.sin(x[pos]) / x[pos]) ** 2
+        p.sky_smooth_m = smooth * dAA
+    return p
+
+
+def attach_measurement(p, data, iz):
+    """Measurement part of a plan: the px_data arrays of redshift bin ``iz``."""
+    p.n_A = len(data.theta_min_A_arcmin)
+    p.n_M = len(data.k_M_edges[iz]) - 1
+    p.n_data = 1
+    p.B_A_a = np.asarray(data.B_A_a, dtype=np.float64)
+    p.U_aMn = np.asarray(data.U_ZaMn[iz], dtype=np.float64)
+    p.V_aM = np.asarray(data.V_ZaM[iz], dtype=np.float64)
+    p.Px_AM = np.asarray(data.Px_ZAM[iz], dtype=np.float64)[None]
+    p.cov_AMM = np.asarray(data.cov_ZAM[iz], dtype=np.float64)
+    assert p.U_aMn.shape == (p.n_a, p.n_M, p.n_m), "window matrices do not match the binning"
+    return p
+
+
+def build_likelihood_plan(theory, cosmo, data, iz, N_theta_average, rule=None):
+    th, grp = fine_theta_grid(data.theta_min_a_arcmin, data.theta_max_a_arcmin, N_theta_average)
+    p = build_theory_plan(theory, cosmo, th, grp, data.k_m[iz], rule)
+    return attach_measurement(p, data, iz)

@@ -1,0 +1,178 @@
+"""GPU parity: the CUDA path (through the C ABI, via the Theory / Likelihood mirrors) against the
+golden vectors of the reference and against the float64 oracle.
+
+Tolerances (BASELINE.json north_star): model Px relative 1e-5, chi2 absolute 1e-3.  "Relative" is
+taken with respect to the largest |Px| of the compared array: Px crosses zero and falls by 18
+decades across (theta, k_par), so an element-wise ratio is meaningless there.  The chi2 tolerance
+is absolute 1e-3 plus 1e-7 relative (float64 chi2 of ~1e4 has that much representational slack in
+the float32 cell evaluation).
+"""
+import numpy as np
+import pytest
+
+from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
+from cupix_b200.px_data import synthetic
+from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2
+from tests import helpers as H
+from tests.golden.ref_theory_param_sets import FLAG_SETS, PARAM_SETS
+
+pytestmark = pytest.mark.gpu
+
+PX_RTOL = 1e-5
+CHI2_ATOL = 1e-3
+CHI2_RTOL = 1e-7
+
+G = H.golden("ref_theory_px.npz")
+CASES = sorted({tuple(k.split("|")[1:4]) for k in G if k.startswith("px|")})
+
+
+def assert_px(got, ref, tol=PX_RTOL, msg=""):
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max() / scale
+    assert err <= tol, "%s: max |dPx| / max|Px| = %.3e > %.1e" % (msg, err, tol)
+    return err
+
+
+def assert_chi2(got, ref, msg=""):
+    got, ref = np.asarray(got), np.asarray(ref)
+    bad = np.abs(got - ref) > CHI2_ATOL + CHI2_RTOL * np.abs(ref)
+    assert not bad.any(), "%s: max |dchi2| = %.3e (chi2 ~ %.3e)" % (msg, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+@pytest.mark.parametrize("model,z,fname", CASES)
+def test_theory_px_vs_reference_golden(model, z, fname):
+    th = H.make_theory(float(z), model, FLAG_SETS[fname])
+    for pname, params in PARAM_SETS.items():
+        ref = G["px|%s|%s|%s|%s" % (model, z, fname, pname)]
+        got = th.get_px_obs(G["theta_arc"], G["k_AA"], params=params)
+        assert got.shape == ref.shape
+        assert_px(got, ref, msg="%s %s %s %s" % (model, z, fname, pname))
+
+
+def test_theory_batch_equals_scalar():
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS["all"])
+    rng = np.random.default_rng(3)
+    names = ["bias", "beta", "q1", "kp_Mpc", "b_H", "pC"]
+    pts = np.stack([rng.uniform(-0.2, -0.1, 37), rng.uniform(1.0, 2.0, 37), rng.uniform(0.1, 0.9, 37),
+                    rng.uniform(8, 25, 37), rng.uniform(-0.04, -0.01, 37), rng.uniform(0.4, 0.9, 37)], axis=1)
+    batch = th.get_px_obs_batch(G["theta_arc"], G["k_AA"], pts, names)
+    for i in (0, 17, 36):
+        one = th.get_px_obs(G["theta_arc"], G["k_AA"], params=dict(zip(names, pts[i])))
+        np.testing.assert_array_equal(batch[i], one)
+
+
+def _load_like_fixture(shape):
+    g = H.golden("ref_likelihood_%s.npz" % shape)
+    data = DESI_DR2({k: g[k] for k in ("z_centers", "k_m", "k_M_edges", "theta_min_a", "theta_max_a", "theta_min_A",
+                                      "theta_max_A", "N_fft", "L_fft", "B_A_a", "U_ZaMn", "V_ZaM", "Px_ZAM", "cov_ZAM")})
+    flags = {str(f): True for f in g["flags"]}
+    trial = dict(zip([str(k) for k in g["trial_keys"]], [float(v) for v in g["trial_vals"]]))
+    truth = dict(zip([str(k) for k in g["truth_keys"]], [float(v) for v in g["truth_vals"]]))
+    likes = [Likelihood(data, H.make_theory(float(data.z[iz]), "best_fit_arinyo_from_colore", flags), iz,
+                        config={"N_theta_average": int(g["N_theta_average"])}) for iz in range(len(data.z))]
+    return g, data, likes, trial, truth
+
+
+@pytest.mark.parametrize("shape", ["tiny", "tiny_rebin"])
+def test_likelihood_vs_reference_golden(shape):
+    g, data, likes, trial, truth = _load_like_fixture(shape)
+    for iz, like in enumerate(likes):
+        assert_px(like._compute_Px_Zam(trial), g["Px_Zam_trial_%d" % iz], msg="Px_Zam z%d" % iz)
+        assert_px(like.get_convolved_px(trial), g["model_trial_%d" % iz], msg="model z%d" % iz)
+        chi2, info = like.get_chi2(trial, return_info=True)
+        assert_chi2(chi2, g["chi2_trial_%d" % iz], "chi2 trial z%d" % iz)
+        assert_chi2(-2 * info["log_like_all"], -2 * g["log_like_all_trial_%d" % iz], "log_like_all z%d" % iz)
+        assert_chi2(like.get_chi2(truth), g["chi2_truth_%d" % iz], "chi2 truth z%d" % iz)
+        np.testing.assert_allclose(like.get_log_like(trial), -0.5 * chi2, rtol=0, atol=0)
+        assert like.get_ndata() == data.Px_ZAM[iz].size
+    # all z bins in one device call == sum of the per-z likelihoods
+    joint = JointLikelihood(likes)
+    tot = sum(float(g["chi2_trial_%d" % iz]) for iz in range(len(likes)))
+    assert_chi2(joint.get_chi2(trial), tot, "joint chi2")
+
+
+def _s1_like(N_t=2, flags=None, shape="S1", model="best_fit_arinyo_from_colore", noise=True, **over):
+    d = synthetic.make_measurement_dict(shape, **over)
+    z = float(d["z_centers"][0])
+    th = H.make_theory(z, model, flags or {})
+    like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": N_t})
+    truth = {"bias": -0.115, "beta": 1.5}
+    filled = synthetic.fill_from_model(d, like.get_convolved_px(truth)[None], add_noise=noise)
+    return Likelihood(DESI_DR2(filled), th, 0, config={"N_theta_average": N_t}), truth
+
+
+def test_chi2_scan_16x16_vs_oracle():
+    """16 x 16 (bias, beta) grid around truth on the S1 shape, |dchi2| <= 1e-3."""
+    like, truth = _s1_like(N_t=2)
+    lo, hi, n = [truth["bias"] - 0.02, truth["beta"] - 0.2], [truth["bias"] + 0.02, truth["beta"] + 0.2], [16, 16]
+    chi2 = like.get_chi2_grid(["bias", "beta"], lo, hi, n).reshape(16, 16)
+    # the same points, explicitly, through the points path
+    bb, ee = np.meshgrid(np.linspace(lo[0], hi[0], 16), np.linspace(lo[1], hi[1], 16), indexing="ij")
+    pts = np.stack([bb.ravel(), ee.ravel()], axis=1)
+    np.testing.assert_array_equal(like.get_chi2_batch(pts, ["bias", "beta"]).reshape(16, 16), chi2)
+    orc = H.oracle_likelihood(like)
+    sel = [(0, 0), (3, 12), (8, 8), (15, 15), (15, 0), (7, 9), (11, 2)]
+    for i, j in sel:
+        ref = orc.get_chi2({"bias": bb[i, j], "beta": ee[i, j]})
+        assert_chi2(chi2[i, j], ref, "grid point (%d,%d)" % (i, j))
+    # a grid slice (how a rank takes its shard) equals the same slice of the full grid
+    part = like.get_chi2_grid(["bias", "beta"], lo, hi, n, first=100, count=57)
+    np.testing.assert_array_equal(part, chi2.ravel()[100:157])
+
+
+def test_forecast_self_consistency():
+    """chi2 ~ 0 when the truth is scored against its own noiseless forecast
+    (notebooks/examples/example_user_interface_notebook.py:337-359)."""
+    like, truth = _s1_like(N_t=1, noise=False, flags=FLAG_SETS["all"])
+    assert abs(like.get_chi2(truth)) < 1e-6
+    assert like.get_chi2({"bias": -0.12, "beta": 1.5}) > 1.0
+
+
+def test_rebinned_thetas_and_all_contaminants_vs_oracle():
+    like, truth = _s1_like(N_t=3, flags=FLAG_SETS["all"], shape="S1_rebin", N_A=6, N_m=60)
+    orc = H.oracle_likelihood(like)
+    rng = np.random.default_rng(11)
+    names = ["bias", "beta", "q1", "b_H", "b_X", "b_noise_Mpc", "kC_Mpc"]
+    pts = np.stack([rng.uniform(-0.13, -0.10, 6), rng.uniform(1.3, 1.7, 6), rng.uniform(0.2, 0.7, 6),
+                    rng.uniform(-0.03, -0.01, 6), rng.uniform(-0.01, -0.002, 6), rng.uniform(0.001, 0.005, 6),
+                    rng.uniform(0.01, 0.03, 6)], axis=1)
+    chi2, info = like.get_chi2_batch(pts, names, return_info=True)
+    model = like.get_convolved_px_batch(pts, names)
+    for i in range(pts.shape[0]):
+        params = dict(zip(names, pts[i]))
+        assert_px(model[i], orc.get_convolved_px(params), msg="model %d" % i)
+        ref, rinfo = orc.get_chi2(params, return_info=True)
+        assert_chi2(chi2[i], ref, "chi2 %d" % i)
+        assert_chi2(-2 * info["log_like_all"][i], -2 * rinfo["log_like_all"], "per-theta chi2 %d" % i)
+
+
+def test_many_mocks_data_index():
+    """S4 shape: one window/covariance, several data vectors, per-point data index."""
+    like, truth = _s1_like(N_t=1, N_A=5, N_m=48)
+    rng = np.random.default_rng(5)
+    base = like.data.Px_ZAM[0]
+    mocks = base[None] * (1 + 0.02 * rng.normal(size=(4,) + base.shape))
+    like.set_mock_data(mocks)
+    pts = np.tile([[truth["bias"], truth["beta"]]], (8, 1))
+    didx = np.array([0, 1, 2, 3, 3, 2, 1, 0])
+    chi2 = like.get_chi2_batch(pts, ["bias", "beta"], data_idx=didx)
+    orc = H.oracle_likelihood(like)
+    for j in range(4):
+        orc.Px_AM = mocks[j]
+        ref = orc.get_chi2(truth)
+        assert_chi2(chi2[didx == j], np.full(2, ref), "mock %d" % j)
+
+
+def test_unknown_keys_ignored_and_errors_are_loud():
+    like, truth = _s1_like(N_t=1, N_A=4, N_m=32)
+    a = like.get_chi2(dict(truth))
+    b = like.get_chi2(dict(truth, not_a_parameter=1.0, kCb_Mpc=3.0))
+    assert a == b
+    with pytest.raises(KeyError):
+        like.get_chi2_batch(np.zeros((2, 1)), ["not_a_parameter"])
+    bad = synthetic.make_measurement_dict("tiny")
+    bad["cov_ZAM"] = -bad["cov_ZAM"]
+    from cupix_b200.engine import CpxError
+    with pytest.raises(CpxError):
+        Likelihood(DESI_DR2(bad), H.make_theory(2.2, "best_fit_arinyo_from_colore", {}), 0,
+                   config={"N_theta_average": 1}).get_chi2({})
