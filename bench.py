@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark: Px likelihood evaluations per second on the S5 stress shape
+(12 z x 20 theta x 256 k_par, dense window matrices; BASELINE.json configs[4]).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference ...                     (CPU arm: the reference algorithm)
+
+A step = one pass of the hot path over one batch of `--points` parameter points per GPU, taken as
+consecutive slices of a 4-parameter (bias, beta, q1, kp_Mpc) scan grid; every point is scored
+against the whole data vector (all 12 z bins).  See DESIGN.md section 6 for what each JSON key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NAMES = ["bias", "beta", "q1", "kp_Mpc"]
+GRID_N = [64, 64, 64, 40]              # 10 485 760 points ("1e7 grid points")
+
+
+def grid_bounds(defaults):
+    from cupix_b200.plan import SLOT_INDEX
+    lo, hi = [], []
+    for nm, half in zip(NAMES, (0.02, 0.2, 0.15, 4.0)):
+        c = defaults[SLOT_INDEX[nm]]
+        lo.append(c - half)
+        hi.append(c + half)
+    return lo, hi
+
+
+def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True):
+    """Synthetic S5 measurement: windows/weights seeded, data = model(truth) + noise."""
+    from cupix_b200.cosmology import Cosmology
+    from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
+    from cupix_b200.likelihood.theory import Theory
+    from cupix_b200.px_data import synthetic
+    from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2
+    d = synthetic.make_measurement_dict(shape)
+    cosmo = Cosmology()
+    cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": n_q}
+    theories = [Theory(float(z), fid_cosmo=cosmo, config=cfg) for z in d["z_centers"]]
+    data = DESI_DR2(d)
+    likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
+    if not need_engine:
+        return d, data, likes, None
+    joint = JointLikelihood(likes, device=int(os.environ.get("LOCAL_RANK", "0")))
+    model = joint.get_convolved_px_batch(np.zeros((1, 0)), [])[0]          # truth = per-z defaults
+    filled = synthetic.fill_from_model(d, model, add_noise=add_noise)
+    data = DESI_DR2(filled)
+    for lk in likes:
+        lk.data = data
+    for iz in range(len(likes)):
+        joint.engine().set_data(iz, filled["Px_ZAM"][iz])
+    return filled, data, likes, joint
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def algorithmic_work(likes, n_q):
+    """Per evaluation (one point, all z): FP64 Hankel FMAs, P3D cells, window FMAs."""
+    hankel = cells = window = chi2 = 0
+    for lk in likes:
+        n_a, n_m = len(lk.data.theta_min_a_arcmin), len(lk.data.k_m[lk.iz])
+        n_M, n_A = len(lk.data.k_M_edges[lk.iz]) - 1, len(lk.data.theta_min_A_arcmin)
+        cells += n_m * n_q
+        hankel += n_a * n_m * n_q
+        window += int(np.count_nonzero(lk.data.B_A_a)) * n_M * n_m
+        chi2 += n_A * n_M
+    return {"p3d_cells": cells, "hankel_dfma": hankel, "window_dfma": window, "chi2_dfma": chi2}
+
+
+def cpu_worker(args):
+    """One process of the CPU arm: evaluates its block of points serially (the reference pattern,
+    scripts/chi2_scan_mock.py:140), BLAS pinned to one thread (scripts/profile.py:2-7)."""
+    flavour, shape, n_t, n_q, pts = args
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle.hankel import FFTLogHankel
+    from tests import helpers as H
+    d, data, likes, _ = build_workload(shape, n_t, n_q, need_engine=False)
+    orcs = []
+    for lk in likes:
+        o = H.oracle_likelihood(lk)
+        if flavour == "fftlog":
+            o.theory.hankel = FFTLogHankel()
+        else:
+            # fixed-node rule: per-theta weights are parameter independent -> computed once, outside the timing
+            r = lk.theory.rule
+            cache = {}
+
+            def wfn(rr, r=r, cache=cache):
+                key = rr.tobytes()
+                if key not in cache:
+                    cache[key] = r.weights(rr, nthreads=1)
+                return cache[key]
+            o.theory.hankel.weight_fn = wfn
+            o.get_chi2({})
+        orcs.append(o)
+    t0 = time.time()
+    out = [sum(o.get_chi2(dict(zip(NAMES, p))) for o in orcs) for p in pts]
+    return time.time() - t0, out
+
+
+def run_cpu(flavour, shape, n_t, n_q, per_core, defaults):
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    lo, hi = grid_bounds(defaults)
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(lo, hi, size=(cores * per_core, len(NAMES)))
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(cpu_worker, [(flavour, shape, n_t, n_q, pts[i::cores]) for i in range(cores)])
+    wall = time.time() - t0
+    busy = max(r[0] for r in res)
+    return {"value": len(pts) / busy, "unit": "evals/s", "cores": cores, "evals": len(pts),
+            "busy_s": busy, "wall_s": wall}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 17, help="parameter points per GPU per step")
+    ap.add_argument("--shape", default="S5")
+    ap.add_argument("--n-theta-average", type=int, default=100)
+    ap.add_argument("--n-q", type=int, default=96)
+    ap.add_argument("--cpu-evals-per-core", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "S5 stress: 12 z x 20 theta x 256 k_par, dense windows, %d-point 4-parameter grid" % int(np.prod(GRID_N)) \
+        if a.shape == "S5" else a.shape
+    config = {"workload": workload, "shape": a.shape, "points_per_gpu_per_step": a.points, "params": NAMES,
+              "grid_n": GRID_N, "N_theta_average": a.n_theta_average, "n_q": a.n_q, "include_hcd": True,
+              "parallelism": "points sharded over %d GPU(s), NCCL all_gather of chi2" % a.gpus,
+              "l2": "per-chunk Px_Zam scratch (GiBs) >> 126 MB L2, no explicit flush"}
+
+    # ------------------------------------------------------------------ CPU reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import cupix_b200.plan as _plan
+        d, data, likes, _ = build_workload(a.shape, a.n_theta_average, a.n_q, need_engine=False)
+        defaults = _plan.default_vector(likes[0].theory, likes[0].theory.fid_cosmo)
+        vals, t0 = [], time.time()
+        for _ in range(max(1, min(a.steps, 2))):
+            r = run_cpu("fftlog", a.shape, a.n_theta_average, a.n_q, 1, defaults)
+            vals.append(r)
+        best = max(vals, key=lambda r: r["value"])
+        line = {"impl": "reference", "metric": "Px likelihood evals/sec", "value": best["value"], "unit": "evals/s",
+                "n_gpus": a.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * best["busy_s"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": best["value"], "unit": "evals/s", "cores": best["cores"], "kind": "port",
+                                 "sample": "%d evaluations (1 per core per step) of the S5 workload with the reference's "
+                                           "FFTLog Hankel algorithm (oracle A), N_theta_average=%d, one process per core"
+                                           % (best["evals"], a.n_theta_average)},
+                "e2e": {"value": best["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q)
+    eng = joint.engine()
+    import cupix_b200.plan as _plan
+    from cupix_b200.engine import slots_from_names, probe_peaks
+    defaults = _plan.default_vector(likes[0].theory, likes[0].theory.fid_cosmo)
+    lo, hi = grid_bounds(defaults)
+    slots, zsel = slots_from_names(NAMES)
+    total = int(np.prod(GRID_N))
+    B = a.points
+    stream = torch.cuda.Stream(device=dev)
+    chi2_dev = torch.empty(B, dtype=torch.float64, device=dev)
+    gathered = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device(i):
+        first = ((i * world + rank) * B) % max(total - B, 1)
+        eng.eval_device(B, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=first, zsel=zsel,
+                        chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, chi2_dev)
+
+    def sync_all():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        step_device(i)
+    sync_all()
+    launches0 = eng.info("kernel_launches")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for i in range(a.steps):
+        step_device(a.warmup + i)
+    e1.record(stream)
+    sync_all()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = eng.info("kernel_launches") - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = a.steps * B * world / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream, inside the library) ----
+    stage = np.zeros(4)
+    for i in range(a.steps):
+        first = ((i * world + rank) * B) % max(total - B, 1)
+        stage += eng.eval_device(B, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=first, zsel=zsel,
+                                 chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, stage_ms=True)
+    stage /= a.steps
+    chunk = eng.info("chunk")
+    n_chunks = (B + chunk - 1) // chunk
+
+    # ---- end to end through the public API with pinned host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        rng = np.random.default_rng(1234 + rank)
+        pts_host = torch.empty((B, len(NAMES)), dtype=torch.float64).pin_memory()
+        out_host = torch.empty(B, dtype=torch.float64).pin_memory()
+        pts_np, out_np = pts_host.numpy(), out_host.numpy()
+
+        def step_host(i):
+            pts_np[:] = rng.uniform(lo, hi, size=pts_np.shape)          # this step's inputs (host side, untimed cost is tiny)
+            res = joint.get_chi2_batch(pts_np, NAMES)                   # H2D + kernels + D2H inside
+            out_np[:] = res
+            return res
+        for i in range(a.warmup):
+            step_host(i)
+        sync_all()
+        t0 = time.time()
+        for i in range(a.steps):
+            step_host(i)
+        sync_all()
+        dt = time.time() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": a.steps * B * world / dt, "unit": "evals/s", "h2d_bytes_per_step": B * len(NAMES) * 8,
+               "d2h_bytes_per_step": B * 8, "api": "JointLikelihood.get_chi2_batch (host numpy in / out, C ABI cpx_eval)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    work = algorithmic_work(likes, a.n_q)
+    peaks = probe_peaks(local_rank)
+    k1_s = stage[1] * 1e-3
+    k2_s = stage[2] * 1e-3
+    dfma_flops = 2.0 * work["hankel_dfma"] * B
+    achieved = dfma_flops / k1_s / 1e12
+    peak = 2.0 * peaks["dfma_per_s"] / 1e12
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "k_p3d_hankel_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_p3d_hankel", "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "cpx_probe_peaks: dependent-chain DFMA microbenchmark on this GPU, same process "
+                               "(MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure)",
+                "launches_per_step": int(n_chunks), "ms_per_launch": float(stage[1] / n_chunks),
+                "share_of_step": float(stage[1] / stage.sum()),
+                "algorithmic": dict(work, per="evaluation (one point, all z)"),
+                "fp32_pipe_frac": float(9.0 * work["p3d_cells"] * B / k1_s / peaks["ffma_per_s"]),
+                "mufu_pipe_frac": float(2.0 * work["p3d_cells"] * B / k1_s / peaks["mufu_per_s"]),
+                "window_kernel": {"kernel": "k_window", "achieved": 2.0 * work["window_dfma"] * B / k2_s / 1e12,
+                                  "frac": 2.0 * work["window_dfma"] * B / k2_s / 1e12 / peak,
+                                  "share_of_step": float(stage[2] / stage.sum())},
+                "stage_ms": {"params": float(stage[0]), "p3d_hankel": float(stage[1]), "window_chi2": float(stage[2]),
+                             "reduce": float(stage[3])},
+                "measured_peaks": peaks}
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roofline["hbm_gbs_measured"] = hbm.get("hbm_gbs")
+    except Exception:
+        pass
+
+    cpu = None
+    if not a.no_cpu_baseline and a.gpus == 1:
+        r = run_cpu("node", a.shape, a.n_theta_average, a.n_q, a.cpu_evals_per_core, defaults)
+        cpu = {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": "port",
+               "sample": "%d evaluations (%d per core) of the same S5 workload with the float64 NumPy oracle using the "
+                         "same fixed-node Hankel rule as the GPU (oracle B); the reference's own FFTLog algorithm is "
+                         "timed by --impl reference" % (r["evals"], a.cpu_evals_per_core)}
+
+    line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "per_point_z_rate": value * len(likes)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -115,33 +115,36 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   Z.n_m_pad = Z.n_tiles * kTileRows;
   Z.na_blk = na_blk;
   Z.n_ablk = (d.n_a + na_blk - 1) / na_blk;
+  Z.n_q4 = (d.n_q + 3) / 4;
   Z.flags = d.flags;
   Z.dAA = d.dAA_dMpc;
   std::memcpy(Z.defaults, d.defaults, sizeof(Z.defaults));
   size_t& bytes = h->device_bytes;
   auto keep = [&](void* p) { if (p) zh.owned.push_back(p); };
 
-  // cell constants [tile][q][6][32]
+  // cell constants in DMMA A-fragment order, m-tile pairs packed: [tile][ks][6][pair][lane = 4*g + t][2]
   {
-    std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * d.n_q * kCellConsts * kTileRows, 0.0f);
+    std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * Z.n_q4 * kCellConsts * 4 * 32, 0.0f);
     const double two_pi2 = 2.0 * M_PI * M_PI;
     for (int m = 0; m < d.n_m; ++m) {
-      const int tile = m / kTileRows, r = m % kTileRows;
+      const int tile = m / kTileRows, r = m % kTileRows, mt = r / 8, g = r % 8;
       const double kp = d.kpar_Mpc[m];
       for (int q = 0; q < d.n_q; ++q) {
+        const int ks = q / 4, t = q % 4;
         const double kt = d.kperp_Mpc[q];
         const double k2 = kp * kp + kt * kt;
-        float* c = &cell[((static_cast<size_t>(tile) * d.n_q + q) * kCellConsts) * kTileRows + r];
+        float* c = &cell[((((static_cast<size_t>(tile) * Z.n_q4 + ks) * kCellConsts) * 2 + mt / 2) * 32 + 4 * g + t) * 2 + (mt & 1)];
         if (!(k2 > 0.0)) continue;   // k == 0: P_L(0) = 0, cell contributes nothing
         const double k = std::sqrt(k2);
         const double mu = kp / k;
         const double PL = d.linP_cell[static_cast<size_t>(m) * d.n_q + q];
-        c[0 * kTileRows] = static_cast<float>(k * k2 * PL / two_pi2);            // Delta^2(k)
-        c[1 * kTileRows] = static_cast<float>(std::log2(k));
-        c[2 * kTileRows] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;   // mu = 0: mu^bv -> 0 (bv>0) or 1 (bv=0)
-        c[3 * kTileRows] = static_cast<float>(mu * mu);
-        c[4 * kTileRows] = static_cast<float>(k2);
-        c[5 * kTileRows] = static_cast<float>(PL);
+        const size_t cs = 4 * 32;    // stride between the six constants
+        c[0 * cs] = static_cast<float>(k * k2 * PL / two_pi2);            // Delta^2(k)
+        c[1 * cs] = static_cast<float>(std::log2(k));
+        c[2 * cs] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;   // mu = 0: mu^bv -> 0 (bv>0) or 1 (bv=0)
+        c[3 * cs] = static_cast<float>(mu * mu);
+        c[4 * cs] = static_cast<float>(-k2);
+        c[5 * cs] = static_cast<float>(PL);
       }
     }
     float* dptr;
@@ -150,12 +153,15 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     Z.cellc = dptr;
     keep(dptr);
   }
-  // Hankel weights [ablk][q][na_blk]
+  // Hankel weights in DMMA B-fragment order [ablk][ks][j][lane = 4*g + t] = W[a = ablk*na_blk + 8j + g][q = 4ks + t]
   {
-    std::vector<double> W(static_cast<size_t>(Z.n_ablk) * d.n_q * na_blk, 0.0);
+    const int nt = na_blk / 8;
+    std::vector<double> W(static_cast<size_t>(Z.n_ablk) * Z.n_q4 * nt * 32, 0.0);
     for (int a = 0; a < d.n_a; ++a)
-      for (int q = 0; q < d.n_q; ++q)
-        W[(static_cast<size_t>(a / na_blk) * d.n_q + q) * na_blk + a % na_blk] = d.hankel_w[static_cast<size_t>(a) * d.n_q + q];
+      for (int q = 0; q < d.n_q; ++q) {
+        const int ablk = a / na_blk, j = (a % na_blk) / 8, g = a % 8, ks = q / 4, t = q % 4;
+        W[((static_cast<size_t>(ablk) * Z.n_q4 + ks) * nt + j) * 32 + 4 * g + t] = d.hankel_w[static_cast<size_t>(a) * d.n_q + q];
+      }
     double* dptr;
     int rc = upload(W, &dptr, &bytes);
     if (rc) return rc;
@@ -297,27 +303,24 @@ int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
 // ---- kernel dispatch -----------------------------------------------------------------------
 typedef void (*K1Fn)(const cpx::ZDev*, int, int, long long);
 
-template <int PP>
-K1Fn k1_for_na(int na) {
-  switch (na) {
-    case 4: return cpx::k_p3d_hankel<PP, 4>;
-    case 8: return cpx::k_p3d_hankel<PP, 8>;
-    case 12: return cpx::k_p3d_hankel<PP, 12>;
-    case 16: return cpx::k_p3d_hankel<PP, 16>;
-    case 20: return cpx::k_p3d_hankel<PP, 20>;
-    case 24: return cpx::k_p3d_hankel<PP, 24>;
+// PP = 1 fits two CTAs per SM (<= 128 registers); PP = 2 runs one CTA per SM
+K1Fn k1_select(int pp, int nt) {
+  if (pp == 1) {
+    switch (nt) {
+      case 1: return cpx::k_p3d_hankel<1, 1, 2>;
+      case 2: return cpx::k_p3d_hankel<1, 2, 2>;
+      case 3: return cpx::k_p3d_hankel<1, 3, 2>;
+    }
+  } else if (pp == 2) {
+    switch (nt) {
+      case 1: return cpx::k_p3d_hankel<2, 1, 1>;
+      case 2: return cpx::k_p3d_hankel<2, 2, 1>;
+      case 3: return cpx::k_p3d_hankel<2, 3, 1>;
+    }
   }
   return nullptr;
 }
-K1Fn k1_select(int pp, int na) {
-  switch (pp) {
-    case 1: return k1_for_na<1>(na);
-    case 2: return k1_for_na<2>(na);
-    case 3: return k1_for_na<3>(na);
-    case 4: return k1_for_na<4>(na);
-  }
-  return nullptr;
-}
+int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
 
 typedef void (*K2Fn)(const cpx::ZDev*, int, cpx::WindowArgs);
 template <bool CHI2>
@@ -336,9 +339,9 @@ K2Fn k2_select(int mt) {
 }
 
 int choose_na_blk(int max_na) {
-  if (max_na <= 24) return round_up(max_na, 4);
+  if (max_na <= 24) return round_up(max_na, 8);
   const int nblk = (max_na + 23) / 24;
-  return round_up((max_na + nblk - 1) / nblk, 4);
+  return round_up((max_na + nblk - 1) / nblk, 8);
 }
 
 int env_int(const char* name, int dflt) {
@@ -399,7 +402,7 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     h->max_nq = std::max(h->max_nq, d.n_q);
   }
   h->na_blk = choose_na_blk(h->max_na);
-  const size_t smem_need = static_cast<size_t>(h->max_nq) * (cpx::kCellConsts * cpx::kTileRows * 4 + h->na_blk * 8);
+  const size_t smem_need = static_cast<size_t>((h->max_nq + 3) / 4) * (cpx::kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
   if (smem_need > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
     return bail(fail(CPX_ERR_UNSUPPORTED, "cpx_create: n_q too large for the shared-memory-resident grid"));
 
@@ -412,7 +415,7 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       rc = upload_yd(h, h->z[i], zbins[i].Px_AM, zbins[i].n_data);
       if (rc) return bail(rc);
     }
-    per_point_bytes += static_cast<size_t>(h->z[i].dev.n_a) * h->z[i].dev.n_m_pad * 8 + sizeof(cpx::PtPar);
+    per_point_bytes += static_cast<size_t>(h->z[i].dev.n_a) * h->z[i].dev.n_m_pad * 8 + sizeof(cpx::PtPar) + sizeof(cpx::RowPar) * h->z[i].dev.n_m_pad;
   }
   // chunk: Px_Zam scratch of all z within the budget (default 4 GiB), multiple of 256 points
   const size_t budget = static_cast<size_t>(env_int("CPX_SCRATCH_MB", 4096)) << 20;
@@ -430,6 +433,9 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
   for (int i = 0; i < n_zbins; ++i) {
     cpx::ZDev& Z = h->z[i].dev;
     if ((rc = dmalloc(reinterpret_cast<void**>(&Z.ptpar), sizeof(cpx::PtPar) * h->chunk))) return bail(rc);
+    if (Z.flags & (CPX_INCLUDE_HCD | CPX_INCLUDE_CONTINUUM))
+      if ((rc = dmalloc(reinterpret_cast<void**>(&Z.rowpar), sizeof(cpx::RowPar) * static_cast<size_t>(h->chunk) * Z.n_m_pad)))
+        return bail(rc);
     if ((rc = dmalloc(reinterpret_cast<void**>(&Z.pxzam),
                       static_cast<size_t>(h->chunk) * Z.n_a * Z.n_m_pad * 8 + 256)))
       return bail(rc);
@@ -446,8 +452,8 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       return bail(rc);
 
   // opt in to the large dynamic shared memory for every k_p3d_hankel instantiation we may launch
-  for (int pp = 1; pp <= 4; ++pp) {
-    K1Fn fn = k1_select(pp, h->na_blk);
+  for (int pp = 1; pp <= 2; ++pp) {
+    K1Fn fn = k1_select(pp, h->na_blk / 8);
     if (!fn) return bail(fail(CPX_ERR_UNSUPPORTED, "no k_p3d_hankel instantiation for this theta-bin count"));
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
       return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
@@ -564,6 +570,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     if (a->grid_n) {
       pa.grid_n[j] = a->grid_n[j];
       pa.grid_lo[j] = a->grid_lo[j];
+      pa.grid_hi[j] = a->grid_hi[j];
       pa.grid_step[j] = a->grid_n[j] > 1 ? (a->grid_hi[j] - a->grid_lo[j]) / (a->grid_n[j] - 1) : 0.0;
     }
   }
@@ -585,7 +592,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   int last_table_count = -1, last_pp = -1;
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
-    int pp = pp_env > 0 ? std::min(pp_env, 4) : (count > 2048 ? 4 : (count > 256 ? 2 : 1));
+    int pp = pp_env > 0 ? std::min(pp_env, 2) : (count > 2048 ? 2 : 1);
     const int n_pg = (count + kK1Warps * pp - 1) / (kK1Warps * pp);
     if (count != last_table_count || pp != last_pp) {
       long long items = 0;
@@ -630,13 +637,24 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       dim3 grid((count + 127) / 128, n_zl);
       k_params<<<grid, 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
       ++h->launches;
+      bool any_rowwise = false;
+      int nm_pad_max = 0;
+      for (int i = 0; i < n_zl; ++i) {
+        any_rowwise |= (tab[i].flags & (CPX_INCLUDE_HCD | CPX_INCLUDE_CONTINUUM)) != 0;
+        nm_pad_max = std::max(nm_pad_max, tab[i].n_m_pad);
+      }
+      if (any_rowwise) {
+        dim3 rgrid((nm_pad_max + 127) / 128, count, n_zl);
+        k_rowpars<<<rgrid, 128, 0, st>>>(h->d_ztab, count);
+        ++h->launches;
+      }
     }
     // ---- stage 1: P3D + Hankel ----
     if ((rc = mark())) return rc;
     {
-      K1Fn fn = k1_select(pp, h->na_blk);
-      const size_t smem = static_cast<size_t>(h->max_nq) * (kCellConsts * kTileRows * 4 + h->na_blk * 8);
-      const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));
+      K1Fn fn = k1_select(pp, h->na_blk / 8);
+      const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
+      const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * k1_ctas_per_sm(pp)));
       fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);
       ++h->launches;
     }

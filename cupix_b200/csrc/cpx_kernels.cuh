@@ -17,7 +17,7 @@
 namespace cpx {
 
 constexpr int kTileRows = 32;        // k_par rows per shared-memory tile (one per lane)
-constexpr int kCellConsts = 6;       // D, L2K, L2MU, MU2, K2, PL
+constexpr int kCellConsts = 6;       // D, L2K, L2MU, MU2, -K2, PL
 constexpr int kK1Warps = 8;
 constexpr int kK1Threads = kK1Warps * 32;
 constexpr int kMaxZ = 64;
@@ -25,11 +25,15 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // per-(z, point) parameters written by k_params and read by k_p3d_hankel
 struct PtPar {
-  // cell evaluation (FP32 pipe)
-  float q1l, q2l;      // q1 * log2(e), q2 * log2(e)
-  float av, bv;
-  float nlkv;          // -av * log2(kv_Mpc)
-  float ikp2l;         // log2(e) / kp_Mpc^2
+  // cell evaluation (FP32 pipe).  Scalars whose float32 rounding would shift every cell the same
+  // way (and so survive the averaging over cells) are carried as hi + lo pairs.
+  float q1l, q1l_lo;   // q1 * log2(e)
+  float q2l, q2l_lo;   // q2 * log2(e)
+  float av, av_lo;
+  float bv;
+  float nlkv, nlkv_lo; // -av * log2(kv_Mpc)
+  float ikp2l, ikp2l_lo;   // log2(e) / kp_Mpc^2
+  float pad;
   // epilogues (FP64)
   double bias, beta;
   double b_H, beta_H, L_H;
@@ -37,17 +41,19 @@ struct PtPar {
   double b_noise;
   double kC, pC;
 };
-static_assert(sizeof(PtPar) == 104, "PtPar layout");
+static_assert(sizeof(PtPar) == 128, "PtPar layout");
 
 // per-z device data for k_p3d_hankel / k_params
+struct RowPar;
 struct ZDev {
   int n_a, n_m, n_q, n_tiles;          // n_tiles = ceil(n_m / 32)
   int n_m_pad;                          // 32 * n_tiles
-  int na_blk, n_ablk;                   // a-block width (template NA) and count
+  int na_blk, n_ablk;                   // theta-block width (8 * NT) and count
   int flags;
+  int n_q4, pad1;                       // ceil(n_q / 4): k-steps of the DMMA contraction
   double dAA;
-  const float* cellc;                   // [n_tiles][n_q][6][32]
-  const double* Wd;                     // [n_ablk][n_q][na_blk]
+  const float* cellc;                   // [n_tiles][n_q4][6][2][32][2] A-fragment order: lane = 4*g + t holds rows 8*(2*pr+e)+g, e = 0,1 (packed pair), node 4*ks+t
+  const double* Wd;                     // [n_ablk][n_q4][NT][32]     B-fragment order: lane = 4*g + t holds W[theta 8*j+g][node 4*ks+t]
   const double* kpar;                   // [n_m_pad]
   const double* metal_auto;             // [3][n_a][n_m] or null
   const double* metal_cross;            // [3][n_a][n_m] or null
@@ -64,6 +70,7 @@ struct ZDev {
   const double* yd;                     // [n_data][n_A][n_M_pad]       L^-1 d
   // per-chunk buffers
   PtPar* ptpar;                         // [chunk]
+  struct RowPar* rowpar;                // [chunk][n_m_pad], valid when flags & (HCD | CONTINUUM)
   double* pxzam;                        // [chunk][n_a][n_m_pad]
   long long item_start;                 // first k_p3d_hankel work item of this z in the launch
 };
@@ -132,11 +139,16 @@ struct ParamsArgs {
   long long first;        // chunk offset into points / grid
   int count;              // points in this chunk
   int grid_mode;
-  double grid_lo[16], grid_step[16];
+  double grid_lo[16], grid_hi[16], grid_step[16];
   int grid_n[16];
   int slot[16], zsel[16];
   long long grid_first;
 };
+
+__device__ __forceinline__ void split_hi_lo(double x, float& hi, float& lo) {
+  hi = static_cast<float>(x);
+  lo = static_cast<float>(x - static_cast<double>(hi));
+}
 
 __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int* __restrict__ zlist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,7 +165,9 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
       const int n = a.grid_n[j];
       const int ij = static_cast<int>(idx % n);
       idx /= n;
-      const double x = a.grid_lo[j] + ij * a.grid_step[j];
+      // bit-identical to numpy.linspace: arange * step + start without FMA contraction, last = stop
+      const double x = (ij == n - 1 && n > 1) ? a.grid_hi[j]
+                                              : __dadd_rn(__dmul_rn(static_cast<double>(ij), a.grid_step[j]), a.grid_lo[j]);
       if (a.zsel[j] < 0 || a.zsel[j] == zglobal) v[a.slot[j]] = x;
     }
   } else {
@@ -163,12 +177,13 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
   }
   PtPar o;
   const double l2e = 1.4426950408889634074;
-  o.q1l = static_cast<float>(v[2] * l2e);
-  o.q2l = static_cast<float>(v[3] * l2e);
-  o.av = static_cast<float>(v[5]);
+  split_hi_lo(v[2] * l2e, o.q1l, o.q1l_lo);
+  split_hi_lo(v[3] * l2e, o.q2l, o.q2l_lo);
+  split_hi_lo(v[5], o.av, o.av_lo);
   o.bv = static_cast<float>(v[6]);
-  o.nlkv = static_cast<float>(-v[5] * log2(v[4]));
-  o.ikp2l = static_cast<float>(l2e / (v[7] * v[7]));
+  split_hi_lo(-v[5] * log2(v[4]), o.nlkv, o.nlkv_lo);
+  split_hi_lo(l2e / (v[7] * v[7]), o.ikp2l, o.ikp2l_lo);
+  o.pad = 0.f;
   o.bias = v[0];
   o.beta = v[1];
   o.b_H = v[8];
@@ -183,24 +198,111 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
 }
 
 // ------------------------------------------------------------------------------------------
+// k_rowpars: per-(point, k_par row) scalars that need float64 transcendentals -- the HCD
+// scale-dependent bias/beta (theory.py:267-282) and the continuum distortion (theory.py:525-535).
+// Computed once here so that the fused kernel's prologue/epilogue stay free of FP64 exp/pow/tanh.
+// Only launched when include_hcd or include_continuum is set; otherwise the values are uniform.
+// ------------------------------------------------------------------------------------------
+struct RowPar {
+  float betaT_hi, betaT_lo;   // Kaiser beta of the row (hi + lo float pair)
+  double amp;                 // b_T(k_par)^2 * dAA_dMpc
+  double cont;                // tanh((k_par / kC)^pC), 1 without continuum distortion
+};
+static_assert(sizeof(RowPar) == 24, "RowPar layout");
+
+__global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
+  const ZDev& Z = ztab[blockIdx.z];
+  if ((Z.flags & 9) == 0) return;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pt = blockIdx.y;
+  if (m >= Z.n_m_pad || pt >= count) return;
+  const PtPar& pr = Z.ptpar[pt];
+  const double kpar = Z.kpar[m];
+  double bT = pr.bias, betaT = pr.beta;
+  if (Z.flags & 1) {
+    const double F = exp(-kpar * pr.L_H);
+    bT = pr.bias + pr.b_H * F;
+    betaT = (pr.bias * pr.beta + pr.b_H * pr.beta_H * F) / bT;
+  }
+  RowPar o;
+  split_hi_lo(betaT, o.betaT_hi, o.betaT_lo);
+  o.amp = bT * bT * Z.dAA;
+  o.cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;
+  Z.rowpar[static_cast<size_t>(pt) * Z.n_m_pad + m] = o;
+}
+
+// ------------------------------------------------------------------------------------------
 // k_p3d_hankel
 // ------------------------------------------------------------------------------------------
-// One CTA = 8 warps.  Lane = one k_par row of a 32-row tile; each warp carries PP parameter
-// points at a time through the whole k_perp loop, so a CTA pass covers 8*PP points.  The cell
-// constants of the tile ([n_q][6][32] floats) and the Hankel weights of the a-block ([n_q][NA]
-// doubles) are staged in shared memory with TMA bulk copies and stay resident while the CTA
-// walks its contiguous range of work items (z, tile, a-block, point-group).
+// Px_Zam[pt][a][m] = amp(m) * sum_q W[a][q] * P3D'(m, q; pt)   as an FP64 tensor-core contraction.
 //
-// Per cell and point: 9 FP32 ops + 2 MUFU.EX2 (Arinyo P3D, theory.py:285-308) and NA FP64 FMAs
-// (Hankel accumulation).  The FP64 pipe is the bound: NA DFMA per (cell, point).
-template <int PP, int NA>
-__global__ void __launch_bounds__(kK1Threads, 1)
+// The Hankel sum is a GEMM with M = (point, k_par row), K = k_perp node, N = theta bin whose A
+// operand is *generated* in registers: lane (g, t) of a warp evaluates the Arinyo P3D cell
+// (row 8*mt + g, node 4*ks + t), which is exactly the A-fragment element the m8n8k4 DMMA wants
+// from that lane, so no shuffle or shared-memory round trip is needed.  B fragments are the Hankel
+// weights (conflict-free LDS.64), accumulators stay in registers for the whole k_perp loop.
+//
+// One CTA = 8 warps.  A warp owns a 32-row k_par tile (4 m-tiles) and PP parameter points at a
+// time; a CTA pass covers 8*PP points.  The cell constants of the tile ([n_q/4][6][4][32] floats,
+// fragment order) and the weights of the theta block ([n_q/4][NT][32] doubles) are staged in shared
+// memory by TMA bulk copies and stay resident while the CTA walks its contiguous range of work
+// items (z, tile, theta-block, point-group).
+//
+// Per cell and point: ~35 FP32/ALU instructions (hi+lo scalars, polynomial exp2 for D_NL,
+// range-reduced MUFU.EX2 for the velocity term), 2 XU, NT DMMAs.  Bound: FP64 pipe.
+
+// Packed FP32 (FFMA2 / FADD2 / FMUL2, new on sm_100): two P3D cells per instruction.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+// Range reduction shared by the two exp2 flavours: x = n + f, n = round(x) (returned in the low
+// mantissa bits of t), |f| <= 0.5 exactly.
+__device__ __forceinline__ void exp2_reduce(float2 x, float2& t, float2& f) {
+  t = add2(x, dup2(12582912.0f));
+  f = fma2(add2(t, dup2(-12582912.0f)), dup2(-1.0f), x);
+}
+__device__ __forceinline__ float exp2_scale(float p, float t) {
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// 2^x, unbiased: 2^f is a degree-7 polynomial on the FMA pipe.  MUFU.EX2 alone is biased by
+// -2e-8 .. -5e-8 on this range (tools/mufu_error.cu, profiles/mufu_error_r01.txt), which is coherent
+// over all cells and would shift chi2 by ~5e-7 relative.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -125.0f), 126.0f);
+  x.y = fminf(fmaxf(x.y, -125.0f), 126.0f);
+  float2 t, f;
+  exp2_reduce(x, t, f);
+  float2 p = dup2(1.529732435301412e-05f);
+  p = fma2(p, f, dup2(0.00015461444854736328f));
+  p = fma2(p, f, dup2(0.0013333501992747188f));
+  p = fma2(p, f, dup2(0.009618056938052177f));
+  p = fma2(p, f, dup2(0.05550410971045494f));
+  p = fma2(p, f, dup2(0.24022650718688965f));
+  p = fma2(p, f, dup2(0.6931471824645996f));
+  p = fma2(p, f, dup2(1.0f));
+  return make_float2(exp2_scale(p.x, t.x), exp2_scale(p.y, t.y));
+}
+// 2^x with MUFU.EX2 on the reduced argument only (bias ~ -8e-9: enough for the velocity term, which
+// enters the exponent of D_NL multiplied by Delta^2 (q1 + q2 Delta^2)).  x <= ~30 here.
+__device__ __forceinline__ float2 exp2_rr2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  float2 t, f;
+  exp2_reduce(x, t, f);
+  return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
+}
+
+template <int PP, int NT, int MINB>
+__global__ void __launch_bounds__(kK1Threads, MINB)
     k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int n_pg = (count + kK1Warps * PP - 1) / (kK1Warps * PP);
 
   // contiguous slice of the flattened item space for this CTA
@@ -214,10 +316,7 @@ __global__ void __launch_bounds__(kK1Threads, 1)
   }
   __syncthreads();
   uint32_t phase = 0;
-
   int cur_z = -1, cur_tile = -1, cur_ablk = -1;
-  float* s_cell = reinterpret_cast<float*>(smem_raw);
-  double* s_w = nullptr;
 
   for (long long it = it0; it < it1; ++it) {
     // decode item -> (zi, tile, ablk, pg); z bins are few, linear scan
@@ -229,15 +328,16 @@ __global__ void __launch_bounds__(kK1Threads, 1)
     r /= n_pg;
     const int ablk = static_cast<int>(r % Z.n_ablk);
     const int tile = static_cast<int>(r / Z.n_ablk);
-    const int n_q = Z.n_q;
+    const int n_ks = Z.n_q4;
+    const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
+    const uint32_t w_bytes = static_cast<uint32_t>(n_ks) * (NT * 32 * 8u);
+    const float2* s_cell = reinterpret_cast<const float2*>(smem_raw);
+    const double* s_w = reinterpret_cast<const double*>(smem_raw + cell_bytes);
 
     const bool new_tile = (zi != cur_z) || (tile != cur_tile);
     const bool new_w = (zi != cur_z) || (ablk != cur_ablk);
     if (new_tile || new_w) {
       __syncthreads();   // every warp is done reading the previous tile / weights
-      const uint32_t cell_bytes = static_cast<uint32_t>(n_q) * kCellConsts * kTileRows * 4u;
-      const uint32_t w_bytes = static_cast<uint32_t>(n_q) * NA * 8u;
-      s_w = reinterpret_cast<double*>(smem_raw + cell_bytes);
       if (threadIdx.x == 0) {
         fence_proxy_async();
         mbar_expect_tx(&bar, (new_tile ? cell_bytes : 0u) + (new_w ? w_bytes : 0u));
@@ -249,7 +349,7 @@ __global__ void __launch_bounds__(kK1Threads, 1)
         if (new_w) {
           const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.Wd) + static_cast<size_t>(ablk) * w_bytes;
           for (uint32_t off = 0; off < w_bytes; off += 32768u)
-            bulk_g2s(reinterpret_cast<unsigned char*>(s_w) + off, src + off, min(32768u, w_bytes - off), &bar);
+            bulk_g2s(smem_raw + cell_bytes + off, src + off, min(32768u, w_bytes - off), &bar);
         }
       }
       mbar_wait(&bar, phase);
@@ -261,97 +361,134 @@ __global__ void __launch_bounds__(kK1Threads, 1)
 
     const int pt0 = (pg * kK1Warps + warp) * PP;       // first point of this warp
     if (pt0 >= count) continue;
-    const int m = tile * kTileRows + lane;
-    const bool row_ok = m < Z.n_m;
-    const double kpar = Z.kpar[m];                      // padded rows hold 0
+    const int m_base = tile * kTileRows;
+    const bool rowwise = (Z.flags & 9) != 0;   // HCD or continuum: per-row scalars from k_rowpars
 
-    // ---- per-point scalars ----
-    float q1l[PP], q2l[PP], av[PP], bv[PP], nlkv[PP], ikp2l[PP], betaT[PP];
-    double amp[PP];
+    // ---- per-point scalars (warp-uniform, duplicated into both halves of a packed register) and
+    //      the Kaiser beta of this lane's rows; m-tiles are processed in pairs (2*pr, 2*pr + 1) ----
+    float2 q1l[PP], q1lo[PP], q2l[PP], q2lo[PP], av[PP], avlo[PP], bv[PP], nlkv[PP], nlkvlo[PP], ikp2l[PP], ikp2lo[PP];
+    float2 betaT[2][PP], betaTlo[2][PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
-      const int pt = min(pt0 + p, count - 1);
-      const PtPar& pr = Z.ptpar[pt];
-      q1l[p] = pr.q1l;
-      q2l[p] = pr.q2l;
-      av[p] = pr.av;
-      bv[p] = pr.bv;
-      nlkv[p] = pr.nlkv;
-      ikp2l[p] = pr.ikp2l;
-      double bT = pr.bias, betaTd = pr.beta;
-      if (Z.flags & 1) {   // HCD: scale-dependent bias, theory.py:267-282
-        const double F = exp(-kpar * pr.L_H);
-        bT = pr.bias + pr.b_H * F;
-        betaTd = (pr.bias * pr.beta + pr.b_H * pr.beta_H * F) / bT;
-      }
-      betaT[p] = static_cast<float>(betaTd);
-      amp[p] = bT * bT * Z.dAA;
-    }
-
-    double acc[PP][NA];
+      const PtPar& pr = Z.ptpar[min(pt0 + p, count - 1)];
+      q1l[p] = dup2(pr.q1l);
+      q1lo[p] = dup2(pr.q1l_lo);
+      q2l[p] = dup2(pr.q2l);
+      q2lo[p] = dup2(pr.q2l_lo);
+      av[p] = dup2(pr.av);
+      avlo[p] = dup2(pr.av_lo);
+      bv[p] = dup2(pr.bv);
+      nlkv[p] = dup2(pr.nlkv);
+      nlkvlo[p] = dup2(pr.nlkv_lo);
+      ikp2l[p] = dup2(pr.ikp2l);
+      ikp2lo[p] = dup2(pr.ikp2l_lo);
 #pragma unroll
-    for (int p = 0; p < PP; ++p)
-#pragma unroll
-      for (int a = 0; a < NA; ++a) acc[p][a] = 0.0;
-
-    // ---- k_perp loop: P3D cell -> Hankel accumulation ----
-    const float* c = s_cell + lane;
-    const double2* w2 = reinterpret_cast<const double2*>(s_w);
-#pragma unroll 2
-    for (int q = 0; q < n_q; ++q) {
-      const float D = c[0], L2K = c[32], L2MU = c[64], MU2 = c[96], K2 = c[128], PL = c[160];
-      c += kCellConsts * kTileRows;
-      double pd[PP];
-#pragma unroll
-      for (int p = 0; p < PP; ++p) {
-        const float nl = D * fmaf(q2l[p], D, q1l[p]);                       // Delta^2 (q1 + q2 Delta^2) log2e
-        const float v = ex2_approx(fmaf(av[p], L2K, fmaf(bv[p], L2MU, nlkv[p])));   // (k/kv)^av mu^bv
-        const float t = fmaf(-K2, ikp2l[p], nl);
-        const float e = ex2_approx(fmaf(-nl, v, t));                        // D_NL
-        const float ka = fmaf(betaT[p], MU2, 1.0f);
-        pd[p] = static_cast<double>((PL * ka) * (ka * e));
-      }
-#pragma unroll
-      for (int a2 = 0; a2 < NA / 2; ++a2) {
-        const double2 w = w2[a2];
-#pragma unroll
-        for (int p = 0; p < PP; ++p) {
-          acc[p][2 * a2] = fma(w.x, pd[p], acc[p][2 * a2]);
-          acc[p][2 * a2 + 1] = fma(w.y, pd[p], acc[p][2 * a2 + 1]);
+      for (int mt = 0; mt < 4; ++mt) {
+        float hi, lo;
+        if (rowwise) {
+          const RowPar& rp = Z.rowpar[static_cast<size_t>(min(pt0 + p, count - 1)) * Z.n_m_pad + m_base + 8 * mt + g];
+          hi = rp.betaT_hi;
+          lo = rp.betaT_lo;
+        } else {
+          split_hi_lo(pr.beta, hi, lo);
+        }
+        if (mt & 1) {
+          betaT[mt >> 1][p].y = hi;
+          betaTlo[mt >> 1][p].y = lo;
+        } else {
+          betaT[mt >> 1][p].x = hi;
+          betaTlo[mt >> 1][p].x = lo;
         }
       }
-      w2 += NA / 2;
+    }
+
+    double acc[4][PP][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int p = 0; p < PP; ++p)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[mt][p][j][0] = acc[mt][p][j][1] = 0.0;
+
+    // ---- k_perp loop: P3D cells (A fragments) -> DMMA against the Hankel weights (B fragments) ----
+    const float2* c = s_cell + lane;
+    const double* wb = s_w + lane;
+#pragma unroll 2
+    for (int ks = 0; ks < n_ks; ++ks) {
+      double bfrag[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
+#pragma unroll
+      for (int pr2 = 0; pr2 < 2; ++pr2) {
+        const float2 D = c[(0 * 2 + pr2) * 32], L2K = c[(1 * 2 + pr2) * 32], L2MU = c[(2 * 2 + pr2) * 32];
+        const float2 MU2 = c[(3 * 2 + pr2) * 32], NK2 = c[(4 * 2 + pr2) * 32], PL = c[(5 * 2 + pr2) * 32];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+          // Delta^2 (q1 + q2 Delta^2) log2e
+          const float2 nl = mul2(D, add2(fma2(q2l[p], D, q1l[p]), fma2(q2lo[p], D, q1lo[p])));
+          // (k/kv)^av mu^bv
+          const float2 v = exp2_rr2(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), fma2(avlo[p], L2K, nlkvlo[p])));
+          // D_NL = 2^(nl (1 - v) - (k/kp)^2 log2e)
+          const float2 tt = fma2(NK2, ikp2lo[p], fma2(NK2, ikp2l[p], nl));
+          const float2 e = exp2_poly2(fma2(mul2(nl, dup2(-1.0f)), v, tt));
+          // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice) so that its
+          // float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded on its own takes the
+          // same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
+          float2 x = mul2(PL, e);
+          x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));
+          x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));
+          const double pd0 = static_cast<double>(x.x), pd1 = static_cast<double>(x.y);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma_884(acc[2 * pr2][p][j][0], acc[2 * pr2][p][j][1], pd0, bfrag[j]);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma_884(acc[2 * pr2 + 1][p][j][0], acc[2 * pr2 + 1][p][j][1], pd1, bfrag[j]);
+        }
+      }
+      c += kCellConsts * 2 * 32;
+      wb += NT * 32;
     }
 
     // ---- epilogue: amplitude, metals, sky, continuum; store Px_Zam[pt][a][m] ----
-    const int a0 = ablk * NA;
+    // C fragment: row 8*mt + g, theta columns 8*j + 2*t + {0, 1}
+    const int a_blk0 = ablk * (8 * NT);
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
       const int pt = pt0 + p;
       if (pt >= count) break;
       const PtPar& pr = Z.ptpar[pt];
-      double cont = 1.0;
-      if (Z.flags & 8) cont = tanh(pow(kpar / pr.kC, pr.pC));               // theory.py:525-535
-      double sky = 0.0;
-      if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];      // theory.py:476-506
-      double* out = Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a0) * Z.n_m_pad + m;
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        if (a0 + a >= Z.n_a) break;
-        double px = 0.0;
-        if (row_ok) {
-          px = amp[p] * acc[p][a];
-          if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
-            const size_t o = static_cast<size_t>(a0 + a) * Z.n_m + m, st = static_cast<size_t>(Z.n_a) * Z.n_m;
-            const double bx = pr.b_X, btx = pr.beta_X;
-            px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
-            px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
-                                  pr.beta * btx * Z.metal_cross[o + 2 * st]);
-          }
-          if (Z.flags & 4) px += sky * Z.sky_xi[a0 + a];
-          px *= cont;
+      for (int mt = 0; mt < 4; ++mt) {
+        const int m = m_base + 8 * mt + g;
+        const bool row_ok = m < Z.n_m;
+        double amp = pr.bias * pr.bias * Z.dAA, cont = 1.0;
+        if (rowwise) {
+          const RowPar& rp = Z.rowpar[static_cast<size_t>(pt) * Z.n_m_pad + m];
+          amp = rp.amp;
+          cont = rp.cont;
         }
-        out[static_cast<size_t>(a) * Z.n_m_pad] = px;
+        double sky = 0.0;
+        if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];    // theory.py:476-506
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int a = a_blk0 + 8 * j + 2 * t + cc;
+            if (a >= Z.n_a) continue;
+            double px = 0.0;
+            if (row_ok) {
+              px = amp * acc[mt][p][j][cc];
+              if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
+                const size_t o = static_cast<size_t>(a) * Z.n_m + m, st = static_cast<size_t>(Z.n_a) * Z.n_m;
+                const double bx = pr.b_X, btx = pr.beta_X;
+                px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+                px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                      pr.beta * btx * Z.metal_cross[o + 2 * st]);
+              }
+              if (Z.flags & 4) px += sky * Z.sky_xi[a];
+              px *= cont;
+            }
+            Z.pxzam[(static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + m] = px;
+          }
       }
     }
   }
