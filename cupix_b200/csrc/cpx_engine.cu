@@ -592,7 +592,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   int last_table_count = -1, last_pp = -1;
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
-    int pp = pp_env > 0 ? std::min(pp_env, 2) : (count > 2048 ? 2 : 1);
+    int pp = pp_env > 0 ? std::min(pp_env, 2) : 1;   // one point per warp, two CTAs per SM measured fastest
     const int n_pg = (count + kK1Warps * pp - 1) / (kK1Warps * pp);
     if (count != last_table_count || pp != last_pp) {
       long long items = 0;

@@ -181,6 +181,8 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
   split_hi_lo(v[3] * l2e, o.q2l, o.q2l_lo);
   split_hi_lo(v[5], o.av, o.av_lo);
   o.bv = static_cast<float>(v[6]);
+  // av itself stays a single float: its rounding moves chi2 by < 2e-5; the
+  // offset -av*log2(kv) is formed from the rounded av so that only that residual is left
   split_hi_lo(-v[5] * log2(v[4]), o.nlkv, o.nlkv_lo);
   split_hi_lo(l2e / (v[7] * v[7]), o.ikp2l, o.ikp2l_lo);
   o.pad = 0.f;
@@ -294,6 +296,20 @@ __device__ __forceinline__ float2 exp2_rr2(float2 x) {
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 
+// advance (zi, tile, ablk, pg) to the next work item without divisions
+__device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int& tile, int& ablk, int& pg) {
+  if (++pg == n_pg) {
+    pg = 0;
+    if (++ablk == Z.n_ablk) {
+      ablk = 0;
+      if (++tile == Z.n_tiles) {
+        tile = 0;
+        ++zi;
+      }
+    }
+  }
+}
+
 template <int PP, int NT, int MINB>
 __global__ void __launch_bounds__(kK1Threads, MINB)
     k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
@@ -318,16 +334,20 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   uint32_t phase = 0;
   int cur_z = -1, cur_tile = -1, cur_ablk = -1;
 
-  for (long long it = it0; it < it1; ++it) {
-    // decode item -> (zi, tile, ablk, pg); z bins are few, linear scan
-    int zi = (cur_z >= 0) ? cur_z : 0;
-    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
-    const ZDev& Z = ztab[zi];
-    long long r = it - Z.item_start;
-    const int pg = static_cast<int>(r % n_pg);
+  // first item: decode once with divisions, then advance incrementally
+  int zi, tile, ablk, pg;
+  {
+    zi = 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it0) ++zi;
+    long long r = it0 - ztab[zi].item_start;
+    pg = static_cast<int>(r % n_pg);
     r /= n_pg;
-    const int ablk = static_cast<int>(r % Z.n_ablk);
-    const int tile = static_cast<int>(r / Z.n_ablk);
+    ablk = static_cast<int>(r % ztab[zi].n_ablk);
+    tile = static_cast<int>(r / ztab[zi].n_ablk);
+  }
+
+  for (long long it = it0; it < it1; ++it) {
+    const ZDev& Z = ztab[zi];
     const int n_ks = Z.n_q4;
     const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
     const uint32_t w_bytes = static_cast<uint32_t>(n_ks) * (NT * 32 * 8u);
@@ -360,13 +380,16 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     }
 
     const int pt0 = (pg * kK1Warps + warp) * PP;       // first point of this warp
-    if (pt0 >= count) continue;
+    if (pt0 >= count) {
+      next_item(Z, n_pg, zi, tile, ablk, pg);
+      continue;
+    }
     const int m_base = tile * kTileRows;
     const bool rowwise = (Z.flags & 9) != 0;   // HCD or continuum: per-row scalars from k_rowpars
 
     // ---- per-point scalars (warp-uniform, duplicated into both halves of a packed register) and
     //      the Kaiser beta of this lane's rows; m-tiles are processed in pairs (2*pr, 2*pr + 1) ----
-    float2 q1l[PP], q1lo[PP], q2l[PP], q2lo[PP], av[PP], avlo[PP], bv[PP], nlkv[PP], nlkvlo[PP], ikp2l[PP], ikp2lo[PP];
+    float2 q1l[PP], q1lo[PP], q2l[PP], q2lo[PP], av[PP], bv[PP], nlkv[PP], nlkvlo[PP], ikp2l[PP], ikp2lo[PP];
     float2 betaT[2][PP], betaTlo[2][PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
@@ -376,7 +399,6 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       q2l[p] = dup2(pr.q2l);
       q2lo[p] = dup2(pr.q2l_lo);
       av[p] = dup2(pr.av);
-      avlo[p] = dup2(pr.av_lo);
       bv[p] = dup2(pr.bv);
       nlkv[p] = dup2(pr.nlkv);
       nlkvlo[p] = dup2(pr.nlkv_lo);
@@ -394,10 +416,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
         }
         if (mt & 1) {
           betaT[mt >> 1][p].y = hi;
-          betaTlo[mt >> 1][p].y = lo;
+          betaTlo[mt >> 1][p].y = 2.0f * lo;
         } else {
           betaT[mt >> 1][p].x = hi;
-          betaTlo[mt >> 1][p].x = lo;
+          betaTlo[mt >> 1][p].x = 2.0f * lo;
         }
       }
     }
@@ -427,16 +449,16 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
           // Delta^2 (q1 + q2 Delta^2) log2e
           const float2 nl = mul2(D, add2(fma2(q2l[p], D, q1l[p]), fma2(q2lo[p], D, q1lo[p])));
           // (k/kv)^av mu^bv
-          const float2 v = exp2_rr2(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), fma2(avlo[p], L2K, nlkvlo[p])));
+          const float2 v = exp2_rr2(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), nlkvlo[p]));
           // D_NL = 2^(nl (1 - v) - (k/kp)^2 log2e)
           const float2 tt = fma2(NK2, ikp2lo[p], fma2(NK2, ikp2l[p], nl));
           const float2 e = exp2_poly2(fma2(mul2(nl, dup2(-1.0f)), v, tt));
-          // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice) so that its
-          // float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded on its own takes the
-          // same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
+          // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice, plus the first-order
+          // beta_lo term) so that its float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded
+          // on its own takes the same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
           float2 x = mul2(PL, e);
-          x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));
-          x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));
+          x = fma2(mul2(x, betaT[pr2][p]), MU2, x);
+          x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));   // betaTlo holds 2 * lo
           const double pd0 = static_cast<double>(x.x), pd1 = static_cast<double>(x.y);
 #pragma unroll
           for (int j = 0; j < NT; ++j) dmma_884(acc[2 * pr2][p][j][0], acc[2 * pr2][p][j][1], pd0, bfrag[j]);
@@ -491,6 +513,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
           }
       }
     }
+    next_item(Z, n_pg, zi, tile, ablk, pg);
   }
 }
 

@@ -1,0 +1,95 @@
+"""CPU: host-side logic that needs no GPU -- parameter naming, sharding, posterior, data I/O."""
+import os
+
+import numpy as np
+import pytest
+
+from cupix_b200 import plan as _plan
+from cupix_b200.engine import slots_from_names
+from cupix_b200.likelihood.free_parameter import FreeParameter
+from cupix_b200.likelihood.likelihood_parameter import LikelihoodParameter, dict_from_likeparam, likeparam_from_dict
+from cupix_b200.likelihood.posterior import Posterior
+from cupix_b200.parallel import block_partition, scan_chi2_sharded
+from cupix_b200.px_data import synthetic
+from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2, write_px_file
+
+
+def test_slot_names_match_header():
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "cupix_b200.h")).read()
+    for i, n in enumerate(_plan.SLOT_NAMES):
+        assert "CPX_%s = %d" % (n.upper(), i) in hdr, n
+
+
+def test_slots_from_names():
+    s, z = slots_from_names(["bias", "beta_3", "kp_Mpc", "b_noise_Mpc_0"])
+    assert list(s) == [0, 1, 7, 13] and list(z) == [-1, 3, -1, 0]
+    with pytest.raises(KeyError):
+        slots_from_names(["kCb_Mpc"])
+
+
+def test_block_partition_matches_reference_rule():
+    counts, starts = block_partition(16384, 64)
+    assert sum(counts) == 16384 and counts[0] == 256 and starts[-1] == 16384 - 256
+    counts, starts = block_partition(10, 4)
+    assert counts == [3, 3, 2, 2] and starts == [0, 3, 6, 8]
+
+
+def test_sharded_scan_single_rank_equals_full():
+    lo, hi, n = [0.0, 1.0], [1.0, 2.0], [5, 7]
+    grid = np.stack(np.meshgrid(np.linspace(0, 1, 5), np.linspace(1, 2, 7), indexing="ij"), -1).reshape(-1, 2)
+
+    def evaluate(first, count):
+        return (grid[first:first + count] ** 2).sum(axis=1)
+    full = scan_chi2_sharded(None, ["a", "b"], lo, hi, n, evaluate=evaluate)
+    parts = [scan_chi2_sharded(None, ["a", "b"], lo, hi, n, rank=r, world_size=3, gather=False, evaluate=evaluate)
+             for r in range(3)]
+    np.testing.assert_array_equal(np.concatenate(parts), full)
+
+
+class _FakeLike(object):
+    """quadratic log-likelihood with the batched interface of Likelihood"""
+    verbose = False
+
+    def get_ndata(self):
+        return 10
+
+    def get_log_like(self, params={}):
+        return -0.5 * sum((v - 1.0) ** 2 for v in params.values())
+
+    def get_log_like_batch(self, values, names, data_idx=None):
+        return -0.5 * ((np.asarray(values) - 1.0) ** 2).sum(axis=1)
+
+
+def test_posterior_scalar_and_batch_agree():
+    fp = [FreeParameter("bias", -2, 2, gauss_prior_mean=0.5, gauss_prior_width=0.3), FreeParameter("beta", 0, 3)]
+    post = Posterior(_FakeLike(), fp)
+    vals = np.array([[0.3, 1.2], [1.0, 1.0], [5.0, 1.0], [0.0, -1.0]])
+    batch = post.get_log_posterior_batch(vals)
+    for v, b in zip(vals, batch):
+        assert post.get_log_posterior_from_values(v) == pytest.approx(b)
+    assert batch[2] == -np.inf and batch[3] == -np.inf      # out of bounds is -inf, not the reference's +inf
+    assert post.get_ndf() == 8
+
+
+def test_likelihood_parameter_helpers():
+    ps = likeparam_from_dict({"bias": -0.1, "beta": 1.5})
+    assert isinstance(ps[0], LikelihoodParameter)
+    assert dict_from_likeparam(ps) == {"bias": -0.1, "beta": 1.5}
+    assert dict_from_likeparam({"q1": 0.2}) == {"q1": 0.2}
+
+
+def test_npz_roundtrip(tmp_path):
+    d = synthetic.make_measurement_dict("tiny_rebin")
+    path = str(tmp_path / "px.npz")
+    write_px_file(path, d)
+    a, b = DESI_DR2(d), DESI_DR2(path)
+    for key in ("Px_ZAM", "cov_ZAM", "U_ZaMn", "V_ZaM", "k_m", "k_M_edges", "B_A_a"):
+        np.testing.assert_array_equal(np.asarray(getattr(a, key)), np.asarray(getattr(b, key)))
+
+
+def test_synthetic_covariance_is_spd():
+    d = synthetic.make_measurement_dict("tiny")
+    model = np.abs(np.random.default_rng(0).normal(size=d["Px_ZAM"].shape)) + 0.1
+    f = synthetic.fill_from_model(d, model, add_noise=True)
+    for blk in f["cov_ZAM"].reshape(-1, model.shape[-1], model.shape[-1]):
+        assert np.all(np.linalg.eigvalsh(blk) > 0)
