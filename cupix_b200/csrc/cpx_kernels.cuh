@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) ZDev s_Z;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -347,7 +348,16 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   }
 
   for (long long it = it0; it < it1; ++it) {
-    const ZDev& Z = ztab[zi];
+    if (zi != cur_z) {
+      // keep this z bin's descriptor in shared memory: every later field access is an LDS, and the
+      // per-item parameter loads no longer wait on a pointer fetched from global memory
+      __syncthreads();
+      const int* src = reinterpret_cast<const int*>(&ztab[zi]);
+      int* dst = reinterpret_cast<int*>(&s_Z);
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(ZDev) / 4); i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+    }
+    const ZDev& Z = s_Z;
     const int n_ks = Z.n_q4;
     const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
     const uint32_t w_bytes = static_cast<uint32_t>(n_ks) * (NT * 32 * 8u);

@@ -1,0 +1,130 @@
+"""GPU: the BASELINE.json workload configurations, as parity / property tests on synthetic data.
+
+  S2  validate_pipeline: full theta x k_par Px with window matrices over all z bins vs the oracle
+  S3  chi2_scan_forecast: 4-parameter grid -- slices of the 64^4 grid by flat index == explicit points
+  S4  fit_many_mocks: many noisy mocks fitted concurrently (lock-step batched minimiser)
+  S5  stress shape: size-independent properties at full size (self-consistency, additivity over z,
+      batch-order invariance)
+"""
+import numpy as np
+import pytest
+
+from cupix_b200.likelihood.batch_minimizer import BatchMinimizer
+from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
+from cupix_b200.px_data import synthetic
+from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2
+from tests import helpers as H
+from tests.test_gpu_parity import assert_chi2, assert_px
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(shape, model, flags, N_t, noise=True, seed=synthetic.SEED + 1, **over):
+    d = synthetic.make_measurement_dict(shape, **over)
+    theories = [H.make_theory(float(z), model, flags) for z in d["z_centers"]]
+    data = DESI_DR2(d)
+    likes = [Likelihood(data, th, iz, config={"N_theta_average": N_t}) for iz, th in enumerate(theories)]
+    joint = JointLikelihood(likes)
+    truth_model = joint.get_convolved_px_batch(np.zeros((1, 0)), [])[0]
+    filled = synthetic.fill_from_model(d, truth_model, rng=np.random.default_rng(seed), add_noise=noise)
+    data = DESI_DR2(filled)
+    likes = [Likelihood(data, th, iz, config={"N_theta_average": N_t}) for iz, th in enumerate(theories)]
+    return data, likes, JointLikelihood(likes)
+
+
+def test_S2_validate_pipeline_all_z_vs_oracle():
+    data, likes, joint = _build("S2", "best_fit_arinyo_from_gadget", {"include_hcd": True, "include_continuum": True},
+                                N_t=2, N_m=60, N_A=8)
+    rng = np.random.default_rng(2)
+    names = ["bias", "beta", "q1", "kp_Mpc", "b_H"]
+    d0 = likes[0].build_plan().defaults
+    pts = np.stack([rng.uniform(-0.13, -0.10, 5), rng.uniform(1.3, 1.7, 5), rng.uniform(0.2, 0.5, 5),
+                    rng.uniform(10, 16, 5), rng.uniform(-0.03, -0.01, 5)], axis=1)
+    chi2, info = joint.get_chi2_batch(pts, names, return_info=True)
+    model = joint.get_convolved_px_batch(pts, names)
+    orcs = [H.oracle_likelihood(lk) for lk in likes]
+    for i in range(pts.shape[0]):
+        params = dict(zip(names, pts[i]))
+        ref = 0.0
+        for iz, o in enumerate(orcs):
+            assert_px(model[i, iz], o.get_convolved_px(params), msg="model pt %d z %d" % (i, iz))
+            c, inf = o.get_chi2(params, return_info=True)
+            assert_chi2(-2 * info["log_like_all"][i, iz], -2 * inf["log_like_all"], "per-theta pt %d z %d" % (i, iz),
+                        n_data=likes[iz].get_ndata() / len(inf["log_like_all"]))
+            ref += c
+        assert_chi2(chi2[i], ref, "joint chi2 pt %d" % i, n_data=joint.get_ndata())
+
+
+def test_S3_forecast_grid_slices():
+    data, likes, joint = _build("S1", "best_fit_arinyo_from_gadget", {}, N_t=1, N_m=48, N_A=6)
+    like = likes[0]
+    d0 = like.build_plan().defaults
+    names = ["bias", "beta", "q1", "kp_Mpc"]
+    lo = [d0[0] - 0.02, d0[1] - 0.2, d0[2] - 0.1, d0[7] - 3]
+    hi = [d0[0] + 0.02, d0[1] + 0.2, d0[2] + 0.1, d0[7] + 3]
+    n = [64, 64, 64, 64]                                     # 16 777 216 points; only slices are evaluated
+    total = 64 ** 4
+    axes = [np.linspace(lo[j], hi[j], n[j]) for j in range(4)]
+    for first, count in ((0, 300), (total // 8 * 3 + 17, 4097), (total - 513, 513)):   # rank-style shards
+        chi2 = like.get_chi2_grid(names, lo, hi, n, first=first, count=count)
+        idx = np.arange(first, first + count)
+        sub = np.stack(np.unravel_index(idx, n), axis=1)
+        pts = np.stack([axes[j][sub[:, j]] for j in range(4)], axis=1)
+        np.testing.assert_array_equal(chi2, like.get_chi2_batch(pts, names))
+    assert np.isfinite(chi2).all() and (chi2 > 0).all()
+
+
+def test_S4_fit_many_mocks_lockstep():
+    data, likes, joint = _build("S1", "best_fit_arinyo_from_colore", {}, N_t=1, N_m=48, N_A=8, noise=False)
+    like = likes[0]
+    truth = like.build_plan().defaults[:2]
+    rng = np.random.default_rng(9)
+    n_mocks = 64
+    cov = data.cov_ZAM[0]
+    L = np.linalg.cholesky(cov)
+    base = data.Px_ZAM[0]
+    mocks = base[None] + np.einsum("aij,naj->nai", L, rng.normal(size=(n_mocks,) + base.shape))
+    like.set_mock_data(mocks)
+    fitter = BatchMinimizer(like, ["bias", "beta"], steps=[2e-4, 5e-3])
+    x0 = np.tile(truth * np.array([1.05, 0.93]), (n_mocks, 1))
+    res = fitter.minimize(x0, data_idx=np.arange(n_mocks))
+    assert res["converged"].all()
+    chi2_truth = like.get_chi2_batch(np.tile(truth, (n_mocks, 1)), ["bias", "beta"], data_idx=np.arange(n_mocks))
+    assert np.all(res["chi2"] <= chi2_truth + 1e-6)
+    # pulls of the recovered parameters are unit Gaussians (errors from 2 H^-1)
+    err = np.sqrt(np.einsum("nii->ni", res["cov"]))
+    pull = (res["x"] - truth) / err
+    assert np.all(np.abs(pull.mean(axis=0)) < 0.5) and np.all(np.abs(pull.std(axis=0) - 1.0) < 0.35)
+    ndof = like.get_ndata() - 2
+    assert abs(res["chi2"].mean() / ndof - 1.0) < 0.15
+    assert fitter.n_calls < 60            # vs ~100 likelihood calls per mock with MIGRAD, serial
+
+
+def test_S5_stress_shape_properties():
+    """Full stress size: 12 z x 20 theta x 256 k_par x 64 k_M, dense windows, N_theta_average = 100."""
+    data, likes, joint = _build("S5", "best_fit_arinyo_from_gadget", {"include_hcd": True}, N_t=100, noise=False)
+    rng = np.random.default_rng(3)
+    names = ["bias", "beta", "q1", "kp_Mpc"]
+    d0 = likes[0].build_plan().defaults
+    B = 4096
+    pts = np.stack([rng.uniform(-0.02, 0.02, B), rng.uniform(-0.2, 0.2, B), rng.uniform(-0.1, 0.1, B),
+                    rng.uniform(-3, 3, B)], axis=1)
+    # self-consistency: the noiseless forecast scored with the parameters that made it has chi2 ~ 0
+    assert abs(joint.get_chi2({})) < 1e-6
+    # offsets are applied per z bin relative to that bin's defaults -> use per-z names for an exact check
+    p0 = np.array([[-0.004, 0.03]])
+    tot = joint.get_chi2_batch(p0 + np.array([[likes[0].build_plan().defaults[0], likes[0].build_plan().defaults[1]]]),
+                               ["bias_0", "beta_0"], return_info=True)
+    # additivity over z: joint chi2 == sum of chi2_zA, and only bin 0 moved
+    assert tot[0][0] == pytest.approx((-2 * tot[1]["log_like_all"][0]).sum(), rel=1e-14)
+    assert (-2 * tot[1]["log_like_all"][0, 1:]).sum() < 1e-6 and (-2 * tot[1]["log_like_all"][0, 0]).sum() > 1.0
+    # batch-order invariance and chunk-boundary independence (B spans several device chunks of 8192? no: force it)
+    absolute = pts * 0 + np.array([[d0[0], d0[1], d0[2], d0[7]]]) + pts * np.array([[1, 1, 1, 1]])
+    a = joint.get_chi2_batch(absolute, ["bias_3", "beta_3", "q1_3", "kp_Mpc_3"])
+    perm = rng.permutation(B)
+    b = joint.get_chi2_batch(absolute[perm], ["bias_3", "beta_3", "q1_3", "kp_Mpc_3"])
+    np.testing.assert_array_equal(a[perm], b)
+    assert (a > 0).all() and np.isfinite(a).all()
+    # the single-z Likelihood of bin 3 gives the same numbers as the joint engine restricted to it
+    c = likes[3].get_chi2_batch(absolute[:64], names)
+    np.testing.assert_allclose(c, a[:64], rtol=1e-12, atol=1e-9)
