@@ -169,7 +169,20 @@ def run_cpu(flavour, shape, n_t, n_q, per_core, defaults):
             "busy_s": busy, "wall_s": wall}
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL banners...)
+    was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # stdout of this process and its children -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -215,7 +228,7 @@ def main():
                                            "FFTLog Hankel algorithm (oracle A), N_theta_average=%d, one process per core"
                                            % (best["evals"], a.n_theta_average)},
                 "e2e": {"value": best["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -371,7 +384,7 @@ def main():
             "vs_baseline": None, "dtype": "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "per_point_z_rate": value * len(likes)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
