@@ -303,23 +303,26 @@ int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
 // ---- kernel dispatch -----------------------------------------------------------------------
 typedef void (*K1Fn)(const cpx::ZDev*, int, int, long long);
 
-// PP = 1 fits two CTAs per SM (<= 128 registers); PP = 2 runs one CTA per SM
-K1Fn k1_select(int pp, int nt) {
+// PP = 1 fits two CTAs per SM (<= 128 registers); PP = 2 runs one CTA per SM.
+// ADD: some evaluated z bin has additive contaminants (SiIII metals or sky) in its epilogue.
+template <bool ADD>
+K1Fn k1_select_add(int pp, int nt) {
   if (pp == 1) {
     switch (nt) {
-      case 1: return cpx::k_p3d_hankel<1, 1, 2>;
-      case 2: return cpx::k_p3d_hankel<1, 2, 2>;
-      case 3: return cpx::k_p3d_hankel<1, 3, 2>;
+      case 1: return cpx::k_p3d_hankel<1, 1, 2, ADD>;
+      case 2: return cpx::k_p3d_hankel<1, 2, 2, ADD>;
+      case 3: return cpx::k_p3d_hankel<1, 3, 2, ADD>;
     }
   } else if (pp == 2) {
     switch (nt) {
-      case 1: return cpx::k_p3d_hankel<2, 1, 1>;
-      case 2: return cpx::k_p3d_hankel<2, 2, 1>;
-      case 3: return cpx::k_p3d_hankel<2, 3, 1>;
+      case 1: return cpx::k_p3d_hankel<2, 1, 1, ADD>;
+      case 2: return cpx::k_p3d_hankel<2, 2, 1, ADD>;
+      case 3: return cpx::k_p3d_hankel<2, 3, 1, ADD>;
     }
   }
   return nullptr;
 }
+K1Fn k1_select(int pp, int nt, bool add) { return add ? k1_select_add<true>(pp, nt) : k1_select_add<false>(pp, nt); }
 int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
 
 typedef void (*K2Fn)(const cpx::ZDev*, int, cpx::WindowArgs);
@@ -452,12 +455,13 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       return bail(rc);
 
   // opt in to the large dynamic shared memory for every k_p3d_hankel instantiation we may launch
-  for (int pp = 1; pp <= 2; ++pp) {
-    K1Fn fn = k1_select(pp, h->na_blk / 8);
-    if (!fn) return bail(fail(CPX_ERR_UNSUPPORTED, "no k_p3d_hankel instantiation for this theta-bin count"));
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
-      return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
-  }
+  for (int pp = 1; pp <= 2; ++pp)
+    for (int add = 0; add < 2; ++add) {
+      K1Fn fn = k1_select(pp, h->na_blk / 8, add != 0);
+      if (!fn) return bail(fail(CPX_ERR_UNSUPPORTED, "no k_p3d_hankel instantiation for this theta-bin count"));
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
+        return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
+    }
   *out = h;
   return CPX_OK;
 }
@@ -652,7 +656,9 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     // ---- stage 1: P3D + Hankel ----
     if ((rc = mark())) return rc;
     {
-      K1Fn fn = k1_select(pp, h->na_blk / 8);
+      bool additive = false;
+      for (int i = 0; i < n_zl; ++i) additive |= (tab[i].flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)) != 0;
+      K1Fn fn = k1_select(pp, h->na_blk / 8, additive);
       const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
       const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * k1_ctas_per_sm(pp)));
       fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);

@@ -310,7 +310,7 @@ __device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int&
   }
 }
 
-template <int PP, int NT, int MINB>
+template <int PP, int NT, int MINB, bool ADD>
 __global__ void __launch_bounds__(kK1Threads, MINB)
     k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -480,46 +480,50 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       wb += NT * 32;
     }
 
-    // ---- epilogue: amplitude, metals, sky, continuum; store Px_Zam[pt][a][m] ----
-    // C fragment: row 8*mt + g, theta columns 8*j + 2*t + {0, 1}
-    const int a_blk0 = ablk * (8 * NT);
+    // ---- epilogue: amplitude, continuum (row scalars), metals + sky (ADD); store Px_Zam[pt][a][m] ----
+    // C fragment: row 8*mt + g, theta columns 8*j + 2*t + {0, 1}.  Px = (amp * acc + additive) * cont.
+    const int a_lane0 = ablk * (8 * NT) + 2 * t;
+    const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
       const int pt = pt0 + p;
       if (pt >= count) break;
       const PtPar& pr = Z.ptpar[pt];
+      const double amp0 = pr.bias * pr.bias * Z.dAA;
+      double* outp = Z.pxzam + (static_cast<size_t>(pt) * n_a + a_lane0) * n_m_pad + m_base + g;
+      const RowPar* rp = Z.rowpar + static_cast<size_t>(pt) * n_m_pad + m_base + g;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int m = m_base + 8 * mt + g;
-        const bool row_ok = m < Z.n_m;
-        double amp = pr.bias * pr.bias * Z.dAA, cont = 1.0;
+        const bool row_ok = m < n_m;
+        double amp = amp0, cont = 1.0;
         if (rowwise) {
-          const RowPar& rp = Z.rowpar[static_cast<size_t>(pt) * Z.n_m_pad + m];
-          amp = rp.amp;
-          cont = rp.cont;
+          amp = rp[8 * mt].amp;
+          cont = rp[8 * mt].cont;
         }
+        const double scale = row_ok ? amp * cont : 0.0;
         double sky = 0.0;
-        if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];    // theory.py:476-506
+        if (ADD && (Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];    // theory.py:476-506
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
-            const int a = a_blk0 + 8 * j + 2 * t + cc;
-            if (a >= Z.n_a) continue;
-            double px = 0.0;
-            if (row_ok) {
-              px = amp * acc[mt][p][j][cc];
+            const int a = a_lane0 + 8 * j + cc;
+            if (a >= n_a) continue;
+            double px = scale * acc[mt][p][j][cc];
+            if (ADD && row_ok) {
+              double add = 0.0;
               if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
-                const size_t o = static_cast<size_t>(a) * Z.n_m + m, st = static_cast<size_t>(Z.n_a) * Z.n_m;
+                const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
                 const double bx = pr.b_X, btx = pr.beta_X;
-                px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
-                px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
-                                      pr.beta * btx * Z.metal_cross[o + 2 * st]);
+                add += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+                add += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                       pr.beta * btx * Z.metal_cross[o + 2 * st]);
               }
-              if (Z.flags & 4) px += sky * Z.sky_xi[a];
-              px *= cont;
+              if (Z.flags & 4) add += sky * Z.sky_xi[a];
+              px = fma(add, cont, px);
             }
-            Z.pxzam[(static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + m] = px;
+            outp[static_cast<size_t>(8 * j + cc) * n_m_pad + 8 * mt] = px;
           }
       }
     }
