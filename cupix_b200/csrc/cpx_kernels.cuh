@@ -112,6 +112,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
@@ -266,7 +267,9 @@ __device__ __forceinline__ void exp2_reduce(float2 x, float2& t, float2& f) {
   f = fma2(add2(t, dup2(-12582912.0f)), dup2(-1.0f), x);
 }
 __device__ __forceinline__ float exp2_scale(float p, float t) {
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+  // funnel shift + add keep this on the ALU pipe; a plain (t << 23) + p becomes an IMAD on the FMA
+  // pipe, which is the one the FP64 tensor pipe competes with (profiles/dmma_contention_r01.txt)
+  return __int_as_float(__float_as_int(p) + static_cast<int>(__funnelshift_l(0u, static_cast<unsigned>(__float_as_int(t)), 23)));
 }
 // 2^x, unbiased: 2^f is a degree-7 polynomial on the FMA pipe.  MUFU.EX2 alone is biased by
 // -2e-8 .. -5e-8 on this range (tools/mufu_error.cu, profiles/mufu_error_r01.txt), which is coherent
@@ -286,13 +289,25 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   p = fma2(p, f, dup2(1.0f));
   return make_float2(exp2_scale(p.x, t.x), exp2_scale(p.y, t.y));
 }
-// 2^x with MUFU.EX2 on the reduced argument only (bias ~ -8e-9: enough for the velocity term, which
-// enters the exponent of D_NL multiplied by Delta^2 (q1 + q2 Delta^2)).  x <= ~30 here.
+// 2^x with MUFU.EX2 on the reduced argument only (round-to-nearest reduction, f in [-0.5, 0.5]:
+// bias ~ -8e-9, enough for the velocity term, which enters the exponent of D_NL multiplied by
+// Delta^2 (q1 + q2 Delta^2)).  x <= ~30 here.
 __device__ __forceinline__ float2 exp2_rr2(float2 x) {
   x.x = fmaxf(x.x, -125.0f);
   x.y = fmaxf(x.y, -125.0f);
   float2 t, f;
   exp2_reduce(x, t, f);
+  return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
+}
+// 2^x with MUFU.EX2 on f = x - floor(x) in [0, 1): the bias of MUFU.EX2 depends on the sign and
+// the integer part of its argument (profiles/mufu_bias_curve_r01.txt: -2e-8..-6e-8 for x < 0,
+// +2e-8..+5e-8 for x > 1, but +5.6e-9 averaged over [0, 1)).  Six FMA-pipe instructions cheaper
+// per cell pair than the polynomial, at the price of that 5.6e-9 bias.
+__device__ __forceinline__ float2 exp2_fl2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -125.0f), 126.0f);
+  x.y = fminf(fmaxf(x.y, -125.0f), 126.0f);
+  const float2 t = add2(add2(x, dup2(-0.5f)), dup2(12582912.0f));        // integer part = floor(x) (ties: round)
+  const float2 f = fma2(add2(t, dup2(-12582912.0f)), dup2(-1.0f), x);    // x - floor(x), exact
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 
@@ -309,6 +324,12 @@ __device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int&
     }
   }
 }
+
+#ifdef CPX_DNL_MUFU
+#define kExpDnl exp2_fl2
+#else
+#define kExpDnl exp2_poly2
+#endif
 
 template <int PP, int NT, int MINB, bool ADD>
 __global__ void __launch_bounds__(kK1Threads, MINB)
@@ -434,6 +455,13 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       }
     }
 
+    // warm L1/L2 with the parameters of this warp's next item (same tile, next point group)
+    if (pg + 1 < n_pg) {
+      const int ptn = min(pt0 + kK1Warps * PP, count - 1);
+      if (lane == 0) prefetch_l1(&Z.ptpar[ptn]);
+      if (rowwise && lane < 8) prefetch_l1(&Z.rowpar[static_cast<size_t>(ptn) * Z.n_m_pad + m_base + 4 * lane]);
+    }
+
     double acc[4][PP][NT][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
@@ -462,7 +490,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
           const float2 v = exp2_rr2(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), nlkvlo[p]));
           // D_NL = 2^(nl (1 - v) - (k/kp)^2 log2e)
           const float2 tt = fma2(NK2, ikp2lo[p], fma2(NK2, ikp2l[p], nl));
-          const float2 e = exp2_poly2(fma2(mul2(nl, dup2(-1.0f)), v, tt));
+          const float2 e = kExpDnl(fma2(mul2(nl, dup2(-1.0f)), v, tt));
           // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice, plus the first-order
           // beta_lo term) so that its float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded
           // on its own takes the same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
