@@ -205,10 +205,14 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   if (d.n_A > 0) {
     if (!d.B_A_a || !d.U_aMn || !d.V_aM || !d.Px_AM || !d.cov_AMM || d.n_M <= 0 || d.n_data <= 0)
       return fail(CPX_ERR_ARG, "measurement arrays missing for a z bin with n_A > 0");
-    if (d.n_M > 64) return fail(CPX_ERR_UNSUPPORTED, "n_M > 64 coarse k bins is not supported yet");
     const int nA = d.n_A, nM = d.n_M, na = d.n_a, nm = d.n_m;
     Z.n_M = nM;
-    Z.n_M_pad = round_up(nM, 8);
+    {   // coarse-k columns in n_mblk blocks of 8*MT (MT <= 8 n-tiles per k_window pass)
+      const int tiles = (nM + 7) / 8;
+      Z.n_mblk = (tiles + 7) / 8;
+      const int mt = (tiles + Z.n_mblk - 1) / Z.n_mblk;
+      Z.n_M_pad = Z.n_mblk * mt * 8;
+    }
     Z.n_data = d.n_data;
     std::vector<int> pair_start(nA + 1, 0), pair_a;
     for (int A = 0; A < nA; ++A) {
@@ -685,11 +689,11 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       w.model = model_dst;
       dim3 grid((count + kWinPts - 1) / kWinPts, std::max(Z.n_A, 1));
       if (want_chi2) {
-        k2_select<true>(Z.n_M_pad / 8)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        k2_select<true>(Z.n_M_pad / 8 / Z.n_mblk)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
         ++h->launches;
       }
       if (want_model) {
-        k2_select<false>(Z.n_M_pad / 8)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        k2_select<false>(Z.n_M_pad / 8 / Z.n_mblk)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
         ++h->launches;
       }
       if (want_px) {

@@ -50,7 +50,8 @@ struct ZDev {
   int n_m_pad;                          // 32 * n_tiles
   int na_blk, n_ablk;                   // theta-block width (8 * NT) and count
   int flags;
-  int n_q4, pad1;                       // ceil(n_q / 4): k-steps of the DMMA contraction
+  int n_q4;                             // ceil(n_q / 4): k-steps of the DMMA contraction
+  int n_mblk;                           // coarse-k column blocks of k_window (n_M_pad = n_mblk * 8 * MT)
   double dAA;
   const float* cellc;                   // [n_tiles][n_q4][6][2][32][2] A-fragment order: lane = 4*g + t holds rows 8*(2*pr+e)+g, e = 0,1 (packed pair), node 4*ks+t
   const double* Wd;                     // [n_ablk][n_q4][NT][32]     B-fragment order: lane = 4*g + t holds W[theta 8*j+g][node 4*ks+t]
@@ -594,88 +595,99 @@ __global__ void __launch_bounds__(128) k_window(const ZDev* __restrict__ ztab, i
   const int kchunks = Z.n_m_pad / kWinKC;
   const int n_steps = (p1 - p0) * kchunks;
   const double* Tbase = CHI2 ? Z.T_chi : Z.T_model;
+  double chi2_part[2] = {0.0, 0.0};
 
-  double acc[2][MT][2];
+  // coarse-k columns in blocks of 8*MT (one block unless n_M > 64)
+  for (int mb = 0; mb < Z.n_mblk; ++mb) {
+    const int col0 = mb * 8 * MT;
+    double acc[2][MT][2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto load_stage = [&](int step, int buf) {
-    const int pair = p0 + step / kchunks;
-    const int k0 = (step % kchunks) * kWinKC;
-    const int a = Z.pair_a[pair];
-    // A tile: 64 points x 16 doubles = 512 x 16B
-    for (int i = tid; i < kWinPts * (kWinKC / 2); i += 128) {
-      const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
-      const int pt = min(pt_base + row, w.count - 1);
-      const double* src = Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + k0 + 2 * c2;
-      cp_async16(&sA[buf][row][2 * c2], src);
-    }
-    // B tile: (8*MT) coarse-k rows x 16 doubles
-    for (int i = tid; i < 8 * MT * (kWinKC / 2); i += 128) {
-      const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
-      const double* src = Tbase + (static_cast<size_t>(pair) * Z.n_M_pad + row) * Z.n_m_pad + k0 + 2 * c2;
-      cp_async16(&sB[buf][row][2 * c2], src);
-    }
-    cp_async_commit();
-  };
+    auto load_stage = [&](int step, int buf) {
+      const int pair = p0 + step / kchunks;
+      const int k0 = (step % kchunks) * kWinKC;
+      const int a = Z.pair_a[pair];
+      // A tile: 64 points x 16 doubles = 512 x 16B
+      for (int i = tid; i < kWinPts * (kWinKC / 2); i += 128) {
+        const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+        const int pt = min(pt_base + row, w.count - 1);
+        const double* src = Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + k0 + 2 * c2;
+        cp_async16(&sA[buf][row][2 * c2], src);
+      }
+      // B tile: (8*MT) coarse-k rows x 16 doubles
+      for (int i = tid; i < 8 * MT * (kWinKC / 2); i += 128) {
+        const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+        const double* src = Tbase + (static_cast<size_t>(pair) * Z.n_M_pad + col0 + row) * Z.n_m_pad + k0 + 2 * c2;
+        cp_async16(&sB[buf][row][2 * c2], src);
+      }
+      cp_async_commit();
+    };
 
-  load_stage(0, 0);
-  for (int step = 0; step < n_steps; ++step) {
-    const int buf = step & 1;
-    if (step + 1 < n_steps) {
-      load_stage(step + 1, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+    load_stage(0, 0);
+    for (int step = 0; step < n_steps; ++step) {
+      const int buf = step & 1;
+      if (step + 1 < n_steps) {
+        load_stage(step + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kWinKC; kk += 4) {
+        double af[2];
+        af[0] = sA[buf][warp * 16 + g][kk + t];
+        af[1] = sA[buf][warp * 16 + 8 + g][kk + t];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const double bf = sB[buf][8 * j + g][kk + t];
+          dmma_884(acc[0][j][0], acc[0][j][1], af[0], bf);
+          dmma_884(acc[1][j][0], acc[1][j][1], af[1], bf);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
+
+    // epilogue of this column block.  C fragment: rows g (+8), columns 8j + 2t + {0,1}
 #pragma unroll
-    for (int kk = 0; kk < kWinKC; kk += 4) {
-      double af[2];
-      af[0] = sA[buf][warp * 16 + g][kk + t];
-      af[1] = sA[buf][warp * 16 + 8 + g][kk + t];
+    for (int i = 0; i < 2; ++i) {
+      const int pt = pt_base + warp * 16 + 8 * i + g;
+      if (CHI2) {
+        const int d = (w.data_idx != nullptr && pt < w.count) ? w.data_idx[pt] : 0;
+        const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad + col0;
+        double s = chi2_part[i];
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const double bf = sB[buf][8 * j + g][kk + t];
-        dmma_884(acc[0][j][0], acc[0][j][1], af[0], bf);
-        dmma_884(acc[1][j][0], acc[1][j][1], af[1], bf);
+        for (int j = 0; j < MT; ++j) {
+          const int col = 8 * j + 2 * t;
+          const double y0 = yd[col] - acc[i][j][0];
+          const double y1 = yd[col + 1] - acc[i][j][1];
+          s = fma(y0, y0, s);
+          s = fma(y1, y1, s);
+        }
+        chi2_part[i] = s;
+      } else if (pt < w.count) {
+        double* out = w.model + ((static_cast<size_t>(pt) * w.n_zl + w.zslot) * w.nA_max + A) * w.nM_max + col0;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int col = 8 * j + 2 * t;
+          if (col0 + col < Z.n_M) out[col] = acc[i][j][0];
+          if (col0 + col + 1 < Z.n_M) out[col + 1] = acc[i][j][1];
+        }
       }
     }
-    __syncthreads();
   }
-
-  // epilogue.  C fragment: rows g (+8), columns 8j + 2t + {0,1}
+  if (CHI2) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int pt = pt_base + warp * 16 + 8 * i + g;
-    if (CHI2) {
-      const int d = (w.data_idx != nullptr && pt < w.count) ? w.data_idx[pt] : 0;
-      const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const int col = 8 * j + 2 * t;
-        const double y0 = yd[col] - acc[i][j][0];
-        const double y1 = yd[col + 1] - acc[i][j][1];
-        s = fma(y0, y0, s);
-        s = fma(y1, y1, s);
-      }
+    for (int i = 0; i < 2; ++i) {
+      const int pt = pt_base + warp * 16 + 8 * i + g;
+      double s = chi2_part[i];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       if (t == 0 && pt < w.count)
         w.chi2_zA[(static_cast<size_t>(pt) * w.n_zl + w.zslot) * w.nA_max + A] = s;
-    } else {
-      if (pt < w.count) {
-        double* out = w.model + ((static_cast<size_t>(pt) * w.n_zl + w.zslot) * w.nA_max + A) * w.nM_max;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-          const int col = 8 * j + 2 * t;
-          if (col < Z.n_M) out[col] = acc[i][j][0];
-          if (col + 1 < Z.n_M) out[col + 1] = acc[i][j][1];
-        }
-      }
     }
   }
 }

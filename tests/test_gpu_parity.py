@@ -186,3 +186,16 @@ def test_unknown_keys_ignored_and_errors_are_loud():
     with pytest.raises(CpxError):
         Likelihood(DESI_DR2(bad), H.make_theory(2.2, "best_fit_arinyo_from_colore", {}), 0,
                    config={"N_theta_average": 1}).get_chi2({})
+
+
+def test_more_than_64_coarse_k_bins():
+    """n_M = 70 > 64: k_window walks the coarse-k columns in two blocks."""
+    like, truth = _s1_like(N_t=1, N_A=3, N_m=140, rebin_k=2)
+    assert like.data.Px_ZAM.shape[-1] == 70
+    orc = H.oracle_likelihood(like)
+    params = {"bias": -0.118, "beta": 1.57}
+    assert_px(like.get_convolved_px(params), orc.get_convolved_px(params), msg="model n_M=70")
+    ref, rinfo = orc.get_chi2(params, return_info=True)
+    got, info = like.get_chi2(params, return_info=True)
+    assert_chi2(got, ref, "chi2 n_M=70", n_data=like.get_ndata())
+    assert_chi2(-2 * info["log_like_all"], -2 * rinfo["log_like_all"], "per-theta n_M=70", n_data=like.get_ndata() / 3)

@@ -93,3 +93,14 @@ def test_synthetic_covariance_is_spd():
     f = synthetic.fill_from_model(d, model, add_noise=True)
     for blk in f["cov_ZAM"].reshape(-1, model.shape[-1], model.shape[-1]):
         assert np.all(np.linalg.eigvalsh(blk) > 0)
+
+
+def test_ensemble_sampler_recovers_gaussian():
+    from cupix_b200.likelihood.sampler import Sampler
+    fp = [FreeParameter("bias", -4, 6, ini_value=0.5), FreeParameter("beta", -4, 6, ini_value=0.5)]
+    post = Posterior(_FakeLike(), fp)
+    smp = Sampler(post, {"nwalkers": 32, "max_nsteps": 600, "nburnin": 150, "seed": 3})
+    flat = smp.run_sampler()
+    assert 0.2 < smp.acceptance_fraction < 0.9
+    assert np.all(np.abs(flat.mean(axis=0) - 1.0) < 0.1)      # _FakeLike: unit Gaussian centred on 1
+    assert np.all(np.abs(flat.std(axis=0) - 1.0) < 0.15)
