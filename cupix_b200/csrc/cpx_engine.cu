@@ -676,31 +676,43 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     if (want_model) model_dst = dev_io ? a->model_zAM + first * n_zl * nA_max * nM_max : h->d_model;
     double* px_dst = nullptr;
     if (want_px) px_dst = dev_io ? a->px_zam + first * n_zl * na_max * nm_max : h->d_pxout;
-    for (int i = 0; i < n_zl; ++i) {
+    bool same_window_shape = true;
+    for (int i = 1; i < n_zl; ++i)
+      same_window_shape &= tab[i].n_M_pad == tab[0].n_M_pad && tab[i].n_mblk == tab[0].n_mblk;
+    auto window_launch = [&](int i, int zslot, int gz, int nA_grid) {
       const ZDev& Z = tab[i];
       WindowArgs w;
       w.count = count;
-      w.zslot = i;
+      w.zslot = zslot;
       w.n_zl = n_zl;
       w.nA_max = nA_max;
       w.nM_max = nM_max;
       w.data_idx = d_didx;
       w.chi2_zA = chi2_zA_dst;
       w.model = model_dst;
-      dim3 grid((count + kWinPts - 1) / kWinPts, std::max(Z.n_A, 1));
+      dim3 grid((count + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
+      const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
-        k2_select<true>(Z.n_M_pad / 8 / Z.n_mblk)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        k2_select<true>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
         ++h->launches;
       }
       if (want_model) {
-        k2_select<false>(Z.n_M_pad / 8 / Z.n_mblk)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        k2_select<false>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
         ++h->launches;
       }
-      if (want_px) {
+    };
+    if (want_chi2 || want_model) {
+      if (same_window_shape) {
+        window_launch(0, -1, n_zl, nA_max);          // one grid over (point tiles, theta_A, z)
+      } else {
+        for (int i = 0; i < n_zl; ++i) window_launch(i, i, 1, tab[i].n_A);
+      }
+    }
+    if (want_px)
+      for (int i = 0; i < n_zl; ++i) {
         k_unpad_pxzam<<<std::min(4 * h->sm_count, 1024), 256, 0, st>>>(h->d_ztab, i, i, n_zl, na_max, nm_max, count, px_dst);
         ++h->launches;
       }
-    }
     // ---- stage 3: reduce ----
     if ((rc = mark())) return rc;
     if (a->chi2) {

@@ -572,7 +572,7 @@ constexpr int kWinLd = kWinKC + 4;   // padded row stride (doubles): conflict-fr
 
 struct WindowArgs {
   int count;          // points in chunk
-  int zslot;          // index of this z in the evaluated list
+  int zslot;          // index of this z in the evaluated list, or -1: one launch covers all z (blockIdx.z)
   int n_zl;           // number of evaluated z
   int nA_max, nM_max; // output strides
   const int* data_idx;   // [count] or null
@@ -582,6 +582,10 @@ struct WindowArgs {
 
 template <int MT, bool CHI2>
 __global__ void __launch_bounds__(128) k_window(const ZDev* __restrict__ ztab, int zi, WindowArgs w) {
+  if (w.zslot < 0) {   // all evaluated z bins in one grid: fewer launches, no per-z wave quantisation
+    zi = blockIdx.z;
+    w.zslot = blockIdx.z;
+  }
   const ZDev& Z = ztab[zi];
   const int A = blockIdx.y;
   const int pt_base = blockIdx.x * kWinPts;
