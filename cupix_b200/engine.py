@@ -224,6 +224,27 @@ class PxEngine(object):
             out["stage_ms"] = np.array(list(ms))
         return out
 
+    def eval_host_into(self, points, slots, zsel, chi2_out, data_idx=None):
+        """chi2 for host ``points`` [B, P] written into the caller's host array ``chi2_out`` [B]
+        (e.g. pinned memory); H2D, kernels and D2H all happen inside this one cpx_eval call."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        assert points.flags.c_contiguous and points.dtype == np.float64 and chi2_out.flags.c_contiguous
+        args = EvalArgs()
+        args.B, args.P, args.flags = points.shape[0], points.shape[1], 0
+        args.points = points.ctypes.data_as(C.c_void_p)
+        args.slot = slots.ctypes.data_as(c_ip)
+        if zsel is not None:
+            zsel = np.ascontiguousarray(zsel, dtype=np.int32)
+            args.zsel = zsel.ctypes.data_as(c_ip)
+        if data_idx is not None:
+            data_idx = np.ascontiguousarray(data_idx, dtype=np.int32)
+            args.data_idx = data_idx.ctypes.data_as(C.c_void_p)
+        args.chi2 = chi2_out.ctypes.data_as(C.c_void_p)
+        rc = self.lib.cpx_eval(self._h, C.byref(args))
+        if rc != 0:
+            raise CpxError("cpx_eval failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        return chi2_out
+
     def eval_device(self, B, P, slots, points_ptr=None, grid=None, grid_first=0, zsel=None,
                     data_idx_ptr=None, z_list=None, chi2_ptr=None, chi2_zA_ptr=None, model_ptr=None,
                     px_ptr=None, stream=None, stage_ms=False):

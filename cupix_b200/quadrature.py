@@ -16,7 +16,8 @@ is evaluated once per (z, binning) in float64 with Gauss-Legendre panels that re
 ``Px(k_par, r) = sum_q W[r, q] P3D(k_par, k_q)`` for every parameter point.  Because the rule is
 linear, the reference's theta sub-sampling average (cupix/likelihood/likelihood.py:99-130) is
 folded into the weights as well.  Measured error against a 2^20-point brute-force integral is
-< 1e-7 of the Px scale at n_q = 96 over the ForestFlow training box (tests/test_quadrature.py).
+< 2e-7 of the Px scale at the default n_q = 88 over the ForestFlow training box
+(tests/test_quadrature.py; 64 nodes: 4e-7, 96 nodes: 7e-8 -- `n_q` is a Theory config key).
 """
 from concurrent.futures import ThreadPoolExecutor
 import os
@@ -25,7 +26,7 @@ import numpy as np
 from scipy.interpolate import BSpline, make_interp_spline
 from scipy.special import j0
 
-DEFAULT_NQ = 96
+DEFAULT_NQ = 88
 DEFAULT_K0 = 0.01
 DEFAULT_KMAX = 200.0
 SPLINE_ORDER = 5
@@ -92,7 +93,9 @@ class KperpRule(object):
             ng = int(n_groups if n_groups is not None else gi.max() + 1)
         norm = np.bincount(gi, weights=gw, minlength=ng)
         jbar = np.zeros((ng, kf.size))
-        nthreads = nthreads or min(8, len(os.sched_getaffinity(0)))
+        # one process per GPU: share the host cores between the ranks of this node
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        nthreads = nthreads or max(1, min(8, len(os.sched_getaffinity(0)) // ranks))
 
         def work(g):
             sel = np.where(gi == g)[0]

@@ -36,17 +36,17 @@ def brute():
 
 @pytest.mark.parametrize("name", sorted(LYA_SETS))
 def test_node_rule_converged(name, brute):
-    """Quadrature error of the default rule (n_q = 96) is < 3e-7 of the Px scale -- 30x inside the
+    """Quadrature error of the default rule (n_q = 88) is < 2e-7 of the Px scale -- 50x inside the
     1e-5 model tolerance -- for central and extreme Arinyo parameters, all contaminants on."""
     cosmo = Cosmology()
     rule = KperpRule()
-    assert rule.n_q == 96
+    assert rule.n_q == 88
     res = {}
     for key, h in (("node", NodeHankel(rule.k, lambda r: rule.weights(r, nthreads=1))), ("brute", brute)):
         th = OracleTheory(2.2, cosmo, LYA_SETS[name], CONT, XI, h, include_hcd=True, include_metal=True)
         res[key] = th.get_px_obs(THETA, K_AA, {})
     err = np.abs(res["node"] - res["brute"]).max() / np.abs(res["brute"]).max()
-    assert err < 3e-7, err
+    assert err < 2e-7, err
 
 
 def test_reference_algorithm_agrees_with_node_rule():
