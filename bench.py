@@ -340,9 +340,14 @@ def main():
     peaks = probe_peaks(local_rank)
     k1_s = stage[1] * 1e-3
     k2_s = stage[2] * 1e-3
-    dfma_flops = 2.0 * work["hankel_dfma"] * B
-    achieved = dfma_flops / k1_s / 1e12
-    peak = 2.0 * peaks["dfma_per_s"] / 1e12
+    # dominant kernel: k_p3d_hankel, bound by the FP64 tensor pipe (DMMA m8n8k4).  `achieved` counts the
+    # ALGORITHMIC flops (2 n_a n_m n_q per point and z); the kernel issues 24/20 of that because the
+    # 20 theta bins occupy three 8-wide MMA column tiles.
+    useful_flops = 2.0 * work["hankel_dfma"] * B
+    achieved = useful_flops / k1_s / 1e12
+    peak = 2.0 * peaks["dmma_fma_per_s"] / 1e12
+    n_a = len(likes[0].data.theta_min_a_arcmin)
+    pad = (8.0 * ((n_a + 7) // 8) if n_a <= 24 else float(n_a)) / n_a
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "k_p3d_hankel_traffic.json")
     if os.path.exists(tfile):
@@ -350,16 +355,18 @@ def main():
             traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_p3d_hankel", "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    roofline = {"kernel": "k_p3d_hankel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "cpx_probe_peaks: dependent-chain DFMA microbenchmark on this GPU, same process "
-                               "(MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure)",
+                "peak_source": "FP64 tensor pipe (DMMA m8n8k4) rate of this GPU measured in this process by "
+                               "cpx_probe_peaks; MEASURED_PEAKS.json holds only HBM and bf16 figures, which do not "
+                               "bound this FP64 path",
+                "pipe_frac_incl_padding": achieved * pad / peak,
                 "launches_per_step": int(n_chunks), "ms_per_launch": float(stage[1] / n_chunks),
                 "share_of_step": float(stage[1] / stage.sum()),
                 "algorithmic": dict(work, per="evaluation (one point, all z)"),
-                "fp32_pipe_frac": float(9.0 * work["p3d_cells"] * B / k1_s / peaks["ffma_per_s"]),
+                "fp32_fma_pipe_frac": float(31.0 * work["p3d_cells"] * B / k1_s / peaks["ffma_per_s"]),
                 "mufu_pipe_frac": float(2.0 * work["p3d_cells"] * B / k1_s / peaks["mufu_per_s"]),
-                "window_kernel": {"kernel": "k_window", "achieved": 2.0 * work["window_dfma"] * B / k2_s / 1e12,
+                "window_kernel": {"kernel": "k_window", "bound": "tensor", "achieved": 2.0 * work["window_dfma"] * B / k2_s / 1e12,
                                   "frac": 2.0 * work["window_dfma"] * B / k2_s / 1e12 / peak,
                                   "share_of_step": float(stage[2] / stage.sum())},
                 "stage_ms": {"params": float(stage[0]), "p3d_hankel": float(stage[1]), "window_chi2": float(stage[2]),

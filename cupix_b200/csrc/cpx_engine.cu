@@ -125,6 +125,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   // cell constants in DMMA A-fragment order, m-tile pairs packed: [tile][ks][6][pair][lane = 4*g + t][2]
   {
     std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * Z.n_q4 * kCellConsts * 4 * 32, 0.0f);
+    std::vector<double> cell64(cell.size(), 0.0);   // [tile][ks][6][mt][lane], unpaired, for CPX_PRECISE_CELLS
     const double two_pi2 = 2.0 * M_PI * M_PI;
     for (int m = 0; m < d.n_m; ++m) {
       const int tile = m / kTileRows, r = m % kTileRows, mt = r / 8, g = r % 8;
@@ -145,6 +146,13 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
         c[3 * cs] = static_cast<float>(mu * mu);
         c[4 * cs] = static_cast<float>(-k2);
         c[5 * cs] = static_cast<float>(PL);
+        double* c64 = &cell64[(((static_cast<size_t>(tile) * Z.n_q4 + ks) * kCellConsts) * 4 + mt) * 32 + 4 * g + t];
+        c64[0 * cs] = k * k2 * PL / two_pi2;
+        c64[1 * cs] = std::log2(k);
+        c64[2 * cs] = (mu > 0.0) ? std::log2(mu) : -1.0e300;
+        c64[3 * cs] = mu * mu;
+        c64[4 * cs] = k2;
+        c64[5 * cs] = PL;
       }
     }
     float* dptr;
@@ -152,6 +160,11 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     if (rc) return rc;
     Z.cellc = dptr;
     keep(dptr);
+    double* dptr64;
+    rc = upload(cell64, &dptr64, &bytes);
+    if (rc) return rc;
+    Z.cell64 = dptr64;
+    keep(dptr64);
   }
   // Hankel weights in DMMA B-fragment order [ablk][ks][j][lane = 4*g + t] = W[a = ablk*na_blk + 8j + g][q = 4ks + t]
   {
@@ -328,6 +341,15 @@ K1Fn k1_select_add(int pp, int nt) {
 }
 K1Fn k1_select(int pp, int nt, bool add) { return add ? k1_select_add<true>(pp, nt) : k1_select_add<false>(pp, nt); }
 int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
+
+K1Fn k1_select_f64(int nt) {
+  switch (nt) {
+    case 1: return cpx::k_p3d_hankel_f64<1>;
+    case 2: return cpx::k_p3d_hankel_f64<2>;
+    case 3: return cpx::k_p3d_hankel_f64<3>;
+  }
+  return nullptr;
+}
 
 typedef void (*K2Fn)(const cpx::ZDev*, int, cpx::WindowArgs);
 template <bool CHI2>
@@ -510,6 +532,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   CPX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : h->stream;
   const bool dev_io = (a->flags & CPX_DEVICE_IO) != 0;
+  const bool precise = (a->flags & CPX_PRECISE_CELLS) != 0;
 
   // ---- z selection ----
   std::vector<int> zl;
@@ -601,7 +624,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
     int pp = pp_env > 0 ? std::min(pp_env, 2) : 1;   // one point per warp, two CTAs per SM measured fastest
-    const int n_pg = (count + kK1Warps * pp - 1) / (kK1Warps * pp);
+    const int n_pg = precise ? count : (count + kK1Warps * pp - 1) / (kK1Warps * pp);
     if (count != last_table_count || pp != last_pp) {
       long long items = 0;
       for (int i = 0; i < n_zl; ++i) {
@@ -662,10 +685,16 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     {
       bool additive = false;
       for (int i = 0; i < n_zl; ++i) additive |= (tab[i].flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)) != 0;
-      K1Fn fn = k1_select(pp, h->na_blk / 8, additive);
-      const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
-      const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * k1_ctas_per_sm(pp)));
-      fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);
+      if (precise) {
+        K1Fn fn = k1_select_f64(h->na_blk / 8);
+        const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
+        fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);
+      } else {
+        K1Fn fn = k1_select(pp, h->na_blk / 8, additive);
+        const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
+        const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * k1_ctas_per_sm(pp)));
+        fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);
+      }
       ++h->launches;
     }
     // ---- stage 2: window (+ whitening, chi2) ----
@@ -753,7 +782,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   return CPX_OK;
 }
 
-int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s) {
+int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s, double* dmma_fma_per_s) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
     return fail(CPX_ERR_CUDA, "cpx_probe_peaks: no such CUDA device");
@@ -766,21 +795,24 @@ int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, doub
   cudaEvent_t e0, e1;
   CPX_CUDA(cudaEventCreate(&e0));
   CPX_CUDA(cudaEventCreate(&e1));
-  double* outs[3] = {dfma_per_s, ffma_per_s, mufu_per_s};
-  for (int which = 0; which < 3; ++which) {
+  double* outs[4] = {dfma_per_s, ffma_per_s, mufu_per_s, dmma_fma_per_s};
+  for (int which = 0; which < 4; ++which) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
       CPX_CUDA(cudaEventRecord(e0));
       if (which == 0) cpx::k_probe_dfma<<<blocks, threads>>>(dbuf, iters, 1.0000001);
       if (which == 1) cpx::k_probe_ffma<<<blocks, threads>>>(reinterpret_cast<float*>(dbuf), iters, 1.0000001f);
       if (which == 2) cpx::k_probe_mufu<<<blocks, threads>>>(reinterpret_cast<float*>(dbuf), iters, -0.5f);
+      if (which == 3) cpx::k_probe_dmma<<<blocks, threads>>>(dbuf, iters / 8, 1.0000001);
       CPX_CUDA(cudaEventRecord(e1));
       CPX_CUDA(cudaEventSynchronize(e1));
       float ms;
       CPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       if (rep > 0) best = std::min(best, ms);
     }
-    if (outs[which]) *outs[which] = 8.0 * iters * static_cast<double>(blocks) * threads / (best * 1e-3);
+    // ops per launch: 8 chains x iters per thread; a DMMA is 256 FMAs per warp = 8 per thread
+    const double per_thread = which == 3 ? 8.0 * (iters / 8) * 8.0 : 8.0 * iters;
+    if (outs[which]) *outs[which] = per_thread * static_cast<double>(blocks) * threads / (best * 1e-3);
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

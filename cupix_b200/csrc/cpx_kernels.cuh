@@ -40,8 +40,10 @@ struct PtPar {
   double b_X, beta_X;
   double b_noise;
   double kC, pC;
+  // float64 copies for the reference-precision cell evaluation (CPX_PRECISE_CELLS)
+  double q1_64, q2_64, av_64, bv_64, l2kv_64, ikp2_64;
 };
-static_assert(sizeof(PtPar) == 128, "PtPar layout");
+static_assert(sizeof(PtPar) == 176, "PtPar layout");
 
 // per-z device data for k_p3d_hankel / k_params
 struct RowPar;
@@ -55,6 +57,7 @@ struct ZDev {
   double dAA;
   const float* cellc;                   // [n_tiles][n_q4][6][2][32][2] A-fragment order: lane = 4*g + t holds rows 8*(2*pr+e)+g, e = 0,1 (packed pair), node 4*ks+t
   const double* Wd;                     // [n_ablk][n_q4][NT][32]     B-fragment order: lane = 4*g + t holds W[theta 8*j+g][node 4*ks+t]
+  const double* cell64;                 // [n_tiles][n_q4][6][4][32]  float64 cell constants (+K2, not -K2) for CPX_PRECISE_CELLS
   const double* kpar;                   // [n_m_pad]
   const double* metal_auto;             // [3][n_a][n_m] or null
   const double* metal_cross;            // [3][n_a][n_m] or null
@@ -188,6 +191,12 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
   split_hi_lo(-v[5] * log2(v[4]), o.nlkv, o.nlkv_lo);
   split_hi_lo(l2e / (v[7] * v[7]), o.ikp2l, o.ikp2l_lo);
   o.pad = 0.f;
+  o.q1_64 = v[2];
+  o.q2_64 = v[3];
+  o.av_64 = v[5];
+  o.bv_64 = v[6];
+  o.l2kv_64 = log2(v[4]);
+  o.ikp2_64 = 1.0 / (v[7] * v[7]);
   o.bias = v[0];
   o.beta = v[1];
   o.b_H = v[8];
@@ -561,6 +570,106 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 }
 
 // ------------------------------------------------------------------------------------------
+// k_p3d_hankel_f64: reference-precision variant (CPX_PRECISE_CELLS).  Same DMMA contraction and
+// epilogue, but the P3D cell is evaluated in float64 straight from the formulas of
+// theory.py:285-308 with float64 cell constants read from global memory.  One warp per
+// (z, tile, theta-block, point); no shared-memory staging -- this is the parity mode, not the fast one.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = wid; it < n_items; it += nwarps) {
+    int zi = 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
+    const ZDev& Z = ztab[zi];
+    long long r = it - Z.item_start;
+    const int pt = static_cast<int>(r % count);
+    r /= count;
+    const int ablk = static_cast<int>(r % Z.n_ablk);
+    const int tile = static_cast<int>(r / Z.n_ablk);
+    const int m_base = tile * kTileRows;
+    const bool rowwise = (Z.flags & 9) != 0;
+    const PtPar& pr = Z.ptpar[pt];
+    const double q1 = pr.q1_64, q2 = pr.q2_64, av = pr.av_64, bv = pr.bv_64, l2kv = pr.l2kv_64, ikp2 = pr.ikp2_64;
+    double betaT[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      betaT[mt] = pr.beta;
+      if (Z.flags & 1) {
+        const double F = exp(-Z.kpar[m_base + 8 * mt + g] * pr.L_H);
+        betaT[mt] = (pr.bias * pr.beta + pr.b_H * pr.beta_H * F) / (pr.bias + pr.b_H * F);
+      }
+    }
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+    const double* c = Z.cell64 + static_cast<size_t>(tile) * Z.n_q4 * (kCellConsts * 4 * 32) + lane;
+    const double* wb = Z.Wd + static_cast<size_t>(ablk) * Z.n_q4 * (NT * 32) + lane;
+    for (int ks = 0; ks < Z.n_q4; ++ks) {
+      double bfrag[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const double D = c[(0 * 4 + mt) * 32], L2K = c[(1 * 4 + mt) * 32], L2MU = c[(2 * 4 + mt) * 32];
+        const double MU2 = c[(3 * 4 + mt) * 32], K2 = c[(4 * 4 + mt) * 32], PL = c[(5 * 4 + mt) * 32];
+        const double nl = D * (q1 + q2 * D);                                   // natural-log units here
+        const double v = exp2(av * (L2K - l2kv) + bv * L2MU);                  // (k/kv)^av mu^bv
+        const double e = exp(nl * (1.0 - v) - K2 * ikp2);
+        const double ka = 1.0 + betaT[mt] * MU2;
+        const double pd = PL * ka * ka * e;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_884(acc[mt][j][0], acc[mt][j][1], pd, bfrag[j]);
+      }
+      c += kCellConsts * 4 * 32;
+      wb += NT * 32;
+    }
+    // epilogue (same composition as k_p3d_hankel)
+    const int a_lane0 = ablk * (8 * NT) + 2 * t;
+    const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int m = m_base + 8 * mt + g;
+      const bool row_ok = m < n_m;
+      const double kpar = Z.kpar[m];
+      double bT = pr.bias;
+      if (Z.flags & 1) bT = pr.bias + pr.b_H * exp(-kpar * pr.L_H);
+      const double amp = bT * bT * Z.dAA;
+      const double cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;
+      double sky = 0.0;
+      if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int a = a_lane0 + 8 * j + cc;
+          if (a >= n_a) continue;
+          double px = 0.0;
+          if (row_ok) {
+            px = amp * acc[mt][j][cc];
+            if (Z.flags & 2) {
+              const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
+              const double bx = pr.b_X, btx = pr.beta_X;
+              px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+              px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                    pr.beta * btx * Z.metal_cross[o + 2 * st]);
+            }
+            if (Z.flags & 4) px += sky * Z.sky_xi[a];
+            px *= cont;
+          }
+          Z.pxzam[(static_cast<size_t>(pt) * n_a + a) * n_m_pad + m] = px;
+        }
+    }
+    (void)rowwise;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_window: Y[pt][M] = sum_{pairs (A,a)} sum_m T[pair][M][m] * Px_Zam[pt][a][m]   (FP64 DMMA)
 //   MODE_CHI2 : T = L^-1 diag(V/Vsum) U, out chi2_zA[pt] = || yd[data_idx[pt]][A] - Y ||^2
 //   MODE_MODEL: T =      diag(V/Vsum) U, out model[pt][A][M] = Y
@@ -740,6 +849,19 @@ __global__ void k_probe_dfma(double* out, int iters, double x) {
     a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
   }
   if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+__global__ void k_probe_dmma(double* out, int iters, double x) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_884(c[i][0], c[i][1], x, 0.5);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
 }
 __global__ void k_probe_ffma(float* out, int iters, float x) {
   float a0 = threadIdx.x, a1 = 1, a2 = 2, a3 = 3, a4 = 4, a5 = 5, a6 = 6, a7 = 7;

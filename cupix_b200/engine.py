@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libc
 
 NSLOTS = 16
 DEVICE_IO = 1
+PRECISE_CELLS = 2
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -69,7 +70,7 @@ def load_library(path=None):
     lib.cpx_version.restype = C.c_int
     lib.cpx_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
     lib.cpx_get_info.restype = C.c_int
-    lib.cpx_probe_peaks.argtypes = [C.c_int32, c_dp, c_dp, c_dp]
+    lib.cpx_probe_peaks.argtypes = [C.c_int32, c_dp, c_dp, c_dp, c_dp]
     lib.cpx_probe_peaks.restype = C.c_int
     _LIB = lib
     return lib
@@ -84,12 +85,12 @@ def _f64(a):
 
 
 def probe_peaks(device=0):
-    """Measured FP64-FMA, FP32-FMA and MUFU.EX2 rates of the GPU [ops/s]."""
+    """Measured FP64-FMA, FP32-FMA, MUFU.EX2 and FP64-tensor (DMMA, in FMAs) rates of the GPU [ops/s]."""
     lib = load_library()
-    d, f, m = C.c_double(), C.c_double(), C.c_double()
-    if lib.cpx_probe_peaks(device, C.byref(d), C.byref(f), C.byref(m)) != 0:
+    d, f, m, t = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    if lib.cpx_probe_peaks(device, C.byref(d), C.byref(f), C.byref(m), C.byref(t)) != 0:
         raise CpxError(lib.cpx_last_error().decode())
-    return {"dfma_per_s": d.value, "ffma_per_s": f.value, "mufu_per_s": m.value}
+    return {"dfma_per_s": d.value, "ffma_per_s": f.value, "mufu_per_s": m.value, "dmma_fma_per_s": t.value}
 
 
 class PxEngine(object):
@@ -98,7 +99,10 @@ class PxEngine(object):
     INFO = {"n_zbins": 0, "max_na": 1, "max_nm": 2, "max_nA": 3, "max_nM": 4, "chunk": 5,
             "device_bytes": 6, "kernel_launches": 7, "sm_count": 8}
 
-    def __init__(self, plans, device=0):
+    def __init__(self, plans, device=0, precise=False):
+        """``precise=True`` evaluates the P3D cells in float64 as well (CPX_PRECISE_CELLS): the
+        reference-precision mode, ~4x slower, chi2 within ~1e-9 of the float64 oracle everywhere."""
+        self.precise = bool(precise)
         self.lib = load_library()
         self.plans = list(plans)
         self.device = int(device)
@@ -185,7 +189,7 @@ class PxEngine(object):
             B = points.shape[0]
             args.points = points.ctypes.data_as(C.c_void_p) if P > 0 else None
             keep.append(points)
-        args.B, args.P, args.flags = int(B), P, 0
+        args.B, args.P, args.flags = int(B), P, (PRECISE_CELLS if self.precise else 0)
         args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
         if zsel is not None:
             zsel = np.ascontiguousarray(zsel, dtype=np.int32)
@@ -230,7 +234,7 @@ class PxEngine(object):
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         assert points.flags.c_contiguous and points.dtype == np.float64 and chi2_out.flags.c_contiguous
         args = EvalArgs()
-        args.B, args.P, args.flags = points.shape[0], points.shape[1], 0
+        args.B, args.P, args.flags = points.shape[0], points.shape[1], (PRECISE_CELLS if self.precise else 0)
         args.points = points.ctypes.data_as(C.c_void_p)
         args.slot = slots.ctypes.data_as(c_ip)
         if zsel is not None:
@@ -252,7 +256,7 @@ class PxEngine(object):
         (e.g. ``torch.Tensor.data_ptr()``).  Returns stage times if requested (this synchronises)."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         args = EvalArgs()
-        args.B, args.P, args.flags = int(B), int(P), DEVICE_IO
+        args.B, args.P, args.flags = int(B), int(P), DEVICE_IO | (PRECISE_CELLS if self.precise else 0)
         args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
         args.points = points_ptr
         keep = [slots]

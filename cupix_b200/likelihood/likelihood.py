@@ -27,6 +27,8 @@ class Likelihood(object):
         self.verbose = config.get('verbose', False)
         self.N_theta_average = config.get('N_theta_average', 100)
         self.device = config.get('device', getattr(theory, 'device', 0))
+        # float64 P3D cells as well (reference-precision mode, slower); default: float32 cells
+        self.precise_cells = config.get('precise_cells', getattr(theory, 'precise_cells', False))
         self._engines = {}
         if self.verbose:
             print("Likelihood will evaluate redshift bin", self.iz, "corresponds to z =", self.theory.z)
@@ -44,7 +46,7 @@ class Likelihood(object):
         if key not in self._engines:
             if len(self._engines) > 4:
                 self._engines.pop(next(iter(self._engines))).close()
-            self._engines[key] = PxEngine([self.build_plan(cosmo)], device=self.device)
+            self._engines[key] = PxEngine([self.build_plan(cosmo)], device=self.device, precise=self.precise_cells)
         return self._engines[key]
 
     def _scalar_eval(self, params, want):
@@ -128,14 +130,15 @@ class JointLikelihood(object):
     """Several redshift bins scored in one device call: chi2 = sum over z (full-shape evaluation).
     Parameter names may carry a ``_<iz>`` suffix to apply to one bin only."""
 
-    def __init__(self, likes, device=0):
+    def __init__(self, likes, device=0, precise_cells=None):
         self.likes = list(likes)
         self.device = device
+        self.precise_cells = all(lk.precise_cells for lk in self.likes) if precise_cells is None else precise_cells
         self._engine = None
 
     def engine(self):
         if self._engine is None:
-            self._engine = PxEngine([lk.build_plan() for lk in self.likes], device=self.device)
+            self._engine = PxEngine([lk.build_plan() for lk in self.likes], device=self.device, precise=self.precise_cells)
         return self._engine
 
     def get_ndata(self):

@@ -40,6 +40,7 @@ class Theory(object):
         self.rule = KperpRule(config.get('n_q', DEFAULT_NQ), config.get('k0_Mpc', DEFAULT_K0),
                               config.get('kmax_Mpc', DEFAULT_KMAX))
         self.device = config.get('device', 0)
+        self.precise_cells = config.get('precise_cells', False)
         self._engines = {}
 
     # -- cosmology (theory.py:49-64) ---------------------------------------------------------
@@ -83,7 +84,7 @@ class Theory(object):
             if len(self._engines) > 8:
                 self._engines.pop(next(iter(self._engines))).close()
             p = _plan.build_theory_plan(self, cosmo, theta_arc, np.arange(theta_arc.size), k_AA, self.rule)
-            self._engines[key] = PxEngine([p], device=self.device)
+            self._engines[key] = PxEngine([p], device=self.device, precise=self.precise_cells)
         return self._engines[key]
 
     # -- predictions --------------------------------------------------------------------------

@@ -96,12 +96,16 @@ typedef struct cpx_handle cpx_handle;
 /* Arguments of one batched evaluation.  Input/outputs may live on the host (default; the call
  * copies and synchronises) or on the device (CPX_DEVICE_IO; the call is asynchronous on `stream`).
  * Any output pointer may be NULL. */
-enum { CPX_DEVICE_IO = 1 };
+enum {
+  CPX_DEVICE_IO = 1,      /* points / outputs are device pointers, call is asynchronous on `stream`          */
+  CPX_PRECISE_CELLS = 2   /* evaluate the P3D cells in float64 too (reference-precision mode, ~4x slower):   */
+                          /* chi2 then agrees with the float64 oracle to ~1e-9 everywhere */
+};
 
 typedef struct cpx_eval_args {
   int64_t B;                 /* number of parameter points                                      */
   int32_t P;                 /* varied parameters per point                                     */
-  int32_t flags;             /* CPX_DEVICE_IO                                                   */
+  int32_t flags;             /* CPX_DEVICE_IO | CPX_PRECISE_CELLS                               */
   const double* points;      /* [B][P] row-major; NULL when grid_n is given                     */
   const int32_t* slot;       /* [P] host: CPX_* slot of each column                             */
   const int32_t* zsel;       /* [P] host: z bin index the column applies to, -1 = all; NULL = all -1 */
@@ -139,8 +143,10 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
        CPX_INFO_SM_COUNT = 8 };
 
 /* Pipe-rate probes for the roofline denominators MEASURED_PEAKS.json does not hold: sustained
- * FP64 FMA, FP32 FMA and MUFU.EX2 rates of this GPU (results in ops/s; an FMA counts as one op). */
-int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s);
+ * FP64 FMA (DFMA), FP32 FMA, MUFU.EX2 and FP64 tensor (DMMA m8n8k4, counted in FMAs) rates of this
+ * GPU (results in ops/s; an FMA counts as one op).  Any pointer may be NULL. */
+int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s,
+                    double* dmma_fma_per_s);
 
 #ifdef __cplusplus
 }

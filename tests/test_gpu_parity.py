@@ -199,3 +199,30 @@ def test_more_than_64_coarse_k_bins():
     got, info = like.get_chi2(params, return_info=True)
     assert_chi2(got, ref, "chi2 n_M=70", n_data=like.get_ndata())
     assert_chi2(-2 * info["log_like_all"], -2 * rinfo["log_like_all"], "per-theta n_M=70", n_data=like.get_ndata() / 3)
+
+
+def test_precise_cells_mode_meets_absolute_chi2_tolerance_everywhere():
+    """CPX_PRECISE_CELLS: with float64 P3D cells the absolute 1e-3 chi2 tolerance of the north star
+    holds for every point of the scan (here to 1e-6 at chi2 up to 2e4), and Px to 1e-10."""
+    d = synthetic.make_measurement_dict("S1")
+    z = float(d["z_centers"][0])
+    flags = FLAG_SETS["all"]
+    th = H.make_theory(z, "best_fit_arinyo_from_gadget", flags, extra={"precise_cells": True})
+    like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 2})
+    truth = {"bias": -0.115, "beta": 1.5}
+    filled = synthetic.fill_from_model(d, like.get_convolved_px(truth)[None], add_noise=True)
+    like = Likelihood(DESI_DR2(filled), th, 0, config={"N_theta_average": 2})
+    assert like.precise_cells
+    orc = H.oracle_likelihood(like)
+    rng = np.random.default_rng(21)
+    names = ["bias", "beta", "q1", "kp_Mpc", "b_H"]
+    dflt = like.build_plan().defaults
+    pts = np.stack([rng.uniform(-0.135, -0.095, 8), rng.uniform(1.3, 1.7, 8), dflt[2] * rng.uniform(0.7, 1.3, 8),
+                    dflt[7] * rng.uniform(0.8, 1.2, 8), rng.uniform(-0.03, -0.01, 8)], axis=1)
+    chi2 = like.get_chi2_batch(pts, names)
+    model = like.get_convolved_px_batch(pts, names)
+    for i in range(len(pts)):
+        params = dict(zip(names, pts[i]))
+        assert_px(model[i], orc.get_convolved_px(params), tol=1e-10, msg="precise model %d" % i)
+        ref = orc.get_chi2(params)
+        assert abs(chi2[i] - ref) <= 1e-6, "precise chi2 %d: %.3e at chi2 %.1f" % (i, abs(chi2[i] - ref), ref)
