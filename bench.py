@@ -36,7 +36,7 @@ def grid_bounds(defaults):
     return lo, hi
 
 
-def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True):
+def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True, precise=False):
     """Synthetic S5 measurement: windows/weights seeded, data = model(truth) + noise."""
     from cupix_b200.cosmology import Cosmology
     from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
@@ -51,7 +51,7 @@ def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True
     likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
     if not need_engine:
         return d, data, likes, None
-    joint = JointLikelihood(likes, device=int(os.environ.get("LOCAL_RANK", "0")))
+    joint = JointLikelihood(likes, device=int(os.environ.get("LOCAL_RANK", "0")), precise_cells=precise)
     model = joint.get_convolved_px_batch(np.zeros((1, 0)), [])[0]          # truth = per-z defaults
     filled = synthetic.fill_from_model(d, model, add_noise=add_noise)
     data = DESI_DR2(filled)
@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--cpu-evals-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precise", action="store_true", help="float64 P3D cells (CPX_PRECISE_CELLS, reference-precision mode)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +204,7 @@ def main():
     workload = "S5 stress: 12 z x 20 theta x 256 k_par, dense windows, %d-point 4-parameter grid" % int(np.prod(GRID_N)) \
         if a.shape == "S5" else a.shape
     config = {"workload": workload, "shape": a.shape, "points_per_gpu_per_step": a.points, "params": NAMES,
-              "grid_n": GRID_N, "N_theta_average": a.n_theta_average, "n_q": a.n_q, "include_hcd": True,
+              "grid_n": GRID_N, "N_theta_average": a.n_theta_average, "n_q": a.n_q, "include_hcd": True, "precise_cells": bool(a.precise),
               "parallelism": "points sharded over %d GPU(s), NCCL all_gather of chi2" % a.gpus,
               "l2": "per-chunk Px_Zam scratch (GiBs) >> 126 MB L2, no explicit flush"}
 
@@ -241,7 +242,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q)
+    filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q, precise=a.precise)
     eng = joint.engine()
     import cupix_b200.plan as _plan
     from cupix_b200.engine import slots_from_names, probe_peaks
@@ -389,7 +390,7 @@ def main():
 
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "per_point_z_rate": value * len(likes)}
     emit(line)
