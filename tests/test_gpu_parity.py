@@ -226,3 +226,46 @@ def test_precise_cells_mode_meets_absolute_chi2_tolerance_everywhere():
         assert_px(model[i], orc.get_convolved_px(params), tol=1e-10, msg="precise model %d" % i)
         ref = orc.get_chi2(params)
         assert abs(chi2[i] - ref) <= 1e-6, "precise chi2 %d: %.3e at chi2 %.1f" % (i, abs(chi2[i] - ref), ref)
+
+
+@pytest.mark.parametrize("N_A,fpc,N_m,rebin_k,n_q", [(10, 1, 50, 5, 88), (5, 6, 45, 3, 90), (3, 9, 33, 3, 64), (1, 1, 8, 2, 48),
+                                                     (24, 1, 64, 4, 88), (25, 1, 40, 2, 72)])
+def test_ragged_shapes_vs_float64_emulation(N_A, fpc, N_m, rebin_k, n_q):
+    """Shapes that exercise padding everywhere: theta bins not a multiple of 8 (and > 24: several
+    theta blocks), k_par rows not a multiple of 32, coarse k not a multiple of 8, n_q not a multiple
+    of 4.  Checked against the float64 NumPy emulation of the plan (itself pinned to the reference in
+    tests/test_oracle_golden.py)."""
+    d = synthetic.make_measurement_dict("S1", N_A=N_A, fine_per_coarse=fpc, N_m=N_m, rebin_k=rebin_k, Nz=2)
+    flags = {"include_hcd": True, "include_metal": True, "include_sky": True, "include_continuum": True}
+    likes = []
+    for iz, z in enumerate(d["z_centers"]):
+        th = H.make_theory(float(z), "best_fit_arinyo_from_gadget", flags, n_q=n_q)
+        likes.append(Likelihood(DESI_DR2(d), th, iz, config={"N_theta_average": 2}))
+    rng = np.random.default_rng(N_A * 100 + N_m)
+    d["Px_ZAM"] = 0.05 * rng.normal(size=d["Px_ZAM"].shape) + 0.1
+    data = DESI_DR2(d)
+    for lk in likes:
+        lk.data = data
+    joint = JointLikelihood(likes)
+    names = ["bias", "beta", "q1", "b_H", "b_X", "b_noise_Mpc", "pC"]
+    pts = np.stack([rng.uniform(-0.2, -0.1, 5), rng.uniform(1.0, 2.0, 5), rng.uniform(0.1, 0.6, 5),
+                    rng.uniform(-0.03, -0.01, 5), rng.uniform(-0.01, -0.002, 5), rng.uniform(0.001, 0.004, 5),
+                    rng.uniform(0.4, 0.9, 5)], axis=1)
+    chi2, info = joint.get_chi2_batch(pts, names, return_info=True)
+    model = joint.get_convolved_px_batch(pts, names)
+    plans = [lk.build_plan() for lk in likes]
+    for i in range(len(pts)):
+        params = dict(zip(names, pts[i]))
+        tot = 0.0
+        for iz, p in enumerate(plans):
+            m_ref, c_ref = H.emulate_plan_chi2(p, params)
+            assert_px(model[i, iz], m_ref, msg="ragged model pt %d z %d" % (i, iz))
+            np.testing.assert_allclose(-2 * info["log_like_all"][i, iz], c_ref, rtol=2e-6)
+            tot += c_ref.sum()
+        np.testing.assert_allclose(chi2[i], tot, rtol=2e-6)
+    # one point, one z bin of the joint engine, and the empty batch
+    one = joint.engine().eval(points=pts[:1], slots=[0, 1, 2, 8, 11, 13, 15], z_list=[1], want=("chi2", "model"))
+    np.testing.assert_allclose(one["chi2"][0], H.emulate_plan_chi2(plans[1], dict(zip(names, pts[0])))[1].sum(), rtol=2e-6)
+    assert one["model"].shape == (1, 1, N_A, plans[1].n_M)
+    empty = joint.get_chi2_batch(np.zeros((0, 2)), ["bias", "beta"])
+    assert empty.shape == (0,)
