@@ -1,15 +1,20 @@
 // cupix_b200 device kernels (sm_100a).  See DESIGN.md section 3 for the data layout and section 4
 // for the roofline of each kernel.
 //
-//   k_params   per-(point, z) parameter expansion: defaults (+) overrides, derived scalars
-//              (model_lya.py:190-196, model_contaminants.py:103-144; grid generation of
-//              scripts/chi2_scan_mock.py:107-111)
-//   k_p3d_hankel  fused Arinyo P3D evaluation on the shared-memory-staged (k_par, k_perp) grid +
-//              J0 Hankel quadrature + contaminant epilogues  (theory.py:95-123,250-344; the theta
-//              average of likelihood.py:99-130 is inside the weights)
-//   k_window   window convolution + theta rebinning (+ Cholesky whitening and chi2) as a batched
-//              FP64 tensor-core (DMMA) contraction  (likelihood.py:53-88,170-194)
-//   k_reduce   chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
+//   k_params      per-(point, z) parameter expansion: defaults (+) overrides, derived scalars as
+//                 float32 hi + lo pairs (model_lya.py:190-196, model_contaminants.py:103-144; grid
+//                 generation of scripts/chi2_scan_mock.py:107-111, bit-identical to numpy.linspace)
+//   k_rowpars     per-(point, k_par row) float64 scalars of the HCD bias mixing and the continuum
+//                 distortion (theory.py:267-282, 525-535)
+//   k_p3d_hankel  fused Arinyo P3D evaluation on the shared-memory-staged (k_par, k_perp) grid
+//                 (packed FP32) + J0 Hankel quadrature as an FP64 tensor-core (DMMA) contraction +
+//                 contaminant epilogues (theory.py:95-123, 250-344; the theta average of
+//                 likelihood.py:99-130 is inside the weights)
+//   k_p3d_hankel_f64  the same with float64 cells (CPX_PRECISE_CELLS, reference-precision mode)
+//   k_window      window convolution + theta rebinning (+ Cholesky whitening and chi2) as a batched
+//                 FP64 tensor-core (DMMA) contraction (likelihood.py:53-88, 170-194)
+//   k_reduce      chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
+//   k_probe_*     pipe-rate probes for the roofline denominators
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +26,6 @@ constexpr int kCellConsts = 6;       // D, L2K, L2MU, MU2, -K2, PL
 constexpr int kK1Warps = 8;
 constexpr int kK1Threads = kK1Warps * 32;
 constexpr int kMaxZ = 64;
-constexpr float kLog2e = 1.4426950408889634f;
 
 // per-(z, point) parameters written by k_params and read by k_p3d_hankel
 struct PtPar {

@@ -121,6 +121,24 @@ class Likelihood(object):
         slots, _ = slots_from_names(names)
         return self.engine().eval(slots=slots, grid=(lo, hi, n), grid_first=first, B=count)["chi2"]
 
+    def get_chi2_from_arinyo_tensor(self, arinyo, names=("bias", "beta", "q1", "kvav", "av", "bv", "kp", "q2")):
+        """Tensor hand-off from the ForestFlow emulator (model_lya.py:200-235): ``arinyo`` is a
+        float64 CUDA tensor [B, 8] in ForestFlow's naming (the output of ``predict_Arinyos`` for B
+        IGM-parameter points, evaluated in PyTorch).  The kp -> kp_Mpc, kvav -> kv_Mpc = exp(ln(kvav)/av)
+        renaming of model_lya.py:13-18 is done on the device and the points are scored without
+        leaving the GPU; returns a CUDA tensor chi2 [B] (asynchronous on the current stream)."""
+        import torch
+        assert arinyo.is_cuda and arinyo.dtype == torch.float64 and arinyo.dim() == 2 and arinyo.shape[1] == len(names)
+        assert arinyo.device.index == self.device, "tensor lives on another GPU than this likelihood's engine"
+        col = {n: arinyo[:, i] for i, n in enumerate(names)}
+        kv = torch.exp(torch.log(col["kvav"]) / col["av"])
+        pts = torch.stack([col["bias"], col["beta"], col["q1"], col["q2"], kv, col["av"], col["bv"], col["kp"]], dim=1).contiguous()
+        out = torch.empty(pts.shape[0], dtype=torch.float64, device=arinyo.device)
+        self.engine().eval_device(pts.shape[0], 8, np.arange(8, dtype=np.int32), points_ptr=pts.data_ptr(),
+                                  chi2_ptr=out.data_ptr(), stream=torch.cuda.current_stream(arinyo.device).cuda_stream)
+        out._cpx_keepalive = pts          # the kernels read pts asynchronously
+        return out
+
     def set_mock_data(self, Px_AM):
         """Replace the data vector(s) [n_data, N_A, N_M] scored by ``data_idx`` (many-mock fits)."""
         self.engine().set_data(0, Px_AM)

@@ -128,3 +128,24 @@ def test_S5_stress_shape_properties():
     # the single-z Likelihood of bin 3 gives the same numbers as the joint engine restricted to it
     c = likes[3].get_chi2_batch(absolute[:64], names)
     np.testing.assert_allclose(c, a[:64], rtol=1e-12, atol=1e-9)
+
+
+def test_emulator_tensor_handoff():
+    """[B, 8] Arinyo tensor in ForestFlow naming, living on the GPU (what the cINN emulator returns),
+    scored through device pointers == the host path with the renamed parameters."""
+    import torch
+    data, likes, joint = _build("S1", "best_fit_arinyo_from_gadget", {}, N_t=1, N_m=48, N_A=6)
+    like = likes[0]
+    rng = np.random.default_rng(4)
+    B = 300
+    ff = np.stack([rng.uniform(-0.14, -0.10, B), rng.uniform(1.3, 1.8, B), rng.uniform(0.1, 0.5, B),
+                   rng.uniform(0.3, 0.8, B), rng.uniform(0.2, 0.6, B), rng.uniform(1.5, 1.8, B),
+                   rng.uniform(9, 20, B), rng.uniform(0.1, 0.4, B)], axis=1)     # bias beta q1 kvav av bv kp q2
+    t = torch.from_numpy(ff).cuda()
+    chi2_t = like.get_chi2_from_arinyo_tensor(t)
+    assert chi2_t.is_cuda and chi2_t.shape == (B,)
+    kv = np.exp(np.log(ff[:, 3]) / ff[:, 4])
+    host = like.get_chi2_batch(np.stack([ff[:, 0], ff[:, 1], ff[:, 2], ff[:, 7], kv, ff[:, 4], ff[:, 5], ff[:, 6]], axis=1),
+                               ["bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc"])
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(chi2_t.cpu().numpy(), host, rtol=1e-9)
