@@ -675,8 +675,8 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         nm_pad_max = std::max(nm_pad_max, tab[i].n_m_pad);
       }
       if (any_rowwise) {
-        dim3 rgrid((nm_pad_max + 127) / 128, count, n_zl);
-        k_rowpars<<<rgrid, 128, 0, st>>>(h->d_ztab, count);
+        dim3 rgrid(static_cast<unsigned>((static_cast<long long>(count) * nm_pad_max + 255) / 256), n_zl);
+        k_rowpars<<<rgrid, 256, 0, st>>>(h->d_ztab, count);
         ++h->launches;
       }
     }

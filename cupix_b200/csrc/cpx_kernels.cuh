@@ -228,11 +228,12 @@ struct RowPar {
 static_assert(sizeof(RowPar) == 24, "RowPar layout");
 
 __global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
-  const ZDev& Z = ztab[blockIdx.z];
+  const ZDev& Z = ztab[blockIdx.y];
   if ((Z.flags & 9) == 0) return;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pt = blockIdx.y;
-  if (m >= Z.n_m_pad || pt >= count) return;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // flat (point, row)
+  if (i >= static_cast<long long>(count) * Z.n_m_pad) return;
+  const int pt = static_cast<int>(i / Z.n_m_pad);
+  const int m = static_cast<int>(i % Z.n_m_pad);
   const PtPar& pr = Z.ptpar[pt];
   const double kpar = Z.kpar[m];
   double bT = pr.bias, betaT = pr.beta;

@@ -269,3 +269,15 @@ def test_ragged_shapes_vs_float64_emulation(N_A, fpc, N_m, rebin_k, n_q):
     assert one["model"].shape == (1, 1, N_A, plans[1].n_M)
     empty = joint.get_chi2_batch(np.zeros((0, 2)), ["bias", "beta"])
     assert empty.shape == (0,)
+
+
+def test_large_batch_spans_chunks():
+    """70 000 points on a small shape: the device chunk is 65 536 points here, so this crosses a chunk
+    boundary and exercises the largest launch grids; results must not depend on the batch layout."""
+    like, truth = _s1_like(N_t=1, N_A=4, N_m=32, flags={"include_hcd": True})
+    B = 70000
+    pts = np.stack([np.linspace(-0.13, -0.10, B), np.linspace(1.3, 1.7, B)], axis=1)
+    chi2 = like.get_chi2_batch(pts, ["bias", "beta"])
+    sel = np.array([0, 1, 65535, 65536, 65537, B - 1])
+    np.testing.assert_array_equal(chi2[sel], like.get_chi2_batch(pts[sel], ["bias", "beta"]))
+    assert np.isfinite(chi2).all()
