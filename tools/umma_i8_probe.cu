@@ -1,0 +1,277 @@
+// Probe for the 5th-generation tensor cores in integer mode (tcgen05.mma kind::i8, u8 x s8 -> s32 in
+// TMEM) as the engine of an error-free ("Ozaki") split of the FP64 Hankel contraction:
+//   * correctness of hand-built shared-memory / instruction descriptors (K-major, no swizzle) for the
+//     exact operand shapes k_p3d_hankel_tc uses: A = 4 byte-slices of a [128 x 96] u32 cell tile,
+//     B = 4 signed digit-slices of the weights stacked along N (4 x 32 = 128 columns), D columns
+//     32*s accumulate all slice pairs with i + j = s;
+//   * cycles per 12-MMA item, alone and next to FFMA2 warps (does FP32 work slow down?);
+//   * issue cost of the conversion instructions the slicing needs (F2I, I2F.F64, PRMT).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_i8_probe tools/umma_i8_probe.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int kM = 128, kK = 96, kNB = 32, kSlices = 4, kN = kNB * kSlices;
+constexpr int kChunkStride = 2048;   // bytes between 16-byte K chunks (16 row groups x 128 B)
+constexpr int kGroupStride = 128;    // bytes between 8-row groups
+constexpr int kTileBytes = kM * kK;  // one u8/s8 [128 x 96] tile in canonical order
+
+__host__ __device__ inline int canon_off(int r, int k) {
+  return ((k >> 4) * 16 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 15);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  // c = S32 (2) at [4,6); a = U8 (0) at [7,10); b = S8 (1) at [10,13); K-major both; n>>3 at [17,23); m>>4 at [24,29)
+  return (2u << 4) | (0u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// the 12 MMAs of one item: 3 K32 steps x 4 cell slices; slice i meets digit blocks 0 .. 3-i and lands at column 32*i
+__device__ __forceinline__ void issue_item(uint32_t tmem, uint32_t a_base, uint32_t b_base, uint32_t lbo, uint32_t sbo) {
+#pragma unroll
+  for (int kc = 0; kc < 3; ++kc)
+#pragma unroll
+    for (int i = 0; i < kSlices; ++i) {
+      const uint64_t ad = make_desc(a_base + i * kTileBytes + kc * 2 * kChunkStride, lbo, sbo);
+      const uint64_t bd = make_desc(b_base + kc * 2 * kChunkStride, lbo, sbo);
+      umma_i8(tmem + 32 * i, ad, bd, make_idesc(kM, kN - 32 * i), (kc > 0 || i > 0) ? 1u : 0u);
+    }
+}
+
+// mode bit 0: swap LBO/SBO in the descriptors (to find out which field is which)
+// warps 0..3: tensor side (thread 0 issues, all four read TMEM back); warps 4..15: optional FFMA2 load
+__global__ void __launch_bounds__(512, 1)
+    k_probe(const uint8_t* __restrict__ a_img, const int8_t* __restrict__ b_img, int32_t* __restrict__ d_out, int mode, int rounds,
+            int ffma_iters, long long* cyc, float* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* sA = smem;                         // 4 tiles
+  unsigned char* sB = smem + kSlices * kTileBytes;  // 1 tile (N = 128 rows)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < kSlices * kTileBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+  for (int i = threadIdx.x; i < kTileBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lbo = (mode & 1) ? kGroupStride : kChunkStride;
+  const uint32_t sbo = (mode & 1) ? kChunkStride : kGroupStride;
+
+  if (warp >= 4) {
+    if (ffma_iters > 0) {
+      float2 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x + i, i);
+      const float2 y = make_float2(1.0000001f, 1.0000001f), z = make_float2(0.5f, 0.5f);
+      const long long t0 = clock64();
+      for (int it = 0; it < ffma_iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], y, z);
+      }
+      const long long t1 = clock64();
+      float s = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+      if (s == 1.2345f) sink[0] = s;
+      if (blockIdx.x == 0 && threadIdx.x == 128) cyc[1] = t1 - t0;
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int r = 0; r < rounds; ++r) issue_item(tmem, smem_u32(sA), smem_u32(sB), lbo, sbo);
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) cyc[0] = t1 - t0;
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (blockIdx.x == 0) {
+      for (int c0 = 0; c0 < kN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(32 * warp) << 16) + c0, v);
+        for (int j = 0; j < 16; ++j) d_out[(32 * warp + lane) * kN + c0 + j] = static_cast<int32_t>(v[j]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128) : "memory");
+}
+
+// ---- issue-cost probes for the slicing instructions -------------------------------------------
+template <int OP>
+__global__ void k_rate(float* sink, long long* cyc, int iters) {
+  uint32_t u[8];
+  float f[8];
+  double d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    u[i] = threadIdx.x * 977 + i * 131071;
+    f[i] = 1.0f + threadIdx.x + i;
+    d[i] = f[i];
+  }
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) {   // F2I.U32.F32 (+ I2F back to keep a chain)
+        asm volatile("cvt.rni.u32.f32 %0, %1;" : "=r"(u[i]) : "f"(f[i]));
+        f[i] = __uint_as_float((u[i] & 0x007fffffu) | 0x4b000000u);
+      } else if (OP == 1) {   // I2F.F64.S32
+        asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(d[i]) : "r"(u[i]));
+        u[i] = static_cast<uint32_t>(__double2loint(d[i])) ^ u[i];
+      } else if (OP == 2) {   // PRMT
+        asm volatile("prmt.b32 %0, %1, %2, 0x6240;" : "=r"(u[i]) : "r"(u[i]), "r"(u[(i + 1) & 7]));
+      } else if (OP == 3) {   // FMNMX
+        asm volatile("max.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(f[i]), "f"(f[(i + 1) & 7]));
+      } else if (OP == 4) {   // I2F.F64.S64
+        long long v = (static_cast<long long>(u[i]) << 20) ^ u[(i + 1) & 7];
+        asm volatile("cvt.rn.f64.s64 %0, %1;" : "=d"(d[i]) : "l"(v));
+        u[i] ^= static_cast<uint32_t>(__double2hiint(d[i]));
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += f[i] + u[i] + static_cast<float>(d[i]);
+  if (s == 1.2345f) sink[0] = s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+int main() {
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, 0);
+  std::vector<uint8_t> A(kSlices * kTileBytes), Aimg(kSlices * kTileBytes);
+  std::vector<int8_t> B(kTileBytes), Bimg(kTileBytes);   // B[n][k], n = 32*j + theta
+  srand(1234);
+  for (auto& v : A) v = static_cast<uint8_t>(rand() & 255);
+  for (auto& v : B) v = static_cast<int8_t>((rand() & 255) - 128);
+  for (int i = 0; i < kSlices; ++i)
+    for (int r = 0; r < kM; ++r)
+      for (int k = 0; k < kK; ++k) Aimg[i * kTileBytes + canon_off(r, k)] = A[(i * kM + r) * kK + k];
+  for (int n = 0; n < kN; ++n)
+    for (int k = 0; k < kK; ++k) Bimg[canon_off(n, k)] = B[n * kK + k];
+  // expected: D[r][32*s + c] = sum_{i+j=s} sum_k A_i[r][k] * B[32*j + c][k]
+  std::vector<int32_t> ref(kM * kN, 0);
+  for (int r = 0; r < kM; ++r)
+    for (int i = 0; i < kSlices; ++i)
+      for (int j = 0; i + j < kSlices; ++j)
+        for (int c = 0; c < kNB; ++c) {
+          int32_t s = 0;
+          for (int k = 0; k < kK; ++k) s += static_cast<int32_t>(A[(i * kM + r) * kK + k]) * static_cast<int32_t>(B[(32 * j + c) * kK + k]);
+          ref[r * kN + 32 * (i + j) + c] += s;
+        }
+  uint8_t* dA;
+  int8_t* dB;
+  int32_t* dD;
+  long long* dc;
+  float* ds;
+  cudaMalloc(&dA, Aimg.size());
+  cudaMalloc(&dB, Bimg.size());
+  cudaMalloc(&dD, kM * kN * 4);
+  cudaMalloc(&dc, 16);
+  cudaMalloc(&ds, 16);
+  cudaMemcpy(dA, Aimg.data(), Aimg.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, Bimg.data(), Bimg.size(), cudaMemcpyHostToDevice);
+  const size_t smem = (kSlices + 1) * kTileBytes + 1024;
+  cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  for (int mode = 0; mode < 2; ++mode) {
+    cudaMemset(dD, 0xff, kM * kN * 4);
+    k_probe<<<1, 512, smem>>>(dA, dB, dD, mode, 1, 0, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<int32_t> out(kM * kN);
+    cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost);
+    long bad = 0;
+    for (size_t i = 0; i < out.size(); ++i) bad += out[i] != ref[i];
+    printf("descriptor mode %d (LBO = %s): %s, %ld of %d outputs differ from the host integer GEMM; D[0][0..3] = %d %d %d %d (ref %d %d %d %d)\n",
+           mode, mode ? "row-group stride" : "K-chunk stride", cudaGetErrorString(e), bad, kM * kN, out[0], out[1], out[2], out[3],
+           ref[0], ref[1], ref[2], ref[3]);
+    if (e != cudaSuccess) return 1;
+  }
+  const int R = 2000;
+  struct { int rounds, ff; const char* name; } cases[] = {{R, 0, "12-MMA items alone"}, {0, 200000, "FFMA2 alone (3 warps/SMSP)"}, {R, 200000, "both"}};
+  for (auto& cs : cases) {
+    cudaMemset(dc, 0, 16);
+    k_probe<<<p.multiProcessorCount, 512, smem>>>(dA, dB, dD, 0, cs.rounds, cs.ff, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, dc, 16, cudaMemcpyDeviceToHost);
+    printf("%-30s %s", cs.name, cudaGetErrorString(e));
+    if (cs.rounds) {
+      const double cyc_item = static_cast<double>(h[0]) / cs.rounds;
+      const double macs = 3.0 * (128 + 96 + 64 + 32) * kM * 32;
+      printf("  %.1f cycles per item (%.0f int8 MAC/clk/SM)", cyc_item, macs / cyc_item);
+    }
+    if (cs.ff) printf("  FFMA2: %.2f cycles each per SMSP", static_cast<double>(h[1]) / (cs.ff * 8.0) / 3.0);
+    printf("\n");
+  }
+  const char* names[] = {"F2I.U32.F32 + LOP3", "I2F.F64.S32 + LOP3", "PRMT", "FMNMX", "I2F.F64.S64 + shifts"};
+  for (int op = 0; op < 5; ++op)
+    for (int wps = 1; wps <= 4; wps *= 4) {
+      const int iters = 20000;
+      cudaMemset(dc, 0, 16);
+      switch (op) {
+        case 0: k_rate<0><<<p.multiProcessorCount, 128 * wps>>>(ds, dc, iters); break;
+        case 1: k_rate<1><<<p.multiProcessorCount, 128 * wps>>>(ds, dc, iters); break;
+        case 2: k_rate<2><<<p.multiProcessorCount, 128 * wps>>>(ds, dc, iters); break;
+        case 3: k_rate<3><<<p.multiProcessorCount, 128 * wps>>>(ds, dc, iters); break;
+        case 4: k_rate<4><<<p.multiProcessorCount, 128 * wps>>>(ds, dc, iters); break;
+      }
+      cudaDeviceSynchronize();
+      long long h[2];
+      cudaMemcpy(h, dc, 16, cudaMemcpyDeviceToHost);
+      printf("%-24s %d warp(s)/SMSP: %.2f cycles per instruction group per SMSP\n", names[op], wps, static_cast<double>(h[0]) / (iters * 8.0) / wps);
+    }
+  return 0;
+}
