@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cpx_kernels.cuh"
+#include "cpx_hankel_tc.cuh"
 
 namespace {
 
@@ -62,6 +63,7 @@ struct cpx_handle {
   int chunk = 0;                     // points per chunk
   size_t device_bytes = 0;
   long long launches = 0;
+  int tc_np = 0;                     // > 0: k_p3d_hankel_tc (tcgen05 Hankel contraction) with this many cell pairs per lane
   // per-chunk scratch
   double* d_points = nullptr;        // [chunk][16]
   int* d_data_idx = nullptr;         // [chunk]
@@ -180,6 +182,80 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     if (rc) return rc;
     Z.Wd = dptr;
     keep(dptr);
+  }
+  // ---- tensor-core Hankel path (cpx_hankel_tc.cuh): scaled cell constants, weight digits, column scales ----
+  Z.tc_np = 0;
+  if (d.n_q <= 96) {
+    const int np = d.n_q <= 64 ? 16 : (d.n_q <= 88 ? 22 : 24);
+    const int KP = tc_kp(np);
+    Z.tc_np = np;
+    Z.tc_nt16 = Z.n_m_pad / kTcRows;
+    Z.tc_nablk = (d.n_a + kTcNB - 1) / kTcNB;
+    // node q -> (lane half, pair, component) and K index of the operand tiles
+    auto k_index = [&](int q) { return (q / (2 * np)) * (KP / 2) + q % (2 * np); };
+    // s_q: power of two nearest to max_a |W[a][q]|, folded into P_L so that every node enters the fixed-point
+    // conversion with the magnitude of its largest contribution to any theta bin
+    std::vector<double> sq(d.n_q, 1.0);
+    for (int q = 0; q < d.n_q; ++q) {
+      double mx = 0.0;
+      for (int a = 0; a < d.n_a; ++a) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q]));
+      if (mx > 0.0) sq[q] = std::ldexp(1.0, std::max(-100, std::min(100, static_cast<int>(std::lround(std::log2(mx))))));
+    }
+    std::vector<float> cell(static_cast<size_t>(Z.tc_nt16) * kTcConsts * 2 * np * kTcRows * 2, 0.0f);
+    const double two_pi2 = 2.0 * M_PI * M_PI;
+    for (int m = 0; m < d.n_m; ++m) {
+      const int t16 = m / kTcRows, row = m % kTcRows;
+      const double kp = d.kpar_Mpc[m];
+      for (int q = 0; q < d.n_q; ++q) {
+        const double kt = d.kperp_Mpc[q];
+        const double k2 = kp * kp + kt * kt;
+        if (!(k2 > 0.0)) continue;
+        const int half = q / (2 * np), pr = (q % (2 * np)) / 2, comp = q % 2;
+        const double k = std::sqrt(k2), mu = kp / k;
+        const double PL = d.linP_cell[static_cast<size_t>(m) * d.n_q + q];
+        const size_t cs = static_cast<size_t>(2) * np * kTcRows * 2;     // float stride between the six constants
+        float* c = &cell[(((static_cast<size_t>(t16) * kTcConsts) * 2 + half) * np + pr) * kTcRows * 2 + row * 2 + comp];
+        c[0 * cs] = static_cast<float>(k * k2 * PL / two_pi2);
+        c[1 * cs] = static_cast<float>(std::log2(k));
+        c[2 * cs] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;
+        c[3 * cs] = static_cast<float>(mu * mu);
+        c[4 * cs] = static_cast<float>(-k2);
+        c[5 * cs] = static_cast<float>(PL) * static_cast<float>(sq[q]);      // power-of-two scale: exact
+      }
+    }
+    float* dcell;
+    int rc = upload(cell, &dcell, &bytes);
+    if (rc) return rc;
+    Z.tc_cell = dcell;
+    keep(dcell);
+    std::vector<double> ta(static_cast<size_t>(Z.tc_nablk) * kTcNB, 1.0);
+    std::vector<signed char> dig(static_cast<size_t>(Z.tc_nablk) * kTcBRows * KP, 0);
+    for (int a = 0; a < d.n_a; ++a) {
+      double mx = 0.0;
+      for (int q = 0; q < d.n_q; ++q) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q] / sq[q]));
+      const double t = mx > 0.0 ? 2.05 * mx : 1.0;
+      ta[a] = t;
+      const int ablk = a / kTcNB, al = a % kTcNB;
+      for (int q = 0; q < d.n_q; ++q) {
+        // balanced base-256 digits, least significant first: X = sum_j dgt_j 256^(NW-1-j)
+        long long X = std::llrint(d.hankel_w[static_cast<size_t>(a) * d.n_q + q] / sq[q] / t * 1099511627776.0);   // 256^5
+        for (int j = kTcNW - 1; j >= 0; --j) {
+          long long dg = ((X + 128) % 256 + 256) % 256 - 128;
+          X = (X - dg) / 256;
+          dig[static_cast<size_t>(ablk) * kTcBRows * KP + tc_canon(kTcNB * j + al, k_index(q), kTcBRows / 8)] = static_cast<signed char>(dg);
+        }
+      }
+    }
+    signed char* ddig;
+    rc = upload(dig, &ddig, &bytes);
+    if (rc) return rc;
+    Z.tc_wdig = ddig;
+    keep(ddig);
+    double* dta;
+    rc = upload(ta, &dta, &bytes);
+    if (rc) return rc;
+    Z.tc_ta = dta;
+    keep(dta);
   }
   auto up_copy = [&](const double* src, size_t n, const double** dst) -> int {
     *dst = nullptr;
@@ -342,6 +418,15 @@ K1Fn k1_select_add(int pp, int nt) {
 K1Fn k1_select(int pp, int nt, bool add) { return add ? k1_select_add<true>(pp, nt) : k1_select_add<false>(pp, nt); }
 int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
 
+K1Fn k1_select_tc(int np, bool add) {
+  switch (np) {
+    case 16: return add ? cpx::k_p3d_hankel_tc<16, true> : cpx::k_p3d_hankel_tc<16, false>;
+    case 22: return add ? cpx::k_p3d_hankel_tc<22, true> : cpx::k_p3d_hankel_tc<22, false>;
+    case 24: return add ? cpx::k_p3d_hankel_tc<24, true> : cpx::k_p3d_hankel_tc<24, false>;
+  }
+  return nullptr;
+}
+
 K1Fn k1_select_f64(int nt) {
   switch (nt) {
     case 1: return cpx::k_p3d_hankel_f64<1>;
@@ -488,6 +573,23 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
     }
+  // tensor-core Hankel path: every z must have its tables (n_q <= 96) and share the pairs-per-lane template value
+  h->tc_np = 0;
+  if (env_int("CPX_TC", 1) != 0) {
+    int np = 0;
+    bool ok = true;
+    for (auto& zh : h->z) {
+      ok &= zh.dev.tc_np > 0;
+      np = std::max(np, zh.dev.tc_np);
+    }
+    for (auto& zh : h->z) ok &= zh.dev.tc_np == np;
+    if (ok && static_cast<size_t>(cpx::tc_smem_bytes(np)) + 4096 <= static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
+      for (int add = 0; add < 2; ++add)
+        if (cudaFuncSetAttribute(k1_select_tc(np, add != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::tc_smem_bytes(np)) != cudaSuccess)
+          return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_p3d_hankel_tc"));
+      h->tc_np = np;
+    }
+  }
   *out = h;
   return CPX_OK;
 }
@@ -624,13 +726,17 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
     int pp = pp_env > 0 ? std::min(pp_env, 2) : 1;   // one point per warp, two CTAs per SM measured fastest
-    const int n_pg = precise ? count : (count + kK1Warps * pp - 1) / (kK1Warps * pp);
+    const bool tc = h->tc_np > 0 && !precise;
+    const int n_pg = precise ? count : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
+    auto items_of = [&](const ZDev& Z) {
+      return tc ? static_cast<long long>(Z.tc_nt16) * Z.tc_nablk * n_pg : static_cast<long long>(Z.n_tiles) * Z.n_ablk * n_pg;
+    };
     if (count != last_table_count || pp != last_pp) {
       long long items = 0;
       for (int i = 0; i < n_zl; ++i) {
         tab[i] = h->z[zl[i]].dev;
         tab[i].item_start = items;
-        items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * n_pg;
+        items += items_of(tab[i]);
       }
       // stream-ordered: the previous chunk's kernels have been enqueued before this copy
       CPX_CUDA(cudaMemcpyAsync(h->d_ztab, tab.data(), sizeof(ZDev) * n_zl, cudaMemcpyHostToDevice, st));
@@ -638,7 +744,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       last_pp = pp;
     }
     long long n_items = 0;
-    for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * n_pg;
+    for (int i = 0; i < n_zl; ++i) n_items += items_of(tab[i]);
 
     // ---- stage 0: parameters ----
     if ((rc = mark())) return rc;
@@ -689,6 +795,10 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         K1Fn fn = k1_select_f64(h->na_blk / 8);
         const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
         fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);
+      } else if (tc) {
+        K1Fn fn = k1_select_tc(h->tc_np, additive);
+        const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));
+        fn<<<grid, kTcThreads, tc_smem_bytes(h->tc_np), st>>>(h->d_ztab, n_zl, count, n_items);
       } else {
         K1Fn fn = k1_select(pp, h->na_blk / 8, additive);
         const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);

@@ -1,0 +1,425 @@
+// k_p3d_hankel_tc: the P3D -> Px Hankel contraction on the 5th-generation tensor cores.
+//
+// Same mathematics as k_p3d_hankel (theory.py:250-344 + the theta average of likelihood.py:99-130):
+//   Px_Zam[pt][a][m] = amp(m) * sum_q W[a][q] * P3D'(m, q; pt)
+// but the FP64 contraction, which on B200 runs at the plain DFMA rate and shares the issue port with
+// the FP32 cell evaluation, is replaced by an *error-free integer split* executed
+// by tcgen05.mma kind::i8 with INT32 accumulators in tensor memory:
+//
+//   * the weights are constants of the batch:  W[a][q] = s_q * t_a * sum_j B_j[a][q] 256^-(j+1) with
+//     balanced base-256 digits B_j in [-128, 127] (5 digits = 40 bits), s_q = 2^round(log2 max_a |W[a][q]|)
+//     folded into the linear-power constant of the cell, t_a applied in the epilogue;
+//   * each FP32 cell is turned into a 32-bit fixed-point number relative to the exact maximum of its
+//     (point, k_par row): U = rni(cell * 2^(158 - e)), e = biased exponent of the row maximum.  The
+//     four bytes of U are the four u8 operand slices A_0..A_3 -- no further arithmetic;
+//   * sum_q A_i[q] B_j[q] is exact in INT32 (<= 4 * 96 * 255 * 128 < 2^24 per accumulator); all slice
+//     pairs with i + j = s accumulate into the same 32 TMEM columns (digit blocks are stacked along N,
+//     slice i starts at column 32 i), pairs with i + j > 4 (< 2^-40 of the row scale) are not issued;
+//   * the epilogue reads the five INT32 partial sums per output, combines them by Horner in float64
+//     (exact to 2^-53) and applies 2^(e - 174) t_a amp cont.
+//
+// Error of the split against the float64 dot product of the same FP32 cells: <= 1e-9 of the Px scale
+// per theta bin over the whole ForestFlow parameter box and far outside it (tests/test_tc_split.py
+// emulates the integer pipeline in NumPy); the FP32 cell rounding itself is 3e-8 .. 1e-7.
+//
+// CTA = 13 warps, one CTA per SM, persistent over a contiguous range of work items
+// (z, 16-row k_par tile, theta block of 32, group of 8 parameter points):
+//   warps 0-7   one parameter point each: lane = (row, half) evaluates NP packed cell pairs of its row
+//               into registers, the two halves exchange the row maximum, then the cells are scaled,
+//               converted (F2I), byte-transposed (PRMT) and stored as the four K-major u8 operand
+//               tiles [128 x KP] (canonical no-swizzle core-matrix order, STS.128, conflict free);
+//   warp 12     one thread issues NKC x 4 tcgen05.mma (M = 128, N = 160/128/96/64, K = 32) per item and
+//               commits to an mbarrier;
+//   warps 8-11  epilogue: tcgen05.ld of the accumulators (TMEM lane = (point, row)), Horner, scaling,
+//               contaminant terms, coalesced stores of Px_Zam.
+// Operand tiles and accumulators are double buffered (2 x 48 KB shared memory, 2 x 256 TMEM columns),
+// so cell evaluation of item n+1, the MMAs of item n and the epilogue of item n-1 overlap; the
+// tensor pipe needs ~900 cycles per item and does not take SM issue slots (tools/umma_i8_probe.cu).
+#pragma once
+#include "cpx_kernels.cuh"
+
+namespace cpx {
+
+constexpr int kTcRows = 16;                 // k_par rows per tile
+constexpr int kTcPts = 8;                   // parameter points per item (= compute warps)
+constexpr int kTcM = kTcRows * kTcPts;      // 128 = UMMA M
+constexpr int kTcNA = 4;                    // cell bytes (u8 slices)
+constexpr int kTcNW = 5;                    // weight digits (s8 slices)
+constexpr int kTcNB = 32;                   // theta columns per block
+constexpr int kTcBRows = kTcNW * kTcNB;     // 160 = rows of the stacked digit tile
+constexpr int kTcEpiWarps = 4;
+constexpr int kTcThreads = 32 * (kTcPts + kTcEpiWarps + 1);
+constexpr int kTcStageCols = 256;           // TMEM columns per accumulator stage (160 used)
+constexpr int kTcConsts = 6;
+
+__host__ __device__ constexpr int tc_kp(int np) { return np <= 16 ? 64 : 96; }
+__host__ __device__ constexpr int tc_const_bytes(int np) { return kTcConsts * 2 * np * kTcRows * 8; }
+__host__ __device__ constexpr int tc_smem_bytes(int np) {
+  return tc_const_bytes(np) + kTcBRows * tc_kp(np) + 2 * kTcNA * kTcM * tc_kp(np) + 2 * kTcM * 4;
+}
+// byte offset of element (row r, K index k) in a K-major no-swizzle operand tile with `groups` 8-row groups
+__host__ __device__ constexpr int tc_canon(int r, int k, int groups) {
+  return ((k >> 4) * groups + (r >> 3)) * 128 + (r & 7) * 16 + (k & 15);
+}
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  // start >> 4 at [0,14), leading (K-chunk) byte offset >> 4 at [16,30), stride (8-row group) byte offset >> 4 at [32,46),
+  // descriptor version 1 at [46,48), no swizzle
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc_u8s8(int m, int n) {
+  // D = S32 (2) at [4,6); A = U8 (0) at [7,10); B = S8 (1) at [10,13); both K-major; N >> 3 at [17,23); M >> 4 at [24,29)
+  return (2u << 4) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t f2u_rni(float x) {
+  uint32_t u;
+  asm("cvt.rni.u32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// exact int32 -> float64 on the ALU + FP64 pipes (I2F.F64 runs at the MUFU rate)
+__device__ __forceinline__ double i2d(int32_t v) {
+  return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+// first work item of a CTA: decode once with divisions (tile / theta-block counts of the tensor path)
+__device__ __forceinline__ void tc_decode(const ZDev* __restrict__ ztab, int n_z, int n_pg, long long it0, int& zi, int& tile,
+                                          int& ablk, int& pg) {
+  zi = 0;
+  while (zi + 1 < n_z && ztab[zi + 1].item_start <= it0) ++zi;
+  long long r = it0 - ztab[zi].item_start;
+  pg = static_cast<int>(r % n_pg);
+  r /= n_pg;
+  ablk = static_cast<int>(r % ztab[zi].tc_nablk);
+  tile = static_cast<int>(r / ztab[zi].tc_nablk);
+}
+__device__ __forceinline__ void tc_next(int nablk, int nt16, int n_pg, int& zi, int& tile, int& ablk, int& pg) {
+  if (++pg == n_pg) {
+    pg = 0;
+    if (++ablk == nablk) {
+      ablk = 0;
+      if (++tile == nt16) {
+        tile = 0;
+        ++zi;
+      }
+    }
+  }
+}
+
+template <int NP, bool ADD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    k_p3d_hankel_tc(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
+  constexpr int KP = tc_kp(NP);
+  constexpr int NKC = KP / 32;                      // K = 32 steps per item
+  constexpr int KCH = KP / 32;                      // 16-byte K chunks per lane half
+  constexpr int A_SLICE = kTcM * KP;
+  constexpr int A_STAGE = kTcNA * A_SLICE;
+  constexpr int B_BYTES = kTcBRows * KP;
+  constexpr int CONST_BYTES = tc_const_bytes(NP);
+  constexpr uint32_t A_CHUNK = (kTcM / 8) * 128;    // bytes between 16-byte K chunks of a cell tile
+  constexpr uint32_t B_CHUNK = (kTcBRows / 8) * 128;
+  static_assert(2 * NP <= KP / 2, "cells of one lane must fit its half of the K range");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* const sConst = smem_raw;
+  unsigned char* const sB = smem_raw + CONST_BYTES;
+  unsigned char* const sA = sB + B_BYTES;
+  int* const sX = reinterpret_cast<int*>(sA + 2 * A_STAGE);      // [2][128] biased exponent of the row maximum
+  __shared__ __align__(8) uint64_t bar_tma, bar_full[2], bar_dfull[2], bar_epi[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) ZDev s_Z;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_pg = (count + kTcPts - 1) / kTcPts;
+  const long long it0 = n_items * blockIdx.x / gridDim.x;
+  const long long it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+  if (it0 >= it1) return;
+  const int n_local = static_cast<int>(it1 - it0);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_tma, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_full[b], kTcPts);
+      mbar_init(&bar_dfull[b], 1);
+      mbar_init(&bar_epi[b], kTcEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kTcPts + kTcEpiWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * kTcStageCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  int zi, tile, ablk, pg;
+  tc_decode(ztab, n_z, n_pg, it0, zi, tile, ablk, pg);
+
+  if (warp < kTcPts) {
+    // =============================== cell evaluation + slicing ===============================
+    const int row = lane & 15, half = lane >> 4;
+    const int r_mma = warp * kTcRows + row;                 // row of the 128-row operand tile
+    uint32_t tma_phase = 0;
+    int cur_z = -1, cur_tile = -1, cur_ablk = -1;
+    for (int n = 0; n < n_local; ++n) {
+      const int b = n & 1;
+      if (zi != cur_z) {
+        bar_compute();
+        const int* src = reinterpret_cast<const int*>(&ztab[zi]);
+        int* dst = reinterpret_cast<int*>(&s_Z);
+        for (int i = threadIdx.x; i < static_cast<int>(sizeof(ZDev) / 4); i += kTcPts * 32) dst[i] = src[i];
+        bar_compute();
+      }
+      const ZDev& Z = s_Z;
+      const bool new_tile = (zi != cur_z) || (tile != cur_tile);
+      const bool new_w = (zi != cur_z) || (ablk != cur_ablk);
+      if (new_tile || new_w) {
+        bar_compute();   // every compute warp is done reading the previous constants
+        if (threadIdx.x == 0) {
+          // the MMAs of the previous item are the last readers of the digit tile
+          if (new_w && n >= 1) mbar_wait(&bar_epi[(n - 1) & 1], static_cast<uint32_t>((n - 1) >> 1) & 1u);
+          fence_proxy_async();
+          mbar_expect_tx(&bar_tma, (new_tile ? static_cast<uint32_t>(CONST_BYTES) : 0u) + (new_w ? static_cast<uint32_t>(B_BYTES) : 0u));
+          if (new_tile) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.tc_cell) + static_cast<size_t>(tile) * CONST_BYTES;
+            for (uint32_t off = 0; off < static_cast<uint32_t>(CONST_BYTES); off += 16384u)
+              bulk_g2s(sConst + off, src + off, min(16384u, static_cast<uint32_t>(CONST_BYTES) - off), &bar_tma);
+          }
+          if (new_w) bulk_g2s(sB, reinterpret_cast<const unsigned char*>(Z.tc_wdig) + static_cast<size_t>(ablk) * B_BYTES, B_BYTES, &bar_tma);
+        }
+        mbar_wait(&bar_tma, tma_phase);
+        tma_phase ^= 1u;
+        cur_z = zi;
+        cur_tile = tile;
+        cur_ablk = ablk;
+      }
+
+      const int ptc = min(pg * kTcPts + warp, count - 1);
+      const int m = tile * kTcRows + row;
+      const PtPar& pr = Z.ptpar[ptc];
+      const float2 q1l = dup2(pr.q1l), q1lo = dup2(pr.q1l_lo), q2l = dup2(pr.q2l), q2lo = dup2(pr.q2l_lo);
+      const float2 av = dup2(pr.av), bv = dup2(pr.bv), nlkv = dup2(pr.nlkv), nlkvlo = dup2(pr.nlkv_lo);
+      const float2 ikp2l = dup2(pr.ikp2l), ikp2lo = dup2(pr.ikp2l_lo);
+      float bhi, blo;
+      if (Z.flags & 9) {
+        const RowPar& rp = Z.rowpar[static_cast<size_t>(ptc) * Z.n_m_pad + m];
+        bhi = rp.betaT_hi;
+        blo = rp.betaT_lo;
+      } else {
+        split_hi_lo(pr.beta, bhi, blo);
+      }
+      const float2 betaT = dup2(bhi), betaTlo = dup2(2.0f * blo);
+      if (pg + 1 < n_pg && lane == 0) prefetch_l1(&Z.ptpar[min(ptc + kTcPts, count - 1)]);
+
+      // ---- the lane's 2 NP cells (nodes half * 2 NP + 2 p + {0, 1}), kept in registers ----
+      float2 x[NP];
+      float rmax = 0.0f;
+      const float2* cc = reinterpret_cast<const float2*>(sConst) + (half * NP) * kTcRows + row;
+      constexpr int CS = 2 * NP * kTcRows;     // float2 stride between the six constants
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const float2 D = cc[0 * CS + p * kTcRows], L2K = cc[1 * CS + p * kTcRows], L2MU = cc[2 * CS + p * kTcRows];
+        const float2 MU2 = cc[3 * CS + p * kTcRows], NK2 = cc[4 * CS + p * kTcRows], PL = cc[5 * CS + p * kTcRows];
+        // identical arithmetic to k_p3d_hankel (see the comments there)
+        const float2 nl = mul2(D, add2(fma2(q2l, D, q1l), fma2(q2lo, D, q1lo)));
+        const float2 v = exp2_rr2(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
+        const float2 tt = fma2(NK2, ikp2lo, fma2(NK2, ikp2l, nl));
+        const float2 e = kExpDnl(fma2(mul2(nl, dup2(-1.0f)), v, tt));
+        float2 y = mul2(PL, e);
+        y = fma2(mul2(y, betaT), MU2, y);
+        y = fma2(mul2(y, betaT), MU2, fma2(mul2(y, betaTlo), MU2, y));
+        x[p] = y;
+        rmax = fmaxf(rmax, fmaxf(y.x, y.y));
+      }
+      rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 16));
+      // fixed point relative to the row maximum: rmax < 2^(e - 126)  =>  cell * 2^(158 - e) < 2^32
+      const uint32_t eb = min(max(__float_as_uint(rmax) >> 23, 31u), 254u);
+      const float2 scale = dup2(__uint_as_float((285u - eb) << 23));
+
+      // stage b is free once the epilogue of item n - 2 has drained its accumulators (which also
+      // means the MMAs of item n - 2 have finished reading the operand tiles)
+      if (n >= 2) mbar_wait(&bar_epi[b], static_cast<uint32_t>((n >> 1) - 1) & 1u);
+      if (half == 0) sX[b * kTcM + r_mma] = static_cast<int>(eb);
+      unsigned char* const arow = sA + b * A_STAGE + (r_mma >> 3) * 128 + (r_mma & 7) * 16 + (half * KCH) * A_CHUNK;
+#pragma unroll
+      for (int g = 0; g < KCH; ++g) {
+        uint32_t w[kTcNA][4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int p0 = 8 * g + 2 * q4;       // pairs p0, p0 + 1 = cells 16 g + 4 q4 .. + 3
+          uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+          if (p0 < NP) {
+            const float2 s = mul2(x[p0 < NP ? p0 : 0], scale);
+            u0 = f2u_rni(s.x);
+            u1 = f2u_rni(s.y);
+          }
+          if (p0 + 1 < NP) {
+            const float2 s = mul2(x[p0 + 1 < NP ? p0 + 1 : 0], scale);
+            u2 = f2u_rni(s.x);
+            u3 = f2u_rni(s.y);
+          }
+          // 4 x 4 byte transpose: slice i takes byte 3 - i of the four cells, cell 0 at the lowest address
+          const uint32_t xa = prmt(u0, u1, 0x6273), ya = prmt(u0, u1, 0x4051);
+          const uint32_t xb = prmt(u2, u3, 0x6273), yb = prmt(u2, u3, 0x4051);
+          w[0][q4] = prmt(xa, xb, 0x5410);
+          w[1][q4] = prmt(xa, xb, 0x7632);
+          w[2][q4] = prmt(ya, yb, 0x5410);
+          w[3][q4] = prmt(ya, yb, 0x7632);
+        }
+#pragma unroll
+        for (int i = 0; i < kTcNA; ++i)
+          *reinterpret_cast<uint4*>(arow + i * A_SLICE + g * A_CHUNK) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+      }
+      fence_proxy_async();     // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&bar_full[b]);
+      tc_next(Z.tc_nablk, Z.tc_nt16, n_pg, zi, tile, ablk, pg);
+    }
+  } else if (warp == kTcPts + kTcEpiWarps) {
+    // =============================== MMA issue (one thread) ===============================
+    if (lane == 0) {
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      for (int n = 0; n < n_local; ++n) {
+        const int b = n & 1;
+        mbar_wait(&bar_full[b], static_cast<uint32_t>(n >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem + b * kTcStageCols;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+          for (int i = 0; i < kTcNA; ++i) {
+            const uint64_t ad = umma_smem_desc(a_base + b * A_STAGE + i * A_SLICE + kc * 2 * A_CHUNK, A_CHUNK, 128);
+            const uint64_t bd = umma_smem_desc(b_base + kc * 2 * B_CHUNK, B_CHUNK, 128);
+            umma_i8(d0 + kTcNB * i, ad, bd, umma_idesc_u8s8(kTcM, kTcNB * (kTcNW - i)), (kc > 0 || i > 0) ? 1u : 0u);
+          }
+        umma_commit(&bar_dfull[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    const int ew = warp - kTcPts;                       // TMEM lanes 32 ew .. 32 ew + 31
+    const int r_mma = 32 * ew + lane;
+    const int wpt = r_mma / kTcRows, row = r_mma % kTcRows;
+    int cur_z = -1;
+    int n_a = 0, n_m = 0, n_m_pad = 0, flags = 0, nablk = 1, nt16 = 1;
+    double dAA = 0.0;
+    const PtPar* ptpar = nullptr;
+    const RowPar* rowpar = nullptr;
+    double* pxzam = nullptr;
+    const double *ta = nullptr, *metal_auto = nullptr, *metal_cross = nullptr, *sky_xi = nullptr, *sky_smooth = nullptr;
+    for (int n = 0; n < n_local; ++n) {
+      const int b = n & 1;
+      if (zi != cur_z) {
+        const ZDev& Zg = ztab[zi];
+        n_a = Zg.n_a;
+        n_m = Zg.n_m;
+        n_m_pad = Zg.n_m_pad;
+        flags = Zg.flags;
+        nablk = Zg.tc_nablk;
+        nt16 = Zg.tc_nt16;
+        dAA = Zg.dAA;
+        ptpar = Zg.ptpar;
+        rowpar = Zg.rowpar;
+        pxzam = Zg.pxzam;
+        ta = Zg.tc_ta;
+        metal_auto = Zg.metal_auto;
+        metal_cross = Zg.metal_cross;
+        sky_xi = Zg.sky_xi;
+        sky_smooth = Zg.sky_smooth;
+        cur_z = zi;
+      }
+      const int pt = pg * kTcPts + wpt;
+      const int m = tile * kTcRows + row;
+      const bool pt_ok = pt < count, row_ok = m < n_m;
+      const PtPar& pr = ptpar[min(pt, count - 1)];
+      double amp = pr.bias * pr.bias * dAA, cont = 1.0;
+      if (flags & 9) {
+        const RowPar& rp = rowpar[static_cast<size_t>(min(pt, count - 1)) * n_m_pad + m];
+        amp = rp.amp;
+        cont = rp.cont;
+      }
+      double sky = 0.0;
+      if (ADD && (flags & 4) && row_ok) sky = pr.b_noise * sky_smooth[m];
+
+      mbar_wait(&bar_dfull[b], static_cast<uint32_t>(n >> 1) & 1u);
+      tc_fence_after();
+      const int eb = sX[b * kTcM + r_mma];
+      // 2^(eb - 174) * amp * cont; padded rows store zeros
+      const double rowfac = row_ok ? __hiloint2double((eb - 174 + 1023) << 20, 0) * amp * cont : 0.0;
+      const int a0 = ablk * kTcNB;
+      const int na_here = min(kTcNB, n_a - a0);
+      const uint32_t taddr = tmem + b * kTcStageCols + (static_cast<uint32_t>(32 * ew) << 16);
+      double* const outp = pxzam + (static_cast<size_t>(min(pt, count - 1)) * n_a + a0) * n_m_pad + m;
+      for (int c0 = 0; c0 < na_here; c0 += 4) {
+        int32_t v[kTcNW][4];
+#pragma unroll
+        for (int s = 0; s < kTcNW; ++s) tmem_ld4(taddr + kTcNB * s + c0, v[s]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int a = a0 + c0 + j;
+          if (c0 + j >= na_here) break;
+          // sum_s D_s 256^(4-s): the upper three and the lower two digits are exact on their own
+          const double hi = fma(fma(i2d(v[0][j]), 256.0, i2d(v[1][j])), 256.0, i2d(v[2][j]));
+          const double lo = fma(i2d(v[3][j]), 256.0, i2d(v[4][j]));
+          double px = fma(hi, 65536.0, lo) * (rowfac * ta[a]);
+          if (ADD && row_ok) {
+            double add = 0.0;
+            if (flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
+              const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
+              const double bx = pr.b_X, btx = pr.beta_X;
+              add += bx * bx * (metal_auto[o] + 2.0 * btx * metal_auto[o + st] + btx * btx * metal_auto[o + 2 * st]);
+              add += pr.bias * bx * (metal_cross[o] + (pr.beta + btx) * metal_cross[o + st] + pr.beta * btx * metal_cross[o + 2 * st]);
+            }
+            if (flags & 4) add += sky * sky_xi[a];   // theory.py:476-506
+            px = fma(add, cont, px);
+          }
+          if (pt_ok) outp[static_cast<size_t>(c0 + j) * n_m_pad] = px;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&bar_epi[b]);
+      tc_next(nablk, nt16, n_pg, zi, tile, ablk, pg);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kTcPts + kTcEpiWarps)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * kTcStageCols) : "memory");
+}
+
+}  // namespace cpx

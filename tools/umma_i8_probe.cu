@@ -226,7 +226,7 @@ int main() {
   cudaMemcpy(dB, Bimg.data(), Bimg.size(), cudaMemcpyHostToDevice);
   const size_t smem = (kSlices + 1) * kTileBytes + 1024;
   cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  for (int mode = 0; mode < 2; ++mode) {
+  for (int mode = 0; mode < 1; ++mode) {   // mode 1 (LBO/SBO swapped) faults: LBO is the K-chunk stride, SBO the 8-row-group stride
     cudaMemset(dD, 0xff, kM * kN * 4);
     k_probe<<<1, 512, smem>>>(dA, dB, dD, mode, 1, 0, dc, ds);
     cudaError_t e = cudaDeviceSynchronize();
