@@ -186,13 +186,13 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   // ---- tensor-core Hankel path (cpx_hankel_tc.cuh): scaled cell constants, weight digits, column scales ----
   Z.tc_np = 0;
   if (d.n_q <= 96) {
-    const int np = d.n_q <= 64 ? 16 : (d.n_q <= 88 ? 22 : 24);
-    const int KP = tc_kp(np);
+    const int np = d.n_q <= 64 ? 8 : (d.n_q <= 88 ? 11 : 12);     // packed cell pairs per lane (4 lanes per k_par row)
+    const int KP = tc_kp(np), QS = tc_qs(np);
     Z.tc_np = np;
-    Z.tc_nt16 = Z.n_m_pad / kTcRows;
+    Z.tc_nt = Z.n_m_pad / kTcRows;
     Z.tc_nablk = (d.n_a + kTcNB - 1) / kTcNB;
-    // node q -> (lane half, pair, component) and K index of the operand tiles
-    auto k_index = [&](int q) { return (q / (2 * np)) * (KP / 2) + q % (2 * np); };
+    // node q -> (lane quarter, pair, component) and K index of the operand tiles
+    auto k_index = [&](int q) { return (q / (2 * np)) * (KP / kTcQuarters) + q % (2 * np); };
     // s_q: power of two nearest to max_a |W[a][q]|, folded into P_L so that every node enters the fixed-point
     // conversion with the magnitude of its largest contribution to any theta bin
     std::vector<double> sq(d.n_q, 1.0);
@@ -201,26 +201,27 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
       for (int a = 0; a < d.n_a; ++a) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q]));
       if (mx > 0.0) sq[q] = std::ldexp(1.0, std::max(-100, std::min(100, static_cast<int>(std::lround(std::log2(mx))))));
     }
-    std::vector<float> cell(static_cast<size_t>(Z.tc_nt16) * kTcConsts * 2 * np * kTcRows * 2, 0.0f);
+    // [tile][3 constant pairs (D, log2 k), (log2 mu, mu^2), (-k^2, P_L s_q)][quarter][QS][row][4]: one LDS.128 per pair
+    const size_t cs = static_cast<size_t>(kTcQuarters) * QS * kTcRows * 4;     // float stride between the constant pairs
+    std::vector<float> cell(static_cast<size_t>(Z.tc_nt) * 3 * cs, 0.0f);
     const double two_pi2 = 2.0 * M_PI * M_PI;
     for (int m = 0; m < d.n_m; ++m) {
-      const int t16 = m / kTcRows, row = m % kTcRows;
+      const int t8 = m / kTcRows, row = m % kTcRows;
       const double kp = d.kpar_Mpc[m];
       for (int q = 0; q < d.n_q; ++q) {
         const double kt = d.kperp_Mpc[q];
         const double k2 = kp * kp + kt * kt;
         if (!(k2 > 0.0)) continue;
-        const int half = q / (2 * np), pr = (q % (2 * np)) / 2, comp = q % 2;
+        const int quarter = q / (2 * np), pr = (q % (2 * np)) / 2, comp = q % 2;
         const double k = std::sqrt(k2), mu = kp / k;
         const double PL = d.linP_cell[static_cast<size_t>(m) * d.n_q + q];
-        const size_t cs = static_cast<size_t>(2) * np * kTcRows * 2;     // float stride between the six constants
-        float* c = &cell[(((static_cast<size_t>(t16) * kTcConsts) * 2 + half) * np + pr) * kTcRows * 2 + row * 2 + comp];
-        c[0 * cs] = static_cast<float>(k * k2 * PL / two_pi2);
-        c[1 * cs] = static_cast<float>(std::log2(k));
-        c[2 * cs] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;
-        c[3 * cs] = static_cast<float>(mu * mu);
-        c[4 * cs] = static_cast<float>(-k2);
-        c[5 * cs] = static_cast<float>(PL) * static_cast<float>(sq[q]);      // power-of-two scale: exact
+        float* c = &cell[static_cast<size_t>(t8) * 3 * cs + ((static_cast<size_t>(quarter) * QS + pr) * kTcRows + row) * 4 + comp];
+        c[0 * cs + 0] = static_cast<float>(k * k2 * PL / two_pi2);
+        c[0 * cs + 2] = static_cast<float>(std::log2(k));
+        c[1 * cs + 0] = (mu > 0.0) ? static_cast<float>(std::log2(mu)) : -1.0e30f;
+        c[1 * cs + 2] = static_cast<float>(mu * mu);
+        c[2 * cs + 0] = static_cast<float>(-k2);
+        c[2 * cs + 2] = static_cast<float>(PL) * static_cast<float>(sq[q]);      // power-of-two scale: exact
       }
     }
     float* dcell;
@@ -420,9 +421,9 @@ int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
 
 K1Fn k1_select_tc(int np, bool add) {
   switch (np) {
-    case 16: return add ? cpx::k_p3d_hankel_tc<16, true> : cpx::k_p3d_hankel_tc<16, false>;
-    case 22: return add ? cpx::k_p3d_hankel_tc<22, true> : cpx::k_p3d_hankel_tc<22, false>;
-    case 24: return add ? cpx::k_p3d_hankel_tc<24, true> : cpx::k_p3d_hankel_tc<24, false>;
+    case 8: return add ? cpx::k_p3d_hankel_tc<8, true> : cpx::k_p3d_hankel_tc<8, false>;
+    case 11: return add ? cpx::k_p3d_hankel_tc<11, true> : cpx::k_p3d_hankel_tc<11, false>;
+    case 12: return add ? cpx::k_p3d_hankel_tc<12, true> : cpx::k_p3d_hankel_tc<12, false>;
   }
   return nullptr;
 }
@@ -729,7 +730,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     const bool tc = h->tc_np > 0 && !precise;
     const int n_pg = precise ? count : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
     auto items_of = [&](const ZDev& Z) {
-      return tc ? static_cast<long long>(Z.tc_nt16) * Z.tc_nablk * n_pg : static_cast<long long>(Z.n_tiles) * Z.n_ablk * n_pg;
+      return tc ? static_cast<long long>(Z.tc_nt) * Z.tc_nablk * n_pg : static_cast<long long>(Z.n_tiles) * Z.n_ablk * n_pg;
     };
     if (count != last_table_count || pp != last_pp) {
       long long items = 0;

@@ -82,11 +82,11 @@ struct ZDev {
   double* pxzam;                        // [chunk][n_a][n_m_pad]
   long long item_start;                 // first k_p3d_hankel work item of this z in the launch
   // tensor-core (tcgen05) Hankel path, cpx_hankel_tc.cuh; tc_np == 0: not available for this z (n_q > 96)
-  int tc_np;                            // packed cell pairs per lane (n_q <= 4 * tc_np)
-  int tc_nt16;                          // 16-row k_par tiles (n_m_pad / 16)
+  int tc_np;                            // packed cell pairs per lane (n_q <= 8 * tc_np)
+  int tc_nt;                            // 8-row k_par tiles (n_m_pad / 8)
   int tc_nablk;                         // theta blocks of 32
   int pad1;
-  const float* tc_cell;                 // [tc_nt16][6][half 2][tc_np][row 16][2] cell constants, P_L scaled by s_q
+  const float* tc_cell;                 // [tc_nt][6][quarter 4][tc_np | 1][row 8][2] cell constants, P_L scaled by s_q
   const signed char* tc_wdig;           // [tc_nablk][160 x KP] balanced base-256 digits of W / (s_q t_a), K-major core-matrix order
   const double* tc_ta;                  // [tc_nablk * 32] column scales t_a
 };
