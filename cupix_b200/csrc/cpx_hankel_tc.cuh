@@ -385,12 +385,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       if (m >= Z.n_m) ampcont = 0.0;
       const float2 betaT = dup2(bhi), betaTlo = dup2(2.0f * blo);
-      // Half of the warps of every SM sub-partition do their epilogue share of the previous item first,
-      // the other half after the operand stores: the phases of a work item use different pipes (FP32
-      // for the cells, XU/ALU for the slicing, TMEM/FP64 for the epilogue) and the per-item barrier would
-      // otherwise keep all 16 warps in the same phase.
-      const bool epi_first = warp >= kTcPts / 2;
-      if (epi_first && n >= 1) epilogue(n - 1, p_zi, p_tile, p_ablk, p_pg);
 
       // ---- the lane's 2 NP cells (nodes quarter * 2 NP + 2 p + {0, 1}), kept in registers ----
       float2 x[NP];
@@ -461,7 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // epilogue share of the previous item (its MMAs ran while this warp evaluated the cells above);
       // it must precede the arrival: arriving for item n licenses the issuer to overwrite accumulator
       // stage b, and item n + 1 to overwrite what item n - 1 occupies
-      if (!epi_first && n >= 1) epilogue(n - 1, p_zi, p_tile, p_ablk, p_pg);
+      if (n >= 1) epilogue(n - 1, p_zi, p_tile, p_ablk, p_pg);
       __syncwarp();
       if (lane == 0) mbar_arrive1(&bar_full[b]);
       p_zi = zi;
