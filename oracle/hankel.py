@@ -3,7 +3,8 @@
     Px(k_par, r) = 1/(2 pi) int_0^kmax dk_perp k_perp J0(k_perp r) P3D(k, mu),
 
 the step the reference delegates to ``forestflow.pcross.Px_Mpc_detailed`` (call site
-cupix/likelihood/theory.py:250-264; third-party, un-pinned, absent here: PARITY UNPINNED).
+cupix/likelihood/theory.py:250-264; third-party, un-pinned, absent here; pinned instead to the
+reference's in-tree copy of the algorithm, see FFTLogHankel below).
 All three have the call signature ``hankel(rt_Mpc[Nr], kp_Mpc[Nk], p3d_func(k, mu)) -> [Nr, Nk]``.
 
   NodeHankel    "oracle B": the fixed-node rule the device evaluates -- nodes k_q and a callable
@@ -14,9 +15,11 @@ All three have the call signature ``hankel(rt_Mpc[Nr], kp_Mpc[Nk], p3d_func(k, m
                 (cupix/likelihood/lyaP3D.py:272-351): FFTLog (Hamilton 2000; ``hankl.FFTLog(x, f,
                 q=0, mu=0)`` at :324-326) of P3D*k_perp on 2^11 log-spaced k_perp in [1e-7, 1e3],
                 P1D splice below r ~ 0.02-0.2 Mpc (:291-298, :329-347), cubic spline to the
-                requested r (:349-350).  hankl's source is not available either, so FFTLog is
-                restated from the published algorithm and checked on an analytic pair
-                (tests/test_oracle_hankel.py).
+                requested r (:349-350).  hankl's source is not available, so FFTLog is restated
+                from the published algorithm; it equals scipy.fft.fht to 1e-14, and this class
+                equals the output of the reference's lyaP3D.py run with scipy.fft.fht in hankl's
+                place to 1e-10 (tests/golden/make_golden_hankel.py,
+                tests/test_oracle_hankel_golden.py).
 """
 import numpy as np
 from scipy.integrate import simpson

@@ -10,10 +10,14 @@ Parity status
   rebin and chi2: PINNED -- tests/golden/make_golden.py imports the unmodified reference modules
   (with stand-ins for the absent third-party packages lace / forestflow / astropy) and stores
   their outputs; tests/test_oracle_golden.py checks this restatement against them.
-* the P3D -> Px Hankel transform itself (``forestflow.pcross.Px_Mpc_detailed``, third-party,
-  un-pinned, absent): PARITY UNPINNED.  Three interchangeable transforms are provided
-  (oracle/hankel.py): the fixed-node rule the device uses, a brute-force integral, and an FFTLog
-  restatement of the in-tree copy of the ForestFlow algorithm (cupix/likelihood/lyaP3D.py:272-351).
+* the P3D -> Px Hankel transform (``forestflow.pcross.Px_Mpc_detailed``, third-party, un-pinned,
+  absent): PINNED TO THE REFERENCE'S IN-TREE COPY of that algorithm.  tests/golden/make_golden_hankel.py
+  runs cupix/likelihood/lyaP3D.py (Px_Mpc_withSiIII :127-362, P1D_Mpc :66-106, "copied from ForestFlow")
+  unmodified, with hankl.FFTLog supplied by scipy.fft.fht, and stores its Px for four Arinyo parameter
+  sets; tests/test_oracle_hankel_golden.py checks the FFTLog restatement in oracle/hankel.py against it
+  (1e-10) and the fixed-node rule the device evaluates (<= 1e-5 of the Px scale for r >= 0.3 Mpc).  What
+  stays unpinned is only the difference between that in-tree copy and today's ForestFlow HEAD (the
+  ``max_k_for_p3d`` argument of theory.py:264, which the in-tree copy does not have).
 """
 import numpy as np
 
