@@ -15,7 +15,10 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
-        "smsp__warps_eligible.avg.per_cycle_active"]
+        "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg"]
 STALLS = "smsp__average_warps_issue_stalled_"
 
 
@@ -24,6 +27,9 @@ def main(rep, out, traffic_json=None):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, val = rows[0], rows[1], rows[2]
     d = {h: (u, v) for h, u, v in zip(hdr, units, val)}
+    for h in list(d):            # some counters carry a section prefix ("TPC.TriageCompute.")
+        if h[:1].isupper() and h.count(".") >= 2 and d[h][1] != "":
+            d.setdefault(h.split(".", 2)[-1], d[h])
     lines = ["kernel: %s" % d.get("Kernel Name", ("", "?"))[1], "source: %s (ncu --set full --clock-control none, one launch)" % rep]
     for k in KEYS:
         if k in d:
