@@ -13,7 +13,7 @@ from cupix_b200.engine import PxEngine, slots_from_names
 from cupix_b200.likelihood.likelihood_parameter import dict_from_likeparam
 from cupix_b200.likelihood.model_contaminants import ContaminantsModel
 from cupix_b200.likelihood.model_lya import LyaModel
-from cupix_b200.quadrature import DEFAULT_K0, DEFAULT_KMAX, DEFAULT_NQ, KperpRule
+from cupix_b200.quadrature import DEFAULT_K0, DEFAULT_KMAX, DEFAULT_NQ, PRESETS, KperpRule
 
 COSMO_KEYS = ("H0", "omch2", "ombh2", "mnu", "omk", "As", "ns", "nrun", "w")
 
@@ -26,7 +26,7 @@ class Theory(object):
             - z: redshift of the Lya bin
             - fid_cosmo: fiducial cosmology object (unit conversions, linear power)
             - config: include_hcd / include_metal / include_sky / include_continuum, the LyaModel and
-              ContaminantsModel keys, plus engine settings n_q, k0_Mpc, kmax_Mpc, device."""
+              ContaminantsModel keys, plus engine settings kperp_rule, n_q, k0_Mpc, kmax_Mpc, device."""
         self.verbose = config.get('verbose', False)
         self.z = z
         self.zs = z
@@ -37,8 +37,14 @@ class Theory(object):
         self.include_metal = config.get('include_metal', False)
         self.include_sky = config.get('include_sky', False)
         self.include_continuum = config.get('include_continuum', False)
-        self.rule = KperpRule(config.get('n_q', DEFAULT_NQ), config.get('k0_Mpc', DEFAULT_K0),
-                              config.get('kmax_Mpc', DEFAULT_KMAX))
+        # k_perp quadrature: 'kperp_rule' picks a preset ('smooth': 88 log-uniform nodes, for a linear power
+        # without wiggles; 'bao': 112 nodes refined below ~0.3 1/Mpc, for a CAMB-like power with baryon
+        # acoustic oscillations); n_q / kperp_refine / kperp_k_refine override its fields
+        preset = dict(PRESETS[config.get('kperp_rule', 'smooth')])
+        self.rule = KperpRule(config.get('n_q', preset['n_q']), config.get('k0_Mpc', DEFAULT_K0),
+                              config.get('kmax_Mpc', DEFAULT_KMAX),
+                              refine=config.get('kperp_refine', preset.get('refine', 0.0)),
+                              k_refine=config.get('kperp_k_refine', preset.get('k_refine', 0.3)))
         self.device = config.get('device', 0)
         self.precise_cells = config.get('precise_cells', False)
         self._engines = {}

@@ -281,3 +281,22 @@ def test_large_batch_spans_chunks():
     sel = np.array([0, 1, 65535, 65536, 65537, B - 1])
     np.testing.assert_array_equal(chi2[sel], like.get_chi2_batch(pts[sel], ["bias", "beta"]))
     assert np.isfinite(chi2).all()
+
+
+def test_bao_refined_rule_on_device():
+    """The 'bao' k_perp preset (112 non-log-uniform nodes = 28 DMMA k-steps) through the CUDA path against the
+    float64 emulation of the same plan and, for the model Px, against the oracle."""
+    d = synthetic.make_measurement_dict("S1", N_A=7, N_m=40, Nz=1)
+    th = H.make_theory(2.2, "best_fit_arinyo_from_gadget", {"include_hcd": True}, n_q=112, extra={"kperp_rule": "bao"})
+    assert th.rule.n_q == 112 and th.rule.refine == 50.0
+    like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 2})
+    names = ["bias", "beta", "q1", "kp_Mpc"]
+    rng = np.random.default_rng(2)
+    pts = np.stack([rng.uniform(-0.2, -0.1, 9), rng.uniform(1.0, 2.0, 9), rng.uniform(0.1, 0.6, 9), rng.uniform(8, 20, 9)], axis=1)
+    model = like.get_convolved_px_batch(pts, names)
+    p = like.build_plan()
+    orc = H.oracle_likelihood(like)
+    for i in (0, 4, 8):
+        params = dict(zip(names, pts[i]))
+        assert_px(model[i], H.emulate_plan_chi2(p, params)[0], msg="bao rule, emulation, pt %d" % i)
+        assert_px(model[i], orc.get_convolved_px(params), msg="bao rule, oracle, pt %d" % i)
