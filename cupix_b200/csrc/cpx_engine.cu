@@ -13,6 +13,7 @@
 
 #include "cpx_kernels.cuh"
 #include "cpx_hankel_tc.cuh"
+#include "cpx_window_tc.cuh"
 
 namespace {
 
@@ -63,6 +64,7 @@ struct cpx_handle {
   int chunk = 0;                     // points per chunk
   size_t device_bytes = 0;
   long long launches = 0;
+  int wt_nb = 0;                     // > 0: k_window_tc (tcgen05 window contraction) for the chi2 stage
   int tc_np = 0;                     // > 0: k_p3d_hankel_tc (tcgen05 Hankel contraction) with this many cell pairs per lane
   // per-chunk scratch
   double* d_points = nullptr;        // [chunk][16]
@@ -361,6 +363,66 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     keep(dpa);
     keep(dTm);
     keep(dTc);
+
+    // ---- tensor-core window path (cpx_window_tc.cuh): column scales, row scales and base-256 digits of T_chi ----
+    Z.wt_nb = 0;
+    if (Z.n_mblk == 1 && Z.n_M_pad <= 64) {
+      const int NB = round_up(nM, 16);
+      const int cpp = Z.n_m_pad / kWtKC, bpp = Z.n_m_pad / 16;
+      std::vector<int> cs(static_cast<size_t>(Z.n_pairs) * bpp, 0), off(nA, 0);
+      std::vector<double> rs(static_cast<size_t>(nA) * NB, 1.0);
+      for (int p = 0; p < Z.n_pairs; ++p)
+        for (int b = 0; b < bpp; ++b) {
+          double mx = 0.0;
+          for (int M = 0; M < nM; ++M)
+            for (int m = 16 * b; m < 16 * b + 16; ++m) mx = std::max(mx, std::fabs(Tc[p * tstride + static_cast<size_t>(M) * Z.n_m_pad + m]));
+          if (mx > 0.0) cs[static_cast<size_t>(p) * bpp + b] = std::max(-300, std::min(300, static_cast<int>(std::lround(std::log2(mx)))));
+        }
+      int chunks = 0;
+      for (int A = 0; A < nA; ++A) {
+        off[A] = chunks;
+        chunks += (pair_start[A + 1] - pair_start[A]) * cpp;
+      }
+      const size_t tile = static_cast<size_t>(wt_b_stage(NB));
+      std::vector<signed char> dig(static_cast<size_t>(chunks) * tile, 0);
+      for (int A = 0; A < nA; ++A) {
+        for (int M = 0; M < nM; ++M) {
+          double mx = 0.0;
+          for (int p = pair_start[A]; p < pair_start[A + 1]; ++p)
+            for (int m = 0; m < nm; ++m)
+              mx = std::max(mx, std::fabs(std::ldexp(Tc[p * tstride + static_cast<size_t>(M) * Z.n_m_pad + m], -cs[static_cast<size_t>(p) * bpp + m / 16])));
+          const double r = mx > 0.0 ? 2.05 * mx : 1.0;
+          rs[static_cast<size_t>(A) * NB + M] = r;
+          for (int p = pair_start[A]; p < pair_start[A + 1]; ++p)
+            for (int m = 0; m < nm; ++m) {
+              const double v = std::ldexp(Tc[p * tstride + static_cast<size_t>(M) * Z.n_m_pad + m], -cs[static_cast<size_t>(p) * bpp + m / 16]) / r;
+              long long X = std::llrint(v * 1099511627776.0);   // 256^5
+              const size_t chunk = static_cast<size_t>(off[A]) + static_cast<size_t>(p - pair_start[A]) * cpp + m / kWtKC;
+              for (int j = kWtNW - 1; j >= 0; --j) {
+                const long long dg = ((X + 128) % 256 + 256) % 256 - 128;
+                X = (X - dg) / 256;
+                dig[chunk * tile + tc_canon(NB * j + M, m % kWtKC, kWtNW * NB / 8)] = static_cast<signed char>(dg);
+              }
+            }
+        }
+      }
+      signed char* ddig;
+      int *doff, *dcs;
+      double* drs;
+      if ((rc = upload(dig, &ddig, &bytes))) return rc;
+      if ((rc = upload(off, &doff, &bytes))) return rc;
+      if ((rc = upload(cs, &dcs, &bytes))) return rc;
+      if ((rc = upload(rs, &drs, &bytes))) return rc;
+      Z.wt_nb = NB;
+      Z.wt_dig = ddig;
+      Z.wt_off = doff;
+      Z.wt_cs = dcs;
+      Z.wt_rs = drs;
+      keep(ddig);
+      keep(doff);
+      keep(dcs);
+      keep(drs);
+    }
   }
   return CPX_OK;
 }
@@ -589,6 +651,22 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
         if (cudaFuncSetAttribute(k1_select_tc(np, add != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::tc_smem_bytes(np)) != cudaSuccess)
           return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_p3d_hankel_tc"));
       h->tc_np = np;
+    }
+  }
+  // tensor-core window path: every z with a measurement needs its digit tables
+  h->wt_nb = 0;
+  if (env_int("CPX_WTC", 1) != 0) {
+    int nb = 0;
+    bool ok = true;
+    for (auto& zh : h->z)
+      if (zh.dev.n_A > 0) {
+        ok &= zh.dev.wt_nb > 0;
+        nb = std::max(nb, zh.dev.wt_nb);
+      }
+    if (ok && nb > 0 && static_cast<size_t>(cpx::wt_smem_bytes(nb)) + 2048 <= static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
+      if (cudaFuncSetAttribute(cpx::k_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::wt_smem_bytes(nb)) != cudaSuccess)
+        return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_window_tc"));
+      h->wt_nb = nb;
     }
   }
   *out = h;
@@ -833,7 +911,12 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       dim3 grid((count + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
-        k2_select<true>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        if (h->wt_nb > 0) {
+          dim3 tgrid((count + kWtPts - 1) / kWtPts, std::max(nA_grid, 1), gz);
+          k_window_tc<<<tgrid, kWtThreads, wt_smem_bytes(h->wt_nb), st>>>(h->d_ztab, i, w);
+        } else {
+          k2_select<true>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+        }
         ++h->launches;
       }
       if (want_model) {

@@ -89,6 +89,13 @@ struct ZDev {
   const float* tc_cell;                 // [tc_nt][6][quarter 4][tc_np | 1][row 8][2] cell constants, P_L scaled by s_q
   const signed char* tc_wdig;           // [tc_nablk][160 x KP] balanced base-256 digits of W / (s_q t_a), K-major core-matrix order
   const double* tc_ta;                  // [tc_nablk * 32] column scales t_a
+  // tensor-core window path, cpx_window_tc.cuh; wt_nb == 0: not available (more than 64 coarse-k bins)
+  int wt_nb;                            // coarse-k columns rounded up to 16
+  int pad2;
+  const signed char* wt_dig;            // [chunk][5 * wt_nb x 32] digits of T_chi / (2^c rs), chunks ordered (A, pair in A, m / 32)
+  const int* wt_off;                    // [n_A] first chunk of coarse bin A
+  const int* wt_cs;                     // [n_pairs][n_m_pad / 16] exponent c of the column scale
+  const double* wt_rs;                  // [n_A][wt_nb] row scales
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,240 @@
+// k_window_tc: window convolution + theta rebinning + whitening + chi2 on the 5th-generation tensor cores.
+//
+// Same mathematics as k_window<MT, CHI2 = true> (likelihood.py:53-88, 170-194):
+//   chi2_A[pt] = || yd[A] - Y ||^2,   Y[pt][M] = sum_{pairs p in A} sum_m T_chi[p][M][m] * Px_Zam[pt][a_p][m]
+// with the FP64 contraction done by an error-free integer split on tcgen05.mma kind::i8 (INT32
+// accumulators in tensor memory), as in cpx_hankel_tc.cuh.  Here both operands are plain matrices, so
+// the split costs a few instructions per *input* element and nothing per multiply-add:
+//
+//   * T_chi is a constant of the batch:  T[p][M][m] = 2^c(p, m/16) * rs[A][M] * sum_j B_j 256^-(j+1)  with five
+//     balanced base-256 digits (s8) stacked along N (5 x NB columns, NB = coarse-k count rounded up to 16).
+//     The column scale 2^c ~ max_M |T[p][M][m]| over blocks of 16 fine-k columns is moved onto Px, so that
+//     every Px element enters the fixed-point conversion with the size of its largest contribution to any
+//     output -- Px falls by many decades along k_par while T rises with 1/sigma;
+//   * the Px row of a (point, theta_A) -- all pairs, all m -- becomes 40-bit two's-complement fixed point
+//     relative to its exact maximum (pass 1 finds the maximum exponent, pass 2 converts with one DMUL and
+//     one magic-number DADD per element); its five bytes are the operand slices (top byte s8, others u8);
+//   * slice pairs with i + j = s share TMEM columns NB*s .. NB*s + NB, pairs with i + j > 4 (< 2^-40) are
+//     dropped; the epilogue combines the five INT32 per output by Horner in float64.
+//
+// CTA = 8 worker warps + one MMA-issuing thread + one TMA thread, one CTA per SM (5 x 64 accumulator
+// columns round up to the whole tensor memory), one tile = 128 points x one theta_A x one z per CTA.
+// Worker thread (point r, half h) loads 16 consecutive doubles per K = 32 chunk, converts them and writes
+// one 16-byte core-matrix row into each of the five u8/s8 operand tiles (4-stage ring, mbarriers); the
+// digit tiles of T stream in with TMA bulk copies.  HBM traffic is one read of Px_Zam (pass 2 hits L2).
+#pragma once
+#include "cpx_hankel_tc.cuh"
+
+namespace cpx {
+
+constexpr int kWtPts = 128;          // points per tile = UMMA M
+constexpr int kWtNA = 5;             // Px bytes
+constexpr int kWtNW = 5;             // T digits
+constexpr int kWtStages = 4;
+constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
+constexpr int kWtWorkers = 8;        // worker warps
+constexpr int kWtThreads = 32 * (kWtWorkers + 2);
+constexpr int kWtASlice = kWtPts * kWtKC;               // 4 KB
+constexpr int kWtAStage = kWtNA * kWtASlice;            // 20 KB
+__host__ __device__ constexpr int wt_b_stage(int nb) { return kWtNW * nb * kWtKC; }
+__host__ __device__ constexpr int wt_smem_bytes(int nb) {
+  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtPts * 4 + 2 * kWtPts * 8;
+}
+
+__device__ __forceinline__ uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 2, %0;" ::"n"(kWtWorkers * 32) : "memory"); }
+
+__global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restrict__ ztab, int zi, WindowArgs w) {
+  if (w.zslot < 0) {
+    zi = blockIdx.z;
+    w.zslot = blockIdx.z;
+  }
+  const ZDev& Z = ztab[zi];
+  const int A = blockIdx.y;
+  if (A >= Z.n_A) return;
+  const int NB = Z.wt_nb;
+  const int B_STAGE = wt_b_stage(NB);
+  const uint32_t A_CHUNK = (kWtPts / 8) * 128;              // bytes between the two 16-byte K chunks of a Px tile
+  const uint32_t B_CHUNK = (kWtNW * NB / 8) * 128;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* const sA = smem_raw;
+  unsigned char* const sB = sA + kWtStages * kWtAStage;
+  int* const sE = reinterpret_cast<int*>(sB + kWtStages * B_STAGE);       // [128] biased exponent of the row maximum
+  double* const sChi = reinterpret_cast<double*>(sE + kWtPts);            // [2][128] partial chi2 of the two column halves
+  __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pt_base = blockIdx.x * kWtPts;
+  const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
+  const int cpp = Z.n_m_pad / kWtKC;                        // chunks per pair
+  const int n_chunks = (p1 - p0) * cpp;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWtStages; ++s) {
+      mbar_init(&bar_fullA[s], kWtWorkers);
+      mbar_init(&bar_fullB[s], 1);
+      mbar_init(&bar_free[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWtWorkers) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == kWtWorkers) {
+    // =============================== MMA issue (one thread) ===============================
+    if (lane == 0) {
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % kWtStages;
+        const uint32_t ph = static_cast<uint32_t>(c / kWtStages) & 1u;
+        while (!mbar_test(&bar_fullB[s], ph)) __nanosleep(32);
+        while (!mbar_test(&bar_fullA[s], ph)) __nanosleep(32);
+        tc_fence_after();
+        const uint64_t bd = umma_smem_desc(b_base + s * B_STAGE, B_CHUNK, 128);
+#pragma unroll
+        for (int i = 0; i < kWtNA; ++i) {
+          const uint64_t ad = umma_smem_desc(a_base + s * kWtAStage + i * kWtASlice, A_CHUNK, 128);
+          const int n = NB * (kWtNW - i);                    // digits 0 .. 4 - i
+          const uint32_t acc = (c > 0 || i > 0) ? 1u : 0u;
+          if (n <= 256) {
+            umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, n, i == 0), acc);
+          } else {                                           // N = 320: digits 0-3, then digit 4
+            umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, 4 * NB, i == 0), acc);
+            const uint64_t bd4 = umma_smem_desc(b_base + s * B_STAGE + (4 * NB / 8) * 128, B_CHUNK, 128);
+            umma_i8(tmem + NB * (i + 4), ad, bd4, umma_idesc_i8(kWtPts, NB, i == 0), acc);
+          }
+        }
+        umma_commit(&bar_free[s]);
+      }
+      umma_commit(&bar_done);
+    }
+    __syncwarp();
+  } else if (warp == kWtWorkers + 1) {
+    // =============================== TMA: digit tiles of T ===============================
+    if (lane == 0) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.wt_dig) + static_cast<size_t>(Z.wt_off[A]) * B_STAGE;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % kWtStages;
+        if (c >= kWtStages) {
+          const uint32_t ph = static_cast<uint32_t>(c / kWtStages - 1) & 1u;
+          while (!mbar_test(&bar_free[s], ph)) __nanosleep(32);
+        }
+        mbar_expect_tx(&bar_fullB[s], static_cast<uint32_t>(B_STAGE));
+        bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(c) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== workers: slicing of Px, then the epilogue ===============================
+    const int r = tid >> 1, h = tid & 1;                     // point of the tile, half of the 32-wide K chunk
+    const int pt = min(pt_base + r, w.count - 1);
+    const double* const prow = Z.pxzam + static_cast<size_t>(pt) * Z.n_a * Z.n_m_pad + 16 * h;
+    const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
+
+    // ---- pass 1: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) ----
+    int emax = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int pr = c / cpp, mc = c - pr * cpp;
+      const uint2* src = reinterpret_cast<const uint2*>(prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC);
+      const int cexp = cs[2 * c];
+      int hmax = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) hmax = max(hmax, static_cast<int>(src[k].y & 0x7fffffffu));
+      const int e = hmax >> 20;
+      if (e > 0) emax = max(emax, e + cexp);
+    }
+    emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+    emax = min(max(emax, 64), 2000);
+    if (h == 0) sE[r] = emax;
+
+    // ---- pass 2: convert, slice, store; one 16-byte core-matrix row per slice and chunk ----
+    unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % kWtStages;
+      const int pr = c / cpp, mc = c - pr * cpp;
+      const double2* src = reinterpret_cast<const double2*>(prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC);
+      // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
+      const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
+      const double mult = __hiloint2double((1023 + sh) << 20, 0);
+      double2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = src[k];
+      uint32_t wd[kWtNA][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t L[4], H[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double x = (k & 1) ? v[2 * q + (k >> 1)].y : v[2 * q + (k >> 1)].x;
+          const double y = fma(x, mult, 6755399441055744.0);      // 1.5 * 2^52: low 40 bits = rni(x mult), two's complement
+          L[k] = static_cast<uint32_t>(__double2loint(y));
+          H[k] = static_cast<uint32_t>(__double2hiint(y));
+        }
+        const uint32_t xa = prmt(L[0], L[1], 0x6273), ya = prmt(L[0], L[1], 0x4051);
+        const uint32_t xb = prmt(L[2], L[3], 0x6273), yb = prmt(L[2], L[3], 0x4051);
+        wd[0][q] = prmt(prmt(H[0], H[1], 0x4040), prmt(H[2], H[3], 0x4040), 0x5410);   // bits 32..39, signed
+        wd[1][q] = prmt(xa, xb, 0x5410);                                               // byte 3
+        wd[2][q] = prmt(xa, xb, 0x7632);
+        wd[3][q] = prmt(ya, yb, 0x5410);
+        wd[4][q] = prmt(ya, yb, 0x7632);                                               // byte 0
+      }
+      if (c >= kWtStages) mbar_wait(&bar_free[s], static_cast<uint32_t>(c / kWtStages - 1) & 1u);
+#pragma unroll
+      for (int i = 0; i < kWtNA; ++i)
+        *reinterpret_cast<uint4*>(arow + s * kWtAStage + i * kWtASlice) = make_uint4(wd[i][0], wd[i][1], wd[i][2], wd[i][3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&bar_fullA[s]);
+    }
+
+    // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int er = 32 * (warp & 3) + lane, hh = warp >> 2;
+    const int ept = pt_base + er;
+    const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
+    const double* const yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
+    const double* const rs = Z.wt_rs + static_cast<size_t>(A) * NB;
+    // Y = rs[M] 2^(e - 1069) sum_s D_s 256^(4-s)
+    const double rowfac = __hiloint2double((sE[er] - 1069 + 1023) << 20, 0);
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+    const int c_end = min((hh + 1) * (NB / 2), Z.n_M_pad);
+    double chi = 0.0;
+    for (int col = hh * (NB / 2); col < c_end; col += 4) {
+      int32_t v[kWtNW][4];
+#pragma unroll
+      for (int sg = 0; sg < kWtNW; ++sg) tmem_ld4(taddr + NB * sg + col, v[sg]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double hi = fma(fma(i2d(v[0][j]), 256.0, i2d(v[1][j])), 256.0, i2d(v[2][j]));
+        const double lo = fma(i2d(v[3][j]), 256.0, i2d(v[4][j]));
+        const double y = fma(hi, 65536.0, lo) * (rowfac * rs[col + j]);
+        const double res = yd[col + j] - y;
+        chi = fma(res, res, chi);
+      }
+    }
+    sChi[hh * kWtPts + er] = chi;
+    tc_fence_before();
+    bar_workers();
+    if (warp < 4 && ept < w.count)
+      w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWtWorkers) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+}  // namespace cpx
