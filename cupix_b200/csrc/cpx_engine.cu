@@ -413,6 +413,12 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
       if ((rc = upload(off, &doff, &bytes))) return rc;
       if ((rc = upload(cs, &dcs, &bytes))) return rc;
       if ((rc = upload(rs, &drs, &bytes))) return rc;
+      std::vector<int> apair(na, -1);
+      for (int p = 0; p < Z.n_pairs; ++p) apair[pair_a[p]] = p;
+      int* dap;
+      if ((rc = upload(apair, &dap, &bytes))) return rc;
+      Z.a_pair = dap;
+      keep(dap);
       Z.wt_nb = NB;
       Z.wt_dig = ddig;
       Z.wt_off = doff;
@@ -667,6 +673,9 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       if (cudaFuncSetAttribute(cpx::k_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::wt_smem_bytes(nb)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_window_tc"));
       h->wt_nb = nb;
+      for (auto& zh : h->z)
+        if (zh.dev.n_A > 0)
+          if ((rc = dmalloc(reinterpret_cast<void**>(&zh.dev.rowexp), sizeof(int) * static_cast<size_t>(h->chunk) * zh.dev.n_a))) return bail(rc);
     }
   }
   *out = h;
@@ -867,6 +876,11 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     }
     // ---- stage 1: P3D + Hankel ----
     if ((rc = mark())) return rc;
+    // k_window_tc takes the fixed-point scale of every Px row from exponents that k_p3d_hankel collects
+    const bool wtc = h->wt_nb > 0 && !precise && !tc && want_chi2;
+    if (wtc)
+      for (int i = 0; i < n_zl; ++i)
+        if (tab[i].rowexp) CPX_CUDA(cudaMemsetAsync(tab[i].rowexp, 0, sizeof(int) * static_cast<size_t>(count) * tab[i].n_a, st));
     {
       bool additive = false;
       for (int i = 0; i < n_zl; ++i) additive |= (tab[i].flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)) != 0;
@@ -911,7 +925,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       dim3 grid((count + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
-        if (h->wt_nb > 0) {
+        if (wtc) {
           dim3 tgrid((count + kWtPts - 1) / kWtPts, std::max(nA_grid, 1), gz);
           k_window_tc<<<tgrid, kWtThreads, wt_smem_bytes(h->wt_nb), st>>>(h->d_ztab, i, w);
         } else {

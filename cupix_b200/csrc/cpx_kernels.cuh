@@ -96,6 +96,9 @@ struct ZDev {
   const int* wt_off;                    // [n_A] first chunk of coarse bin A
   const int* wt_cs;                     // [n_pairs][n_m_pad / 16] exponent c of the column scale
   const double* wt_rs;                  // [n_A][wt_nb] row scales
+  const int* a_pair;                    // [n_a] pair index (= position in pair_a) of fine bin a, -1 if it is in no coarse bin
+  int* rowexp;                          // [chunk][n_a] max over m of (biased exponent of |Px_Zam| + column-scale exponent), written by
+                                        // k_p3d_hankel with atomicMax when not null (k_window_tc takes its fixed-point scale from it)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -550,6 +553,11 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       const double amp0 = pr.bias * pr.bias * Z.dAA;
       double* outp = Z.pxzam + (static_cast<size_t>(pt) * n_a + a_lane0) * n_m_pad + m_base + g;
       const RowPar* rp = Z.rowpar + static_cast<size_t>(pt) * n_m_pad + m_base + g;
+      int hmax[NT][2][2];      // per theta column of this lane and 16-row block: largest high word of |Px|
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) hmax[j][cc][0] = hmax[j][cc][1] = 0;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int m = m_base + 8 * mt + g;
@@ -582,6 +590,30 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
               px = fma(add, cont, px);
             }
             outp[static_cast<size_t>(8 * j + cc) * n_m_pad + 8 * mt] = px;
+            hmax[j][cc][mt >> 1] = max(hmax[j][cc][mt >> 1], __double2hiint(px) & 0x7fffffff);
+          }
+      }
+      if (Z.rowexp != nullptr) {
+        // scale of the fixed-point conversion in k_window_tc: max over this tile's rows of the exponent of
+        // |Px| 2^c, c = column-scale exponent of the 16-row block; reduce over the 8 row lanes, one atomic per column
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int a = a_lane0 + 8 * j + cc;
+            int e = 0;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              int v = hmax[j][cc][b];
+              v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+              v = max(v, __shfl_xor_sync(0xffffffffu, v, 8));
+              v = max(v, __shfl_xor_sync(0xffffffffu, v, 16));
+              if (a < n_a && (v >> 20) > 0) {
+                const int pr_idx = Z.a_pair[a];
+                if (pr_idx >= 0) e = max(e, (v >> 20) + Z.wt_cs[static_cast<size_t>(pr_idx) * (n_m_pad >> 4) + 2 * tile + b]);
+              }
+            }
+            if (g == 0 && e > 0) atomicMax(&Z.rowexp[static_cast<size_t>(pt) * n_a + a], e);
           }
       }
     }

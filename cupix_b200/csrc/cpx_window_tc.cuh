@@ -12,16 +12,18 @@
 //     every Px element enters the fixed-point conversion with the size of its largest contribution to any
 //     output -- Px falls by many decades along k_par while T rises with 1/sigma;
 //   * the Px row of a (point, theta_A) -- all pairs, all m -- becomes 40-bit two's-complement fixed point
-//     relative to its exact maximum (pass 1 finds the maximum exponent, pass 2 converts with one DMUL and
-//     one magic-number DADD per element); its five bytes are the operand slices (top byte s8, others u8);
+//     relative to its exact maximum exponent (collected by k_p3d_hankel with one atomicMax per tile and
+//     theta column while it stores Px_Zam), converted with one magic-number DFMA per element; its five
+//     bytes are the operand slices (top byte s8, others u8);
 //   * slice pairs with i + j = s share TMEM columns NB*s .. NB*s + NB, pairs with i + j > 4 (< 2^-40) are
 //     dropped; the epilogue combines the five INT32 per output by Horner in float64.
 //
 // CTA = 8 worker warps + one MMA-issuing thread + one TMA thread, one CTA per SM (5 x 64 accumulator
 // columns round up to the whole tensor memory), one tile = 128 points x one theta_A x one z per CTA.
-// Worker thread (point r, half h) loads 16 consecutive doubles per K = 32 chunk, converts them and writes
-// one 16-byte core-matrix row into each of the five u8/s8 operand tiles (4-stage ring, mbarriers); the
-// digit tiles of T stream in with TMA bulk copies.  HBM traffic is one read of Px_Zam (pass 2 hits L2).
+// Worker thread (point r, half h) streams 16 consecutive doubles per K = 32 chunk through a 4-deep cp.async
+// ring, converts them and writes one 16-byte core-matrix row into each of the five u8/s8 operand tiles
+// (3 stages, mbarriers); the digit tiles of T stream in with TMA bulk copies.  HBM traffic is one read of
+// Px_Zam: the kernel is bound by that read.
 #pragma once
 #include "cpx_hankel_tc.cuh"
 
@@ -30,15 +32,17 @@ namespace cpx {
 constexpr int kWtPts = 128;          // points per tile = UMMA M
 constexpr int kWtNA = 5;             // Px bytes
 constexpr int kWtNW = 5;             // T digits
-constexpr int kWtStages = 4;
+constexpr int kWtStages = 3;            // operand stages (u8 slices of Px + digit tile of T)
+constexpr int kWtRing = 4;              // float64 chunks of Px in flight per thread (cp.async)
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
 constexpr int kWtWorkers = 8;        // worker warps
 constexpr int kWtThreads = 32 * (kWtWorkers + 2);
 constexpr int kWtASlice = kWtPts * kWtKC;               // 4 KB
 constexpr int kWtAStage = kWtNA * kWtASlice;            // 20 KB
+constexpr int kWtRingBytes = kWtWorkers * 32 * 16 * 8;  // 32 KB: 128 bytes per worker thread, laid out [8][256 threads][16 B]
 __host__ __device__ constexpr int wt_b_stage(int nb) { return kWtNW * nb * kWtKC; }
 __host__ __device__ constexpr int wt_smem_bytes(int nb) {
-  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtPts * 4 + 2 * kWtPts * 8;
+  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + kWtPts * 4 + 2 * kWtPts * 8;
 }
 
 __device__ __forceinline__ uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
@@ -62,7 +66,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const sA = smem_raw;
   unsigned char* const sB = sA + kWtStages * kWtAStage;
-  int* const sE = reinterpret_cast<int*>(sB + kWtStages * B_STAGE);       // [128] biased exponent of the row maximum
+  unsigned char* const sR = sB + kWtStages * B_STAGE;                      // float64 ring
+  int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [128] biased exponent of the row maximum
   double* const sChi = reinterpret_cast<double*>(sE + kWtPts);            // [2][128] partial chi2 of the two column halves
   __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -142,41 +147,44 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     const double* const prow = Z.pxzam + static_cast<size_t>(pt) * Z.n_a * Z.n_m_pad + 16 * h;
     const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
 
-    // ---- pass 1: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) ----
+    // ---- fixed-point scale of the row: largest biased exponent of Px * 2^c over all pairs of A and all m,
+    //      collected by k_p3d_hankel while it stored Px_Zam (atomicMax per tile) ----
     int emax = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-      const int pr = c / cpp, mc = c - pr * cpp;
-      const uint2* src = reinterpret_cast<const uint2*>(prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC);
-      const int cexp = cs[2 * c];
-      int hmax = 0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) hmax = max(hmax, static_cast<int>(src[k].y & 0x7fffffffu));
-      const int e = hmax >> 20;
-      if (e > 0) emax = max(emax, e + cexp);
-    }
-    emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+    for (int p = p0; p < p1; ++p) emax = max(emax, Z.rowexp[static_cast<size_t>(pt) * Z.n_a + Z.pair_a[p]]);
     emax = min(max(emax, 64), 2000);
     if (h == 0) sE[r] = emax;
 
-    // ---- pass 2: convert, slice, store; one 16-byte core-matrix row per slice and chunk ----
+    // ---- stream the row: 16 doubles per thread and chunk through a 3-deep cp.async ring (own slots only, so
+    //      no cross-thread synchronisation), convert, slice, store one 16-byte core-matrix row per slice ----
+    auto fetch = [&](int c) {
+      const int pr = c / cpp, mc = c - pr * cpp;
+      const double* src = prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC;
+      unsigned char* dst = sR + (c % kWtRing) * kWtRingBytes + tid * 16;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cp_async16(dst + k * (kWtWorkers * 32 * 16), src + 2 * k);
+    };
+    for (int c = 0; c < kWtRing - 1; ++c) {
+      if (c < n_chunks) fetch(c);
+      cp_async_commit();
+    }
     unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
     for (int c = 0; c < n_chunks; ++c) {
       const int s = c % kWtStages;
-      const int pr = c / cpp, mc = c - pr * cpp;
-      const double2* src = reinterpret_cast<const double2*>(prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC);
+      if (c + kWtRing - 1 < n_chunks) fetch(c + kWtRing - 1);
+      cp_async_commit();
+      cp_async_wait<kWtRing - 1>();
       // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
       const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
       const double mult = __hiloint2double((1023 + sh) << 20, 0);
-      double2 v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = src[k];
+      const double2* vsrc = reinterpret_cast<const double2*>(sR + (c % kWtRing) * kWtRingBytes + tid * 16);
       uint32_t wd[kWtNA][4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        const double2 va = vsrc[(2 * q) * (kWtWorkers * 32)], vb = vsrc[(2 * q + 1) * (kWtWorkers * 32)];
         uint32_t L[4], H[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const double x = (k & 1) ? v[2 * q + (k >> 1)].y : v[2 * q + (k >> 1)].x;
+          const double x = k == 0 ? va.x : (k == 1 ? va.y : (k == 2 ? vb.x : vb.y));
           const double y = fma(x, mult, 6755399441055744.0);      // 1.5 * 2^52: low 40 bits = rni(x mult), two's complement
           L[k] = static_cast<uint32_t>(__double2loint(y));
           H[k] = static_cast<uint32_t>(__double2hiint(y));
