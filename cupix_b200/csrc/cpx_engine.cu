@@ -926,7 +926,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
         if (wtc) {
-          dim3 tgrid((count + kWtPts - 1) / kWtPts, std::max(nA_grid, 1), gz);
+          dim3 tgrid((count + kWtPts - 1) / kWtPts, std::min(std::max(nA_grid, 1), env_int("CPX_WTC_AGROUPS", 4)), gz);
           k_window_tc<<<tgrid, kWtThreads, wt_smem_bytes(h->wt_nb), st>>>(h->d_ztab, i, w);
         } else {
           k2_select<true>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) ZDev s_Z;
+  __shared__ int s_cs[2][8 * NT];    // column-scale exponents of k_window_tc for this tile's two 16-row blocks and this theta block
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -436,11 +437,20 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
             bulk_g2s(smem_raw + cell_bytes + off, src + off, min(32768u, w_bytes - off), &bar);
         }
       }
+      if (Z.rowexp != nullptr) {
+        if (threadIdx.x < 2 * 8 * NT) {
+          const int b = threadIdx.x / (8 * NT), al = threadIdx.x % (8 * NT), a = ablk * (8 * NT) + al;
+          int v = -100000;                                 // columns outside the measurement never raise an exponent
+          if (a < Z.n_a && Z.a_pair[a] >= 0) v = Z.wt_cs[static_cast<size_t>(Z.a_pair[a]) * (Z.n_m_pad >> 4) + 2 * tile + b];
+          s_cs[b][al] = v;
+        }
+      }
       mbar_wait(&bar, phase);
       phase ^= 1u;
       cur_z = zi;
       cur_tile = tile;
       cur_ablk = ablk;
+      __syncthreads();
     }
 
     const int pt0 = (pg * kK1Warps + warp) * PP;       // first point of this warp
@@ -601,18 +611,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int a = a_lane0 + 8 * j + cc;
-            int e = 0;
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              int v = hmax[j][cc][b];
-              v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
-              v = max(v, __shfl_xor_sync(0xffffffffu, v, 8));
-              v = max(v, __shfl_xor_sync(0xffffffffu, v, 16));
-              if (a < n_a && (v >> 20) > 0) {
-                const int pr_idx = Z.a_pair[a];
-                if (pr_idx >= 0) e = max(e, (v >> 20) + Z.wt_cs[static_cast<size_t>(pr_idx) * (n_m_pad >> 4) + 2 * tile + b]);
-              }
-            }
+            // exponent + column-scale exponent per block (zero stays zero), then one reduction over the 8 row lanes
+            const int e0 = hmax[j][cc][0] >> 20, e1 = hmax[j][cc][1] >> 20;
+            int e = max(e0 > 0 ? e0 + s_cs[0][8 * j + 2 * t + cc] : 0, e1 > 0 ? e1 + s_cs[1][8 * j + 2 * t + cc] : 0);
+            e = __reduce_max_sync(0x11111111u << t, max(e, 0));      // the 8 row lanes that share this lane's theta columns
             if (g == 0 && e > 0) atomicMax(&Z.rowexp[static_cast<size_t>(pt) * n_a + a], e);
           }
       }

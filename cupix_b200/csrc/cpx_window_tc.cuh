@@ -19,7 +19,9 @@
 //     dropped; the epilogue combines the five INT32 per output by Horner in float64.
 //
 // CTA = 8 worker warps + one MMA-issuing thread + one TMA thread, one CTA per SM (5 x 64 accumulator
-// columns round up to the whole tensor memory), one tile = 128 points x one theta_A x one z per CTA.
+// columns round up to the whole tensor memory).  A tile is 128 points x one theta_A x one z; a CTA walks
+// the theta_A bins blockIdx.y, blockIdx.y + gridDim.y, ... of its 128 points so that the Px stream of the
+// next tile is already in flight while the accumulators of the current one are read out.
 // Worker thread (point r, half h) streams 16 consecutive doubles per K = 32 chunk through a 4-deep cp.async
 // ring, converts them and writes one 16-byte core-matrix row into each of the five u8/s8 operand tiles
 // (3 stages, mbarriers); the digit tiles of T stream in with TMA bulk copies.  HBM traffic is one read of
@@ -56,8 +58,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     w.zslot = blockIdx.z;
   }
   const ZDev& Z = ztab[zi];
-  const int A = blockIdx.y;
-  if (A >= Z.n_A) return;
+  const int n_A = Z.n_A;
+  if (static_cast<int>(blockIdx.y) >= n_A) return;
   const int NB = Z.wt_nb;
   const int B_STAGE = wt_b_stage(NB);
   const uint32_t A_CHUNK = (kWtPts / 8) * 128;              // bytes between the two 16-byte K chunks of a Px tile
@@ -69,14 +71,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
   unsigned char* const sR = sB + kWtStages * B_STAGE;                      // float64 ring
   int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [128] biased exponent of the row maximum
   double* const sChi = reinterpret_cast<double*>(sE + kWtPts);            // [2][128] partial chi2 of the two column halves
-  __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done;
+  __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done, bar_epi;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pt_base = blockIdx.x * kWtPts;
-  const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
   const int cpp = Z.n_m_pad / kWtKC;                        // chunks per pair
-  const int n_chunks = (p1 - p0) * cpp;
+  const int a_step = gridDim.y;                             // this CTA takes theta_A = blockIdx.y, + a_step, ...
 
   if (tid == 0) {
     for (int s = 0; s < kWtStages; ++s) {
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       mbar_init(&bar_free[s], 1);
     }
     mbar_init(&bar_done, 1);
+    mbar_init(&bar_epi, kWtWorkers);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWtWorkers) {
@@ -100,43 +102,56 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     // =============================== MMA issue (one thread) ===============================
     if (lane == 0) {
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % kWtStages;
-        const uint32_t ph = static_cast<uint32_t>(c / kWtStages) & 1u;
-        while (!mbar_test(&bar_fullB[s], ph)) __nanosleep(32);
-        while (!mbar_test(&bar_fullA[s], ph)) __nanosleep(32);
-        tc_fence_after();
-        const uint64_t bd = umma_smem_desc(b_base + s * B_STAGE, B_CHUNK, 128);
-#pragma unroll
-        for (int i = 0; i < kWtNA; ++i) {
-          const uint64_t ad = umma_smem_desc(a_base + s * kWtAStage + i * kWtASlice, A_CHUNK, 128);
-          const int n = NB * (kWtNW - i);                    // digits 0 .. 4 - i
-          const uint32_t acc = (c > 0 || i > 0) ? 1u : 0u;
-          if (n <= 256) {
-            umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, n, i == 0), acc);
-          } else {                                           // N = 320: digits 0-3, then digit 4
-            umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, 4 * NB, i == 0), acc);
-            const uint64_t bd4 = umma_smem_desc(b_base + s * B_STAGE + (4 * NB / 8) * 128, B_CHUNK, 128);
-            umma_i8(tmem + NB * (i + 4), ad, bd4, umma_idesc_i8(kWtPts, NB, i == 0), acc);
-          }
+      int gc = 0, tile = 0;
+      for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
+        const int n_chunks = (Z.pair_start[A + 1] - Z.pair_start[A]) * cpp;
+        // the single accumulator is free once the workers have read the previous tile out of tensor memory
+        if (tile > 0) {
+          while (!mbar_test(&bar_epi, static_cast<uint32_t>(tile - 1) & 1u)) __nanosleep(32);
+          tc_fence_after();
         }
-        umma_commit(&bar_free[s]);
+        for (int c = 0; c < n_chunks; ++c, ++gc) {
+          const int s = gc % kWtStages;
+          const uint32_t ph = static_cast<uint32_t>(gc / kWtStages) & 1u;
+          while (!mbar_test(&bar_fullB[s], ph)) __nanosleep(32);
+          while (!mbar_test(&bar_fullA[s], ph)) __nanosleep(32);
+          tc_fence_after();
+          const uint64_t bd = umma_smem_desc(b_base + s * B_STAGE, B_CHUNK, 128);
+#pragma unroll
+          for (int i = 0; i < kWtNA; ++i) {
+            const uint64_t ad = umma_smem_desc(a_base + s * kWtAStage + i * kWtASlice, A_CHUNK, 128);
+            const int n = NB * (kWtNW - i);                    // digits 0 .. 4 - i
+            const uint32_t acc = (c > 0 || i > 0) ? 1u : 0u;
+            if (n <= 256) {
+              umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, n, i == 0), acc);
+            } else {                                           // N = 320: digits 0-3, then digit 4
+              umma_i8(tmem + NB * i, ad, bd, umma_idesc_i8(kWtPts, 4 * NB, i == 0), acc);
+              const uint64_t bd4 = umma_smem_desc(b_base + s * B_STAGE + (4 * NB / 8) * 128, B_CHUNK, 128);
+              umma_i8(tmem + NB * (i + 4), ad, bd4, umma_idesc_i8(kWtPts, NB, i == 0), acc);
+            }
+          }
+          umma_commit(&bar_free[s]);
+        }
+        umma_commit(&bar_done);
       }
-      umma_commit(&bar_done);
     }
     __syncwarp();
   } else if (warp == kWtWorkers + 1) {
     // =============================== TMA: digit tiles of T ===============================
     if (lane == 0) {
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.wt_dig) + static_cast<size_t>(Z.wt_off[A]) * B_STAGE;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % kWtStages;
-        if (c >= kWtStages) {
-          const uint32_t ph = static_cast<uint32_t>(c / kWtStages - 1) & 1u;
-          while (!mbar_test(&bar_free[s], ph)) __nanosleep(32);
+      int gc = 0;
+      for (int A = blockIdx.y; A < n_A; A += a_step) {
+        const int n_chunks = (Z.pair_start[A + 1] - Z.pair_start[A]) * cpp;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.wt_dig) + static_cast<size_t>(Z.wt_off[A]) * B_STAGE;
+        for (int c = 0; c < n_chunks; ++c, ++gc) {
+          const int s = gc % kWtStages;
+          if (gc >= kWtStages) {
+            const uint32_t ph = static_cast<uint32_t>(gc / kWtStages - 1) & 1u;
+            while (!mbar_test(&bar_free[s], ph)) __nanosleep(32);
+          }
+          mbar_expect_tx(&bar_fullB[s], static_cast<uint32_t>(B_STAGE));
+          bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(c) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
         }
-        mbar_expect_tx(&bar_fullB[s], static_cast<uint32_t>(B_STAGE));
-        bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(c) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
       }
     }
     __syncwarp();
@@ -145,99 +160,131 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     const int r = tid >> 1, h = tid & 1;                     // point of the tile, half of the 32-wide K chunk
     const int pt = min(pt_base + r, w.count - 1);
     const double* const prow = Z.pxzam + static_cast<size_t>(pt) * Z.n_a * Z.n_m_pad + 16 * h;
-    const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
-
-    // ---- fixed-point scale of the row: largest biased exponent of Px * 2^c over all pairs of A and all m,
-    //      collected by k_p3d_hankel while it stored Px_Zam (atomicMax per tile) ----
-    int emax = 0;
-    for (int p = p0; p < p1; ++p) emax = max(emax, Z.rowexp[static_cast<size_t>(pt) * Z.n_a + Z.pair_a[p]]);
-    emax = min(max(emax, 64), 2000);
-    if (h == 0) sE[r] = emax;
-
-    // ---- stream the row: 16 doubles per thread and chunk through a 3-deep cp.async ring (own slots only, so
-    //      no cross-thread synchronisation), convert, slice, store one 16-byte core-matrix row per slice ----
-    auto fetch = [&](int c) {
-      const int pr = c / cpp, mc = c - pr * cpp;
-      const double* src = prow + static_cast<size_t>(Z.pair_a[p0 + pr]) * Z.n_m_pad + mc * kWtKC;
-      unsigned char* dst = sR + (c % kWtRing) * kWtRingBytes + tid * 16;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) cp_async16(dst + k * (kWtWorkers * 32 * 16), src + 2 * k);
-    };
-    for (int c = 0; c < kWtRing - 1; ++c) {
-      if (c < n_chunks) fetch(c);
-      cp_async_commit();
-    }
+    const int* const rexp = Z.rowexp + static_cast<size_t>(pt) * Z.n_a;
     unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c % kWtStages;
-      if (c + kWtRing - 1 < n_chunks) fetch(c + kWtRing - 1);
-      cp_async_commit();
-      cp_async_wait<kWtRing - 1>();
-      // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
-      const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
-      const double mult = __hiloint2double((1023 + sh) << 20, 0);
-      const double2* vsrc = reinterpret_cast<const double2*>(sR + (c % kWtRing) * kWtRingBytes + tid * 16);
-      uint32_t wd[kWtNA][4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double2 va = vsrc[(2 * q) * (kWtWorkers * 32)], vb = vsrc[(2 * q + 1) * (kWtWorkers * 32)];
-        uint32_t L[4], H[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double x = k == 0 ? va.x : (k == 1 ? va.y : (k == 2 ? vb.x : vb.y));
-          const double y = fma(x, mult, 6755399441055744.0);      // 1.5 * 2^52: low 40 bits = rni(x mult), two's complement
-          L[k] = static_cast<uint32_t>(__double2loint(y));
-          H[k] = static_cast<uint32_t>(__double2hiint(y));
-        }
-        const uint32_t xa = prmt(L[0], L[1], 0x6273), ya = prmt(L[0], L[1], 0x4051);
-        const uint32_t xb = prmt(L[2], L[3], 0x6273), yb = prmt(L[2], L[3], 0x4051);
-        wd[0][q] = prmt(prmt(H[0], H[1], 0x4040), prmt(H[2], H[3], 0x4040), 0x5410);   // bits 32..39, signed
-        wd[1][q] = prmt(xa, xb, 0x5410);                                               // byte 3
-        wd[2][q] = prmt(xa, xb, 0x7632);
-        wd[3][q] = prmt(ya, yb, 0x5410);
-        wd[4][q] = prmt(ya, yb, 0x7632);                                               // byte 0
-      }
-      if (c >= kWtStages) mbar_wait(&bar_free[s], static_cast<uint32_t>(c / kWtStages - 1) & 1u);
-#pragma unroll
-      for (int i = 0; i < kWtNA; ++i)
-        *reinterpret_cast<uint4*>(arow + s * kWtAStage + i * kWtASlice) = make_uint4(wd[i][0], wd[i][1], wd[i][2], wd[i][3]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive1(&bar_fullA[s]);
-    }
-
-    // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-    const int er = 32 * (warp & 3) + lane, hh = warp >> 2;
+    const int er = 32 * (warp & 3) + lane, hh = warp >> 2;   // epilogue: TMEM lane = point, column half
     const int ept = pt_base + er;
     const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
-    const double* const yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
-    const double* const rs = Z.wt_rs + static_cast<size_t>(A) * NB;
-    // Y = rs[M] 2^(e - 1069) sum_s D_s 256^(4-s)
-    const double rowfac = __hiloint2double((sE[er] - 1069 + 1023) << 20, 0);
     const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
-    const int c_end = min((hh + 1) * (NB / 2), Z.n_M_pad);
-    double chi = 0.0;
-    for (int col = hh * (NB / 2); col < c_end; col += 4) {
-      int32_t v[kWtNW][4];
+
+    // fixed-point scale of a row: largest biased exponent of Px * 2^c over all pairs of A and all m, collected by
+    // k_p3d_hankel while it stored Px_Zam (atomicMax per tile)
+    auto row_exponent = [&](int A) {
+      int e = 0;
+      if (A < n_A)
+        for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) e = max(e, rexp[Z.pair_a[p]]);
+      return min(max(e, 64), 2000);
+    };
+    // the stream of chunks of this CTA, (A, c) with c running over (pair, m / 32); fA / fc run kWtRing - 1 chunks ahead
+    int fA = blockIdx.y, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0;
+    // Loads are coalesced: 16 consecutive lanes copy the 256 bytes one point contributes to a chunk, a warp covers 2
+    // points per instruction and 16 points in 8.  Ring layout [point][16 units of 16 B] with the unit index XOR-swizzled
+    // by (2 (point & 3) + unit / 8), so that the converting thread (point r, half h) reads its 8 units without bank conflicts.
+    const int lp = lane >> 4, lu = lane & 15;                // loader: point within the pair, 16-byte unit
+    auto fetch_next = [&]() {
+      if (fA < n_A) {
+        const int pr = fc / cpp, mc = fc - pr * cpp;
+        const size_t col = static_cast<size_t>(Z.pair_a[Z.pair_start[fA] + pr]) * Z.n_m_pad + mc * kWtKC + 2 * lu;
+        unsigned char* dst = sR + fslot * kWtRingBytes;
 #pragma unroll
-      for (int sg = 0; sg < kWtNW; ++sg) tmem_ld4(taddr + NB * sg + col, v[sg]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double hi = fma(fma(i2d(v[0][j]), 256.0, i2d(v[1][j])), 256.0, i2d(v[2][j]));
-        const double lo = fma(i2d(v[3][j]), 256.0, i2d(v[4][j]));
-        const double y = fma(hi, 65536.0, lo) * (rowfac * rs[col + j]);
-        const double res = yd[col + j] - y;
-        chi = fma(res, res, chi);
+        for (int k = 0; k < 8; ++k) {
+          const int rr = 16 * warp + 2 * k + lp;              // point of the tile
+          const double* src = Z.pxzam + static_cast<size_t>(min(pt_base + rr, w.count - 1)) * Z.n_a * Z.n_m_pad + col;
+          cp_async16(dst + rr * 256 + ((lu ^ ((2 * (rr & 3) + (lu >> 3)) & 7)) << 4), src);
+        }
+        if (++fc == fn) {
+          fA += a_step;
+          fc = 0;
+          fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
+        }
       }
+      fslot = (fslot + 1) % kWtRing;
+      cp_async_commit();
+    };
+    for (int i = 0; i < kWtRing - 1; ++i) fetch_next();
+
+    int gc = 0, tile = 0;
+    int emax = row_exponent(blockIdx.y);
+    for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
+      const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
+      const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
+      if (h == 0) sE[r] = emax;
+      for (int c = 0; c < n_chunks; ++c, ++gc) {
+        const int s = gc % kWtStages;
+        fetch_next();
+        cp_async_wait<kWtRing - 1>();
+        __syncwarp();                                           // a warp copies exactly the 16 points it converts
+        // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
+        const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
+        const double mult = __hiloint2double((1023 + sh) << 20, 0);
+        const unsigned char* vsrc = sR + (gc % kWtRing) * kWtRingBytes + r * 256;
+        const int swz = (2 * (r & 3) + h) & 7;
+        uint32_t wd[kWtNA][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 va = *reinterpret_cast<const double2*>(vsrc + (((8 * h + 2 * q) ^ swz) << 4));
+          const double2 vb = *reinterpret_cast<const double2*>(vsrc + (((8 * h + 2 * q + 1) ^ swz) << 4));
+          uint32_t L[4], H[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double x = k == 0 ? va.x : (k == 1 ? va.y : (k == 2 ? vb.x : vb.y));
+            const double y = fma(x, mult, 6755399441055744.0);      // 1.5 * 2^52: low 40 bits = rni(x mult), two's complement
+            L[k] = static_cast<uint32_t>(__double2loint(y));
+            H[k] = static_cast<uint32_t>(__double2hiint(y));
+          }
+          const uint32_t xa = prmt(L[0], L[1], 0x6273), ya = prmt(L[0], L[1], 0x4051);
+          const uint32_t xb = prmt(L[2], L[3], 0x6273), yb = prmt(L[2], L[3], 0x4051);
+          wd[0][q] = prmt(prmt(H[0], H[1], 0x4040), prmt(H[2], H[3], 0x4040), 0x5410);   // bits 32..39, signed
+          wd[1][q] = prmt(xa, xb, 0x5410);                                               // byte 3
+          wd[2][q] = prmt(xa, xb, 0x7632);
+          wd[3][q] = prmt(ya, yb, 0x5410);
+          wd[4][q] = prmt(ya, yb, 0x7632);                                               // byte 0
+        }
+        if (gc >= kWtStages) mbar_wait(&bar_free[s], static_cast<uint32_t>(gc / kWtStages - 1) & 1u);
+#pragma unroll
+        for (int i = 0; i < kWtNA; ++i)
+          *reinterpret_cast<uint4*>(arow + s * kWtAStage + i * kWtASlice) = make_uint4(wd[i][0], wd[i][1], wd[i][2], wd[i][3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive1(&bar_fullA[s]);
+      }
+      const int emax_next = row_exponent(A + a_step);       // loads in flight while the last MMAs of this tile run
+
+      // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
+      bar_workers();                                           // sE of this tile is complete
+      mbar_wait(&bar_done, static_cast<uint32_t>(tile) & 1u);
+      tc_fence_after();
+      const double* const yd = Z.yd + (static_cast<size_t>(d) * n_A + A) * Z.n_M_pad;
+      const double* const rs = Z.wt_rs + static_cast<size_t>(A) * NB;
+      // Y = rs[M] 2^(e - 1069) sum_s D_s 256^(4-s)
+      const double rowfac = __hiloint2double((sE[er] - 1069 + 1023) << 20, 0);
+      const int c_end = min((hh + 1) * (NB / 2), Z.n_M_pad);
+      double chi = 0.0;
+      for (int col = hh * (NB / 2); col < c_end; col += 4) {
+        int32_t v[kWtNW][4];
+#pragma unroll
+        for (int sg = 0; sg < kWtNW; ++sg) tmem_ld4(taddr + NB * sg + col, v[sg]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double hi = fma(fma(i2d(v[0][j]), 256.0, i2d(v[1][j])), 256.0, i2d(v[2][j]));
+          const double lo = fma(i2d(v[3][j]), 256.0, i2d(v[4][j]));
+          const double y = fma(hi, 65536.0, lo) * (rowfac * rs[col + j]);
+          const double res = yd[col + j] - y;
+          chi = fma(res, res, chi);
+        }
+      }
+      sChi[hh * kWtPts + er] = chi;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&bar_epi);                   // tensor memory may be overwritten by the next tile
+      bar_workers();
+      if (warp < 4 && ept < w.count)
+        w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
+      bar_workers();                                           // sE / sChi are reused by the next tile
+      emax = emax_next;
     }
-    sChi[hh * kWtPts + er] = chi;
-    tc_fence_before();
-    bar_workers();
-    if (warp < 4 && ept < w.count)
-      w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
+    cp_async_wait<0>();
   }
 
   tc_fence_before();
