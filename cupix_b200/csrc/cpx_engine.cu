@@ -64,8 +64,6 @@ struct cpx_handle {
   int chunk = 0;                     // points per chunk
   size_t device_bytes = 0;
   long long launches = 0;
-  int* d_rowexp = nullptr;           // [z][chunk][n_a] row exponents handed from k_p3d_hankel to k_window_tc
-  size_t rowexp_ints = 0;
   int wt_nb = 0;                     // > 0: k_window_tc (tcgen05 window contraction) for the chi2 stage
   int tc_np = 0;                     // > 0: k_p3d_hankel_tc (tcgen05 Hankel contraction) with this many cell pairs per lane
   // per-chunk scratch
@@ -415,12 +413,6 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
       if ((rc = upload(off, &doff, &bytes))) return rc;
       if ((rc = upload(cs, &dcs, &bytes))) return rc;
       if ((rc = upload(rs, &drs, &bytes))) return rc;
-      std::vector<int> apair(na, -1);
-      for (int p = 0; p < Z.n_pairs; ++p) apair[pair_a[p]] = p;
-      int* dap;
-      if ((rc = upload(apair, &dap, &bytes))) return rc;
-      Z.a_pair = dap;
-      keep(dap);
       Z.wt_nb = NB;
       Z.wt_dig = ddig;
       Z.wt_off = doff;
@@ -675,18 +667,6 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       if (cudaFuncSetAttribute(cpx::k_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::wt_smem_bytes(nb)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_window_tc"));
       h->wt_nb = nb;
-      // one pool, so that a single memset per chunk clears the exponents of every z
-      size_t total = 0;
-      for (auto& zh : h->z)
-        if (zh.dev.n_A > 0) total += static_cast<size_t>(h->chunk) * zh.dev.n_a;
-      if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_rowexp), sizeof(int) * total))) return bail(rc);
-      h->rowexp_ints = total;
-      size_t off = 0;
-      for (auto& zh : h->z)
-        if (zh.dev.n_A > 0) {
-          zh.dev.rowexp = h->d_rowexp + off;
-          off += static_cast<size_t>(h->chunk) * zh.dev.n_a;
-        }
     }
   }
   *out = h;
@@ -821,8 +801,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   for (int i = 0; i < n_zl; ++i) nA_of_z[i] = h->z[zl[i]].dev.n_A;
   CPX_CUDA(cudaMemcpyAsync(h->d_nA_of_z, nA_of_z.data(), sizeof(int) * n_zl, cudaMemcpyHostToDevice, st));
 
-  // k_window_tc takes the fixed-point scale of every Px row from exponents that k_p3d_hankel (the DMMA kernel) collects
-  const bool wtc = h->wt_nb > 0 && !precise && h->tc_np == 0 && want_chi2;
+  const bool wtc = h->wt_nb > 0 && want_chi2;     // chi2 stage on the tensor cores (k_window_tc)
   int last_table_count = -1, last_pp = -1;
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
@@ -836,7 +815,6 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       long long items = 0;
       for (int i = 0; i < n_zl; ++i) {
         tab[i] = h->z[zl[i]].dev;
-        if (!wtc) tab[i].rowexp = nullptr;      // k_p3d_hankel collects row exponents only when k_window_tc will use them
         tab[i].item_start = items;
         items += items_of(tab[i]);
       }
@@ -890,7 +868,6 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     }
     // ---- stage 1: P3D + Hankel ----
     if ((rc = mark())) return rc;
-    if (wtc) CPX_CUDA(cudaMemsetAsync(h->d_rowexp, 0, sizeof(int) * h->rowexp_ints, st));
     {
       bool additive = false;
       for (int i = 0; i < n_zl; ++i) additive |= (tab[i].flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)) != 0;

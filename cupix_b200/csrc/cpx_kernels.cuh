@@ -96,9 +96,6 @@ struct ZDev {
   const int* wt_off;                    // [n_A] first chunk of coarse bin A
   const int* wt_cs;                     // [n_pairs][n_m_pad / 16] exponent c of the column scale
   const double* wt_rs;                  // [n_A][wt_nb] row scales
-  const int* a_pair;                    // [n_a] pair index (= position in pair_a) of fine bin a, -1 if it is in no coarse bin
-  int* rowexp;                          // [chunk][n_a] max over m of (biased exponent of |Px_Zam| + column-scale exponent), written by
-                                        // k_p3d_hankel with atomicMax when not null (k_window_tc takes its fixed-point scale from it)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -370,7 +367,6 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) ZDev s_Z;
-  __shared__ int s_cs[2][8 * NT];    // column-scale exponents of k_window_tc for this tile's two 16-row blocks and this theta block
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -437,20 +433,11 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
             bulk_g2s(smem_raw + cell_bytes + off, src + off, min(32768u, w_bytes - off), &bar);
         }
       }
-      if (Z.rowexp != nullptr) {
-        if (threadIdx.x < 2 * 8 * NT) {
-          const int b = threadIdx.x / (8 * NT), al = threadIdx.x % (8 * NT), a = ablk * (8 * NT) + al;
-          int v = -100000;                                 // columns outside the measurement never raise an exponent
-          if (a < Z.n_a && Z.a_pair[a] >= 0) v = Z.wt_cs[static_cast<size_t>(Z.a_pair[a]) * (Z.n_m_pad >> 4) + 2 * tile + b];
-          s_cs[b][al] = v;
-        }
-      }
       mbar_wait(&bar, phase);
       phase ^= 1u;
       cur_z = zi;
       cur_tile = tile;
       cur_ablk = ablk;
-      __syncthreads();
     }
 
     const int pt0 = (pg * kK1Warps + warp) * PP;       // first point of this warp
@@ -563,11 +550,6 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       const double amp0 = pr.bias * pr.bias * Z.dAA;
       double* outp = Z.pxzam + (static_cast<size_t>(pt) * n_a + a_lane0) * n_m_pad + m_base + g;
       const RowPar* rp = Z.rowpar + static_cast<size_t>(pt) * n_m_pad + m_base + g;
-      int hmax[NT][2][2];      // per theta column of this lane and 16-row block: largest high word of |Px|
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) hmax[j][cc][0] = hmax[j][cc][1] = 0;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int m = m_base + 8 * mt + g;
@@ -600,22 +582,6 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
               px = fma(add, cont, px);
             }
             outp[static_cast<size_t>(8 * j + cc) * n_m_pad + 8 * mt] = px;
-            hmax[j][cc][mt >> 1] = max(hmax[j][cc][mt >> 1], __double2hiint(px) & 0x7fffffff);
-          }
-      }
-      if (Z.rowexp != nullptr) {
-        // scale of the fixed-point conversion in k_window_tc: max over this tile's rows of the exponent of
-        // |Px| 2^c, c = column-scale exponent of the 16-row block; reduce over the 8 row lanes, one atomic per column
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int a = a_lane0 + 8 * j + cc;
-            // exponent + column-scale exponent per block (zero stays zero), then one reduction over the 8 row lanes
-            const int e0 = hmax[j][cc][0] >> 20, e1 = hmax[j][cc][1] >> 20;
-            int e = max(e0 > 0 ? e0 + s_cs[0][8 * j + 2 * t + cc] : 0, e1 > 0 ? e1 + s_cs[1][8 * j + 2 * t + cc] : 0);
-            e = __reduce_max_sync(0x11111111u << t, max(e, 0));      // the 8 row lanes that share this lane's theta columns
-            if (g == 0 && e > 0) atomicMax(&Z.rowexp[static_cast<size_t>(pt) * n_a + a], e);
           }
       }
     }

@@ -12,9 +12,9 @@
 //     every Px element enters the fixed-point conversion with the size of its largest contribution to any
 //     output -- Px falls by many decades along k_par while T rises with 1/sigma;
 //   * the Px row of a (point, theta_A) -- all pairs, all m -- becomes 40-bit two's-complement fixed point
-//     relative to its exact maximum exponent (collected by k_p3d_hankel with one atomicMax per tile and
-//     theta column while it stores Px_Zam), converted with one magic-number DFMA per element; its five
-//     bytes are the operand slices (top byte s8, others u8);
+//     relative to its exact maximum exponent (every tile is streamed twice: the first pass, from HBM,
+//     only takes the maximum; the second, from L2, converts with one magic-number DFMA per element);
+//     its five bytes are the operand slices (top byte s8, others u8);
 //   * slice pairs with i + j = s share TMEM columns NB*s .. NB*s + NB, pairs with i + j > 4 (< 2^-40) are
 //     dropped; the epilogue combines the five INT32 per output by Horner in float64.
 //
@@ -160,26 +160,20 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     const int r = tid >> 1, h = tid & 1;                     // point of the tile, half of the 32-wide K chunk
     const int pt = min(pt_base + r, w.count - 1);
     const double* const prow = Z.pxzam + static_cast<size_t>(pt) * Z.n_a * Z.n_m_pad + 16 * h;
-    const int* const rexp = Z.rowexp + static_cast<size_t>(pt) * Z.n_a;
     unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
     const int er = 32 * (warp & 3) + lane, hh = warp >> 2;   // epilogue: TMEM lane = point, column half
     const int ept = pt_base + er;
     const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+    const int swz = (2 * (r & 3) + h) & 7;
 
-    // fixed-point scale of a row: largest biased exponent of Px * 2^c over all pairs of A and all m, collected by
-    // k_p3d_hankel while it stored Px_Zam (atomicMax per tile)
-    auto row_exponent = [&](int A) {
-      int e = 0;
-      if (A < n_A)
-        for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) e = max(e, rexp[Z.pair_a[p]]);
-      return min(max(e, 64), 2000);
-    };
-    // the stream of chunks of this CTA, (A, c) with c running over (pair, m / 32); fA / fc run kWtRing - 1 chunks ahead
-    int fA = blockIdx.y, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0;
+    // The stream of chunks of this CTA: every tile (theta_A) is streamed twice, (A, pass 0, c) then (A, pass 1, c) with
+    // c running over (pair, m / 32).  Pass 0 (from HBM) only finds the largest exponent of the row, pass 1 (the same
+    // bytes again, from L2) converts.  fA / fpass / fc run kWtRing - 1 chunks ahead of the consumer.
     // Loads are coalesced: 16 consecutive lanes copy the 256 bytes one point contributes to a chunk, a warp covers 2
     // points per instruction and 16 points in 8.  Ring layout [point][16 units of 16 B] with the unit index XOR-swizzled
     // by (2 (point & 3) + unit / 8), so that the converting thread (point r, half h) reads its 8 units without bank conflicts.
+    int fA = blockIdx.y, fpass = 0, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0;
     const int lp = lane >> 4, lu = lane & 15;                // loader: point within the pair, 16-byte unit
     auto fetch_next = [&]() {
       if (fA < n_A) {
@@ -193,9 +187,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
           cp_async16(dst + rr * 256 + ((lu ^ ((2 * (rr & 3) + (lu >> 3)) & 7)) << 4), src);
         }
         if (++fc == fn) {
-          fA += a_step;
           fc = 0;
-          fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
+          if (++fpass == 2) {
+            fpass = 0;
+            fA += a_step;
+            fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
+          }
         }
       }
       fslot = (fslot + 1) % kWtRing;
@@ -203,13 +200,31 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     };
     for (int i = 0; i < kWtRing - 1; ++i) fetch_next();
 
-    int gc = 0, tile = 0;
-    int emax = row_exponent(blockIdx.y);
+    int gc = 0, rc = 0, tile = 0;     // operand-stage counter, ring counter, tile counter
     for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
       const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
       const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
+      // ---- pass 0: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) ----
+      int emax = 0;
+      for (int c = 0; c < n_chunks; ++c, ++rc) {
+        fetch_next();
+        cp_async_wait<kWtRing - 1>();
+        __syncwarp();                                           // a warp copies exactly the 16 points it reads
+        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes + r * 256;
+        int hmax = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 v = *reinterpret_cast<const uint4*>(vsrc + (((8 * h + q) ^ swz) << 4));
+          hmax = max(hmax, max(static_cast<int>(v.y & 0x7fffffffu), static_cast<int>(v.w & 0x7fffffffu)));
+        }
+        if ((hmax >> 20) > 0) emax = max(emax, (hmax >> 20) + cs[2 * c]);
+        __syncwarp();                                           // slot may be refilled by the next fetch of any lane
+      }
+      emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+      emax = min(max(emax, 64), 2000);
       if (h == 0) sE[r] = emax;
-      for (int c = 0; c < n_chunks; ++c, ++gc) {
+      // ---- pass 1: convert, slice, store ----
+      for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
         fetch_next();
         cp_async_wait<kWtRing - 1>();
@@ -217,8 +232,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
         const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
         const double mult = __hiloint2double((1023 + sh) << 20, 0);
-        const unsigned char* vsrc = sR + (gc % kWtRing) * kWtRingBytes + r * 256;
-        const int swz = (2 * (r & 3) + h) & 7;
+        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes + r * 256;
         uint32_t wd[kWtNA][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -245,10 +259,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         for (int i = 0; i < kWtNA; ++i)
           *reinterpret_cast<uint4*>(arow + s * kWtAStage + i * kWtASlice) = make_uint4(wd[i][0], wd[i][1], wd[i][2], wd[i][3]);
         fence_proxy_async();
-        __syncwarp();
+        __syncwarp();                                           // also: ring slot free for the next fetch of any lane
         if (lane == 0) mbar_arrive1(&bar_fullA[s]);
       }
-      const int emax_next = row_exponent(A + a_step);       // loads in flight while the last MMAs of this tile run
 
       // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
       bar_workers();                                           // sE of this tile is complete
@@ -282,7 +295,6 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       if (warp < 4 && ept < w.count)
         w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
       bar_workers();                                           // sE / sChi are reused by the next tile
-      emax = emax_next;
     }
     cp_async_wait<0>();
   }
