@@ -173,29 +173,39 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     // Loads are coalesced: 16 consecutive lanes copy the 256 bytes one point contributes to a chunk, a warp covers 2
     // points per instruction and 16 points in 8.  Ring layout [point][16 units of 16 B] with the unit index XOR-swizzled
     // by (2 (point & 3) + unit / 8), so that the converting thread (point r, half h) reads its 8 units without bank conflicts.
-    int fA = blockIdx.y, fpass = 0, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0;
+    int fA = blockIdx.y, fpass = 0, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0, fmc = 0;
     const int lp = lane >> 4, lu = lane & 15;                // loader: point within the pair, 16-byte unit
+    // per-lane constants of the 8 copies of a chunk: source row and swizzled destination
+    const double* rbase[8];
+    uint32_t doff[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rr = 16 * warp + 2 * k + lp;                // point of the tile
+      rbase[k] = Z.pxzam + static_cast<size_t>(min(pt_base + rr, w.count - 1)) * Z.n_a * Z.n_m_pad + 2 * lu;
+      doff[k] = rr * 256 + ((lu ^ ((2 * (rr & 3) + (lu >> 3)) & 7)) << 4);
+    }
+    int fcol = Z.pair_a[Z.pair_start[fA]] * Z.n_m_pad;      // column offset (doubles) of the chunk to fetch next
     auto fetch_next = [&]() {
       if (fA < n_A) {
-        const int pr = fc / cpp, mc = fc - pr * cpp;
-        const size_t col = static_cast<size_t>(Z.pair_a[Z.pair_start[fA] + pr]) * Z.n_m_pad + mc * kWtKC + 2 * lu;
         unsigned char* dst = sR + fslot * kWtRingBytes;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int rr = 16 * warp + 2 * k + lp;              // point of the tile
-          const double* src = Z.pxzam + static_cast<size_t>(min(pt_base + rr, w.count - 1)) * Z.n_a * Z.n_m_pad + col;
-          cp_async16(dst + rr * 256 + ((lu ^ ((2 * (rr & 3) + (lu >> 3)) & 7)) << 4), src);
-        }
-        if (++fc == fn) {
-          fc = 0;
-          if (++fpass == 2) {
-            fpass = 0;
-            fA += a_step;
-            fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
+        for (int k = 0; k < 8; ++k) cp_async16(dst + doff[k], rbase[k] + fcol);
+        fcol += kWtKC;
+        ++fc;
+        if (++fmc == cpp) {                                 // next pair (or next pass / tile)
+          fmc = 0;
+          if (fc == fn) {
+            fc = 0;
+            if (++fpass == 2) {
+              fpass = 0;
+              fA += a_step;
+              fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
+            }
           }
+          if (fA < n_A) fcol = Z.pair_a[Z.pair_start[fA] + fc / cpp] * Z.n_m_pad;
         }
       }
-      fslot = (fslot + 1) % kWtRing;
+      fslot = fslot + 1 == kWtRing ? 0 : fslot + 1;
       cp_async_commit();
     };
     for (int i = 0; i < kWtRing - 1; ++i) fetch_next();
