@@ -118,6 +118,29 @@ def algorithmic_work(likes, n_q):
     return {"p3d_cells": cells, "hankel_dfma": hankel, "window_dfma": window, "chi2_dfma": chi2}
 
 
+def window_roofline(work, likes, B, k2_s, dmma_peak_tflops, share):
+    """Roofline entry of the chi2 stage.  Default: k_window_tc (window contraction as an exact INT8 split on
+    tcgen05) -- bound by the one read of Px_Zam from HBM (n_a * n_m_pad float64 per point and z);
+    CPX_WTC=0: k_window, the FP64 DMMA GEMM, bound by the FP64 tensor pipe."""
+    if os.environ.get("CPX_WTC", "1") != "0":
+        px_bytes = 0
+        for lk in likes:
+            n_a, n_m = len(lk.data.theta_min_a_arcmin), len(lk.data.k_m[lk.iz])
+            px_bytes += 8 * n_a * (-(-n_m // 32) * 32)
+        peak = None
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs"))
+        except Exception:
+            pass
+        achieved = px_bytes * B / k2_s / 1e9
+        return {"kernel": "k_window_tc", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if peak else None, "algorithmic_bytes_per_point_z": px_bytes / len(likes),
+                "int8_mac_per_s": 15.0 * work["window_dfma"] * B / k2_s, "share_of_step": share}
+    achieved = 2.0 * work["window_dfma"] * B / k2_s / 1e12
+    return {"kernel": "k_window", "bound": "tensor", "achieved": achieved, "peak": dmma_peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / dmma_peak_tflops, "share_of_step": share}
+
+
 def cpu_worker(args):
     """One process of the CPU arm: evaluates its block of points serially (the reference pattern,
     scripts/chi2_scan_mock.py:140), BLAS pinned to one thread (scripts/profile.py:2-7)."""
@@ -367,9 +390,7 @@ def main():
                 "algorithmic": dict(work, per="evaluation (one point, all z)"),
                 "fp32_fma_pipe_frac": float(31.0 * work["p3d_cells"] * B / k1_s / peaks["ffma_per_s"]),
                 "mufu_pipe_frac": float(2.0 * work["p3d_cells"] * B / k1_s / peaks["mufu_per_s"]),
-                "window_kernel": {"kernel": "k_window", "bound": "tensor", "achieved": 2.0 * work["window_dfma"] * B / k2_s / 1e12,
-                                  "frac": 2.0 * work["window_dfma"] * B / k2_s / 1e12 / peak,
-                                  "share_of_step": float(stage[2] / stage.sum())},
+                "window_kernel": window_roofline(work, likes, B, k2_s, peak, float(stage[2] / stage.sum())),
                 "stage_ms": {"params": float(stage[0]), "p3d_hankel": float(stage[1]), "window_chi2": float(stage[2]),
                              "reduce": float(stage[3])},
                 "measured_peaks": peaks}

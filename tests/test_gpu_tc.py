@@ -72,3 +72,60 @@ def test_tensor_path_extreme_parameters_stay_finite(monkeypatch):
     assert np.isfinite(got["px_zam"]).all()
     scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
     assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 1e-8
+
+
+def _window_paths(monkeypatch, plans, pts, names, data_idx=None):
+    """chi2 per (z, theta_A) with the window stage on the tensor cores (default) and as the FP64 DMMA GEMM."""
+    slots, zsel = slots_from_names(names)
+    out = {}
+    for wtc in ("0", "1"):
+        monkeypatch.setenv("CPX_WTC", wtc)
+        eng = PxEngine(plans)
+        out[wtc] = eng.eval(pts, slots, zsel=zsel, data_idx=data_idx, want=("chi2", "chi2_zA"))
+        eng.close()
+    return out["0"], out["1"]
+
+
+@pytest.mark.parametrize("shape,over,flags", [
+    ("S2", dict(N_m=70, N_A=9), ALL),                          # ragged rows / columns, 4 z, additive contaminants
+    ("S1_rebin", dict(N_A=6, N_m=60), {"include_hcd": True}),  # three fine theta bins per coarse bin: K spans 3 pairs
+    ("tiny", {}, {}),                                          # 8 coarse-k columns: one column half stays empty
+])
+def test_tensor_window_equals_dmma_window(monkeypatch, shape, over, flags):
+    d = synthetic.make_measurement_dict(shape, **over)
+    rng = np.random.default_rng(17)
+    d["Px_ZAM"] = 0.05 * rng.normal(size=d["Px_ZAM"].shape) + 0.1      # non-trivial data vector and covariance
+    cov = np.empty_like(d["cov_ZAM"])
+    for iz in range(cov.shape[0]):
+        for A in range(cov.shape[1]):
+            n = cov.shape[2]
+            sig = 0.01 * np.geomspace(1.0, 1e-4, n)                      # sigma falling by 4 decades along k: T rises with 1/sigma
+            cov[iz, A] = sig[:, None] * sig[None, :] * 0.3 ** np.abs(np.subtract.outer(np.arange(n), np.arange(n)))
+    d["cov_ZAM"] = cov
+    likes = [Likelihood(DESI_DR2(d), H.make_theory(float(z), "best_fit_arinyo_from_gadget", flags, n_q=88), iz,
+                        config={"N_theta_average": 3}) for iz, z in enumerate(d["z_centers"])]
+    plans = [lk.build_plan() for lk in likes]
+    names = ["bias", "beta", "q1", "kp_Mpc"]
+    base = np.array([plans[0].defaults[_plan.SLOT_INDEX[n]] for n in names])
+    pts = base[None, :] * rng.uniform(0.6, 1.4, size=(150, len(names)))          # 150 points: one full tile of 128 + a tail
+    ref, got = _window_paths(monkeypatch, plans, pts, names)
+    # the integer split is exact to ~2^-40 of the row scales: chi2 values of up to 1e9 agree to better than 1e-9 relative
+    np.testing.assert_allclose(got["chi2_zA"], ref["chi2_zA"], rtol=2e-9, atol=1e-9)
+    np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-9)
+    # and against the float64 emulation of the plan
+    for i in (0, 149):
+        tot = sum(H.emulate_plan_chi2(p, dict(zip(names, pts[i])))[1].sum() for p in plans)
+        np.testing.assert_allclose(got["chi2"][i], tot, rtol=2e-6)
+
+
+def test_tensor_window_many_mocks_data_index(monkeypatch):
+    d = synthetic.make_measurement_dict("S1", N_A=5, N_m=48)
+    like = Likelihood(DESI_DR2(d), H.make_theory(2.2, "best_fit_arinyo_from_gadget", {}, n_q=88), 0, config={"N_theta_average": 1})
+    p = like.build_plan()
+    rng = np.random.default_rng(3)
+    mocks = 0.1 + 0.02 * rng.normal(size=(4,) + p.Px_AM.shape[1:])
+    p.Px_AM, p.n_data = mocks, 4
+    pts = np.stack([rng.uniform(-0.2, -0.1, 300), rng.uniform(1.0, 2.0, 300)], axis=1)
+    idx = rng.integers(0, 4, 300)
+    ref, got = _window_paths(monkeypatch, [p], pts, ["bias", "beta"], data_idx=idx)
+    np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-9)
