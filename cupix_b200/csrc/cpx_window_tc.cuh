@@ -34,8 +34,8 @@ namespace cpx {
 constexpr int kWtPts = 128;          // points per tile = UMMA M
 constexpr int kWtNA = 5;             // Px bytes
 constexpr int kWtNW = 5;             // T digits
-constexpr int kWtStages = 3;            // operand stages (u8 slices of Px + digit tile of T)
-constexpr int kWtRing = 4;              // float64 chunks of Px in flight per thread (cp.async)
+constexpr int kWtStages = 2;            // operand stages (u8 slices of Px + digit tile of T)
+constexpr int kWtRing = 5;              // float64 chunks of Px in the cp.async ring (4 in flight ahead of the consumer)
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
 constexpr int kWtWorkers = 8;        // worker warps
 constexpr int kWtThreads = 32 * (kWtWorkers + 2);
@@ -44,11 +44,16 @@ constexpr int kWtAStage = kWtNA * kWtASlice;            // 20 KB
 constexpr int kWtRingBytes = kWtWorkers * 32 * 16 * 8;  // 32 KB: 128 bytes per worker thread, laid out [8][256 threads][16 B]
 __host__ __device__ constexpr int wt_b_stage(int nb) { return kWtNW * nb * kWtKC; }
 __host__ __device__ constexpr int wt_smem_bytes(int nb) {
-  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + kWtPts * 4 + 2 * kWtPts * 8;
+  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + 2 * kWtPts * 4 + 2 * kWtPts * 8;
 }
 
 __device__ __forceinline__ uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 2, %0;" ::"n"(kWtWorkers * 32) : "memory"); }
 
@@ -69,8 +74,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
   unsigned char* const sA = smem_raw;
   unsigned char* const sB = sA + kWtStages * kWtAStage;
   unsigned char* const sR = sB + kWtStages * B_STAGE;                      // float64 ring
-  int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [128] biased exponent of the row maximum
-  double* const sChi = reinterpret_cast<double*>(sE + kWtPts);            // [2][128] partial chi2 of the two column halves
+  int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [2][128] biased exponent of the row maximum (tile parity)
+  double* const sChi = reinterpret_cast<double*>(sE + 2 * kWtPts);        // [2][128] partial chi2 of the two column halves
   __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done, bar_epi;
   __shared__ uint32_t tmem_slot;
 
@@ -211,10 +216,11 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     for (int i = 0; i < kWtRing - 1; ++i) fetch_next();
 
     int gc = 0, rc = 0, tile = 0;     // operand-stage counter, ring counter, tile counter
-    for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
+
+    // pass 0 of a tile: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) -> sE[tile parity]
+    auto pass0 = [&](int A, int par) {
       const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
       const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
-      // ---- pass 0: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) ----
       int emax = 0;
       for (int c = 0; c < n_chunks; ++c, ++rc) {
         fetch_next();
@@ -232,7 +238,16 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       }
       emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
       emax = min(max(emax, 64), 2000);
-      if (h == 0) sE[r] = emax;
+      if (h == 0) sE[par * kWtPts + r] = emax;
+      return emax;
+    };
+
+    // Software pipeline over the tiles of this CTA:  pass 0 (t+1) runs between pass 1 (t) and the epilogue (t), so that
+    // the tail of the MMAs of tile t is hidden behind HBM streaming instead of being waited for.
+    int emax = pass0(blockIdx.y, 0);
+    for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
+      const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
+      const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;
       // ---- pass 1: convert, slice, store ----
       for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
@@ -272,24 +287,25 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         __syncwarp();                                           // also: ring slot free for the next fetch of any lane
         if (lane == 0) mbar_arrive1(&bar_fullA[s]);
       }
+      const int emax_next = (A + a_step < n_A) ? pass0(A + a_step, (tile + 1) & 1) : 0;
 
       // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
-      bar_workers();                                           // sE of this tile is complete
+      bar_workers();                                           // sE of this tile (written before its pass 1) is visible
       mbar_wait(&bar_done, static_cast<uint32_t>(tile) & 1u);
       tc_fence_after();
       const double* const yd = Z.yd + (static_cast<size_t>(d) * n_A + A) * Z.n_M_pad;
       const double* const rs = Z.wt_rs + static_cast<size_t>(A) * NB;
       // Y = rs[M] 2^(e - 1069) sum_s D_s 256^(4-s)
-      const double rowfac = __hiloint2double((sE[er] - 1069 + 1023) << 20, 0);
+      const double rowfac = __hiloint2double((sE[(tile & 1) * kWtPts + er] - 1069 + 1023) << 20, 0);
       const int c_end = min((hh + 1) * (NB / 2), Z.n_M_pad);
       double chi = 0.0;
-      for (int col = hh * (NB / 2); col < c_end; col += 4) {
-        int32_t v[kWtNW][4];
+      for (int col = hh * (NB / 2); col < c_end; col += 8) {     // NB / 2 and n_M_pad are multiples of 8
+        int32_t v[kWtNW][8];
 #pragma unroll
-        for (int sg = 0; sg < kWtNW; ++sg) tmem_ld4(taddr + NB * sg + col, v[sg]);
+        for (int sg = 0; sg < kWtNW; ++sg) tmem_ld8(taddr + NB * sg + col, v[sg]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const double hi = fma(fma(i2d(v[0][j]), 256.0, i2d(v[1][j])), 256.0, i2d(v[2][j]));
           const double lo = fma(i2d(v[3][j]), 256.0, i2d(v[4][j]));
           const double y = fma(hi, 65536.0, lo) * (rowfac * rs[col + j]);
@@ -304,7 +320,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       bar_workers();
       if (warp < 4 && ept < w.count)
         w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
-      bar_workers();                                           // sE / sChi are reused by the next tile
+      bar_workers();                                           // sChi is reused by the next tile
+      emax = emax_next;
     }
     cp_async_wait<0>();
   }
