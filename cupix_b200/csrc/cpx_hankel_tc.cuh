@@ -127,6 +127,19 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// wait that parks the thread in hardware (suspend-time hint, wakes up as soon as the phase completes): for the
+// single-thread MMA-issue and TMA loops, which would otherwise burn issue slots polling
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITP_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEP_%=;\n\t"
+      "bra WAITP_%=;\n\t"
+      "DONEP_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

@@ -112,14 +112,14 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         const int n_chunks = (Z.pair_start[A + 1] - Z.pair_start[A]) * cpp;
         // the single accumulator is free once the workers have read the previous tile out of tensor memory
         if (tile > 0) {
-          while (!mbar_test(&bar_epi, static_cast<uint32_t>(tile - 1) & 1u)) __nanosleep(32);
+          mbar_wait_parked(&bar_epi, static_cast<uint32_t>(tile - 1) & 1u);
           tc_fence_after();
         }
         for (int c = 0; c < n_chunks; ++c, ++gc) {
           const int s = gc % kWtStages;
           const uint32_t ph = static_cast<uint32_t>(gc / kWtStages) & 1u;
-          while (!mbar_test(&bar_fullB[s], ph)) __nanosleep(32);
-          while (!mbar_test(&bar_fullA[s], ph)) __nanosleep(32);
+          mbar_wait_parked(&bar_fullB[s], ph);
+          mbar_wait_parked(&bar_fullA[s], ph);
           tc_fence_after();
           const uint64_t bd = umma_smem_desc(b_base + s * B_STAGE, B_CHUNK, 128);
 #pragma unroll
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
           const int s = gc % kWtStages;
           if (gc >= kWtStages) {
             const uint32_t ph = static_cast<uint32_t>(gc / kWtStages - 1) & 1u;
-            while (!mbar_test(&bar_free[s], ph)) __nanosleep(32);
+            mbar_wait_parked(&bar_free[s], ph);
           }
           mbar_expect_tx(&bar_fullB[s], static_cast<uint32_t>(B_STAGE));
           bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(c) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
     const int swz = (2 * (r & 3) + h) & 7;
+    uint32_t roff[8];                                        // byte offsets of this thread's 8 units within a ring slot
+#pragma unroll
+    for (int q = 0; q < 8; ++q) roff[q] = r * 256 + (((8 * h + q) ^ swz) << 4);
 
     // The stream of chunks of this CTA: every tile (theta_A) is streamed twice, (A, pass 0, c) then (A, pass 1, c) with
     // c running over (pair, m / 32).  Pass 0 (from HBM) only finds the largest exponent of the row, pass 1 (the same
@@ -226,11 +229,11 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         fetch_next();
         cp_async_wait<kWtRing - 1>();
         __syncwarp();                                           // a warp copies exactly the 16 points it reads
-        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes + r * 256;
+        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes;
         int hmax = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const uint4 v = *reinterpret_cast<const uint4*>(vsrc + (((8 * h + q) ^ swz) << 4));
+          const uint4 v = *reinterpret_cast<const uint4*>(vsrc + roff[q]);
           hmax = max(hmax, max(static_cast<int>(v.y & 0x7fffffffu), static_cast<int>(v.w & 0x7fffffffu)));
         }
         if ((hmax >> 20) > 0) emax = max(emax, (hmax >> 20) + cs[2 * c]);
@@ -257,12 +260,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
         const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
         const double mult = __hiloint2double((1023 + sh) << 20, 0);
-        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes + r * 256;
+        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes;
         uint32_t wd[kWtNA][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const double2 va = *reinterpret_cast<const double2*>(vsrc + (((8 * h + 2 * q) ^ swz) << 4));
-          const double2 vb = *reinterpret_cast<const double2*>(vsrc + (((8 * h + 2 * q + 1) ^ swz) << 4));
+          const double2 va = *reinterpret_cast<const double2*>(vsrc + roff[2 * q]);
+          const double2 vb = *reinterpret_cast<const double2*>(vsrc + roff[2 * q + 1]);
           uint32_t L[4], H[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
