@@ -3,6 +3,8 @@
 // There is deliberately no CPU fallback: every entry point that computes needs a CUDA device.
 #include "../../include/cupix_b200.h"
 
+#include <cuda.h>   // CUtensorMap types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -666,6 +668,33 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     if (ok && nb > 0 && static_cast<size_t>(cpx::wt_smem_bytes(nb)) + 2048 <= static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
       if (cudaFuncSetAttribute(cpx::k_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::wt_smem_bytes(nb)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_window_tc"));
+      // tensor maps of the Px_Zam scratch of every z (k_window_tc streams it with tiled TMA loads)
+      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fnp = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres) != cudaSuccess || !fnp ||
+          qres != cudaDriverEntryPointSuccess)
+        return bail(fail(CPX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver"));
+      std::vector<CUtensorMap> maps(n_zbins);
+      for (int i = 0; i < n_zbins; ++i) {
+        const cpx::ZDev& Z = h->z[i].dev;
+        if (Z.n_A <= 0) continue;
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Z.n_m_pad), static_cast<cuuint64_t>(Z.n_a), static_cast<cuuint64_t>(h->chunk)};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Z.n_m_pad) * 8, static_cast<cuuint64_t>(Z.n_a) * Z.n_m_pad * 8};
+        const cuuint32_t box[3] = {16, 1, static_cast<cuuint32_t>(cpx::kWtPts)};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = reinterpret_cast<EncodeFn>(fnp)(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Z.pxzam, dims, strides, box, estr,
+                                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return bail(fail(CPX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the Px_Zam scratch"));
+      }
+      CUtensorMap* dmaps = nullptr;
+      if ((rc = dmalloc(reinterpret_cast<void**>(&dmaps), sizeof(CUtensorMap) * n_zbins))) return bail(rc);
+      if (cudaMemcpy(dmaps, maps.data(), sizeof(CUtensorMap) * n_zbins, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(CPX_ERR_CUDA, "upload of the tensor maps failed"));
+      for (int i = 0; i < n_zbins; ++i) h->z[i].dev.px_tmap = dmaps + i;
       h->wt_nb = nb;
     }
   }

@@ -96,6 +96,7 @@ struct ZDev {
   const int* wt_off;                    // [n_A] first chunk of coarse bin A
   const int* wt_cs;                     // [n_pairs][n_m_pad / 16] exponent c of the column scale
   const double* wt_rs;                  // [n_A][wt_nb] row scales
+  const void* px_tmap;                  // CUtensorMap of pxzam viewed as [chunk][n_a][n_m_pad] float64, box 128 x 1 x 16, 128-byte swizzle
 };
 
 // ------------------------------------------------------------------------------------------

@@ -22,10 +22,11 @@
 // columns round up to the whole tensor memory).  A tile is 128 points x one theta_A x one z; a CTA walks
 // the theta_A bins blockIdx.y, blockIdx.y + gridDim.y, ... of its 128 points so that the Px stream of the
 // next tile is already in flight while the accumulators of the current one are read out.
-// Worker thread (point r, half h) streams 16 consecutive doubles per K = 32 chunk through a 4-deep cp.async
-// ring, converts them and writes one 16-byte core-matrix row into each of the five u8/s8 operand tiles
-// (3 stages, mbarriers); the digit tiles of T stream in with TMA bulk copies.  HBM traffic is one read of
-// Px_Zam: the kernel is bound by that read.
+// Px_Zam streams into a 5-deep shared-memory ring of 32 KB chunks (128 points x 32 fine-k values) with two
+// 3-D tiled TMA loads per chunk (128-byte swizzle, so that the per-point reads are bank-conflict free); worker
+// thread (point r, half h) converts its 16 doubles and writes one 16-byte core-matrix row into each of the five
+// u8/s8 operand tiles (2 stages, mbarriers); the digit tiles of T stream in with TMA bulk copies.  HBM traffic
+// is one read of Px_Zam: the kernel is bound by that read.
 #pragma once
 #include "cpx_hankel_tc.cuh"
 
@@ -38,13 +39,13 @@ constexpr int kWtStages = 2;            // operand stages (u8 slices of Px + dig
 constexpr int kWtRing = 5;              // float64 chunks of Px in the cp.async ring (4 in flight ahead of the consumer)
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
 constexpr int kWtWorkers = 8;        // worker warps
-constexpr int kWtThreads = 32 * (kWtWorkers + 2);
+constexpr int kWtThreads = 32 * (kWtWorkers + 3);        // workers + MMA issuer + TMA (digit tiles) + TMA (Px stream)
 constexpr int kWtASlice = kWtPts * kWtKC;               // 4 KB
 constexpr int kWtAStage = kWtNA * kWtASlice;            // 20 KB
 constexpr int kWtRingBytes = kWtWorkers * 32 * 16 * 8;  // 32 KB: 128 bytes per worker thread, laid out [8][256 threads][16 B]
 __host__ __device__ constexpr int wt_b_stage(int nb) { return kWtNW * nb * kWtKC; }
 __host__ __device__ constexpr int wt_smem_bytes(int nb) {
-  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + 2 * kWtPts * 4 + 2 * kWtPts * 8;
+  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + 2 * kWtPts * 4 + 2 * kWtPts * 8 + 1024;   // + slack to align the ring to 1 KB
 }
 
 __device__ __forceinline__ uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
@@ -54,6 +55,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
+}
+// 3-D tiled TMA load (coordinates fastest dimension first) into shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 2, %0;" ::"n"(kWtWorkers * 32) : "memory"); }
 
@@ -73,10 +81,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const sA = smem_raw;
   unsigned char* const sB = sA + kWtStages * kWtAStage;
-  unsigned char* const sR = sB + kWtStages * B_STAGE;                      // float64 ring
+  // float64 ring, 1 KB aligned for the 128-byte TMA swizzle: slot = [K half][128 points][128 bytes], the 16-byte unit
+  // index XOR-ed with (point & 7) by the TMA engine
+  unsigned char* const sR = sB + kWtStages * B_STAGE + ((1024u - (smem_u32(sB + kWtStages * B_STAGE) & 1023u)) & 1023u);
   int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [2][128] biased exponent of the row maximum (tile parity)
   double* const sChi = reinterpret_cast<double*>(sE + 2 * kWtPts);        // [2][128] partial chi2 of the two column halves
   __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done, bar_epi;
+  __shared__ __align__(8) uint64_t bar_rfull[kWtRing], bar_rfree[kWtRing];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,6 +103,10 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     }
     mbar_init(&bar_done, 1);
     mbar_init(&bar_epi, kWtWorkers);
+    for (int i = 0; i < kWtRing; ++i) {
+      mbar_init(&bar_rfull[i], 1);
+      mbar_init(&bar_rfree[i], kWtWorkers);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWtWorkers) {
@@ -160,63 +175,38 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       }
     }
     __syncwarp();
+  } else if (warp == kWtWorkers + 2) {
+    // =============================== TMA: the Px stream ===============================
+    // Every tile (theta_A) is streamed twice, (A, pass 0, c) then (A, pass 1, c) with c over (pair, m / 32): pass 0
+    // (from HBM) only finds the largest exponent of each row, pass 1 (the same bytes again, from L2) is converted.
+    if (lane == 0) {
+      int rc = 0;
+      const uint32_t ring = smem_u32(sR);
+      for (int A = blockIdx.y; A < n_A; A += a_step)
+        for (int pass = 0; pass < 2; ++pass)
+          for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) {
+            const int a = Z.pair_a[p];
+            for (int mc = 0; mc < cpp; ++mc, ++rc) {
+              const int slot = rc % kWtRing;
+              if (rc >= kWtRing) mbar_wait_parked(&bar_rfree[slot], static_cast<uint32_t>(rc / kWtRing - 1) & 1u);
+              mbar_expect_tx(&bar_rfull[slot], static_cast<uint32_t>(kWtRingBytes));
+              tma_load_3d(ring + slot * kWtRingBytes, Z.px_tmap, mc * kWtKC, a, pt_base, &bar_rfull[slot]);
+              tma_load_3d(ring + slot * kWtRingBytes + kWtRingBytes / 2, Z.px_tmap, mc * kWtKC + 16, a, pt_base, &bar_rfull[slot]);
+            }
+          }
+    }
+    __syncwarp();
   } else {
     // =============================== workers: slicing of Px, then the epilogue ===============================
-    const int r = tid >> 1, h = tid & 1;                     // point of the tile, half of the 32-wide K chunk
-    const int pt = min(pt_base + r, w.count - 1);
-    const double* const prow = Z.pxzam + static_cast<size_t>(pt) * Z.n_a * Z.n_m_pad + 16 * h;
+    const int h = lane >> 4, r = 16 * warp + (lane & 15);    // half of the 32-wide K chunk, point of the tile
     unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
     const int er = 32 * (warp & 3) + lane, hh = warp >> 2;   // epilogue: TMEM lane = point, column half
     const int ept = pt_base + er;
     const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
-    const int swz = (2 * (r & 3) + h) & 7;
-    uint32_t roff[8];                                        // byte offsets of this thread's 8 units within a ring slot
+    uint32_t roff[8];                                        // byte offsets of this thread's 8 swizzled units within a ring slot
 #pragma unroll
-    for (int q = 0; q < 8; ++q) roff[q] = r * 256 + (((8 * h + q) ^ swz) << 4);
-
-    // The stream of chunks of this CTA: every tile (theta_A) is streamed twice, (A, pass 0, c) then (A, pass 1, c) with
-    // c running over (pair, m / 32).  Pass 0 (from HBM) only finds the largest exponent of the row, pass 1 (the same
-    // bytes again, from L2) converts.  fA / fpass / fc run kWtRing - 1 chunks ahead of the consumer.
-    // Loads are coalesced: 16 consecutive lanes copy the 256 bytes one point contributes to a chunk, a warp covers 2
-    // points per instruction and 16 points in 8.  Ring layout [point][16 units of 16 B] with the unit index XOR-swizzled
-    // by (2 (point & 3) + unit / 8), so that the converting thread (point r, half h) reads its 8 units without bank conflicts.
-    int fA = blockIdx.y, fpass = 0, fc = 0, fn = (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp, fslot = 0, fmc = 0;
-    const int lp = lane >> 4, lu = lane & 15;                // loader: point within the pair, 16-byte unit
-    // per-lane constants of the 8 copies of a chunk: source row and swizzled destination
-    const double* rbase[8];
-    uint32_t doff[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int rr = 16 * warp + 2 * k + lp;                // point of the tile
-      rbase[k] = Z.pxzam + static_cast<size_t>(min(pt_base + rr, w.count - 1)) * Z.n_a * Z.n_m_pad + 2 * lu;
-      doff[k] = rr * 256 + ((lu ^ ((2 * (rr & 3) + (lu >> 3)) & 7)) << 4);
-    }
-    int fcol = Z.pair_a[Z.pair_start[fA]] * Z.n_m_pad;      // column offset (doubles) of the chunk to fetch next
-    auto fetch_next = [&]() {
-      if (fA < n_A) {
-        unsigned char* dst = sR + fslot * kWtRingBytes;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cp_async16(dst + doff[k], rbase[k] + fcol);
-        fcol += kWtKC;
-        ++fc;
-        if (++fmc == cpp) {                                 // next pair (or next pass / tile)
-          fmc = 0;
-          if (fc == fn) {
-            fc = 0;
-            if (++fpass == 2) {
-              fpass = 0;
-              fA += a_step;
-              fn = fA < n_A ? (Z.pair_start[fA + 1] - Z.pair_start[fA]) * cpp : 0;
-            }
-          }
-          if (fA < n_A) fcol = Z.pair_a[Z.pair_start[fA] + fc / cpp] * Z.n_m_pad;
-        }
-      }
-      fslot = fslot + 1 == kWtRing ? 0 : fslot + 1;
-      cp_async_commit();
-    };
-    for (int i = 0; i < kWtRing - 1; ++i) fetch_next();
+    for (int q = 0; q < 8; ++q) roff[q] = h * (kWtRingBytes / 2) + r * 128 + ((q ^ (r & 7)) << 4);
 
     int gc = 0, rc = 0, tile = 0;     // operand-stage counter, ring counter, tile counter
 
@@ -226,9 +216,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
       int emax = 0;
       for (int c = 0; c < n_chunks; ++c, ++rc) {
-        fetch_next();
-        cp_async_wait<kWtRing - 1>();
-        __syncwarp();                                           // a warp copies exactly the 16 points it reads
+        mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
         const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes;
         int hmax = 0;
 #pragma unroll
@@ -237,9 +225,10 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
           hmax = max(hmax, max(static_cast<int>(v.y & 0x7fffffffu), static_cast<int>(v.w & 0x7fffffffu)));
         }
         if ((hmax >> 20) > 0) emax = max(emax, (hmax >> 20) + cs[2 * c]);
-        __syncwarp();                                           // slot may be refilled by the next fetch of any lane
+        __syncwarp();
+        if (lane == 0) mbar_arrive1(&bar_rfree[rc % kWtRing]);  // slot may be refilled
       }
-      emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+      emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 16));
       emax = min(max(emax, 64), 2000);
       if (h == 0) sE[par * kWtPts + r] = emax;
       return emax;
@@ -254,9 +243,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       // ---- pass 1: convert, slice, store ----
       for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
-        fetch_next();
-        cp_async_wait<kWtRing - 1>();
-        __syncwarp();                                           // a warp copies exactly the 16 points it converts
+        mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
         // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
         const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
         const double mult = __hiloint2double((1023 + sh) << 20, 0);
@@ -287,8 +274,11 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
         for (int i = 0; i < kWtNA; ++i)
           *reinterpret_cast<uint4*>(arow + s * kWtAStage + i * kWtASlice) = make_uint4(wd[i][0], wd[i][1], wd[i][2], wd[i][3]);
         fence_proxy_async();
-        __syncwarp();                                           // also: ring slot free for the next fetch of any lane
-        if (lane == 0) mbar_arrive1(&bar_fullA[s]);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive1(&bar_fullA[s]);
+          mbar_arrive1(&bar_rfree[rc % kWtRing]);               // ring slot may be refilled
+        }
       }
       const int emax_next = (A + a_step < n_A) ? pass0(A + a_step, (tile + 1) & 1) : 0;
 
@@ -326,7 +316,6 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       bar_workers();                                           // sChi is reused by the next tile
       emax = emax_next;
     }
-    cp_async_wait<0>();
   }
 
   tc_fence_before();
