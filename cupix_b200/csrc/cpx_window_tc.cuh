@@ -36,16 +36,18 @@ constexpr int kWtPts = 128;          // points per tile = UMMA M
 constexpr int kWtNA = 5;             // Px bytes
 constexpr int kWtNW = 5;             // T digits
 constexpr int kWtStages = 2;            // operand stages (u8 slices of Px + digit tile of T)
-constexpr int kWtRing = 5;              // float64 chunks of Px in the cp.async ring (4 in flight ahead of the consumer)
+constexpr int kWtRing = 3;              // ring slots (32 KB chunks of Px) of the converting workers (second read: L2)
+constexpr int kWtSRing = 2;             // ring slots of the scout warps (first read: HBM)
+constexpr int kWtScouts = 4;            // scout warps
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
 constexpr int kWtWorkers = 8;        // worker warps
-constexpr int kWtThreads = 32 * (kWtWorkers + 3);        // workers + MMA issuer + TMA (digit tiles) + TMA (Px stream)
+constexpr int kWtThreads = 32 * (kWtWorkers + 4 + kWtScouts);   // workers, MMA issuer, 3 TMA threads (digit tiles, Px for the scouts, Px for the workers), scouts
 constexpr int kWtASlice = kWtPts * kWtKC;               // 4 KB
 constexpr int kWtAStage = kWtNA * kWtASlice;            // 20 KB
 constexpr int kWtRingBytes = kWtWorkers * 32 * 16 * 8;  // 32 KB: 128 bytes per worker thread, laid out [8][256 threads][16 B]
 __host__ __device__ constexpr int wt_b_stage(int nb) { return kWtNW * nb * kWtKC; }
 __host__ __device__ constexpr int wt_smem_bytes(int nb) {
-  return kWtStages * (kWtAStage + wt_b_stage(nb)) + kWtRing * kWtRingBytes + 2 * kWtPts * 4 + 2 * kWtPts * 8 + 1024;   // + slack to align the ring to 1 KB
+  return kWtStages * (kWtAStage + wt_b_stage(nb)) + (kWtRing + kWtSRing) * kWtRingBytes + 2 * kWtPts * 4 + 2 * kWtPts * 8 + 1024;   // + slack to align the ring to 1 KB
 }
 
 __device__ __forceinline__ uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
@@ -84,10 +86,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
   // float64 ring, 1 KB aligned for the 128-byte TMA swizzle: slot = [K half][128 points][128 bytes], the 16-byte unit
   // index XOR-ed with (point & 7) by the TMA engine
   unsigned char* const sR = sB + kWtStages * B_STAGE + ((1024u - (smem_u32(sB + kWtStages * B_STAGE) & 1023u)) & 1023u);
-  int* const sE = reinterpret_cast<int*>(sR + kWtRing * kWtRingBytes);    // [2][128] biased exponent of the row maximum (tile parity)
+  unsigned char* const sS = sR + kWtRing * kWtRingBytes;                  // ring of the scouts
+  int* const sE = reinterpret_cast<int*>(sS + kWtSRing * kWtRingBytes);   // [2][128] biased exponent of the row maximum (tile parity)
   double* const sChi = reinterpret_cast<double*>(sE + 2 * kWtPts);        // [2][128] partial chi2 of the two column halves
   __shared__ __align__(8) uint64_t bar_fullA[kWtStages], bar_fullB[kWtStages], bar_free[kWtStages], bar_done, bar_epi;
-  __shared__ __align__(8) uint64_t bar_rfull[kWtRing], bar_rfree[kWtRing];
+  __shared__ __align__(8) uint64_t bar_rfull[kWtRing], bar_rfree[kWtRing], bar_sfull[kWtSRing], bar_sfree[kWtSRing];
+  __shared__ int s_scout_done, s_epi_done;   // counters: scout warps finished with a tile / epilogues completed
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,6 +111,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       mbar_init(&bar_rfull[i], 1);
       mbar_init(&bar_rfree[i], kWtWorkers);
     }
+    for (int i = 0; i < kWtSRing; ++i) {
+      mbar_init(&bar_sfull[i], 1);
+      mbar_init(&bar_sfree[i], kWtScouts);
+    }
+    s_scout_done = 0;
+    s_epi_done = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWtWorkers) {
@@ -175,27 +185,65 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       }
     }
     __syncwarp();
-  } else if (warp == kWtWorkers + 2) {
-    // =============================== TMA: the Px stream ===============================
-    // Every tile (theta_A) is streamed twice, (A, pass 0, c) then (A, pass 1, c) with c over (pair, m / 32): pass 0
-    // (from HBM) only finds the largest exponent of each row, pass 1 (the same bytes again, from L2) is converted.
+  } else if (warp == kWtWorkers + 2 || warp == kWtWorkers + 3) {
+    // =============================== TMA: the two Px streams ===============================
+    // Every tile (theta_A) is read twice, chunk by chunk (c over (pair, m / 32)): once for the scout warps, which only
+    // take the largest exponent of each row and run a tile ahead (this is the read that comes from HBM), and once
+    // for the converting workers (the same bytes again, from L2).
     if (lane == 0) {
+      const bool scout = warp == kWtWorkers + 2;
+      const int nslots = scout ? kWtSRing : kWtRing;
+      uint64_t* const full = scout ? bar_sfull : bar_rfull;
+      uint64_t* const free_ = scout ? bar_sfree : bar_rfree;
+      const uint32_t ring = smem_u32(scout ? sS : sR);
       int rc = 0;
-      const uint32_t ring = smem_u32(sR);
       for (int A = blockIdx.y; A < n_A; A += a_step)
-        for (int pass = 0; pass < 2; ++pass)
-          for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) {
-            const int a = Z.pair_a[p];
-            for (int mc = 0; mc < cpp; ++mc, ++rc) {
-              const int slot = rc % kWtRing;
-              if (rc >= kWtRing) mbar_wait_parked(&bar_rfree[slot], static_cast<uint32_t>(rc / kWtRing - 1) & 1u);
-              mbar_expect_tx(&bar_rfull[slot], static_cast<uint32_t>(kWtRingBytes));
-              tma_load_3d(ring + slot * kWtRingBytes, Z.px_tmap, mc * kWtKC, a, pt_base, &bar_rfull[slot]);
-              tma_load_3d(ring + slot * kWtRingBytes + kWtRingBytes / 2, Z.px_tmap, mc * kWtKC + 16, a, pt_base, &bar_rfull[slot]);
-            }
+        for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) {
+          const int a = Z.pair_a[p];
+          for (int mc = 0; mc < cpp; ++mc, ++rc) {
+            const int slot = rc % nslots;
+            if (rc >= nslots) mbar_wait_parked(&free_[slot], static_cast<uint32_t>(rc / nslots - 1) & 1u);
+            mbar_expect_tx(&full[slot], static_cast<uint32_t>(kWtRingBytes));
+            tma_load_3d(ring + slot * kWtRingBytes, Z.px_tmap, mc * kWtKC, a, pt_base, &full[slot]);
+            tma_load_3d(ring + slot * kWtRingBytes + kWtRingBytes / 2, Z.px_tmap, mc * kWtKC + 16, a, pt_base, &full[slot]);
           }
+        }
     }
     __syncwarp();
+  } else if (warp >= kWtWorkers + 4) {
+    // =============================== scouts: row maxima, one tile ahead of the workers ===============================
+    const int r = tid - 32 * (kWtWorkers + 4);               // point of the tile (both K halves)
+    uint32_t soff[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) soff[q] = (q >> 3) * (kWtRingBytes / 2) + r * 128 + (((q & 7) ^ (r & 7)) << 4);
+    int rc = 0, tile = 0;
+    for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
+      const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
+      const int* const cs = Z.wt_cs + 2 * p0 * cpp;          // exponent of the column scale per (pair, 16 columns)
+      // sE[tile parity] was last read by the epilogue of tile - 2
+      if (tile >= 2) while (*reinterpret_cast<volatile int*>(&s_epi_done) < tile - 1) __nanosleep(64);
+      int emax = 0;
+      for (int c = 0; c < n_chunks; ++c, ++rc) {
+        mbar_wait(&bar_sfull[rc % kWtSRing], static_cast<uint32_t>(rc / kWtSRing) & 1u);
+        const unsigned char* vsrc = sS + (rc % kWtSRing) * kWtRingBytes;
+        int h0 = 0, h1 = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 v0 = *reinterpret_cast<const uint4*>(vsrc + soff[q]);
+          const uint4 v1 = *reinterpret_cast<const uint4*>(vsrc + soff[8 + q]);
+          h0 = max(h0, max(static_cast<int>(v0.y & 0x7fffffffu), static_cast<int>(v0.w & 0x7fffffffu)));
+          h1 = max(h1, max(static_cast<int>(v1.y & 0x7fffffffu), static_cast<int>(v1.w & 0x7fffffffu)));
+        }
+        if ((h0 >> 20) > 0) emax = max(emax, (h0 >> 20) + cs[2 * c]);
+        if ((h1 >> 20) > 0) emax = max(emax, (h1 >> 20) + cs[2 * c + 1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive1(&bar_sfree[rc % kWtSRing]);
+      }
+      sE[(tile & 1) * kWtPts + r] = min(max(emax, 64), 2000);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) atomicAdd(&s_scout_done, 1);
+    }
   } else {
     // =============================== workers: slicing of Px, then the epilogue ===============================
     const int h = lane >> 4, r = 16 * warp + (lane & 15);    // half of the 32-wide K chunk, point of the tile
@@ -210,37 +258,14 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
 
     int gc = 0, rc = 0, tile = 0;     // operand-stage counter, ring counter, tile counter
 
-    // pass 0 of a tile: largest biased exponent of Px * 2^c over the row (all pairs of A, all m) -> sE[tile parity]
-    auto pass0 = [&](int A, int par) {
-      const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
-      const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;      // exponent of the column scale per (pair, 16 columns)
-      int emax = 0;
-      for (int c = 0; c < n_chunks; ++c, ++rc) {
-        mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
-        const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes;
-        int hmax = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint4 v = *reinterpret_cast<const uint4*>(vsrc + roff[q]);
-          hmax = max(hmax, max(static_cast<int>(v.y & 0x7fffffffu), static_cast<int>(v.w & 0x7fffffffu)));
-        }
-        if ((hmax >> 20) > 0) emax = max(emax, (hmax >> 20) + cs[2 * c]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive1(&bar_rfree[rc % kWtRing]);  // slot may be refilled
-      }
-      emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, 16));
-      emax = min(max(emax, 64), 2000);
-      if (h == 0) sE[par * kWtPts + r] = emax;
-      return emax;
-    };
-
-    // Software pipeline over the tiles of this CTA:  pass 0 (t+1) runs between pass 1 (t) and the epilogue (t), so that
-    // the tail of the MMAs of tile t is hidden behind HBM streaming instead of being waited for.
-    int emax = pass0(blockIdx.y, 0);
     for (int A = blockIdx.y; A < n_A; A += a_step, ++tile) {
       const int p0 = Z.pair_start[A], n_chunks = (Z.pair_start[A + 1] - p0) * cpp;
       const int* const cs = Z.wt_cs + 2 * p0 * cpp + h;
-      // ---- pass 1: convert, slice, store ----
+      // the scouts have the row maxima of this tile ready (they run one tile ahead)
+      while (*reinterpret_cast<volatile int*>(&s_scout_done) < kWtScouts * (tile + 1)) __nanosleep(32);
+      __threadfence_block();
+      const int emax = sE[(tile & 1) * kWtPts + r];
+      // ---- convert, slice, store ----
       for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
         mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
@@ -280,10 +305,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
           mbar_arrive1(&bar_rfree[rc % kWtRing]);               // ring slot may be refilled
         }
       }
-      const int emax_next = (A + a_step < n_A) ? pass0(A + a_step, (tile + 1) & 1) : 0;
 
       // ---- epilogue: TMEM lane = point, warp w reads lanes 32 (w % 4) .. and the column half w / 4 ----
-      bar_workers();                                           // sE of this tile (written before its pass 1) is visible
       mbar_wait(&bar_done, static_cast<uint32_t>(tile) & 1u);
       tc_fence_after();
       const double* const yd = Z.yd + (static_cast<size_t>(d) * n_A + A) * Z.n_M_pad;
@@ -314,7 +337,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       if (warp < 4 && ept < w.count)
         w.chi2_zA[(static_cast<size_t>(ept) * w.n_zl + w.zslot) * w.nA_max + A] = sChi[er] + sChi[kWtPts + er];
       bar_workers();                                           // sChi is reused by the next tile
-      emax = emax_next;
+      if (tid == 0) atomicAdd(&s_epi_done, 1);                 // sE[tile parity] may be rewritten by the scouts
     }
   }
 
