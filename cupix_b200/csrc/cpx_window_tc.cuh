@@ -35,8 +35,8 @@ namespace cpx {
 constexpr int kWtPts = 128;          // points per tile = UMMA M
 constexpr int kWtNA = 5;             // Px bytes
 constexpr int kWtNW = 5;             // T digits
-constexpr int kWtStages = 2;            // operand stages (u8 slices of Px + digit tile of T)
-constexpr int kWtRing = 3;              // ring slots (32 KB chunks of Px) of the converting workers (second read: L2)
+constexpr int kWtStages = 3;            // operand stages (u8 slices of Px + digit tile of T)
+constexpr int kWtRing = 2;              // ring slots (32 KB chunks of Px) of the converting workers (second read: L2)
 constexpr int kWtSRing = 2;             // ring slots of the scout warps (first read: HBM)
 constexpr int kWtScouts = 4;            // scout warps
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
@@ -223,7 +223,10 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       // sE[tile parity] was last read by the epilogue of tile - 2
       if (tile >= 2) while (*reinterpret_cast<volatile int*>(&s_epi_done) < tile - 1) __nanosleep(64);
       int emax = 0;
+      int2 cs_next = *reinterpret_cast<const int2*>(cs);       // column-scale exponents of the two K halves, one chunk ahead
       for (int c = 0; c < n_chunks; ++c, ++rc) {
+        const int2 cs_cur = cs_next;
+        if (c + 1 < n_chunks) cs_next = *reinterpret_cast<const int2*>(cs + 2 * (c + 1));
         mbar_wait(&bar_sfull[rc % kWtSRing], static_cast<uint32_t>(rc / kWtSRing) & 1u);
         const unsigned char* vsrc = sS + (rc % kWtSRing) * kWtRingBytes;
         int h0 = 0, h1 = 0;
@@ -234,8 +237,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
           h0 = max(h0, max(static_cast<int>(v0.y & 0x7fffffffu), static_cast<int>(v0.w & 0x7fffffffu)));
           h1 = max(h1, max(static_cast<int>(v1.y & 0x7fffffffu), static_cast<int>(v1.w & 0x7fffffffu)));
         }
-        if ((h0 >> 20) > 0) emax = max(emax, (h0 >> 20) + cs[2 * c]);
-        if ((h1 >> 20) > 0) emax = max(emax, (h1 >> 20) + cs[2 * c + 1]);
+        if ((h0 >> 20) > 0) emax = max(emax, (h0 >> 20) + cs_cur.x);
+        if ((h1 >> 20) > 0) emax = max(emax, (h1 >> 20) + cs_cur.y);
         __syncwarp();
         if (lane == 0) mbar_arrive1(&bar_sfree[rc % kWtSRing]);
       }
@@ -266,11 +269,14 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       __threadfence_block();
       const int emax = sE[(tile & 1) * kWtPts + r];
       // ---- convert, slice, store ----
+      int cs_next = cs[0];                                     // column-scale exponent, loaded one chunk ahead
       for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
+        const int cs_cur = cs_next;
+        if (c + 1 < n_chunks) cs_next = cs[2 * (c + 1)];
         mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
         // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
-        const int sh = min(max(cs[2 * c] + 1061 - emax, -1000), 1000);
+        const int sh = min(max(cs_cur + 1061 - emax, -1000), 1000);
         const double mult = __hiloint2double((1023 + sh) << 20, 0);
         const unsigned char* vsrc = sR + (rc % kWtRing) * kWtRingBytes;
         uint32_t wd[kWtNA][4];
