@@ -13,6 +13,10 @@
 //   k_p3d_hankel_f64  the same with float64 cells (CPX_PRECISE_CELLS, reference-precision mode)
 //   k_window      window convolution + theta rebinning (+ Cholesky whitening and chi2) as a batched
 //                 FP64 tensor-core (DMMA) contraction (likelihood.py:53-88, 170-194)
+//   k_window_tc   (cpx_window_tc.cuh) the chi2 flavour of k_window on tcgen05: exact INT8 split of Px_Zam and of
+//                 the whitened window operator, INT32 accumulators in tensor memory, HBM-bound; the default
+//   k_p3d_hankel_tc  (cpx_hankel_tc.cuh) the Hankel contraction of k_p3d_hankel on tcgen05 with the same split;
+//                 opt-in (CPX_TC=1), currently slower than the DMMA kernel
 //   k_reduce      chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
 //   k_probe_*     pipe-rate probes for the roofline denominators
 #pragma once

@@ -12,21 +12,25 @@
 //     every Px element enters the fixed-point conversion with the size of its largest contribution to any
 //     output -- Px falls by many decades along k_par while T rises with 1/sigma;
 //   * the Px row of a (point, theta_A) -- all pairs, all m -- becomes 40-bit two's-complement fixed point
-//     relative to its exact maximum exponent (every tile is streamed twice: the first pass, from HBM,
+//     relative to its exact maximum exponent (every tile is streamed twice: the first read, from HBM,
 //     only takes the maximum; the second, from L2, converts with one magic-number DFMA per element);
 //     its five bytes are the operand slices (top byte s8, others u8);
 //   * slice pairs with i + j = s share TMEM columns NB*s .. NB*s + NB, pairs with i + j > 4 (< 2^-40) are
 //     dropped; the epilogue combines the five INT32 per output by Horner in float64.
 //
-// CTA = 8 worker warps + one MMA-issuing thread + one TMA thread, one CTA per SM (5 x 64 accumulator
-// columns round up to the whole tensor memory).  A tile is 128 points x one theta_A x one z; a CTA walks
-// the theta_A bins blockIdx.y, blockIdx.y + gridDim.y, ... of its 128 points so that the Px stream of the
-// next tile is already in flight while the accumulators of the current one are read out.
-// Px_Zam streams into a 5-deep shared-memory ring of 32 KB chunks (128 points x 32 fine-k values) with two
-// 3-D tiled TMA loads per chunk (128-byte swizzle, so that the per-point reads are bank-conflict free); worker
-// thread (point r, half h) converts its 16 doubles and writes one 16-byte core-matrix row into each of the five
-// u8/s8 operand tiles (2 stages, mbarriers); the digit tiles of T stream in with TMA bulk copies.  HBM traffic
-// is one read of Px_Zam: the kernel is bound by that read.
+// CTA = 16 warps, one CTA per SM (5 x 64 accumulator columns round up to the whole tensor memory).  A tile is
+// 128 points x one theta_A x one z; a CTA walks the theta_A bins blockIdx.y, blockIdx.y + gridDim.y, ... of its
+// 128 points.  Roles (they synchronise through mbarriers and two shared-memory counters only):
+//   warps 0-7   workers: convert the chunks of the second Px stream (32 KB = 128 points x 32 fine-k values, the
+//               same bytes the scouts saw, now from L2), write one 16-byte core-matrix row per slice and chunk
+//               into a 3-stage operand ring, and run the epilogue of the tile (tcgen05.ld, Horner, chi2);
+//   warp 8      one thread issues the six tcgen05.mma of a chunk and commits them;
+//   warp 9      one thread streams the digit tiles of T (1-D TMA bulk copies);
+//   warps 10-11 one thread each streams Px_Zam with 3-D tiled TMA loads from a tensor map of the scratch buffer
+//               (128-byte swizzle: the per-point reads are bank-conflict free) -- once for the scouts (this is
+//               the read that comes from HBM), once for the workers;
+//   warps 12-15 scouts: run one tile ahead and only take the largest exponent of every row (sE).
+// HBM traffic is one read of Px_Zam; the kernel is bound by that read (profiles/k_window_tc_ncu_r01.txt).
 #pragma once
 #include "cpx_hankel_tc.cuh"
 
