@@ -830,7 +830,10 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   for (int i = 0; i < n_zl; ++i) nA_of_z[i] = h->z[zl[i]].dev.n_A;
   CPX_CUDA(cudaMemcpyAsync(h->d_nA_of_z, nA_of_z.data(), sizeof(int) * n_zl, cudaMemcpyHostToDevice, st));
 
-  const bool wtc = h->wt_nb > 0 && want_chi2;     // chi2 stage on the tensor cores (k_window_tc)
+  // chi2 stage on the tensor cores (k_window_tc) when the call carries enough (point, z) pairs to amortise its per-tile
+  // fixed costs (tensor-memory allocation, pipeline fill); below that the FP64 DMMA GEMM has the lower latency
+  // (profiles/latency_report_r01.txt).  One decision per call, so that all chunks of a batch take the same kernel.
+  const bool wtc = h->wt_nb > 0 && want_chi2 && static_cast<long long>(a->B) * n_zl >= env_int("CPX_WTC_MIN", 49152);
   int last_table_count = -1, last_pp = -1;
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));

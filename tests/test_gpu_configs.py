@@ -126,8 +126,10 @@ def test_S5_stress_shape_properties():
     np.testing.assert_array_equal(a[perm], b)
     assert (a > 0).all() and np.isfinite(a).all()
     # the single-z Likelihood of bin 3 gives the same numbers as the joint engine restricted to it
+    # (64 points of one z take the FP64 DMMA window kernel, the 4096 x 12 batch above the tcgen05 one: the two
+    # agree to the ~2^-40 of the integer split, not bit for bit)
     c = likes[3].get_chi2_batch(absolute[:64], names)
-    np.testing.assert_allclose(c, a[:64], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(c, a[:64], rtol=1e-9, atol=1e-9)
 
 
 def test_emulator_tensor_handoff():

@@ -78,6 +78,7 @@ def _window_paths(monkeypatch, plans, pts, names, data_idx=None):
     """chi2 per (z, theta_A) with the window stage on the tensor cores (default) and as the FP64 DMMA GEMM."""
     slots, zsel = slots_from_names(names)
     out = {}
+    monkeypatch.setenv("CPX_WTC_MIN", "0")      # small batches would otherwise take the (lower-latency) DMMA kernel
     for wtc in ("0", "1"):
         monkeypatch.setenv("CPX_WTC", wtc)
         eng = PxEngine(plans)
