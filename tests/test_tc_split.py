@@ -96,3 +96,76 @@ def test_weight_digits_reconstruct_the_weights():
     rec = sum(B[j].astype(np.float64) * 256.0 ** -(j + 1) for j in range(NW_DIGITS)) * s_q[None, :] * t_a[:, None]
     assert np.abs(rec - p.hankel_w).max() <= 0.5 * 256.0 ** -NW_DIGITS * (s_q[None, :] * t_a[:, None]).max() * (1 + 1e-12)
     assert all(d.min() >= -128 and d.max() <= 127 for d in B)
+
+
+# ------------------------------------------------------------------------------------------------
+# k_window_tc (cupix_b200/csrc/cpx_window_tc.cuh): the same split for the window / whitening / chi2 stage
+# ------------------------------------------------------------------------------------------------
+def window_split_chi2(p, px_am, data_index=0):
+    """chi2_A of one point from Px_Zam[a, m] through the integer pipeline of k_window_tc: T_chi with column
+    scales 2^c per 16 fine-k values and five balanced digits, the Px row of a theta_A as 40-bit two's-complement
+    fixed point below its largest exponent, slice pairs beyond i + j = 4 dropped, Horner in float64."""
+    n_m_pad = -(-p.n_m // 32) * 32
+    chi2 = []
+    for A in range(p.n_A):
+        pairs = np.where(p.B_A_a[A] != 0)[0]
+        vs = p.V_aM[pairs].sum(axis=0)
+        Linv = np.linalg.inv(np.linalg.cholesky(p.cov_AMM[A]))
+        T = np.zeros((len(pairs), p.n_M, n_m_pad))
+        for i, a in enumerate(pairs):
+            T[i, :, :p.n_m] = Linv @ ((p.V_aM[a] / vs)[:, None] * p.U_aMn[a])
+        x = np.zeros((len(pairs), n_m_pad))
+        x[:, :p.n_m] = px_am[pairs]
+        # column scales per (pair, 16 columns), folded onto Px
+        blk = np.abs(T).reshape(len(pairs), p.n_M, n_m_pad // 16, 16).max(axis=(1, 3))
+        c = np.where(blk > 0, np.clip(np.rint(np.log2(np.where(blk > 0, blk, 1.0))), -300, 300), 0.0)
+        cm = np.repeat(c, 16, axis=1)
+        Ts = T * 2.0 ** -cm[:, None, :]
+        rs = 2.05 * np.abs(Ts).max(axis=(0, 2))
+        rs = np.where(rs > 0, rs, 1.0)
+        X = np.rint(Ts / rs[None, :, None] * 256.0 ** 5).astype(np.int64)
+        digits = []
+        for _ in range(5):
+            dgt = (X + 128) % 256 - 128
+            digits.append(dgt)
+            X = (X - dgt) // 256
+        assert np.all(X == 0)
+        digits = digits[::-1]
+        xs = x * 2.0 ** cm
+        e = np.frexp(np.abs(xs).max())[1] + 1022            # biased exponent of the row maximum (0 for an all-zero row)
+        e = int(min(max(e, 64), 2000))
+        I = np.rint(xs * 2.0 ** (1061 - e)).astype(np.int64)   # |I| < 2^39
+        assert np.abs(I).max() < 2 ** 39
+        lo = I & 0xFFFFFFFF
+        sl = [(I >> 32)] + [(lo >> (8 * k)) & 255 for k in (3, 2, 1, 0)]     # signed top byte, then unsigned bytes 3..0
+        S = np.zeros(p.n_M)
+        for s in range(5):
+            D = np.zeros(p.n_M, dtype=np.int64)
+            for i in range(5):
+                j = s - i
+                if 0 <= j < 5:
+                    D += np.einsum("pMm,pm->M", digits[j], sl[i])
+            assert np.abs(D).max() < 2 ** 31
+            S += D.astype(np.float64) * 256.0 ** (4 - s)
+        y = S * 2.0 ** (e - 1069) * rs
+        res = Linv @ p.Px_AM[data_index, A] - y
+        chi2.append(res @ res)
+    return np.array(chi2)
+
+
+@pytest.mark.parametrize("sigma_decades", [0.0, 4.0])
+def test_window_integer_split_matches_float64_chi2(sigma_decades):
+    d = synthetic.make_measurement_dict("tiny_rebin", z0=2.4)
+    rng = np.random.default_rng(5)
+    d["Px_ZAM"] = 0.05 * rng.normal(size=d["Px_ZAM"].shape) + 0.1
+    n = d["cov_ZAM"].shape[2]
+    sig = 0.01 * np.geomspace(1.0, 10.0 ** -sigma_decades, n)           # T_chi rises with 1/sigma along k
+    d["cov_ZAM"] = np.broadcast_to(sig[:, None] * sig[None, :] * 0.3 ** np.abs(np.subtract.outer(np.arange(n), np.arange(n))),
+                                   d["cov_ZAM"].shape).copy()
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", {"include_hcd": True}, n_q=88)
+    p = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 3}).build_plan()
+    for params in ({}, {"bias": -0.2, "beta": 1.1, "kp_Mpc": 9.0}):
+        px = H.emulate_plan_px(p, params)
+        ref = H.emulate_plan_chi2(p, params)[1]
+        got = window_split_chi2(p, px)
+        np.testing.assert_allclose(got, ref, rtol=2e-9, atol=1e-9)
