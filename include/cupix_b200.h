@@ -24,6 +24,12 @@
  *                   builds a new DESI_DR2 + Likelihood per mock).
  *   cpx_destroy     object teardown.
  *
+ * Kernel selection (environment, read by cpx_create / cpx_eval; results agree to 2e-9 relative either way):
+ *   CPX_WTC=0       chi2 stage as the FP64 DMMA GEMM instead of the tcgen05 kernel (k_window_tc, the default for
+ *                   calls with at least CPX_WTC_MIN = 49152 (point, z) pairs)
+ *   CPX_TC=1        Hankel contraction on tcgen05 (k_p3d_hankel_tc) instead of FP64 DMMA
+ *   CPX_SCRATCH_MB  size of the per-chunk Px_Zam scratch buffer (default 4096)
+ *
  * Parameter slots (a point is a row of `P` doubles; slot[j] says which parameter column j sets,
  * zsel[j] restricts it to one z bin of the handle or -1 for all; parameters not named keep the
  * per-z defaults -- the "defaults overridden by matching keys" rule of
