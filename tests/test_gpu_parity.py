@@ -303,3 +303,56 @@ def test_bao_refined_rule_on_device():
         params = dict(zip(names, pts[i]))
         assert_px(model[i], H.emulate_plan_chi2(p, params)[0], msg="bao rule, emulation, pt %d" % i)
         assert_px(model[i], orc.get_convolved_px(params), msg="bao rule, oracle, pt %d" % i)
+
+
+def _training_box(z):
+    """min / max of the eight Arinyo slots at the ForestFlow training redshift nearest to z
+    (cupix_b200/data/ff_training_info.csv, the file the reference ships as data/emulator/ff_training_info.csv)."""
+    import os
+    import cupix_b200
+    ff = np.genfromtxt(os.path.join(os.path.dirname(cupix_b200.__file__), "data", "ff_training_info.csv"), delimiter=",", names=True)
+    row = ff[np.argmin(np.abs(ff["z"] - z))]
+    return {k: (float(row[k + "_min"]), float(row[k + "_max"])) for k in ("bias", "beta", "q1", "q2", "kvav", "av", "bv", "kp")}
+
+
+def test_latin_hypercube_over_all_16_slots_vs_float64_emulation():
+    """256 Latin-hypercube points over the 16-slot parameter box (Arinyo slots over the ForestFlow
+    training range, contaminant slots around their defaults), all contaminants on: model Px within 1e-5 of the
+    array maximum, chi2 within 1e-3 where chi2 <= 2 n_data and 1e-6 relative beyond."""
+    like, _ = _s1_like(N_t=2, flags=FLAG_SETS["all"], model="best_fit_arinyo_from_gadget", N_A=8, N_m=64)
+    box = _training_box(like.theory.z)
+    n = 256
+    rng = np.random.default_rng(256)
+
+    def lhs(lo, hi):
+        return lo + (hi - lo) * (rng.permutation(n) + rng.uniform(size=n)) / n
+    av = lhs(max(box["av"][0], 0.05), box["av"][1])
+    cols = {"bias": lhs(*box["bias"]), "beta": lhs(*box["beta"]), "q1": lhs(*box["q1"]), "q2": lhs(*box["q2"]),
+            "kv_Mpc": np.exp(np.log(lhs(*box["kvav"])) / av), "av": av, "bv": lhs(*box["bv"]), "kp_Mpc": lhs(*box["kp"]),
+            "b_H": lhs(-0.04, -0.005), "beta_H": lhs(0.2, 0.9), "L_H_Mpc": lhs(3.0, 12.0), "b_X": lhs(-0.01, -0.001),
+            "beta_X": lhs(0.2, 0.9), "b_noise_Mpc": lhs(0.0005, 0.006), "kC_Mpc": lhs(0.008, 0.03), "pC": lhs(0.3, 0.9)}
+    names = list(cols)
+    pts = np.stack([cols[k] for k in names], axis=1)
+    chi2 = like.get_chi2_batch(pts, names)
+    model = like.get_convolved_px_batch(pts, names)
+    p = like.build_plan()
+    assert np.isfinite(chi2).all()
+    for i in range(n):
+        m_ref, c_ref = H.emulate_plan_chi2(p, dict(zip(names, pts[i])))
+        assert_px(model[i], m_ref, msg="LHS point %d" % i)
+        assert_chi2(chi2[i], c_ref.sum(), "LHS point %d" % i, n_data=like.get_ndata())
+
+
+@pytest.mark.parametrize("params", [{"bv": 1e-13}, {"q1": 0.0, "q2": 0.0}, {"kp_Mpc": 1e3, "q1": 0.0, "q2": 0.0},
+                                    {"av": 1.0, "bv": 2.2, "kv_Mpc": 1.0}, {"beta": 0.0}, {"b_H": 0.0}])
+def test_edge_parameter_values_vs_float64_emulation(params):
+    """SURVEY 8(c) edge cases: mu^bv -> 1 (CoLoRe fits have bv ~ 0), no non-linear term, kp -> large (linear theory,
+    notebooks/analysis/mock_validation.py:82), the k_par = 0 row (mu = 0) is part of every S1 shape."""
+    like, _ = _s1_like(N_t=1, flags={"include_hcd": True}, model="best_fit_arinyo_from_gadget", N_A=6, N_m=48)
+    names = list(params)
+    pts = np.array([[params[k] for k in names]])
+    p = like.build_plan()
+    assert p.kpar_Mpc[0] == 0.0
+    m_ref, c_ref = H.emulate_plan_chi2(p, params)
+    assert_px(like.get_convolved_px_batch(pts, names)[0], m_ref, msg=str(params))
+    assert_chi2(like.get_chi2_batch(pts, names)[0], c_ref.sum(), str(params), n_data=like.get_ndata())
