@@ -134,3 +134,18 @@ class RescaledCosmology(Cosmology):
 
     def changes_linP(self, fid_cosmo):
         return (self.As != fid_cosmo.As) or (self.ns != fid_cosmo.ns)
+
+
+def cache_key(cosmo, fid_cosmo):
+    """Hashable identity of a cosmology for the engine caches of Theory / Likelihood.
+
+    The fiducial object maps to 0.  Cosmologies of this module are keyed by value, so the
+    RescaledCosmology built afresh by every scalar call with the same ``As, ns`` reuses one device
+    plan.  Foreign objects (a real ``lace`` Cosmology) are keyed by ``id``; the caches keep a reference
+    to the object next to its engine so that the id cannot be recycled for another cosmology while
+    the entry lives."""
+    if cosmo is None or cosmo is fid_cosmo:
+        return 0
+    if isinstance(cosmo, Cosmology):
+        return ("params",) + tuple(sorted(cosmo.params.items()))
+    return ("id", id(cosmo))

@@ -7,6 +7,7 @@ of the ``*_batch`` / ``*_grid`` methods; all of them go through the C ABI (cupix
 import numpy as np
 from scipy.stats.distributions import chi2 as chi2_scipy
 
+from cupix_b200 import cosmology as _cosmology
 from cupix_b200 import plan as _plan
 from cupix_b200.engine import PxEngine, slots_from_names
 from cupix_b200.likelihood.likelihood_parameter import dict_from_likeparam
@@ -42,12 +43,14 @@ class Likelihood(object):
     def engine(self, cosmo=None):
         """Device engine for the current N_theta_average (callers toggle that attribute, e.g.
         notebooks/examples/average_theory.py:267-271) and cosmology."""
-        key = (self.N_theta_average, 0 if cosmo is None or cosmo is self.theory.fid_cosmo else id(cosmo))
+        key = (self.N_theta_average, _cosmology.cache_key(cosmo, self.theory.fid_cosmo))
         if key not in self._engines:
             if len(self._engines) > 4:
-                self._engines.pop(next(iter(self._engines))).close()
-            self._engines[key] = PxEngine([self.build_plan(cosmo)], device=self.device, precise=self.precise_cells)
-        return self._engines[key]
+                self._engines.pop(next(iter(self._engines)))[0].close()
+            # the cosmology object is kept with its engine (see cosmology.cache_key)
+            self._engines[key] = (PxEngine([self.build_plan(cosmo)], device=self.device, precise=self.precise_cells),
+                                  cosmo)
+        return self._engines[key][0]
 
     def _scalar_eval(self, params, want):
         cosmo = self.theory.get_cosmology(params=params)

@@ -85,13 +85,14 @@ class Theory(object):
     def _theta_engine(self, theta_arc, k_AA, cosmo):
         theta_arc = np.atleast_1d(np.asarray(theta_arc, dtype=np.float64))
         k_AA = np.atleast_1d(np.asarray(k_AA, dtype=np.float64))
-        key = (theta_arc.tobytes(), k_AA.tobytes(), id(cosmo) if cosmo is not self.fid_cosmo else 0)
+        key = (theta_arc.tobytes(), k_AA.tobytes(), _cosmology.cache_key(cosmo, self.fid_cosmo))
         if key not in self._engines:
             if len(self._engines) > 8:
-                self._engines.pop(next(iter(self._engines))).close()
+                self._engines.pop(next(iter(self._engines)))[0].close()
             p = _plan.build_theory_plan(self, cosmo, theta_arc, np.arange(theta_arc.size), k_AA, self.rule)
-            self._engines[key] = PxEngine([p], device=self.device, precise=self.precise_cells)
-        return self._engines[key]
+            # the cosmology object is kept with its engine (see cosmology.cache_key)
+            self._engines[key] = (PxEngine([p], device=self.device, precise=self.precise_cells), cosmo)
+        return self._engines[key][0]
 
     # -- predictions --------------------------------------------------------------------------
     def get_px_obs(self, theta_arc, k_AA, cosmo=None, params={}):

@@ -356,3 +356,32 @@ def test_edge_parameter_values_vs_float64_emulation(params):
     m_ref, c_ref = H.emulate_plan_chi2(p, params)
     assert_px(like.get_convolved_px_batch(pts, names)[0], m_ref, msg=str(params))
     assert_chi2(like.get_chi2_batch(pts, names)[0], c_ref.sum(), str(params), n_data=like.get_ndata())
+
+
+def test_cosmology_keys_in_params_vs_oracle():
+    """theory.py:49-64: `As` / `ns` among the params select a RescaledCosmology (same background), a changed
+    background a new cosmology; the device plan is rebuilt per cosmology and cached by value.  Interleaved
+    calls (test_likelihood.py:134-140 scans `ns` this way) must never be answered from another cosmology's plan."""
+    from cupix_b200.cosmology import Cosmology, RescaledCosmology
+    like, truth = _s1_like(N_t=1, flags={"include_hcd": True})
+    orc = H.oracle_likelihood(like)
+    fid = like.theory.fid_cosmo
+    seq = [{"ns": 0.95}, {"ns": 0.98, "As": 2.3e-9}, {}, {"ns": 0.95}, {"As": 1.9e-9}, {"ns": 0.98, "As": 2.3e-9},
+           {"H0": 70.0, "ns": 0.95}]
+    seen = {}
+    for cp in seq:
+        p = dict(truth, bias=-0.12, **cp)
+        got = like.get_chi2(p)
+        if not cp:
+            orc.theory.cosmo = fid
+        elif "H0" in cp:
+            orc.theory.cosmo = Cosmology(dict(fid.params, **cp))
+        else:
+            orc.theory.cosmo = RescaledCosmology(fid, cp)
+        assert_chi2(got, orc.get_chi2(p), "cosmology keys %s" % cp, n_data=like.get_ndata())
+        key = tuple(sorted(cp.items()))
+        if key in seen:
+            assert got == seen[key]          # same cosmology again: same plan, same bits
+        seen[key] = got
+    assert len(set(seen.values())) == len(seen)      # every cosmology moved chi2
+    assert len(like._engines) == len(seen)           # one plan per distinct cosmology, temporaries share by value

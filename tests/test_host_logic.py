@@ -104,3 +104,34 @@ def test_ensemble_sampler_recovers_gaussian():
     assert 0.2 < smp.acceptance_fraction < 0.9
     assert np.all(np.abs(flat.mean(axis=0) - 1.0) < 0.1)      # _FakeLike: unit Gaussian centred on 1
     assert np.all(np.abs(flat.std(axis=0) - 1.0) < 0.15)
+
+
+def test_cosmology_cache_key_and_branches():
+    """theory.py:49-64 branches, and the identity the engine caches use for a cosmology."""
+    from cupix_b200.cosmology import Cosmology, RescaledCosmology, cache_key
+    from cupix_b200.likelihood.theory import Theory
+    fid = Cosmology()
+    th = Theory(2.2, fid_cosmo=fid, config={"default_lya_model": "best_fit_arinyo_from_colore"})
+    assert th.get_cosmology(params={"bias": -0.1}) is fid
+    assert th.get_cosmology(cosmo=fid, params={"ns": 0.9}) is fid         # explicit cosmology wins
+    a = th.get_cosmology(params={"ns": 0.95})
+    b = th.get_cosmology(params={"ns": 0.95, "bias": -0.1})
+    c = th.get_cosmology(params={"ns": 0.96})
+    assert isinstance(a, RescaledCosmology) and a is not b
+    assert a.ns == 0.95 and a.As == fid.As and a.params["H0"] == fid.params["H0"]
+    new = th.get_cosmology(params={"H0": 70.0})
+    assert type(new) is Cosmology and new.params["H0"] == 70.0
+    assert cache_key(fid, fid) == 0 and cache_key(None, fid) == 0
+    assert cache_key(a, fid) == cache_key(b, fid) != cache_key(c, fid)
+    assert cache_key(new, fid) not in (0, cache_key(a, fid))
+
+    class Foreign(object):
+        pass
+    f = Foreign()
+    assert cache_key(f, fid) == ("id", id(f))
+    # the rescaled linear power is the fiducial one times (As'/As) (k/k_pivot)^(ns'-ns)
+    k = np.array([1e-3, 0.05, 0.7, 10.0])
+    r = RescaledCosmology(fid, {"As": 2.3e-9, "ns": 0.95})
+    np.testing.assert_allclose(r.get_linP_Mpc(2.2, k) / fid.get_linP_Mpc(2.2, k),
+                               (2.3e-9 / fid.As) * (k / fid.k_pivot) ** (0.95 - fid.ns), rtol=1e-12)
+    assert r.get_darc_dMpc(2.2) == fid.get_darc_dMpc(2.2)
