@@ -125,6 +125,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   Z.flags = d.flags;
   Z.dAA = d.dAA_dMpc;
   std::memcpy(Z.defaults, d.defaults, sizeof(Z.defaults));
+  Z.k_pivot = (d.k_pivot_Mpc > 0.0 && d.defaults[CPX_AS] > 0.0) ? d.k_pivot_Mpc : 0.0;
   size_t& bytes = h->device_bytes;
   auto keep = [&](void* p) { if (p) zh.owned.push_back(p); };
 
@@ -463,24 +464,28 @@ typedef void (*K1Fn)(const cpx::ZDev*, int, int, long long);
 
 // PP = 1 fits two CTAs per SM (<= 128 registers); PP = 2 runs one CTA per SM.
 // ADD: some evaluated z bin has additive contaminants (SiIII metals or sky) in its epilogue.
-template <bool ADD>
+// COSMO: some column of the call is CPX_AS / CPX_NS (linear power rescaled per point inside the cell loop).
+template <bool ADD, bool COSMO>
 K1Fn k1_select_add(int pp, int nt) {
   if (pp == 1) {
     switch (nt) {
-      case 1: return cpx::k_p3d_hankel<1, 1, 2, ADD>;
-      case 2: return cpx::k_p3d_hankel<1, 2, 2, ADD>;
-      case 3: return cpx::k_p3d_hankel<1, 3, 2, ADD>;
+      case 1: return cpx::k_p3d_hankel<1, 1, 2, ADD, COSMO>;
+      case 2: return cpx::k_p3d_hankel<1, 2, 2, ADD, COSMO>;
+      case 3: return cpx::k_p3d_hankel<1, 3, 2, ADD, COSMO>;
     }
   } else if (pp == 2) {
     switch (nt) {
-      case 1: return cpx::k_p3d_hankel<2, 1, 1, ADD>;
-      case 2: return cpx::k_p3d_hankel<2, 2, 1, ADD>;
-      case 3: return cpx::k_p3d_hankel<2, 3, 1, ADD>;
+      case 1: return cpx::k_p3d_hankel<2, 1, 1, ADD, COSMO>;
+      case 2: return cpx::k_p3d_hankel<2, 2, 1, ADD, COSMO>;
+      case 3: return cpx::k_p3d_hankel<2, 3, 1, ADD, COSMO>;
     }
   }
   return nullptr;
 }
-K1Fn k1_select(int pp, int nt, bool add) { return add ? k1_select_add<true>(pp, nt) : k1_select_add<false>(pp, nt); }
+K1Fn k1_select(int pp, int nt, bool add, bool cosmo = false) {
+  if (cosmo) return add ? k1_select_add<true, true>(pp, nt) : k1_select_add<false, true>(pp, nt);
+  return add ? k1_select_add<true, false>(pp, nt) : k1_select_add<false, false>(pp, nt);
+}
 int k1_ctas_per_sm(int pp) { return pp == 1 ? 2 : 1; }
 
 K1Fn k1_select_tc(int np, bool add) {
@@ -632,8 +637,8 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
 
   // opt in to the large dynamic shared memory for every k_p3d_hankel instantiation we may launch
   for (int pp = 1; pp <= 2; ++pp)
-    for (int add = 0; add < 2; ++add) {
-      K1Fn fn = k1_select(pp, h->na_blk / 8, add != 0);
+    for (int add = 0; add < 4; ++add) {
+      K1Fn fn = k1_select(pp, h->na_blk / 8, (add & 1) != 0, (add & 2) != 0);
       if (!fn) return bail(fail(CPX_ERR_UNSUPPORTED, "no k_p3d_hankel instantiation for this theta-bin count"));
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
@@ -738,6 +743,20 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     if (a->slot[j] < 0 || a->slot[j] >= CPX_NSLOTS) return fail(CPX_ERR_ARG, "cpx_eval: slot out of range");
     if (a->grid_n && a->grid_n[j] < 1) return fail(CPX_ERR_ARG, "cpx_eval: grid_n < 1");
   }
+  // CPX_AS / CPX_NS columns: the linear power is rescaled per point inside the cell loop
+  bool cosmo = false, tilt = false;
+  for (int j = 0; j < a->P; ++j) {
+    cosmo |= a->slot[j] == CPX_AS || a->slot[j] == CPX_NS;
+    tilt |= a->slot[j] == CPX_NS;
+  }
+  if (cosmo)
+    for (auto& zh : h->z) {
+      if (!(zh.dev.k_pivot > 0.0))
+        return fail(CPX_ERR_UNSUPPORTED, "cpx_eval: As / ns columns need k_pivot_Mpc and the default As of the plan's cosmology");
+      // the SiIII tables are Hankel moments of P_L at other redshifts: an amplitude factors out of them, a tilt does not
+      if (tilt && (zh.dev.flags & CPX_INCLUDE_METAL))
+        return fail(CPX_ERR_UNSUPPORTED, "cpx_eval: ns as a batch column is not available with include_metal (rebuild the plan per ns instead)");
+    }
   if (a->B == 0) return CPX_OK;
   CPX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : h->stream;
@@ -838,7 +857,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
     int pp = pp_env > 0 ? std::min(pp_env, 2) : 1;   // one point per warp, two CTAs per SM measured fastest
-    const bool tc = h->tc_np > 0 && !precise;
+    const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
     const int n_pg = precise ? count : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
     auto items_of = [&](const ZDev& Z) {
       return tc ? static_cast<long long>(Z.tc_nt) * Z.tc_nablk * n_pg : static_cast<long long>(Z.n_tiles) * Z.n_ablk * n_pg;
@@ -912,7 +931,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));
         fn<<<grid, kTcThreads, tc_smem_bytes(h->tc_np), st>>>(h->d_ztab, n_zl, count, n_items);
       } else {
-        K1Fn fn = k1_select(pp, h->na_blk / 8, additive);
+        K1Fn fn = k1_select(pp, h->na_blk / 8, additive, cosmo);
         const size_t smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
         const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * k1_ctas_per_sm(pp)));
         fn<<<grid, kK1Threads, smem, st>>>(h->d_ztab, n_zl, count, n_items);

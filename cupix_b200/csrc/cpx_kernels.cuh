@@ -50,8 +50,14 @@ struct PtPar {
   double kC, pC;
   // float64 copies for the reference-precision cell evaluation (CPX_PRECISE_CELLS)
   double q1_64, q2_64, av_64, bv_64, l2kv_64, ikp2_64;
+  // linear-power rescaling f(k) = 2^(dn log2 k + lr) for CPX_AS / CPX_NS columns (appended: k_p3d_hankel_tc
+  // stages the first 64 bytes of this struct); dn = ns - ns0, lr = log2(As / As0) - dn log2(k_pivot)
+  float dn, lr, lr_lo, pad2;
+  double lin_amp;             // As / As0: factor of the SiIII tables (linear in P_L; the tilt is refused with metals)
+  double dn_64, lr_64;
+  double pad3;                // keeps the size a multiple of 16: k_p3d_hankel_tc fetches the head with 16-byte cp.async
 };
-static_assert(sizeof(PtPar) == 176, "PtPar layout");
+static_assert(sizeof(PtPar) == 224 && sizeof(PtPar) % 16 == 0, "PtPar layout");
 
 // per-z device data for k_p3d_hankel / k_params
 struct RowPar;
@@ -71,7 +77,8 @@ struct ZDev {
   const double* metal_cross;            // [3][n_a][n_m] or null
   const double* sky_xi;                 // [n_a] or null
   const double* sky_smooth;             // [n_m] or null
-  double defaults[16];
+  double defaults[18];
+  double k_pivot;                       // pivot of the primordial power law (CPX_AS / CPX_NS), 0 = not available
   // window part
   int n_A, n_M, n_M_pad, n_pairs, n_data;
   int pad0;
@@ -185,9 +192,9 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
   if (i >= a.count) return;
   const ZDev& Z = ztab[zi];
   const int zglobal = zlist[zi];
-  double v[16];
+  double v[18];
 #pragma unroll
-  for (int s = 0; s < 16; ++s) v[s] = Z.defaults[s];
+  for (int s = 0; s < 18; ++s) v[s] = Z.defaults[s];
   if (a.grid_mode) {
     long long idx = a.grid_first + a.first + i;
     for (int j = a.P - 1; j >= 0; --j) {
@@ -231,6 +238,19 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
   o.b_noise = v[13];
   o.kC = v[14];
   o.pC = v[15];
+  // theory.py:54-56: same background, primordial power rescaled relative to the plan's cosmology
+  double dn = 0.0, ratio = 1.0;
+  if (Z.k_pivot > 0.0) {
+    dn = v[17] - Z.defaults[17];
+    ratio = v[16] / Z.defaults[16];
+  }
+  const double lr = log2(ratio) - dn * log2(Z.k_pivot > 0.0 ? Z.k_pivot : 1.0);
+  o.dn = static_cast<float>(dn);
+  split_hi_lo(lr, o.lr, o.lr_lo);
+  o.pad2 = 0.f;
+  o.lin_amp = ratio;
+  o.dn_64 = dn;
+  o.lr_64 = lr;
   Z.ptpar[i] = o;
 }
 
@@ -366,7 +386,7 @@ __device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int&
 #define kExpDnl exp2_poly2
 #endif
 
-template <int PP, int NT, int MINB, bool ADD>
+template <int PP, int NT, int MINB, bool ADD, bool COSMO = false>
 __global__ void __launch_bounds__(kK1Threads, MINB)
     k_p3d_hankel(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -457,9 +477,15 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     //      the Kaiser beta of this lane's rows; m-tiles are processed in pairs (2*pr, 2*pr + 1) ----
     float2 q1l[PP], q1lo[PP], q2l[PP], q2lo[PP], av[PP], bv[PP], nlkv[PP], nlkvlo[PP], ikp2l[PP], ikp2lo[PP];
     float2 betaT[2][PP], betaTlo[2][PP];
+    float2 cdn[PP], clr[PP], clrlo[PP];                 // COSMO: linear-power rescaling 2^(dn log2 k + lr)
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
       const PtPar& pr = Z.ptpar[min(pt0 + p, count - 1)];
+      if (COSMO) {
+        cdn[p] = dup2(pr.dn);
+        clr[p] = dup2(pr.lr);
+        clrlo[p] = dup2(pr.lr_lo);
+      }
       q1l[p] = dup2(pr.q1l);
       q1lo[p] = dup2(pr.q1l_lo);
       q2l[p] = dup2(pr.q2l);
@@ -515,10 +541,16 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
 #pragma unroll
       for (int pr2 = 0; pr2 < 2; ++pr2) {
-        const float2 D = c[(0 * 2 + pr2) * 32], L2K = c[(1 * 2 + pr2) * 32], L2MU = c[(2 * 2 + pr2) * 32];
-        const float2 MU2 = c[(3 * 2 + pr2) * 32], NK2 = c[(4 * 2 + pr2) * 32], PL = c[(5 * 2 + pr2) * 32];
+        const float2 D0 = c[(0 * 2 + pr2) * 32], L2K = c[(1 * 2 + pr2) * 32], L2MU = c[(2 * 2 + pr2) * 32];
+        const float2 MU2 = c[(3 * 2 + pr2) * 32], NK2 = c[(4 * 2 + pr2) * 32], PL0 = c[(5 * 2 + pr2) * 32];
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
+          float2 D = D0, PL = PL0;
+          if (COSMO) {   // P_L and Delta^2 of the rescaled cosmology (theory.py:54-56)
+            const float2 f = exp2_rr2(add2(fma2(cdn[p], L2K, clr[p]), clrlo[p]));
+            D = mul2(D0, f);
+            PL = mul2(PL0, f);
+          }
           // Delta^2 (q1 + q2 Delta^2) log2e
           const float2 nl = mul2(D, add2(fma2(q2l[p], D, q1l[p]), fma2(q2lo[p], D, q1lo[p])));
           // (k/kv)^av mu^bv
@@ -582,6 +614,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
                 add += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
                 add += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
                                        pr.beta * btx * Z.metal_cross[o + 2 * st]);
+                if (COSMO) add *= pr.lin_amp;
               }
               if (Z.flags & 4) add += sky * Z.sky_xi[a];
               px = fma(add, cont, px);
@@ -619,6 +652,7 @@ __global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__
     const bool rowwise = (Z.flags & 9) != 0;
     const PtPar& pr = Z.ptpar[pt];
     const double q1 = pr.q1_64, q2 = pr.q2_64, av = pr.av_64, bv = pr.bv_64, l2kv = pr.l2kv_64, ikp2 = pr.ikp2_64;
+    const bool cosmo = pr.dn_64 != 0.0 || pr.lr_64 != 0.0;
     double betaT[4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -641,8 +675,14 @@ __global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__
       for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
-        const double D = c[(0 * 4 + mt) * 32], L2K = c[(1 * 4 + mt) * 32], L2MU = c[(2 * 4 + mt) * 32];
-        const double MU2 = c[(3 * 4 + mt) * 32], K2 = c[(4 * 4 + mt) * 32], PL = c[(5 * 4 + mt) * 32];
+        const double L2K = c[(1 * 4 + mt) * 32], L2MU = c[(2 * 4 + mt) * 32];
+        const double MU2 = c[(3 * 4 + mt) * 32], K2 = c[(4 * 4 + mt) * 32];
+        double D = c[(0 * 4 + mt) * 32], PL = c[(5 * 4 + mt) * 32];
+        if (cosmo) {                                                           // rescaled linear power, theory.py:54-56
+          const double f = exp2(fma(pr.dn_64, L2K, pr.lr_64));
+          D *= f;
+          PL *= f;
+        }
         const double nl = D * (q1 + q2 * D);                                   // natural-log units here
         const double v = exp2(av * (L2K - l2kv) + bv * L2MU);                  // (k/kv)^av mu^bv
         const double e = exp(nl * (1.0 - v) - K2 * ikp2);
@@ -680,9 +720,15 @@ __global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__
             if (Z.flags & 2) {
               const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
               const double bx = pr.b_X, btx = pr.beta_X;
-              px += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
-              px += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
-                                    pr.beta * btx * Z.metal_cross[o + 2 * st]);
+              double ma = bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+              double mc = pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                          pr.beta * btx * Z.metal_cross[o + 2 * st]);
+              if (cosmo) {
+                ma *= pr.lin_amp;
+                mc *= pr.lin_amp;
+              }
+              px += ma;
+              px += mc;
             }
             if (Z.flags & 4) px += sky * Z.sky_xi[a];
             px *= cont;

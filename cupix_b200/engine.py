@@ -11,7 +11,7 @@ from cupix_b200 import plan as _plan
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcupix_b200.so")
 
-NSLOTS = 16
+NSLOTS = 18
 DEVICE_IO = 1
 PRECISE_CELLS = 2
 
@@ -28,6 +28,7 @@ class ZbinDesc(C.Structure):
         ("metal_auto", c_dp), ("metal_cross", c_dp), ("sky_xi_a", c_dp), ("sky_smooth_m", c_dp),
         ("defaults", C.c_double * NSLOTS),
         ("B_A_a", c_dp), ("U_aMn", c_dp), ("V_aM", c_dp), ("Px_AM", c_dp), ("cov_AMM", c_dp),
+        ("k_pivot_Mpc", C.c_double),
     ]
 
 
@@ -117,6 +118,7 @@ class PxEngine(object):
             d.n_A, d.n_M, d.n_data = p.n_A, p.n_M, p.n_data
             d.flags = p.flags
             d.dAA_dMpc = p.dAA_dMpc
+            d.k_pivot_Mpc = float(getattr(p, "k_pivot_Mpc", 0.0))
             for k, v in arrs.items():
                 setattr(d, k, _dp(v))
             for i in range(NSLOTS):

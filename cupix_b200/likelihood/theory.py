@@ -76,9 +76,10 @@ class Theory(object):
     # -- parameters ---------------------------------------------------------------------------
     @staticmethod
     def split_params(params):
-        """dict -> (names, values) of the keys the device path knows; the rest is dropped silently
-        (model_lya.py:193-196)."""
-        names = [k for k in params if k in _plan.SLOT_INDEX]
+        """dict -> (names, values) of the model keys the device path knows; the rest is dropped silently
+        (model_lya.py:193-196).  Cosmology keys are not columns here: get_cosmology turns them into a
+        cosmology object, as in the reference."""
+        names = [k for k in params if k in _plan.SLOT_INDEX and k not in _plan.COSMO_SLOT_NAMES]
         return names, np.array([[float(params[k]) for k in names]], dtype=np.float64).reshape(1, len(names))
 
     # -- engine cache ---------------------------------------------------------------------------

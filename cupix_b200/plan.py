@@ -14,8 +14,13 @@ import numpy as np
 from cupix_b200.quadrature import KperpRule
 
 SLOT_NAMES = ("bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc",
-              "b_H", "beta_H", "L_H_Mpc", "b_X", "beta_X", "b_noise_Mpc", "kC_Mpc", "pC")
+              "b_H", "beta_H", "L_H_Mpc", "b_X", "beta_X", "b_noise_Mpc", "kC_Mpc", "pC",
+              "As", "ns")
 SLOT_INDEX = {n: i for i, n in enumerate(SLOT_NAMES)}
+# primordial amplitude and tilt at fixed background (theory.py:54-56): batch columns only -- the device
+# rescales the linear power of the plan's cosmology by (As/As0) (k/k_pivot)^(ns-ns0) per point.  The
+# dict-based scalar API keeps the reference behaviour (a new cosmology object, hence a new plan).
+COSMO_SLOT_NAMES = ("As", "ns")
 
 INCLUDE_HCD, INCLUDE_METAL, INCLUDE_SKY, INCLUDE_CONTINUUM = 1, 2, 4, 8
 METAL_KP_MPC = 10.0      # theory.py:378,421
@@ -61,7 +66,9 @@ def _linP_on_cells(cosmo, z, k):
 
 
 def default_vector(theory, cosmo):
-    """The 16 per-z default parameter values in slot order."""
+    """The per-z default parameter values in slot order (16 model parameters, then As and ns of
+    ``cosmo``; 0 for a cosmology object that does not expose them, which switches the As / ns
+    columns off -- see ``k_pivot_of``)."""
     lya = theory.lya_model.get_lya_params(cosmo, {})
     c = theory.cont_model
     vals = dict(lya)
@@ -69,7 +76,18 @@ def default_vector(theory, cosmo):
     vals.update(c.get_metal_params({}))
     vals.update(c.get_sky_params({}))
     vals.update(c.get_continuum_params({}))
+    vals["As"] = getattr(cosmo, "As", 0.0) if k_pivot_of(cosmo) > 0 else 0.0
+    vals["ns"] = getattr(cosmo, "ns", 0.0) if k_pivot_of(cosmo) > 0 else 0.0
     return np.array([float(vals[n]) for n in SLOT_NAMES])
+
+
+def k_pivot_of(cosmo):
+    """Pivot [1/Mpc] of the primordial power law of ``cosmo`` if the object exposes ``As``, ``ns`` and
+    ``k_pivot`` and its linear power follows P_L ~ As (k/k_pivot)^(ns-1) at fixed background (true for
+    cupix_b200.cosmology; a foreign object must opt in by carrying the three attributes), else 0."""
+    if all(hasattr(cosmo, a) for a in ("As", "ns", "k_pivot")):
+        return float(cosmo.k_pivot)
+    return 0.0
 
 
 def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
@@ -94,6 +112,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
     k, _ = _cells(p.kpar_Mpc, p.kperp_Mpc)
     p.linP_cell = _linP_on_cells(cosmo, z, k)
     p.defaults = default_vector(theory, cosmo)
+    p.k_pivot_Mpc = k_pivot_of(cosmo)
     p.flags = (INCLUDE_HCD * bool(theory.include_hcd) | INCLUDE_METAL * bool(theory.include_metal)
                | INCLUDE_SKY * bool(theory.include_sky) | INCLUDE_CONTINUUM * bool(theory.include_continuum))
 

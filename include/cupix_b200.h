@@ -51,7 +51,11 @@ enum {
   CPX_B_X = 11, CPX_BETA_X = 12,                     /* SiIII: theory.py:361-438             */
   CPX_B_NOISE_MPC = 13,                              /* sky: theory.py:476-506               */
   CPX_KC_MPC = 14, CPX_PC = 15,                      /* continuum: theory.py:525-535         */
-  CPX_NSLOTS = 16
+  CPX_AS = 16, CPX_NS = 17,                          /* primordial amplitude and tilt at fixed background: the linear  */
+                                                     /* power of every cell is rescaled by (As/As0) (k/k_pivot)^(ns-ns0), */
+                                                     /* As0, ns0 = defaults[] = the cosmology linP_cell was sampled from  */
+                                                     /* (theory.py:54-56, RescaledCosmology); needs k_pivot_Mpc > 0       */
+  CPX_NSLOTS = 18
 };
 
 enum {
@@ -95,6 +99,8 @@ typedef struct cpx_zbin_desc {
   const double* V_aM;         /* [n_a][n_M]   theta-rebinning weights                            */
   const double* Px_AM;        /* [n_data][n_A][n_M] data vectors                                 */
   const double* cov_AMM;      /* [n_A][n_M][n_M] covariance blocks                               */
+  double k_pivot_Mpc;         /* pivot of the primordial power law for CPX_AS / CPX_NS columns;  */
+                              /* 0: the cosmology object does not expose one, such columns are refused */
 } cpx_zbin_desc;
 
 typedef struct cpx_handle cpx_handle;

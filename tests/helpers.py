@@ -57,7 +57,7 @@ def emulate_plan_px(p, params):
         if k in _plan.SLOT_INDEX:
             v[_plan.SLOT_INDEX[k]] = x
     bias, beta, q1, q2, kv, av, bv, kp = v[:8]
-    b_H, beta_H, L_H, b_X, beta_X, b_noise, kC, pC = v[8:]
+    b_H, beta_H, L_H, b_X, beta_X, b_noise, kC, pC = v[8:16]
     kpar, kperp = p.kpar_Mpc, p.kperp_Mpc
     k2 = kpar[:, None] ** 2 + kperp[None, :] ** 2
     k = np.sqrt(k2)
@@ -65,6 +65,11 @@ def emulate_plan_px(p, params):
     ks = np.where(pos, k, 1.0)
     mu = np.where(pos, kpar[:, None] / ks, 0.0)
     PL = p.linP_cell
+    # As / ns columns: linear power of the plan's cosmology rescaled per point (k_params, CPX_AS / CPX_NS)
+    amp = 1.0
+    if getattr(p, "k_pivot_Mpc", 0.0) > 0 and (v[16] != p.defaults[16] or v[17] != p.defaults[17]):
+        amp = v[16] / p.defaults[16]
+        PL = PL * amp * (ks / p.k_pivot_Mpc) ** (v[17] - p.defaults[17])
     D = ks ** 3 * PL / (2 * np.pi ** 2)
     with np.errstate(all="ignore"):
         vel = (ks / kv) ** av * mu ** bv
@@ -78,8 +83,8 @@ def emulate_plan_px(p, params):
     px = (p.hankel_w @ cell.T) * (bT ** 2 * p.dAA_dMpc)[None, :]                        # [n_a, n_m]
     if p.flags & _plan.INCLUDE_METAL:
         ma, mc = p.metal_auto, p.metal_cross
-        px = px + b_X ** 2 * (ma[0] + 2 * beta_X * ma[1] + beta_X ** 2 * ma[2])
-        px = px + bias * b_X * (mc[0] + (beta + beta_X) * mc[1] + beta * beta_X * mc[2])
+        px = px + amp * b_X ** 2 * (ma[0] + 2 * beta_X * ma[1] + beta_X ** 2 * ma[2])
+        px = px + amp * bias * b_X * (mc[0] + (beta + beta_X) * mc[1] + beta * beta_X * mc[2])
     if p.flags & _plan.INCLUDE_SKY:
         px = px + b_noise * np.outer(p.sky_xi_a, p.sky_smooth_m)
     if p.flags & _plan.INCLUDE_CONTINUUM:

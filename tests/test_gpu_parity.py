@@ -385,3 +385,65 @@ def test_cosmology_keys_in_params_vs_oracle():
         seen[key] = got
     assert len(set(seen.values())) == len(seen)      # every cosmology moved chi2
     assert len(like._engines) == len(seen)           # one plan per distinct cosmology, temporaries share by value
+
+
+def test_As_ns_batch_columns_vs_oracle():
+    """primordial amplitude and tilt as batch columns (CPX_AS, CPX_NS) -- the device rescales the
+    linear power of the plan's cosmology per point; the oracle builds a RescaledCosmology per point
+    (theory.py:54-56).  Points, grid and reference-precision paths; refusals."""
+    from cupix_b200.cosmology import RescaledCosmology
+    from cupix_b200.engine import CpxError
+    like, truth = _s1_like(N_t=1, flags={"include_hcd": True, "include_sky": True, "include_continuum": True})
+    orc = H.oracle_likelihood(like)
+    fid = like.theory.fid_cosmo
+    names = ["bias", "As", "ns", "q1"]
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.uniform(-0.125, -0.105, 40), rng.uniform(1.8e-9, 2.4e-9, 40), rng.uniform(0.93, 1.0, 40),
+                    rng.uniform(0.1, 0.6, 40)], axis=1)
+    pts[0, 1:3] = fid.As, fid.ns                     # fiducial values in the columns: the plain model
+    chi2 = like.get_chi2_batch(pts, names)
+    assert_chi2(chi2[0], like.get_chi2({"bias": pts[0, 0], "q1": pts[0, 3]}), "fiducial As, ns in the columns")
+    fine = like.get_chi2_batch(pts, names)
+    np.testing.assert_array_equal(chi2, fine)
+    like_p = Likelihood(like.data, like.theory, 0, config={"N_theta_average": 1, "precise_cells": True})
+    chi2_p = like_p.get_chi2_batch(pts[:8], names)
+    px = like.get_convolved_px_batch(pts[:8], names)
+    for i in range(8):
+        orc.theory.cosmo = RescaledCosmology(fid, {"As": pts[i, 1], "ns": pts[i, 2]})
+        par = {"bias": pts[i, 0], "q1": pts[i, 3]}
+        ref = orc.get_chi2(par)
+        assert_chi2(chi2[i], ref, "As/ns point %d" % i, n_data=like.get_ndata())
+        np.testing.assert_allclose(chi2_p[i], ref, rtol=2e-8, err_msg="precise cells, point %d" % i)
+        assert_px(px[i], orc.get_convolved_px(par), msg="model, point %d" % i)
+    assert np.ptp(chi2) > 10.0                        # the columns move chi2
+    # a scalar call with the same cosmology keys goes through a rebuilt plan (reference behaviour): same answer
+    assert_chi2(like.get_chi2({"bias": pts[3, 0], "q1": pts[3, 3], "As": pts[3, 1], "ns": pts[3, 2]}), chi2[3],
+                "scalar call with cosmology keys", n_data=like.get_ndata())
+    # on-device grid over (As, ns)
+    lo, hi, n = [1.9e-9, 0.94], [2.3e-9, 0.99], [5, 4]
+    g = like.get_chi2_grid(["As", "ns"], lo, hi, n)
+    aa, nn = np.meshgrid(np.linspace(lo[0], hi[0], 5), np.linspace(lo[1], hi[1], 4), indexing="ij")
+    np.testing.assert_array_equal(g, like.get_chi2_batch(np.stack([aa.ravel(), nn.ravel()], axis=1), ["As", "ns"]))
+    # SiIII: the amplitude factors out of the metal tables, the tilt does not
+    like_m, _ = _s1_like(N_t=1, flags={"include_metal": True, "include_hcd": True})
+    orc_m = H.oracle_likelihood(like_m)
+    got = like_m.get_chi2_batch(np.array([[-0.12, 2.3e-9]]), ["bias", "As"])[0]
+    orc_m.theory.cosmo = RescaledCosmology(fid, {"As": 2.3e-9})
+    assert_chi2(got, orc_m.get_chi2({"bias": -0.12}), "As with SiIII", n_data=like_m.get_ndata())
+    with pytest.raises(CpxError, match="include_metal"):
+        like_m.get_chi2_batch(np.array([[-0.12, 0.95]]), ["bias", "ns"])
+
+    # a cosmology object that does not expose As / ns / k_pivot: the columns are refused, everything else works
+    class Opaque(object):
+        def __init__(self, c):
+            self._c = c
+        def get_linP_Mpc(self, z, k_Mpc): return self._c.get_linP_Mpc(z, k_Mpc)
+        def get_darc_dMpc(self, z): return self._c.get_darc_dMpc(z)
+        def get_dAA_dMpc(self, z, lambda_rest_AA=None): return self._c.get_dAA_dMpc(z, lambda_rest_AA=lambda_rest_AA)
+        def same_background(self, cosmo_params=None): return True
+        def get_linP_Mpc_params(self, z, kp_Mpc=0.7): return self._c.get_linP_Mpc_params(z, kp_Mpc)
+    th_o = H.make_theory(like.theory.z, "best_fit_arinyo_from_colore", {}, cosmo=Opaque(fid))
+    like_o = Likelihood(like.data, th_o, 0, config={"N_theta_average": 1})
+    assert np.isfinite(like_o.get_chi2({"bias": -0.12}))
+    with pytest.raises(CpxError, match="k_pivot"):
+        like_o.get_chi2_batch(np.array([[2.2e-9]]), ["As"])

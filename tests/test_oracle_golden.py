@@ -94,3 +94,25 @@ def test_data_cuts_match_reference():
     np.testing.assert_array_equal(data.B_A_a, g["B_A_a"])
     np.testing.assert_allclose(data.theta_min_A_arcmin, g["theta_min_A"])
     np.testing.assert_allclose(data.theta_min_a_arcmin, g["theta_min_a"])
+
+
+@pytest.mark.parametrize("fname,cosmo_cols", [
+    ("hcd", {"As": 2.4e-9, "ns": 0.93}), ("hcd", {"ns": 1.0}), ("lya", {"As": 1.7e-9}),
+    ("all", {"As": 2.4e-9}),                   # with SiIII only the amplitude may vary (a tilt does not factor out)
+])
+def test_plan_emulation_As_ns_columns_equal_rescaled_cosmology(fname, cosmo_cols):
+    """The per-point linear-power rescaling behind the As / ns batch columns (CPX_AS, CPX_NS) is what the
+    reference gets by building a RescaledCosmology for the point (theory.py:54-56): same Px to 1e-9."""
+    from cupix_b200.cosmology import RescaledCosmology
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS[fname])
+    theta = G["theta_arc"]
+    p = _plan.build_theory_plan(th, th.fid_cosmo, theta, np.arange(theta.size), G["k_AA"], th.rule)
+    assert p.k_pivot_Mpc == th.fid_cosmo.k_pivot and p.defaults[_plan.SLOT_INDEX["ns"]] == th.fid_cosmo.ns
+    orc = H.oracle_for(th)
+    orc.cosmo = RescaledCosmology(th.fid_cosmo, cosmo_cols)
+    for pname in ("defaults", "arinyo", "contaminants"):
+        params = PARAM_SETS[pname]
+        ref = orc.get_px_obs(theta, G["k_AA"], params)
+        got = H.emulate_plan_px(p, dict(params, **cosmo_cols))
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max(), err_msg=pname)
+        assert np.abs(H.emulate_plan_px(p, params) - ref).max() > 1e-4 * np.abs(ref).max()   # the columns did something
