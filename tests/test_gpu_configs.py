@@ -100,6 +100,30 @@ def test_S4_fit_many_mocks_lockstep():
     assert fitter.n_calls < 60            # vs ~100 likelihood calls per mock with MIGRAD, serial
 
 
+def test_minimizer_mirror_recovers_truth_with_cosmology_axis():
+    """BASELINE config 4 shape (fit_true_cont.py): the Minimizer mirror (minimize_posterior.py interface) on a
+    noiseless mock recovers the truth; `ns` is a free parameter next to bias and beta."""
+    from cupix_b200.likelihood.free_parameter import FreeParameter
+    from cupix_b200.likelihood.minimize_posterior import Minimizer
+    from cupix_b200.likelihood.posterior import Posterior
+    data, likes, joint = _build("S1", "best_fit_arinyo_from_colore", {"include_hcd": True}, N_t=1, N_m=48, N_A=8, noise=False)
+    like = likes[0]
+    d0 = like.build_plan().defaults
+    ns0 = like.theory.fid_cosmo.ns
+    pars = [FreeParameter("bias", d0[0] - 0.05, d0[0] + 0.05, ini_value=d0[0] * 1.04, delta=2e-3, true_value=d0[0]),
+            FreeParameter("beta", d0[1] - 0.6, d0[1] + 0.6, ini_value=d0[1] * 0.95, delta=5e-2, true_value=d0[1]),
+            FreeParameter("ns", ns0 - 0.2, ns0 + 0.2, ini_value=ns0 + 0.03, delta=2e-2, true_value=ns0)]
+    mini = Minimizer(Posterior(like, pars), {"n_starts": 3})
+    res = mini.get_results_dict()
+    assert mini.valid
+    for p in pars:
+        assert abs(res[p.name] - p.true_value) < 0.05 * res[p.name + "_err"], p.name    # noiseless: far inside the error
+        assert 0 < res[p.name + "_err"] < (p.max_value - p.min_value)
+    assert res["chi2"] < 1e-3 and res["ndf"] == like.get_ndata() - 3
+    np.testing.assert_allclose(res["cov"], res["cov"].T, rtol=1e-9)
+    assert np.all(np.linalg.eigvalsh(res["cov"]) > 0)
+
+
 def test_S5_stress_shape_properties():
     """Full stress size: 12 z x 20 theta x 256 k_par x 64 k_M, dense windows, N_theta_average = 100."""
     data, likes, joint = _build("S5", "best_fit_arinyo_from_gadget", {"include_hcd": True}, N_t=100, noise=False)

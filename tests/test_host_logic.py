@@ -135,3 +135,70 @@ def test_cosmology_cache_key_and_branches():
     np.testing.assert_allclose(r.get_linP_Mpc(2.2, k) / fid.get_linP_Mpc(2.2, k),
                                (2.3e-9 / fid.As) * (k / fid.k_pivot) ** (0.95 - fid.ns), rtol=1e-12)
     assert r.get_darc_dMpc(2.2) == fid.get_darc_dMpc(2.2)
+
+
+class _QuadraticLike(object):
+    """chi2 = (x - mu)^T C^-1 (x - mu) + 7 with the batched and scalar entry points the fit drivers use."""
+    verbose = False
+
+    def __init__(self, names, mu, cov, ndata=50):
+        self.names, self.mu, self.icov, self.ndata = list(names), np.asarray(mu, float), np.linalg.inv(cov), ndata
+        self.n_batched = 0
+
+    def get_chi2_batch(self, points, names, data_idx=None):
+        self.n_batched += 1
+        d = np.asarray(points)[:, [list(names).index(n) for n in self.names]] - self.mu
+        return np.einsum("ni,ij,nj->n", d, self.icov, d) + 7.0
+
+    def get_log_like_batch(self, points, names, data_idx=None):
+        return -0.5 * self.get_chi2_batch(points, names)
+
+    def get_chi2(self, params={}, return_info=False):
+        c = self.get_chi2_batch(np.array([[params[n] for n in self.names]]), self.names)[0]
+        return (c, {"log_like_all": np.array([-0.5 * c])}) if return_info else c
+
+    def get_log_like(self, params={}, return_info=False):
+        return -0.5 * self.get_chi2(params)
+
+    def get_probability(self, params={}, n_free_p=0):
+        from scipy.stats.distributions import chi2 as chi2_scipy
+        return chi2_scipy.sf(self.get_chi2(params), self.ndata - n_free_p)
+
+    def get_ndata(self):
+        return self.ndata
+
+
+def test_minimizer_mirror_on_a_quadratic(tmp_path):
+    """minimize_posterior.py interface: best fit, HESSE-like errors (errordef 0.5 on -log P), priors, limits."""
+    from cupix_b200.likelihood.minimize_posterior import IminuitMinimizer, Minimizer
+    cov = np.array([[4e-4, 1.2e-4], [1.2e-4, 9e-4]])
+    like = _QuadraticLike(["bias", "beta"], [-0.12, 1.6], cov)
+    pars = [FreeParameter("bias", -0.5, 0.0, ini_value=-0.1, delta=0.02, true_value=-0.12),
+            FreeParameter("beta", 0.5, 3.0, ini_value=1.4, delta=0.05)]
+    mini = Minimizer(Posterior(like, pars), {"n_starts": 4})
+    best = mini.get_best_fit_params()                      # minimises on demand
+    assert mini.valid and abs(best["bias"] + 0.12) < 1e-6 and abs(best["beta"] - 1.6) < 1e-6
+    np.testing.assert_allclose(mini.covariance, cov, rtol=1e-5)
+    v, e = mini.get_best_fit_value("beta", return_hesse=True)
+    np.testing.assert_allclose(e, 0.03, rtol=1e-5)
+    assert abs(mini.get_best_fit_chi2() - 7.0) < 1e-8 and abs(mini.fmin - 3.5) < 1e-8
+    res = mini.get_results_dict()
+    assert set(res) == {"bias", "bias_err", "beta", "beta_err", "cov", "prob", "chi2", "ndata", "ndf"}
+    assert res["ndf"] == 48 and 0.0 < res["prob"] <= 1.0
+    assert like.n_batched < 40                             # a handful of batched stencils, not hundreds of scalar calls
+    path = mini.save_results(outfile="fit.npz", outpath=str(tmp_path))
+    with np.load(path, allow_pickle=True) as f:
+        assert abs(float(f["beta"]) - 1.6) < 1e-6
+    # a Gaussian prior pulls the best fit and tightens the error as for independent measurements
+    pars_p = [FreeParameter("bias", -0.5, 0.0, ini_value=-0.1, delta=0.02),
+              FreeParameter("beta", 0.5, 3.0, ini_value=1.4, delta=0.05, gauss_prior_mean=1.5, gauss_prior_width=0.03)]
+    like1 = _QuadraticLike(["bias", "beta"], [-0.12, 1.6], np.diag([4e-4, 9e-4]))
+    mp = IminuitMinimizer(like1, pars_p)
+    v, e = mp.get_best_fit_value("beta", return_hesse=True)
+    np.testing.assert_allclose([v, e], [1.55, 0.03 / np.sqrt(2)], rtol=1e-5)
+    # a limit that excludes the minimum: the fit stops at the bound
+    pars_l = [FreeParameter("bias", -0.5, 0.0, ini_value=-0.1, delta=0.02),
+              FreeParameter("beta", 0.5, 1.5, ini_value=1.4, delta=0.05)]
+    ml = Minimizer(Posterior(like1, pars_l))
+    assert abs(ml.get_best_fit_value("beta") - 1.5) < 1e-9
+    assert mp.minus_log_prob_interface([-0.12, 1.55]) == pytest.approx(3.5 + 0.5 * (0.05 / 0.03) ** 2 * 2, rel=1e-9)
