@@ -146,6 +146,20 @@ class Likelihood(object):
         """Replace the data vector(s) [n_data, N_A, N_M] scored by ``data_idx`` (many-mock fits)."""
         self.engine().set_data(0, Px_AM)
 
+    def generate_mocks(self, n_mocks, params={}, seed=None, install=True):
+        """``n_mocks`` noisy realisations ``model(params) + L n`` of the data vector, L L^T = cov per coarse theta
+        bin -- ``generate_px_forecast(add_noise=True)`` (likelihood.py:37-50) for many mocks at once, with the
+        Cholesky factors computed once and a seeded generator.  With ``install`` they become the data vectors
+        that ``data_idx = 0 .. n_mocks-1`` selects (scripts/fit_many_mocks.py:151-170 rebuilds data and
+        likelihood per mock instead).  Returns [n_mocks, N_A, N_M]."""
+        model = self.get_convolved_px(params=params)
+        L = np.linalg.cholesky(self.data.cov_ZAM[self.iz])                       # [N_A, N_M, N_M]
+        noise = np.random.default_rng(seed).normal(size=(int(n_mocks),) + model.shape)
+        mocks = model[None] + np.einsum("aij,naj->nai", L, noise)
+        if install:
+            self.set_mock_data(mocks)
+        return mocks
+
 
 class JointLikelihood(object):
     """Several redshift bins scored in one device call: chi2 = sum over z (full-shape evaluation).

@@ -78,13 +78,12 @@ def test_S4_fit_many_mocks_lockstep():
     data, likes, joint = _build("S1", "best_fit_arinyo_from_colore", {}, N_t=1, N_m=48, N_A=8, noise=False)
     like = likes[0]
     truth = like.build_plan().defaults[:2]
-    rng = np.random.default_rng(9)
     n_mocks = 64
-    cov = data.cov_ZAM[0]
-    L = np.linalg.cholesky(cov)
-    base = data.Px_ZAM[0]
-    mocks = base[None] + np.einsum("aij,naj->nai", L, rng.normal(size=(n_mocks,) + base.shape))
-    like.set_mock_data(mocks)
+    mocks = like.generate_mocks(n_mocks, seed=9)              # model(defaults) + L n, installed as data vectors 0..63
+    assert mocks.shape == (n_mocks,) + data.Px_ZAM[0].shape
+    white = np.linalg.solve(np.linalg.cholesky(data.cov_ZAM[0]), (mocks - data.Px_ZAM[0][None]).transpose(1, 2, 0))
+    assert abs(white.std() - 1.0) < 0.02 and abs(white.mean()) < 0.02          # unit Gaussian after whitening
+    np.testing.assert_array_equal(like.generate_mocks(n_mocks, seed=9, install=False), mocks)     # seeded
     fitter = BatchMinimizer(like, ["bias", "beta"], steps=[2e-4, 5e-3])
     x0 = np.tile(truth * np.array([1.05, 0.93]), (n_mocks, 1))
     res = fitter.minimize(x0, data_idx=np.arange(n_mocks))
