@@ -14,6 +14,7 @@ max |dPx| / max|Px| <= 4e-8.
 import numpy as np
 import pytest
 
+from cupix_b200.engine import slots_from_names
 from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
 from cupix_b200.px_data import synthetic
 from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2
@@ -447,3 +448,42 @@ def test_As_ns_batch_columns_vs_oracle():
     assert np.isfinite(like_o.get_chi2({"bias": -0.12}))
     with pytest.raises(CpxError, match="k_pivot"):
         like_o.get_chi2_batch(np.array([[2.2e-9]]), ["As"])
+
+
+@pytest.mark.parametrize("B", [203, 49152 + 77])     # DMMA window with a partial tile; tcgen05 window with a partial tile
+def test_device_outputs_stay_inside_their_buffers(B):
+    """Guard bands around every device output of cpx_eval (chi2, chi2_zA, model_zAM, px_zam) on a shape with
+    padding in every dimension (theta 11 x 2, k_par 50, coarse k 16, two z bins): the bands stay untouched and
+    the interior is fully written.  (compute-sanitizer is not available on the GPU pool.)"""
+    import torch
+    d = synthetic.make_measurement_dict("S1", N_A=11, fine_per_coarse=2, N_m=50, rebin_k=3, Nz=2)
+    likes = [Likelihood(DESI_DR2(d), H.make_theory(float(z), "best_fit_arinyo_from_gadget", {"include_hcd": True}, n_q=72),
+                        iz, config={"N_theta_average": 1}) for iz, z in enumerate(d["z_centers"])]
+    joint = JointLikelihood(likes)
+    eng = joint.engine()
+    n_z, n_A, n_M, n_a, n_m = 2, 11, 16, 22, 50
+    G, SENT = 4096, -7.25e99
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(B)
+    pts = torch.tensor(np.stack([rng.uniform(-0.2, -0.1, B), rng.uniform(1.0, 2.0, B)], axis=1), device=dev)
+    slots, zsel = slots_from_names(["bias", "beta"])
+
+    def guarded(n):
+        t = torch.full((n + 2 * G,), SENT, dtype=torch.float64, device=dev)
+        return t, t.data_ptr() + 8 * G
+
+    sizes = {"chi2": B, "chi2_zA": B * n_z * n_A, "model": B * n_z * n_A * n_M, "px": B * n_z * n_a * n_m}
+    bufs = {k: guarded(n) for k, n in sizes.items()}
+    st = torch.cuda.current_stream(dev).cuda_stream
+    eng.eval_device(B, 2, slots, points_ptr=pts.data_ptr(), zsel=zsel, chi2_ptr=bufs["chi2"][1],
+                    chi2_zA_ptr=bufs["chi2_zA"][1], stream=st)
+    eng.eval_device(B, 2, slots, points_ptr=pts.data_ptr(), zsel=zsel, model_ptr=bufs["model"][1], px_ptr=bufs["px"][1],
+                    stream=st)
+    torch.cuda.synchronize()
+    for k, (t, _) in bufs.items():
+        assert bool((t[:G] == SENT).all()) and bool((t[-G:] == SENT).all()), "write outside the %s buffer" % k
+        inner = t[G:-G]
+        assert bool(torch.isfinite(inner).all()) and not bool((inner == SENT).any()), "%s not fully written" % k
+    chi2 = bufs["chi2"][0][G:-G].cpu().numpy()
+    np.testing.assert_allclose(chi2, bufs["chi2_zA"][0][G:-G].cpu().numpy().reshape(B, -1).sum(axis=1), rtol=1e-12)
+    np.testing.assert_allclose(chi2[:50], joint.get_chi2_batch(pts[:50].cpu().numpy(), ["bias", "beta"]), rtol=1e-9)
