@@ -76,9 +76,36 @@ struct cpx_handle {
   double* d_model = nullptr;         // [chunk][n_z][max_nA][max_nM]  (lazy)
   double* d_pxout = nullptr;         // [chunk][n_z][max_na][max_nm]  (lazy)
   std::vector<void*> owned;
+  // CPX_GUARD=1: every writable scratch buffer sits between two bands of kGuardBytes filled with kGuardByte;
+  // cpx_get_info(CPX_INFO_GUARD_VIOLATIONS) counts the band bytes that changed (the GPU pool has no compute-sanitizer)
+  bool guard = false;
+  std::vector<std::pair<unsigned char*, size_t>> guarded;   // (start of the front band, payload bytes)
 };
 
 namespace {
+constexpr size_t kGuardBytes = 65536;
+constexpr int kGuardByte = 0xA5;
+
+// writable device buffer owned by the handle; with h->guard the payload is fenced by two guard bands
+int scratch_alloc(cpx_handle* h, void** p, size_t bytes) {
+  if (!h->guard) {
+    CPX_CUDA(cudaMalloc(p, bytes));
+    h->owned.push_back(*p);
+    h->device_bytes += bytes;
+    return CPX_OK;
+  }
+  const size_t payload = (bytes + 255) / 256 * 256;         // keeps the rear band (and the payload) 256-byte aligned
+  unsigned char* base = nullptr;
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&base), payload + 2 * kGuardBytes));
+  h->owned.push_back(base);
+  h->device_bytes += payload + 2 * kGuardBytes;
+  CPX_CUDA(cudaMemset(base, kGuardByte, kGuardBytes));
+  CPX_CUDA(cudaMemset(base + kGuardBytes + bytes, kGuardByte, payload - bytes + kGuardBytes));
+  h->guarded.emplace_back(base, bytes);
+  *p = base + kGuardBytes;
+  return CPX_OK;
+}
+
 
 // ---- dense helpers (float64, tiny sizes) ---------------------------------------------------
 bool cholesky_lower(const double* C, int n, std::vector<double>& L) {
@@ -607,12 +634,8 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
   chunk = std::max(256LL, std::min(chunk, 65536LL)) / 256 * 256;
   h->chunk = static_cast<int>(chunk);
 
-  auto dmalloc = [&](void** p, size_t bytes) -> int {
-    CPX_CUDA(cudaMalloc(p, bytes));
-    h->owned.push_back(*p);
-    h->device_bytes += bytes;
-    return CPX_OK;
-  };
+  h->guard = env_int("CPX_GUARD", 0) != 0;
+  auto dmalloc = [&](void** p, size_t bytes) -> int { return scratch_alloc(h, p, bytes); };
   int rc;
   for (int i = 0; i < n_zbins; ++i) {
     cpx::ZDev& Z = h->z[i].dev;
@@ -728,6 +751,24 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
     case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
     case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
     case CPX_INFO_SM_COUNT: *value = h->sm_count; break;
+    case CPX_INFO_GUARD_BUFFERS: *value = static_cast<int64_t>(h->guarded.size()); break;
+    case CPX_INFO_GUARD_VIOLATIONS: {
+      // synchronises the device; counts guard-band bytes that no longer hold the fill pattern
+      if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return fail(CPX_ERR_CUDA, "cpx_get_info: device synchronisation failed");
+      std::vector<unsigned char> band(kGuardBytes + 256);
+      int64_t bad = 0;
+      for (const auto& g : h->guarded) {
+        const size_t payload = (g.second + 255) / 256 * 256;
+        const size_t rear = payload - g.second + kGuardBytes;
+        CPX_CUDA(cudaMemcpy(band.data(), g.first, kGuardBytes, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < kGuardBytes; ++i) bad += band[i] != kGuardByte;
+        CPX_CUDA(cudaMemcpy(band.data(), g.first + kGuardBytes + g.second, rear, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < rear; ++i) bad += band[i] != kGuardByte;
+      }
+      *value = bad;
+      break;
+    }
     default: return fail(CPX_ERR_ARG, "cpx_get_info: unknown item");
   }
   return CPX_OK;
@@ -793,10 +834,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   // lazy scratch for the bulky optional outputs
   auto lazy = [&](double** p, size_t n) -> int {
     if (*p) return CPX_OK;
-    CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(double)));
-    h->owned.push_back(*p);
-    h->device_bytes += n * sizeof(double);
-    return CPX_OK;
+    return scratch_alloc(h, reinterpret_cast<void**>(p), n * sizeof(double));
   };
   int rc;
   const size_t nz_all = h->z.size();

@@ -98,7 +98,8 @@ class PxEngine(object):
     """Device-resident Px likelihood for a list of redshift-bin plans (cupix_b200.plan.ZbinPlan)."""
 
     INFO = {"n_zbins": 0, "max_na": 1, "max_nm": 2, "max_nA": 3, "max_nM": 4, "chunk": 5,
-            "device_bytes": 6, "kernel_launches": 7, "sm_count": 8}
+            "device_bytes": 6, "kernel_launches": 7, "sm_count": 8, "guard_buffers": 9,
+            "guard_violations": 10}
 
     def __init__(self, plans, device=0, precise=False):
         """``precise=True`` evaluates the P3D cells in float64 as well (CPX_PRECISE_CELLS): the

@@ -29,6 +29,8 @@
  *                   calls with at least CPX_WTC_MIN = 49152 (point, z) pairs)
  *   CPX_TC=1        Hankel contraction on tcgen05 (k_p3d_hankel_tc) instead of FP64 DMMA
  *   CPX_SCRATCH_MB  size of the per-chunk Px_Zam scratch buffer (default 4096)
+ *   CPX_GUARD=1     debugging: fence every writable scratch buffer with 64 KiB guard bands, checked by
+ *                   cpx_get_info(CPX_INFO_GUARD_VIOLATIONS)
  *
  * Parameter slots (a point is a row of `P` doubles; slot[j] says which parameter column j sets,
  * zsel[j] restricts it to one z bin of the handle or -1 for all; parameters not named keep the
@@ -152,7 +154,9 @@ int cpx_version(void);
 int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value);
 enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_MAX_N_A = 3,
        CPX_INFO_MAX_N_M = 4, CPX_INFO_CHUNK = 5, CPX_INFO_DEVICE_BYTES = 6, CPX_INFO_KERNEL_LAUNCHES = 7,
-       CPX_INFO_SM_COUNT = 8 };
+       CPX_INFO_SM_COUNT = 8,
+       CPX_INFO_GUARD_BUFFERS = 9,      /* scratch buffers fenced by guard bands (handles created with CPX_GUARD=1) */
+       CPX_INFO_GUARD_VIOLATIONS = 10   /* guard-band bytes overwritten so far; synchronises the device            */ };
 
 /* Pipe-rate probes for the roofline denominators MEASURED_PEAKS.json does not hold: sustained
  * FP64 FMA (DFMA), FP32 FMA, MUFU.EX2 and FP64 tensor (DMMA m8n8k4, counted in FMAs) rates of this

@@ -130,3 +130,36 @@ def test_tensor_window_many_mocks_data_index(monkeypatch):
     idx = rng.integers(0, 4, 300)
     ref, got = _window_paths(monkeypatch, [p], pts, ["bias", "beta"], data_idx=idx)
     np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("tc", ["0", "1"])
+def test_scratch_guard_bands_stay_intact(monkeypatch, tc):
+    """CPX_GUARD=1 fences every writable scratch buffer of the handle (per-point parameters, row parameters,
+    Px_Zam, chi2 partials, lazy model / Px outputs) with 64 KiB guard bands.  After every kind of evaluation --
+    both Hankel kernels, the float64 cells, both window kernels with partial tiles, several chunks, many data
+    vectors -- no band byte has changed.  Shape with padding in every dimension."""
+    monkeypatch.setenv("CPX_GUARD", "1")
+    monkeypatch.setenv("CPX_TC", tc)
+    monkeypatch.setenv("CPX_SCRATCH_MB", "64")               # small chunks: the 9000-point batch spans several
+    plans = _plans("S2", 88, ALL, N_t=2, N_m=70, N_A=9, fine_per_coarse=2)
+    rng = np.random.default_rng(4)
+    for p in plans:
+        p.Px_AM = np.concatenate([p.Px_AM, p.Px_AM * 1.01, p.Px_AM * 0.99])
+        p.n_data = 3
+    names = ["bias", "beta", "q1", "b_H", "b_X", "As"]
+    slots, zsel = slots_from_names(names)
+    base = np.array([plans[0].defaults[_plan.SLOT_INDEX[n]] for n in names])
+    for precise in (False, True):
+        eng = PxEngine(plans, precise=precise)
+        assert eng.info("guard_buffers") >= 5 and eng.info("guard_violations") == 0
+        for B in ((1, 77, 9000, 49152 // 4 + 13) if not precise else (1, 77)):
+            pts = base[None, :] * rng.uniform(0.8, 1.2, size=(B, len(names)))
+            out = eng.eval(pts, slots, zsel=zsel, want=("chi2", "chi2_zA"), data_idx=rng.integers(0, 3, B).astype(np.int32))
+            assert np.isfinite(out["chi2"]).all()
+            if B <= 77:
+                out = eng.eval(pts, slots, zsel=zsel, want=("model", "px_zam"))
+                assert np.isfinite(out["model"]).all() and np.isfinite(out["px_zam"]).all()
+            eng.eval(pts[:, :2], slots[:2], zsel=zsel[:2], want=("chi2",))          # without the As column
+            assert eng.info("guard_violations") == 0, "scratch overrun after B = %d (precise = %s)" % (B, precise)
+        assert eng.info("chunk") < 9000 or precise
+        eng.close()
