@@ -326,21 +326,23 @@ __device__ __forceinline__ float exp2_scale(float p, float t) {
   // pipe, which is the one the FP64 tensor pipe competes with (profiles/dmma_contention_r01.txt)
   return __int_as_float(__float_as_int(p) + static_cast<int>(__funnelshift_l(0u, static_cast<unsigned>(__float_as_int(t)), 23)));
 }
-// 2^x, unbiased: 2^f is a degree-7 polynomial on the FMA pipe.  MUFU.EX2 alone is biased by
+// 2^x, unbiased: 2^f is a degree-6 polynomial on the FMA pipe.  MUFU.EX2 alone is biased by
 // -2e-8 .. -5e-8 on this range (tools/mufu_error.cu, profiles/mufu_error_r01.txt), which is coherent
-// over all cells and would shift chi2 by ~5e-7 relative.
+// over all cells and would shift chi2 by ~5e-7 relative.  Degree 6 (minimax fit of the relative error on
+// [-0.5, 0.5], coefficients rounded to float32 one at a time with the others refitted) approximates 2^f to
+// 3.0e-9 with a mean of -2e-12; evaluated in float32 its error statistics (bias < 3e-10, rms 2.6e-8) are those
+// of the degree-7 polynomial used before: the rounding of the last two Horner steps dominates either way.
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   x.x = fminf(fmaxf(x.x, -125.0f), 126.0f);
   x.y = fminf(fmaxf(x.y, -125.0f), 126.0f);
   float2 t, f;
   exp2_reduce(x, t, f);
-  float2 p = dup2(1.529732435301412e-05f);
-  p = fma2(p, f, dup2(0.00015461444854736328f));
-  p = fma2(p, f, dup2(0.0013333501992747188f));
-  p = fma2(p, f, dup2(0.009618056938052177f));
-  p = fma2(p, f, dup2(0.05550410971045494f));
-  p = fma2(p, f, dup2(0.24022650718688965f));
-  p = fma2(p, f, dup2(0.6931471824645996f));
+  float2 p = dup2(0.00015326094580814242f);
+  p = fma2(p, f, dup2(0.001339080510661006f));
+  p = fma2(p, f, dup2(0.0096185067668557167f));
+  p = fma2(p, f, dup2(0.055503599345684052f));
+  p = fma2(p, f, dup2(0.24022647738456726f));
+  p = fma2(p, f, dup2(0.69314718246459961f));
   p = fma2(p, f, dup2(1.0f));
   return make_float2(exp2_scale(p.x, t.x), exp2_scale(p.y, t.y));
 }
@@ -352,6 +354,16 @@ __device__ __forceinline__ float2 exp2_rr2(float2 x) {
   x.y = fmaxf(x.y, -125.0f);
   float2 t, f;
   exp2_reduce(x, t, f);
+  return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
+}
+// -2^x for free: with 256 added to the rounding constant, bit 8 of the integer part is set, and the shift by 23
+// that moves the integer part into the exponent field moves that bit into the sign.  The caller folds the
+// negation into an FFMA2 instead of spending a packed multiply on it.
+__device__ __forceinline__ float2 exp2_rr2_neg(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = add2(x, dup2(12583168.0f));                              // 1.5 * 2^23 + 256
+  const float2 f = fma2(add2(t, dup2(-12583168.0f)), dup2(-1.0f), x);
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 // 2^x with MUFU.EX2 on f = x - floor(x) in [0, 1): the bias of MUFU.EX2 depends on the sign and
@@ -554,10 +566,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
           // Delta^2 (q1 + q2 Delta^2) log2e
           const float2 nl = mul2(D, add2(fma2(q2l[p], D, q1l[p]), fma2(q2lo[p], D, q1lo[p])));
           // (k/kv)^av mu^bv
-          const float2 v = exp2_rr2(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), nlkvlo[p]));
+          const float2 nv = exp2_rr2_neg(add2(fma2(av[p], L2K, fma2(bv[p], L2MU, nlkv[p])), nlkvlo[p]));   // -(k/kv)^av mu^bv
           // D_NL = 2^(nl (1 - v) - (k/kp)^2 log2e)
           const float2 tt = fma2(NK2, ikp2lo[p], fma2(NK2, ikp2l[p], nl));
-          const float2 e = kExpDnl(fma2(mul2(nl, dup2(-1.0f)), v, tt));
+          const float2 e = kExpDnl(fma2(nl, nv, tt));
           // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice, plus the first-order
           // beta_lo term) so that its float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded
           // on its own takes the same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
