@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         ampcont = bias * bias * Z.dAA;
       }
       if (m >= Z.n_m) ampcont = 0.0;
-      const float2 betaT = dup2(bhi), betaTlo = dup2(2.0f * blo);
+      const float2 betaT = dup2(bhi), betaTlo = dup2(kKaiserLoScale * blo);
 
       // ---- the lane's 2 NP cells (nodes quarter * 2 NP + 2 p + {0, 1}), kept in registers ----
       float2 x[NP];
@@ -411,12 +411,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const float2 MU2 = make_float2(c1.z, c1.w), NK2 = make_float2(c2.x, c2.y), PL = make_float2(c2.z, c2.w);
         // identical arithmetic to k_p3d_hankel (see the comments there)
         const float2 nl = mul2(D, add2(fma2(q2l, D, q1l), fma2(q2lo, D, q1lo)));
-        const float2 v = exp2_rr2(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
+        const float2 nv = exp2_rr2_neg(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
         const float2 tt = fma2(NK2, ikp2lo, fma2(NK2, ikp2l, nl));
-        const float2 e = kExpDnl(fma2(mul2(nl, dup2(-1.0f)), v, tt));
+        const float2 e = kExpDnl(fma2(nl, nv, tt));
         float2 y = mul2(PL, e);
+#if CPX_KAISER == 0
         y = fma2(mul2(y, betaT), MU2, y);
         y = fma2(mul2(y, betaT), MU2, fma2(mul2(y, betaTlo), MU2, y));
+#else
+        const float2 bm = fma2(betaT, MU2, mul2(betaTlo, MU2));
+        y = fma2(y, bm, y);
+        y = fma2(y, bm, y);
+#endif
         x[p] = y;
         rmax = fmax3(rmax, y.x, y.y);
       }

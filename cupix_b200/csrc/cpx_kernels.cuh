@@ -317,9 +317,21 @@ __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
 // Range reduction shared by the two exp2 flavours: x = n + f, n = round(x) (returned in the low
 // mantissa bits of t), |f| <= 0.5 exactly.
+// CPX_EXP_REDUCE 0 (default): three packed FMA-pipe instructions.  1: the rounded value comes from FRND on the
+// conversion pipe and one packed instruction goes away (same t, same f, bit for bit) -- measured slower
+// (37.25 against 36.91 ms per 65 536-point S5 step, profiles/hankel_variants_r01.txt): FRND is not free here.
+#ifndef CPX_EXP_REDUCE
+#define CPX_EXP_REDUCE 0
+#endif
+template <int MAGIC_EXTRA = 0>
 __device__ __forceinline__ void exp2_reduce(float2 x, float2& t, float2& f) {
-  t = add2(x, dup2(12582912.0f));
-  f = fma2(add2(t, dup2(-12582912.0f)), dup2(-1.0f), x);
+  constexpr float magic = 12582912.0f + MAGIC_EXTRA;      // 1.5 * 2^23 (+ 256: see exp2_rr2_neg)
+  t = add2(x, dup2(magic));
+#if CPX_EXP_REDUCE == 0
+  f = fma2(add2(t, dup2(-magic)), dup2(-1.0f), x);
+#else
+  f = fma2(make_float2(rintf(x.x), rintf(x.y)), dup2(-1.0f), x);
+#endif
 }
 __device__ __forceinline__ float exp2_scale(float p, float t) {
   // funnel shift + add keep this on the ALU pipe; a plain (t << 23) + p becomes an IMAD on the FMA
@@ -336,7 +348,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   x.x = fminf(fmaxf(x.x, -125.0f), 126.0f);
   x.y = fminf(fmaxf(x.y, -125.0f), 126.0f);
   float2 t, f;
-  exp2_reduce(x, t, f);
+  exp2_reduce<0>(x, t, f);
   float2 p = dup2(0.00015326094580814242f);
   p = fma2(p, f, dup2(0.001339080510661006f));
   p = fma2(p, f, dup2(0.0096185067668557167f));
@@ -353,7 +365,7 @@ __device__ __forceinline__ float2 exp2_rr2(float2 x) {
   x.x = fmaxf(x.x, -125.0f);
   x.y = fmaxf(x.y, -125.0f);
   float2 t, f;
-  exp2_reduce(x, t, f);
+  exp2_reduce<0>(x, t, f);
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 // -2^x for free: with 256 added to the rounding constant, bit 8 of the integer part is set, and the shift by 23
@@ -362,8 +374,8 @@ __device__ __forceinline__ float2 exp2_rr2(float2 x) {
 __device__ __forceinline__ float2 exp2_rr2_neg(float2 x) {
   x.x = fmaxf(x.x, -125.0f);
   x.y = fmaxf(x.y, -125.0f);
-  const float2 t = add2(x, dup2(12583168.0f));                              // 1.5 * 2^23 + 256
-  const float2 f = fma2(add2(t, dup2(-12583168.0f)), dup2(-1.0f), x);
+  float2 t, f;
+  exp2_reduce<256>(x, t, f);
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 // 2^x with MUFU.EX2 on f = x - floor(x) in [0, 1): the bias of MUFU.EX2 depends on the sign and
@@ -391,6 +403,12 @@ __device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int&
     }
   }
 }
+
+// Kaiser factor (1 + beta mu^2)^2 of a cell: CPX_KAISER 0 = six packed instructions, 1 (default) = four
+#ifndef CPX_KAISER
+#define CPX_KAISER 1
+#endif
+constexpr float kKaiserLoScale = CPX_KAISER == 0 ? 2.0f : 1.0f;
 
 #ifdef CPX_DNL_MUFU
 #define kExpDnl exp2_fl2
@@ -520,10 +538,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
         }
         if (mt & 1) {
           betaT[mt >> 1][p].y = hi;
-          betaTlo[mt >> 1][p].y = 2.0f * lo;
+          betaTlo[mt >> 1][p].y = kKaiserLoScale * lo;
         } else {
           betaT[mt >> 1][p].x = hi;
-          betaTlo[mt >> 1][p].x = 2.0f * lo;
+          betaTlo[mt >> 1][p].x = kKaiserLoScale * lo;
         }
       }
     }
@@ -570,12 +588,20 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
           // D_NL = 2^(nl (1 - v) - (k/kp)^2 log2e)
           const float2 tt = fma2(NK2, ikp2lo[p], fma2(NK2, ikp2l[p], nl));
           const float2 e = kExpDnl(fma2(nl, nv, tt));
-          // Kaiser factor applied to the running product (x -> x + (x beta) mu^2, twice, plus the first-order
-          // beta_lo term) so that its float32 rounding decorrelates from cell to cell; (1 + beta mu^2) rounded
-          // on its own takes the same error for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
+          // Kaiser factor applied to the running product (x -> x + x (beta mu^2), twice) so that its float32
+          // rounding decorrelates from cell to cell; (1 + beta mu^2) rounded on its own takes the same error
+          // for every cell with mu ~ 1 and would bias Px coherently by ~2e-8.
           float2 x = mul2(PL, e);
+#if CPX_KAISER == 0
           x = fma2(mul2(x, betaT[pr2][p]), MU2, x);
           x = fma2(mul2(x, betaT[pr2][p]), MU2, fma2(mul2(x, betaTlo[pr2][p]), MU2, x));   // betaTlo holds 2 * lo
+#else
+          // beta mu^2 of the cell, correctly rounded from the hi + lo pair (its rounding differs from cell to cell),
+          // then x -> x + x (beta mu^2) twice: four packed instructions instead of six
+          const float2 bm = fma2(betaT[pr2][p], MU2, mul2(betaTlo[pr2][p], MU2));         // betaTlo holds lo
+          x = fma2(x, bm, x);
+          x = fma2(x, bm, x);
+#endif
           const double pd0 = static_cast<double>(x.x), pd1 = static_cast<double>(x.y);
 #pragma unroll
           for (int j = 0; j < NT; ++j) dmma_884(acc[2 * pr2][p][j][0], acc[2 * pr2][p][j][1], pd0, bfrag[j]);

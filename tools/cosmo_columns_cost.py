@@ -16,6 +16,9 @@ from cupix_b200.engine import slots_from_names  # noqa: E402
 
 def main():
     B = 65536
+    if os.environ.get("CPX_LIB_VARIANT"):          # time another build of the library (kernel variants, tools/bin/)
+        import cupix_b200.engine as E
+        E.LIB_PATH = os.path.abspath(os.environ["CPX_LIB_VARIANT"])
     filled, data, likes, joint = bench.build_workload("S5", 100, 88)
     eng = joint.engine()
     d = _plan.default_vector(likes[0].theory, likes[0].theory.fid_cosmo)
