@@ -66,6 +66,7 @@ class KperpRule(object):
         self._knots = spl.t
         self._cardinal = np.ascontiguousarray(spl.c)          # [n_coef, n_q]
         self._fine_cache = {}
+        self._weights_cache = {}
 
     def u_of_k(self, k):
         """Node coordinate: log spacing plus, for refine > 0, extra density below ~k_refine."""
@@ -126,7 +127,6 @@ class KperpRule(object):
         W[g, q] = sum_{i in g} w_i W_r[i, q] / sum_{i in g} w_i   (theta-weighted bin average).
         """
         r = np.atleast_1d(np.asarray(r_Mpc, dtype=np.float64))
-        kf, meas, design = self._fine_grid(max(r.max(), 1e-3))
         if group_index is None:
             gi = np.arange(r.size)
             gw = np.ones(r.size)
@@ -135,6 +135,12 @@ class KperpRule(object):
             gi = np.asarray(group_index)
             gw = np.asarray(group_weight, dtype=np.float64)
             ng = int(n_groups if n_groups is not None else gi.max() + 1)
+        # the weights depend on the separations only: plans rebuilt for another primordial power (same
+        # background, theory.py:54-56) or for another Likelihood on the same binning find them here
+        ckey = (r.tobytes(), np.asarray(gi, dtype=np.int64).tobytes(), gw.tobytes(), ng)
+        if ckey in self._weights_cache:
+            return self._weights_cache[ckey].copy()
+        kf, meas, design = self._fine_grid(max(r.max(), 1e-3))
         norm = np.bincount(gi, weights=gw, minlength=ng)
         jbar = np.zeros((ng, kf.size))
         # one process per GPU: share the host cores between the ranks of this node
@@ -155,4 +161,8 @@ class KperpRule(object):
             for g in range(ng):
                 work(g)
         b = design.T.dot(jbar.T)                      # [n_coef, ng]
-        return np.ascontiguousarray((self._cardinal.T @ b).T)      # [ng, n_q]
+        W = np.ascontiguousarray((self._cardinal.T @ b).T)          # [ng, n_q]
+        if len(self._weights_cache) >= 64:
+            self._weights_cache.pop(next(iter(self._weights_cache)))
+        self._weights_cache[ckey] = W
+        return W.copy()

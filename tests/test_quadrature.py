@@ -120,3 +120,18 @@ def test_refined_map_inverse_and_default_unchanged():
     # refine = 0 is the rule the golden fixtures were made with: nodes exactly log-uniform in k + k0
     plain = KperpRule(96)
     np.testing.assert_array_equal(plain.k[1:-1], (np.exp(np.linspace(np.log(0.01), np.log(200.01), 96)) - 0.01)[1:-1])
+
+
+def test_weights_are_cached_by_separation():
+    """Plans rebuilt for another primordial power (same background) reuse the Hankel weights."""
+    from cupix_b200.quadrature import KperpRule
+    rule = KperpRule(64)
+    r = np.array([0.7, 1.3, 2.9, 3.1])
+    grp, wgt = np.array([0, 0, 1, 1]), np.array([1.0, 2.0, 1.0, 1.0])
+    w1 = rule.weights(r, grp, wgt, 2)
+    w2 = rule.weights(r.copy(), grp.copy(), wgt.copy(), 2)
+    assert np.array_equal(w1, w2) and w1 is not w2 and len(rule._weights_cache) == 1
+    w1[:] = 0.0                                              # callers own their copy
+    assert np.array_equal(rule.weights(r, grp, wgt, 2), w2)
+    assert not np.array_equal(rule.weights(r * 1.01, grp, wgt, 2), w2) and len(rule._weights_cache) == 2
+    assert rule.weights(r).shape == (4, 64) and len(rule._weights_cache) == 3
