@@ -52,6 +52,61 @@ def write_px_file(filepath, d, extra_attrs=None):
                 f.create_dataset(f"V_Z_aM/z_{iz}/theta_{a}", data=d["V_ZaM"][iz][a])
 
 
+def data_to_dict(data):
+    """The dict layout of ``_read_hdf5`` / ``synthetic`` from a loaded (possibly cut) data object."""
+    return {"k_m": np.asarray(data.k_m), "k_M_edges": np.asarray(data.k_M_edges),
+            "theta_min_a": np.asarray(data.theta_min_a_arcmin), "theta_max_a": np.asarray(data.theta_max_a_arcmin),
+            "theta_min_A": np.asarray(data.theta_min_A_arcmin), "theta_max_A": np.asarray(data.theta_max_A_arcmin),
+            "z_centers": np.asarray(data.z), "N_fft": data.N_fft, "L_fft": data.L_fft,
+            "B_A_a": np.asarray(data.B_A_a), "Px_ZAM": np.asarray(data.Px_ZAM), "cov_ZAM": np.asarray(data.cov_ZAM),
+            "U_ZaMn": np.asarray(data.U_ZaMn), "V_ZaM": np.asarray(data.V_ZaM)}
+
+
+def write_forecast(likes, savepath, params={}, add_noise=False, seed=None):
+    """Forecast file: the measurement of ``likes[i].data`` with P_Z_AM replaced by the theory of each z bin
+    convolved with the data's own window (``Likelihood.generate_px_forecast``), noise from the data covariance
+    optional -- what notebooks/examples/generate_forecast_data.py:132-173 writes.  Windows, covariances and
+    binning are copied; per z bin the default Lya parameters and the model label used are stored next to the
+    data vector (HDF5: attributes of ``P_Z_AM/z_i`` and its ``lya_params`` group; .npz: ``z{i}_lya_<name>``,
+    ``z{i}_default_lya_model``), plus ``z_centers_orig``.  Returns the forecast Px_ZAM."""
+    data = likes[0].data
+    d = data_to_dict(data)
+    rng = np.random.default_rng(seed)
+    px = []
+    for like in likes:
+        m = like.get_convolved_px(params=params)
+        if add_noise:                                  # likelihood.py:42-49, with a seeded generator
+            L = np.linalg.cholesky(data.cov_ZAM[like.iz])
+            m = m + np.einsum("aij,aj->ai", L, rng.normal(size=m.shape))
+        px.append(m)
+    d["Px_ZAM"] = np.array(px)
+    extra = {"z_centers_orig": np.asarray(data.z), "forecast_add_noise": bool(add_noise)}
+    per_z = []
+    for like in likes:
+        lm = like.theory.lya_model
+        info = {"default_lya_model": str(lm.default_lya_model)}
+        defaults = getattr(lm, "default_lya_params", None) or {}
+        info.update({"lya_" + k: float(v) for k, v in defaults.items()})
+        info.update({"forecast_" + k: float(v) for k, v in params.items()})
+        per_z.append(info)
+    if str(savepath).endswith(".npz"):
+        for iz, info in enumerate(per_z):
+            extra.update({"z%d_%s" % (iz, k): v for k, v in info.items()})
+        write_px_file(savepath, d, extra_attrs=extra)
+    else:
+        import h5py
+        write_px_file(savepath, d, extra_attrs=extra)
+        with h5py.File(savepath, "a") as f:
+            for iz, info in enumerate(per_z):
+                g = f["P_Z_AM/z_%d" % iz]
+                g.attrs["default_lya_model"] = info["default_lya_model"]
+                lp = g.create_group("lya_params")
+                for k, v in info.items():
+                    if k.startswith("lya_"):
+                        lp.attrs[k[4:]] = v
+    return d["Px_ZAM"]
+
+
 class DESI_DR2(BaseDataPx):
     """Px measurement in the DESI DR2 analysis format.  ``filepath`` may be an .hdf5/.h5 file, an
     .npz twin, or an already-loaded dict with the same keys."""

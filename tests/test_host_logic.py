@@ -202,3 +202,43 @@ def test_minimizer_mirror_on_a_quadratic(tmp_path):
     ml = Minimizer(Posterior(like1, pars_l))
     assert abs(ml.get_best_fit_value("beta") - 1.5) < 1e-9
     assert mp.minus_log_prob_interface([-0.12, 1.55]) == pytest.approx(3.5 + 0.5 * (0.05 / 0.03) ** 2 * 2, rel=1e-9)
+
+
+def test_forecast_writer_roundtrip(tmp_path):
+    """generate_forecast_data.py:132-173: data copied, P_Z_AM replaced by window-convolved theory (+ seeded noise),
+    model parameters stored; the file reads back as a measurement."""
+    from cupix_b200.px_data.data_DESI_DR2 import data_to_dict, write_forecast
+    d = synthetic.make_measurement_dict("tiny_rebin", Nz=2)
+    data = DESI_DR2(d)
+
+    class _Lya(object):
+        default_lya_model = "best_fit_arinyo_from_colore"
+        default_lya_params = {"bias": -0.115, "beta": 1.5}
+
+    class _Like(object):                     # stands for a Likelihood: the writer only needs these members
+        def __init__(self, iz):
+            self.iz, self.data = iz, data
+            self.theory = type("T", (), {"lya_model": _Lya()})()
+
+        def get_convolved_px(self, params={}):
+            return np.full(data.Px_ZAM[self.iz].shape, 0.1 * (self.iz + 1) + params.get("bias", 0.0))
+
+    likes = [_Like(0), _Like(1)]
+    path = str(tmp_path / "forecast.npz")
+    px = write_forecast(likes, path, params={"bias": -0.01})
+    back = DESI_DR2(path)
+    np.testing.assert_array_equal(back.Px_ZAM, px)
+    np.testing.assert_allclose(back.Px_ZAM[1], 0.19)
+    for key in ("cov_ZAM", "U_ZaMn", "V_ZaM", "k_m", "B_A_a"):
+        np.testing.assert_array_equal(np.asarray(getattr(back, key)), np.asarray(getattr(data, key)))
+    with np.load(path) as f:
+        assert str(f["attr_z0_default_lya_model"]) == "best_fit_arinyo_from_colore"
+        assert float(f["attr_z1_lya_beta"]) == 1.5 and float(f["attr_z0_forecast_bias"]) == -0.01
+        np.testing.assert_array_equal(f["attr_z_centers_orig"], data.z)
+    # seeded noise: reproducible, and white after the data's own Cholesky factor
+    n1 = write_forecast(likes, str(tmp_path / "n1.npz"), add_noise=True, seed=3)
+    n2 = write_forecast(likes, str(tmp_path / "n2.npz"), add_noise=True, seed=3)
+    np.testing.assert_array_equal(n1, n2)
+    white = np.linalg.solve(np.linalg.cholesky(data.cov_ZAM[0]), (n1[0] - 0.1)[..., None])
+    assert 0.5 < white.std() < 1.5
+    assert set(data_to_dict(data)) >= {"Px_ZAM", "cov_ZAM", "U_ZaMn", "V_ZaM", "B_A_a", "z_centers"}
