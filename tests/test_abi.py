@@ -54,3 +54,49 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_slot_enum_info_enum_and_field_offsets_match_header():
+    """The Python side's slot order (plan.SLOT_NAMES), info items (PxEngine.INFO) and ctypes field offsets are the
+    header's: compiled from include/cupix_b200.h with gcc and compared value by value."""
+    import subprocess
+    import tempfile
+    from cupix_b200 import engine, plan
+    enum_of = {"bias": "CPX_BIAS", "beta": "CPX_BETA", "q1": "CPX_Q1", "q2": "CPX_Q2", "kv_Mpc": "CPX_KV_MPC",
+               "av": "CPX_AV", "bv": "CPX_BV", "kp_Mpc": "CPX_KP_MPC", "b_H": "CPX_B_H", "beta_H": "CPX_BETA_H",
+               "L_H_Mpc": "CPX_L_H_MPC", "b_X": "CPX_B_X", "beta_X": "CPX_BETA_X", "b_noise_Mpc": "CPX_B_NOISE_MPC",
+               "kC_Mpc": "CPX_KC_MPC", "pC": "CPX_PC", "As": "CPX_AS", "ns": "CPX_NS"}
+    assert set(enum_of) == set(plan.SLOT_NAMES)
+    info_of = {"n_zbins": "CPX_INFO_N_ZBINS", "max_na": "CPX_INFO_MAX_NA", "max_nm": "CPX_INFO_MAX_NM",
+               "max_nA": "CPX_INFO_MAX_N_A", "max_nM": "CPX_INFO_MAX_N_M", "chunk": "CPX_INFO_CHUNK",
+               "device_bytes": "CPX_INFO_DEVICE_BYTES", "kernel_launches": "CPX_INFO_KERNEL_LAUNCHES",
+               "sm_count": "CPX_INFO_SM_COUNT", "guard_buffers": "CPX_INFO_GUARD_BUFFERS",
+               "guard_violations": "CPX_INFO_GUARD_VIOLATIONS"}
+    assert set(info_of) == set(engine.PxEngine.INFO)
+    zfields = [f[0] for f in engine.ZbinDesc._fields_]
+    efields = [f[0] for f in engine.EvalArgs._fields_]
+    lines = ['#include "cupix_b200.h"', "#include <stdio.h>", "#include <stddef.h>", "int main(){"]
+    lines += ['printf("slot %s %%d\\n", (int)%s);' % (n, e) for n, e in enum_of.items()]
+    lines += ['printf("info %s %%d\\n", (int)%s);' % (n, e) for n, e in info_of.items()]
+    lines += ['printf("z %s %%zu\\n", offsetof(cpx_zbin_desc, %s));' % (f, f) for f in zfields]
+    lines += ['printf("e %s %%zu\\n", offsetof(cpx_eval_args, %s));' % (f, f) for f in efields]
+    lines += ['printf("nslots x %d\\n", (int)CPX_NSLOTS);', 'printf("flag DEVICE_IO %d\\n", (int)CPX_DEVICE_IO);',
+              'printf("flag PRECISE_CELLS %d\\n", (int)CPX_PRECISE_CELLS);', "return 0;}"]
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write("\n".join(lines) + "\n")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")])
+        out = [ln.split() for ln in subprocess.check_output([os.path.join(td, "s")]).decode().splitlines()]
+    for kind, name, val in out:
+        val = int(val)
+        if kind == "slot":
+            assert plan.SLOT_INDEX[name] == val, name
+        elif kind == "info":
+            assert engine.PxEngine.INFO[name] == val, name
+        elif kind == "z":
+            assert getattr(engine.ZbinDesc, name).offset == val, name
+        elif kind == "e":
+            assert getattr(engine.EvalArgs, name).offset == val, name
+        elif kind == "nslots":
+            assert engine.NSLOTS == val == len(plan.SLOT_NAMES)
+        elif kind == "flag":
+            assert getattr(engine, name) == val
