@@ -100,3 +100,23 @@ def test_slot_enum_info_enum_and_field_offsets_match_header():
             assert engine.NSLOTS == val == len(plan.SLOT_NAMES)
         elif kind == "flag":
             assert getattr(engine, name) == val
+
+
+def test_integration_stub_is_current():
+    """The ctypes stub printed in INTEGRATION.md (what a cupix maintainer would paste) still matches the library:
+    it is executed against the in-tree .so and its structs / slot table are compared with the engine's."""
+    from cupix_b200 import engine, plan
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("# cupix/likelihood/_b200.py")
+    stub = text[start:text.index("```", start)]
+    stub = stub.replace('"libcupix_b200.so"', repr(engine.LIB_PATH))
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    assert ctypes.sizeof(ns["ZbinDesc"]) == ctypes.sizeof(engine.ZbinDesc)
+    assert ctypes.sizeof(ns["EvalArgs"]) == ctypes.sizeof(engine.EvalArgs)
+    for name, _ in engine.ZbinDesc._fields_:
+        assert getattr(ns["ZbinDesc"], name).offset == getattr(engine.ZbinDesc, name).offset, name
+    for name, _ in engine.EvalArgs._fields_:
+        assert getattr(ns["EvalArgs"], name).offset == getattr(engine.EvalArgs, name).offset, name
+    assert ns["SLOT"] == plan.SLOT_INDEX
+    assert callable(ns["chi2_batch"])
