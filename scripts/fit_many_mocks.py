@@ -28,11 +28,7 @@ data, theories, likes = load_measurement(None, "S2", {"default_lya_model": "best
 like = likes[a.iz]
 dflt = like.theory.lya_model.default_lya_params
 truth = np.array([dflt[p] for p in a.pars])
-rng = np.random.default_rng(1234)
-L = np.linalg.cholesky(data.cov_ZAM[a.iz])
-base = data.Px_ZAM[a.iz]
-mocks = base[None] + np.einsum("aij,naj->nai", L, rng.normal(size=(a.nmocks,) + base.shape))   # likelihood.py:42-49
-like.set_mock_data(mocks)
+like.generate_mocks(a.nmocks, seed=1234)            # model(defaults) + L n per mock (likelihood.py:42-49), kept on the device
 steps = [0.002 * max(abs(t), 0.1) for t in truth]
 fitter = BatchMinimizer(like, a.pars, steps)
 t0 = time.time()
