@@ -306,8 +306,9 @@ __global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
 // memory by TMA bulk copies and stay resident while the CTA walks its contiguous range of work
 // items (z, tile, theta-block, point-group).
 //
-// Per cell and point: ~35 FP32/ALU instructions (hi+lo scalars, polynomial exp2 for D_NL,
-// range-reduced MUFU.EX2 for the velocity term), 2 XU, NT DMMAs.  Bound: FP64 pipe.
+// Per pair of cells and point: 27 packed FMA-pipe instructions (hi+lo scalars, degree-6 polynomial exp2 for
+// D_NL, range-reduced MUFU.EX2 for the velocity term, Kaiser factor), ~14 ALU, 2 MUFU, 2 NT DMMAs.
+// Bound: FP64 tensor pipe + FP32 FMA pipe, which share issue.
 
 // Packed FP32 (FFMA2 / FADD2 / FMUL2, new on sm_100): two P3D cells per instruction.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
