@@ -144,7 +144,8 @@ def window_roofline(work, likes, B, k2_s, dmma_peak_tflops, share):
 def cpu_worker(args):
     """One process of the CPU arm: evaluates its block of points serially (the reference pattern,
     scripts/chi2_scan_mock.py:140), BLAS pinned to one thread (scripts/profile.py:2-7)."""
-    flavour, shape, n_t, n_q, pts = args
+    flavour, shape, n_t, n_q, pts = args[:5]
+    want_truth = len(args) > 5 and args[5]
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(1)
@@ -173,7 +174,10 @@ def cpu_worker(args):
         orcs.append(o)
     t0 = time.time()
     out = [sum(o.get_chi2(dict(zip(NAMES, p))) for o in orcs) for p in pts]
-    return time.time() - t0, out
+    dt = time.time() - t0
+    # outside the timing: chi2 at the per-z truth (all parameters at their defaults), the best-fit region of the data
+    truth = sum(o.get_chi2({}) for o in orcs) if want_truth else None
+    return dt, out, truth
 
 
 def run_cpu(flavour, shape, n_t, n_q, per_core, defaults):
@@ -185,11 +189,14 @@ def run_cpu(flavour, shape, n_t, n_q, per_core, defaults):
     ctx = mp.get_context("fork")
     t0 = time.time()
     with ctx.Pool(cores) as pool:
-        res = pool.map(cpu_worker, [(flavour, shape, n_t, n_q, pts[i::cores]) for i in range(cores)])
+        res = pool.map(cpu_worker, [(flavour, shape, n_t, n_q, pts[i::cores], i == 0) for i in range(cores)])
     wall = time.time() - t0
     busy = max(r[0] for r in res)
+    chi2 = np.empty(len(pts))
+    for i in range(cores):
+        chi2[i::cores] = res[i][1]
     return {"value": len(pts) / busy, "unit": "evals/s", "cores": cores, "evals": len(pts),
-            "busy_s": busy, "wall_s": wall}
+            "busy_s": busy, "wall_s": wall, "points": pts, "chi2": chi2, "chi2_truth": res[0][2]}
 
 
 def emit(line):
@@ -405,8 +412,30 @@ def main():
         pass
 
     cpu = None
+    parity = None
     if not a.no_cpu_baseline and a.gpus == 1:
         r = run_cpu("node", a.shape, a.n_theta_average, a.n_q, a.cpu_evals_per_core, defaults)
+        # the CPU leg's sample points scored by the GPU arm as well, inside a full production batch (same kernels,
+        # same host-pointer C-ABI call as the e2e leg): oracle chi2 against device chi2 on the workload the number is quoted on
+        pb = np.random.default_rng(99).uniform(lo, hi, size=(B, len(NAMES)))
+        pb[:len(r["points"])] = r["points"]
+        got = eng.eval_host_into(np.ascontiguousarray(pb), slots, zsel, np.empty(B))[:len(r["points"])]
+        dchi = np.abs(got - r["chi2"])
+        n_data = joint.get_ndata()
+        near = r["chi2"] <= 2.0 * n_data
+        parity = {"n": int(len(dchi)), "against": "float64 NumPy oracle (same node rule), the cpu_baseline sample points",
+                  "max_abs_dchi2": float(dchi.max()), "max_rel_dchi2": float((dchi / np.abs(r["chi2"])).max()),
+                  "frac_within_1e-3": float(np.mean(dchi <= 1e-3)),
+                  "n_within_2ndata": int(near.sum()),
+                  "max_abs_dchi2_within_2ndata": float(dchi[near].max()) if near.any() else None,
+                  "chi2_min": float(r["chi2"].min()), "chi2_max": float(r["chi2"].max()), "n_data": int(n_data),
+                  "rule": "|dchi2| <= 1e-3 where chi2 <= 2 n_data, 1e-6 relative beyond (DESIGN.md section 5)"}
+        if r.get("chi2_truth") is not None:
+            # the grid applies one (bias, beta, q1, kp) to all 12 z, so all of it is far from the best fit of this
+            # data; the per-z truth (no columns: every z at its own defaults) is the point inside chi2 <= 2 n_data
+            t_gpu = float(joint.get_chi2({}))
+            parity["truth"] = {"chi2_oracle": float(r["chi2_truth"]), "chi2_gpu": t_gpu,
+                               "abs_dchi2": abs(t_gpu - float(r["chi2_truth"]))}
         cpu = {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": "port",
                "sample": "%d evaluations (%d per core) of the same S5 workload with the float64 NumPy oracle using the "
                          "same fixed-node Hankel rule as the GPU (oracle B); the reference's own FFTLog algorithm is "
@@ -415,7 +444,7 @@ def main():
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "per_point_z_rate": value * len(likes)}
     emit(line)
     if world > 1:

@@ -1,0 +1,290 @@
+// Factorised chi2 path: the amplitude parameters taken out of the Hankel stage.
+//
+// The Px model of theory.py:95-123 is a *polynomial* in (bias, beta, b_H, beta_H, b_X, beta_X, b_noise) whose
+// coefficients are tables that depend on the point only through the remaining ("tuple") parameters
+// (q1, q2, kv, av, bv, kp; L_H, kC, pC; As, ns):
+//
+//   Lya (+HCD, theory.py:267-344):   P3D = b_T^2 (1 + beta_T mu^2)^2 P_L D_NL,  b_T = b + h F(k_par),
+//                                    b_T beta_T = b beta + h eta F            (F = exp(-k_par L_H))
+//        => Px_Zam = dAA cont(m) sum_{i=0..2} sum_{j=0..2} c_ij F^i H_j,   H_j[a][m] = sum_q W[a][q] mu^2j P_L D_NL
+//           c_0j = (b^2, 2 b^2 beta, b^2 beta^2), c_1j = (2bh, 2bh(beta + eta), 2bh beta eta), c_2j = (h^2, 2h^2 eta, h^2 eta^2)
+//   SiIII (theory.py:361-438):       x^2 (Ma_0 + 2 xi Ma_1 + xi^2 Ma_2) + b x (Mc_0 + (beta + xi) Mc_1 + beta xi Mc_2)
+//   sky (theory.py:476-506):         n xi_noise(theta) sinc^2
+//   continuum (theory.py:525-535):   multiplies every table (cont(m), a tuple parameter)
+//
+// Window convolution, theta rebinning and whitening are linear (likelihood.py:53-88), so with
+// Y_k = L^-1 diag(V/sum V) U B_k the chi2 of likelihood.py:170-194 is a quadratic form per point,
+//
+//   chi2 = sum_z  dd - 2 c.g + c^T G c,      G_kl = Y_k . Y_l,  g_k = (L^-1 d) . Y_k,  dd = |L^-1 d|^2,
+//
+// and the Hankel stage runs once per distinct tuple instead of once per point -- the structure of the
+// reference's scan scripts (scripts/chi2_scan_mock.py:107-140: a bias x beta grid is ONE tuple;
+// scripts/chi2_scan_forecast.py:116-125: 64^4 points are 4096 tuples).  Because so few cells are left, they
+// are evaluated in float64 (the formulas of theory.py:285-308 as written): chi2 from this path agrees with
+// the float64 oracle to ~1e-9 everywhere, not only near the best fit.
+//
+//   k_basis_f64  per (z, tuple): float64 P3D cells, three mu-moment Hankel sums on the FP64 tensor pipe (DMMA), epilogue
+//                writes the n_b basis tables B_k[a][m] as pseudo-points of the Px_Zam scratch
+//   k_window<MT, false> with WindowArgs::whiten: Y_k (the FP64 DMMA window kernel, whitened operator, no data)
+//   k_gram       per (z, tuple): G, g
+//   k_quad       per point: coefficients + quadratic form, summed over z
+#pragma once
+#include "cpx_kernels.cuh"
+
+namespace cpx {
+
+constexpr int kMaxBasis = 16;
+
+// number of basis tables for a flag set (CPX_INCLUDE_*)
+__host__ __device__ constexpr int basis_count(int flags) {
+  return ((flags & 1) ? 9 : 3) + ((flags & 2) ? 6 : 0) + ((flags & 4) ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_basis_f64: one warp per (z, 32-row k_par tile, theta block, tuple).  Same DMMA fragment layout as
+// k_p3d_hankel_f64; the four m-tiles are walked one after the other so that only 3 x NT accumulators are live.
+// Output: Z.pxzam viewed as [tuple * nb + k][a][m_pad].
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items, int nb) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = wid; it < n_items; it += nwarps) {
+    int zi = 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
+    const ZDev& Z = ztab[zi];
+    long long r = it - Z.item_start;
+    const int tp = static_cast<int>(r % count);
+    r /= count;
+    const int ablk = static_cast<int>(r % Z.n_ablk);
+    const int tile = static_cast<int>(r / Z.n_ablk);
+    const int m_base = tile * kTileRows;
+    const PtPar& pr = Z.ptpar[tp];
+    const double q1 = pr.q1_64, q2 = pr.q2_64, av = pr.av_64, bv = pr.bv_64, l2kv = pr.l2kv_64, ikp2 = pr.ikp2_64;
+    const bool cosmo = pr.dn_64 != 0.0 || pr.lr_64 != 0.0;
+    const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
+    const int a_lane0 = ablk * (8 * NT) + 2 * t;
+    const int n_i = (Z.flags & 1) ? 3 : 1;
+    const size_t tab = static_cast<size_t>(n_a) * n_m_pad;                      // doubles per basis table
+    double* const out0 = Z.pxzam + static_cast<size_t>(tp) * nb * tab;
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      double acc[3][NT][2];
+#pragma unroll
+      for (int jm = 0; jm < 3; ++jm)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[jm][j][0] = acc[jm][j][1] = 0.0;
+      const double* c = Z.cell64 + static_cast<size_t>(tile) * Z.n_q4 * (kCellConsts * 4 * 32) + lane;
+      const double* wb = Z.Wd + static_cast<size_t>(ablk) * Z.n_q4 * (NT * 32) + lane;
+      for (int ks = 0; ks < Z.n_q4; ++ks) {
+        double bfrag[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
+        const double L2K = c[(1 * 4 + mt) * 32], L2MU = c[(2 * 4 + mt) * 32];
+        const double MU2 = c[(3 * 4 + mt) * 32], K2 = c[(4 * 4 + mt) * 32];
+        double D = c[(0 * 4 + mt) * 32], PL = c[(5 * 4 + mt) * 32];
+        if (cosmo) {                                                             // rescaled linear power, theory.py:54-56
+          const double f = exp2(fma(pr.dn_64, L2K, pr.lr_64));
+          D *= f;
+          PL *= f;
+        }
+        const double nl = D * (q1 + q2 * D);                                     // theory.py:285-295
+        const double v = exp2(av * (L2K - l2kv) + bv * L2MU);
+        const double p0 = PL * exp(nl * (1.0 - v) - K2 * ikp2);
+        const double p1 = p0 * MU2, p2 = p1 * MU2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          dmma_884(acc[0][j][0], acc[0][j][1], p0, bfrag[j]);
+          dmma_884(acc[1][j][0], acc[1][j][1], p1, bfrag[j]);
+          dmma_884(acc[2][j][0], acc[2][j][1], p2, bfrag[j]);
+        }
+        c += kCellConsts * 4 * 32;
+        wb += NT * 32;
+      }
+      // ---- epilogue of this m-tile: row m = m_base + 8 mt + g, theta columns a_lane0 + 8 j + {0, 1} ----
+      const int m = m_base + 8 * mt + g;
+      const bool row_ok = m < n_m;
+      const double kpar = Z.kpar[m];
+      const double F = (Z.flags & 1) ? exp(-kpar * pr.L_H) : 1.0;                // theory.py:267-282
+      double cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;       // theory.py:525-535
+      if (!row_ok) cont = 0.0;
+      const double lya = cont * Z.dAA;
+      const double sky = ((Z.flags & 4) && row_ok) ? cont * Z.sky_smooth[m] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int a = a_lane0 + 8 * j + cc;
+          if (a >= n_a) continue;
+          double* o = out0 + static_cast<size_t>(a) * n_m_pad + m;
+          double Fi = lya;
+          for (int i = 0; i < n_i; ++i) {
+#pragma unroll
+            for (int jm = 0; jm < 3; ++jm) o[static_cast<size_t>(3 * i + jm) * tab] = Fi * acc[jm][j][cc];
+            Fi *= F;
+          }
+          int k = 3 * n_i;
+          if (Z.flags & 2) {                                                     // SiIII moments, theory.py:361-438
+            const size_t om = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
+            const double f = cont * pr.lin_amp;
+#pragma unroll
+            for (int jm = 0; jm < 3; ++jm) {
+              o[static_cast<size_t>(k + jm) * tab] = row_ok ? f * Z.metal_auto[om + jm * st] : 0.0;
+              o[static_cast<size_t>(k + 3 + jm) * tab] = row_ok ? f * Z.metal_cross[om + jm * st] : 0.0;
+            }
+            k += 6;
+          }
+          if (Z.flags & 4) o[static_cast<size_t>(k) * tab] = sky * Z.sky_xi[a];  // theory.py:476-506
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_gram: block = (tuple, z).  Y[(tuple * nb + k)][z][A][M] (the model-output layout of k_window) ->
+//   G[tuple][z][k][l] = sum_{A, M} Y_k Y_l,   g[tuple][z][d][k] = sum_{A, M} yd[d][A][M] Y_k
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, const double* __restrict__ Y, int n_zl, int nA_max,
+                                              int nM_max, int nb, int nd_max, double* __restrict__ G, double* __restrict__ gv) {
+  extern __shared__ double sY[];                       // [nb][nM_max]
+  const int tp = blockIdx.x, zi = blockIdx.y;
+  const ZDev& Z = ztab[zi];
+  const int tid = threadIdx.x;
+  const int nM = Z.n_M, nd = Z.n_data;
+  const int k = tid / nb, l = tid % nb;
+  double acc = 0.0;
+  double* const gz = gv + (static_cast<size_t>(tp) * n_zl + zi) * nd_max * nb;
+  for (int A = 0; A < Z.n_A; ++A) {
+    __syncthreads();
+    for (int i = tid; i < nb * nM; i += blockDim.x) {
+      const int kk = i / nM, M = i % nM;
+      sY[kk * nM_max + M] = Y[((static_cast<size_t>(tp) * nb + kk) * n_zl + zi) * nA_max * nM_max + static_cast<size_t>(A) * nM_max + M];
+    }
+    __syncthreads();
+    if (tid < nb * nb) {
+      const double* yk = sY + k * nM_max;
+      const double* yl = sY + l * nM_max;
+      for (int M = 0; M < nM; ++M) acc = fma(yk[M], yl[M], acc);
+    }
+    for (int item = tid; item < nd * nb; item += blockDim.x) {
+      const int d = item / nb, kk = item % nb;
+      const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
+      const double* yk = sY + kk * nM_max;
+      double s = (A == 0) ? 0.0 : gz[item];
+      for (int M = 0; M < nM; ++M) s = fma(yd[M], yk[M], s);
+      gz[item] = s;
+    }
+  }
+  if (tid < nb * nb) G[(static_cast<size_t>(tp) * n_zl + zi) * nb * nb + tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_quad: one thread per (tuple of the batch, amplitude point).  Decodes the amplitude values (grid box or explicit
+// points), forms the coefficient vector per z and evaluates the quadratic form.
+// ------------------------------------------------------------------------------------------
+struct QuadArgs {
+  int P, n_z, nb, grid_mode;
+  int slot[16], zsel[16], is_amp[16];
+  // grid box: axis j covers indices ax_start[j] .. ax_start[j] + ax_len[j] - 1
+  int ax_start[16], ax_len[16], grid_n[16];
+  long long ax_stride[16];
+  double grid_lo[16], grid_hi[16], grid_step[16];
+  long long out_first;          // flat grid index of chi2[0]
+  long long n_amp;              // amplitude points per tuple (grid: product of the amplitude-axis lengths; points mode: B)
+  long long t0;                 // first tuple of this batch within the box's tuple enumeration
+  int nt;                       // tuples in this batch
+  int nd_max;
+  const double* points;         // points mode: [B][P]
+  const int* data_idx;          // [B] or null (indexed like chi2)
+  double* chi2;
+  const double* G;              // [nt][n_z][nb][nb]
+  const double* g;              // [nt][n_z][nd_max][nb]
+};
+
+__global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict__ ztab, const int* __restrict__ zlist) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= q.n_amp * q.nt) return;
+  const int tl = static_cast<int>(gid / q.n_amp);
+  long long r = gid % q.n_amp;
+  double x[16];
+  long long out;
+  if (q.grid_mode) {
+    long long tr = q.t0 + tl, flat = 0;
+    for (int j = q.P - 1; j >= 0; --j) {
+      int ij;
+      if (q.is_amp[j]) {
+        ij = q.ax_start[j] + static_cast<int>(r % q.ax_len[j]);
+        r /= q.ax_len[j];
+      } else {
+        ij = q.ax_start[j] + static_cast<int>(tr % q.ax_len[j]);
+        tr /= q.ax_len[j];
+      }
+      flat += ij * q.ax_stride[j];
+      const int n = q.grid_n[j];
+      // bit-identical to numpy.linspace (k_params)
+      x[j] = (ij == n - 1 && n > 1) ? q.grid_hi[j] : __dadd_rn(__dmul_rn(static_cast<double>(ij), q.grid_step[j]), q.grid_lo[j]);
+    }
+    out = flat - q.out_first;
+  } else {
+    out = r;
+    for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
+  }
+  const int d = q.data_idx ? q.data_idx[out] : 0;
+  const int nb = q.nb;
+  double chi2 = 0.0;
+  for (int zi = 0; zi < q.n_z; ++zi) {
+    const ZDev& Z = ztab[zi];
+    const int zglobal = zlist[zi];
+    double b = Z.defaults[0], be = Z.defaults[1], h = Z.defaults[8], eta = Z.defaults[9];
+    double bx = Z.defaults[11], xi = Z.defaults[12], bn = Z.defaults[13];
+    for (int j = 0; j < q.P; ++j) {
+      if (!q.is_amp[j] || !(q.zsel[j] < 0 || q.zsel[j] == zglobal)) continue;
+      const double v = x[j];
+      switch (q.slot[j]) {
+        case 0: b = v; break;
+        case 1: be = v; break;
+        case 8: h = v; break;
+        case 9: eta = v; break;
+        case 11: bx = v; break;
+        case 12: xi = v; break;
+        case 13: bn = v; break;
+      }
+    }
+    double c[kMaxBasis];
+    int k = 0;
+    c[k++] = b * b;
+    c[k++] = 2.0 * b * b * be;
+    c[k++] = b * b * be * be;
+    if (Z.flags & 1) {
+      c[k++] = 2.0 * b * h;
+      c[k++] = 2.0 * b * h * (be + eta);
+      c[k++] = 2.0 * b * h * be * eta;
+      c[k++] = h * h;
+      c[k++] = 2.0 * h * h * eta;
+      c[k++] = h * h * eta * eta;
+    }
+    if (Z.flags & 2) {
+      c[k++] = bx * bx;
+      c[k++] = 2.0 * bx * bx * xi;
+      c[k++] = bx * bx * xi * xi;
+      c[k++] = b * bx;
+      c[k++] = b * bx * (be + xi);
+      c[k++] = b * bx * be * xi;
+    }
+    if (Z.flags & 4) c[k++] = bn;
+    const double* G = q.G + (static_cast<size_t>(tl) * q.n_z + zi) * nb * nb;
+    const double* g = q.g + ((static_cast<size_t>(tl) * q.n_z + zi) * q.nd_max + d) * nb;
+    double s = Z.ydd[d];
+    for (int kk = 0; kk < nb; ++kk) {
+      double row = -2.0 * g[kk];
+      for (int l = 0; l < nb; ++l) row = fma(G[kk * nb + l], c[l], row);
+      s = fma(c[kk], row, s);
+    }
+    chi2 += s;
+  }
+  q.chi2[out] = chi2;
+}
+
+}  // namespace cpx
