@@ -36,14 +36,22 @@ def grid_bounds(defaults):
     return lo, hi
 
 
-def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True, precise=False):
-    """Synthetic S5 measurement: windows/weights seeded, data = model(truth) + noise."""
+def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True, precise=False, filled_path=None,
+                   timings=None):
+    """Synthetic S5 measurement: windows/weights seeded, data = model(truth) + noise, covariance from the model
+    amplitude (px_data/synthetic.py).  The truth model comes from the GPU; CPU workers read the filled data vectors and
+    covariances from ``filled_path`` (written by the B200 arm) so that both arms score the same measurement.  Without
+    either (the --impl reference arm, which is timed only) the placeholder data (zeros, unit covariance) stay."""
     from cupix_b200.cosmology import Cosmology
+    from cupix_b200.engine import PxEngine
     from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
     from cupix_b200.likelihood.theory import Theory
     from cupix_b200.px_data import synthetic
     from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2
     d = synthetic.make_measurement_dict(shape)
+    if filled_path is not None:
+        with np.load(filled_path) as f:
+            d["Px_ZAM"], d["cov_ZAM"] = f["Px_ZAM"], f["cov_ZAM"]
     cosmo = Cosmology()
     cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": n_q}
     theories = [Theory(float(z), fid_cosmo=cosmo, config=cfg) for z in d["z_centers"]]
@@ -51,14 +59,22 @@ def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True
     likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
     if not need_engine:
         return d, data, likes, None
-    joint = JointLikelihood(likes, device=int(os.environ.get("LOCAL_RANK", "0")), precise_cells=precise)
-    model = joint.get_convolved_px_batch(np.zeros((1, 0)), [])[0]          # truth = per-z defaults
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    t0 = time.time()
+    plans = [lk.build_plan() for lk in likes]            # Hankel weights, linear power on the cells: the host side of set-up
+    t1 = time.time()
+    eng0 = PxEngine(plans, device=device, precise=precise)      # cpx_create: Cholesky, operators, digit tables, upload
+    t2 = time.time()
+    if timings is not None:
+        timings.update(plans_s=t1 - t0, cpx_create_s=t2 - t1)
+    slots = np.zeros(0, dtype=np.int32)
+    model = eng0.eval(points=np.zeros((1, 0)), slots=slots, want=("model",))["model"][0]    # truth = per-z defaults
+    eng0.close()
     filled = synthetic.fill_from_model(d, model, add_noise=add_noise)
     data = DESI_DR2(filled)
-    for lk in likes:
-        lk.data = data
-    for iz in range(len(likes)):
-        joint.engine().set_data(iz, filled["Px_ZAM"][iz])
+    likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
+    joint = JointLikelihood(likes, device=device, precise_cells=precise)       # second create: now with the real covariance
+    joint.engine()
     return filled, data, likes, joint
 
 
@@ -146,6 +162,7 @@ def cpu_worker(args):
     scripts/chi2_scan_mock.py:140), BLAS pinned to one thread (scripts/profile.py:2-7)."""
     flavour, shape, n_t, n_q, pts = args[:5]
     want_truth = len(args) > 5 and args[5]
+    filled_path = args[6] if len(args) > 6 else None
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(1)
@@ -153,7 +170,7 @@ def cpu_worker(args):
         pass
     from oracle.hankel import FFTLogHankel
     from tests import helpers as H
-    d, data, likes, _ = build_workload(shape, n_t, n_q, need_engine=False)
+    d, data, likes, _ = build_workload(shape, n_t, n_q, need_engine=False, filled_path=filled_path)
     orcs = []
     for lk in likes:
         o = H.oracle_likelihood(lk)
@@ -180,23 +197,30 @@ def cpu_worker(args):
     return dt, out, truth
 
 
-def run_cpu(flavour, shape, n_t, n_q, per_core, defaults):
+def sample_grid_points(defaults, n, seed=7):
+    """``n`` random points OF THE SCAN GRID (multi-indices [n, 4] in NAMES order, and their coordinates)."""
+    lo, hi = grid_bounds(defaults)
+    rng = np.random.default_rng(seed)
+    idx = np.stack([rng.integers(0, g, n) for g in GRID_N], axis=1)
+    axes = [np.linspace(lo[j], hi[j], GRID_N[j]) for j in range(len(NAMES))]
+    return idx, np.stack([axes[j][idx[:, j]] for j in range(len(NAMES))], axis=1)
+
+
+def run_cpu(flavour, shape, n_t, n_q, per_core, defaults, filled_path=None):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    lo, hi = grid_bounds(defaults)
-    rng = np.random.default_rng(7)
-    pts = rng.uniform(lo, hi, size=(cores * per_core, len(NAMES)))
+    idx, pts = sample_grid_points(defaults, cores * per_core)
     ctx = mp.get_context("fork")
     t0 = time.time()
     with ctx.Pool(cores) as pool:
-        res = pool.map(cpu_worker, [(flavour, shape, n_t, n_q, pts[i::cores], i == 0) for i in range(cores)])
+        res = pool.map(cpu_worker, [(flavour, shape, n_t, n_q, pts[i::cores], i == 0, filled_path) for i in range(cores)])
     wall = time.time() - t0
     busy = max(r[0] for r in res)
     chi2 = np.empty(len(pts))
     for i in range(cores):
         chi2[i::cores] = res[i][1]
     return {"value": len(pts) / busy, "unit": "evals/s", "cores": cores, "evals": len(pts),
-            "busy_s": busy, "wall_s": wall, "points": pts, "chi2": chi2, "chi2_truth": res[0][2]}
+            "busy_s": busy, "wall_s": wall, "points": pts, "grid_index": idx, "chi2": chi2, "chi2_truth": res[0][2]}
 
 
 def emit(line):
@@ -225,6 +249,7 @@ def main():
     ap.add_argument("--cpu-evals-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-grid", action="store_true", help="skip the factorised whole-grid scan (`grid` key)")
     ap.add_argument("--precise", action="store_true", help="float64 P3D cells (CPX_PRECISE_CELLS, reference-precision mode)")
     a = ap.parse_args()
 
@@ -275,8 +300,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q, precise=a.precise)
+    setup = {}
+    filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q, precise=a.precise, timings=setup)
     eng = joint.engine()
+    # what a user pays once per measurement before the first chi2: host plans (cold Hankel-weight cache) + cpx_create
+    setup_s = dict(setup, total_s=setup["plans_s"] + setup["cpx_create_s"])
     import cupix_b200.plan as _plan
     from cupix_b200.engine import slots_from_names, probe_peaks
     defaults = _plan.default_vector(likes[0].theory, likes[0].theory.fid_cosmo)
@@ -290,8 +318,10 @@ def main():
 
     def step_device(i):
         first = ((i * world + rank) * B) % max(total - B, 1)
+        # `value` is the general-points pipeline: every point through P3D + Hankel + window (factor=False); the
+        # factorised scan of the same grid is reported separately as `grid`
         eng.eval_device(B, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=first, zsel=zsel,
-                        chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream)
+                        chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, factor=False)
         if world > 1:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, chi2_dev)
@@ -330,7 +360,7 @@ def main():
     for i in range(a.steps):
         first = ((i * world + rank) * B) % max(total - B, 1)
         stage += eng.eval_device(B, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=first, zsel=zsel,
-                                 chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, stage_ms=True)
+                                 chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, stage_ms=True, factor=False)
     stage /= a.steps
     chunk = eng.info("chunk")
     n_chunks = (B + chunk - 1) // chunk
@@ -363,6 +393,82 @@ def main():
             dt = float(t.item())
         e2e = {"value": a.steps * B * world / dt, "unit": "evals/s", "h2d_bytes_per_step": B * len(NAMES) * 8,
                "d2h_bytes_per_step": B * 8, "api": "PxEngine.eval_host_into = C ABI cpx_eval with pinned host buffers (what JointLikelihood.get_chi2_batch calls)"}
+
+    # ---- the whole 4-parameter grid as ONE scan through the factorised path (cpx_factor.cuh) ----
+    # Same 10 485 760 points, flattened with the tuple axes (q1, kp_Mpc) slowest so that a rank's contiguous slice holds
+    # whole tuples; each rank scans total / N points (strong scaling: the job is the grid), chi2 all-gathered.
+    grid = None
+    grid_host = None
+    if not a.no_grid and not a.precise:
+        from cupix_b200.parallel import block_partition
+        perm = [2, 3, 0, 1]
+        gnames = [NAMES[j] for j in perm]
+        glo, ghi, gn = [lo[j] for j in perm], [hi[j] for j in perm], [GRID_N[j] for j in perm]
+        gslots, gzsel = slots_from_names(gnames)
+        counts, starts = block_partition(total, world)
+        cnt, first = counts[rank], starts[rank]
+        g_dev = torch.empty(max(counts), dtype=torch.float64, device=dev)
+        g_all = torch.empty(max(counts) * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+        def scan_device():
+            eng.eval_device(cnt, len(gnames), gslots, grid=(glo, ghi, gn), grid_first=first, zsel=gzsel,
+                            chi2_ptr=g_dev.data_ptr(), stream=stream.cuda_stream)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(g_all, g_dev)
+        n_scan = max(2, min(a.steps, 5))
+        f0 = eng.info("factored_calls")
+        t0_ = eng.info("factored_tuples")
+        for _ in range(2):
+            scan_device()
+        sync_all()
+        tuples_per_scan = (eng.info("factored_tuples") - t0_) // 2
+        assert eng.info("factored_calls") - f0 == 2, "the grid scan did not take the factorised path"
+        l0 = eng.info("kernel_launches")
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(n_scan):
+            scan_device()
+        g1.record(stream)
+        sync_all()
+        gms = g0.elapsed_time(g1)
+        g_launches = eng.info("kernel_launches") - l0
+        gstage = eng.eval_device(cnt, len(gnames), gslots, grid=(glo, ghi, gn), grid_first=first, zsel=gzsel,
+                                 chi2_ptr=g_dev.data_ptr(), stream=stream.cuda_stream, stage_ms=True)
+        # end to end: host-pointer C-ABI call, chi2 of the rank's slice copied into pinned host memory
+        g_pin = torch.empty(cnt, dtype=torch.float64).pin_memory()
+        g_np = g_pin.numpy()
+        for _ in range(2):
+            eng.eval(slots=gslots, zsel=gzsel, grid=(glo, ghi, gn), grid_first=first, B=cnt, chi2_out=g_np)
+        sync_all()
+        tg = time.time()
+        for _ in range(n_scan):
+            eng.eval(slots=gslots, zsel=gzsel, grid=(glo, ghi, gn), grid_first=first, B=cnt, chi2_out=g_np)
+        sync_all()
+        gdt = time.time() - tg
+        if world > 1:
+            t = torch.tensor([gms, gdt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gms, gdt = float(t[0].item()), float(t[1].item())
+        grid_host = (g_np, first, cnt, gn, perm)
+        grid = {"value": n_scan * total / (gms * 1e-3), "unit": "evals/s", "scaling": "strong",
+                "what": "the whole %d-point grid scanned through the factorised path: P3D (float64 cells) + 3-moment Hankel + "
+                        "window once per distinct (q1, kp_Mpc) tuple and z, chi2 per point as a quadratic form" % total,
+                "points_per_scan": total, "scans": n_scan, "ms_per_scan": gms / n_scan, "axis_order": gnames, "grid_n": gn,
+                "tuples_per_scan_per_gpu": int(tuples_per_scan), "gpu_launches_per_scan": int(g_launches // n_scan),
+                "stage_ms": {"tuple_params": float(gstage[0]), "basis_f64_hankel": float(gstage[1]),
+                             "window_gram": float(gstage[2]), "quadratic_form": float(gstage[3])},
+                "e2e": {"value": n_scan * total / gdt, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": cnt * 8,
+                        "api": "PxEngine.eval(grid=...) = C ABI cpx_eval in grid mode with a pinned host output buffer"},
+                "algorithmic": None}
+        w_ = algorithmic_work(likes, a.n_q)       # per evaluation = summed over z
+        nb_ = 9                                   # basis tables with HCD: F^i H_j, i, j = 0..2 (cpx_factor.cuh)
+        grid["algorithmic"] = {"per": "tuple (all z) / point", "tuples": int(tuples_per_scan), "basis_tables": nb_,
+                               "p3d_cells_f64_per_tuple": w_["p3d_cells"], "hankel_dfma_per_tuple": 3 * w_["hankel_dfma"],
+                               "window_dfma_per_tuple": nb_ * w_["window_dfma"],
+                               "gram_dfma_per_tuple": (nb_ * nb_ + nb_) * w_["chi2_dfma"],
+                               "quadratic_form_dfma_per_point": len(likes) * (nb_ * nb_ + nb_),
+                               "bytes_out_per_point": 8}
 
     if rank != 0:
         if world > 1:
@@ -414,7 +520,11 @@ def main():
     cpu = None
     parity = None
     if not a.no_cpu_baseline and a.gpus == 1:
-        r = run_cpu("node", a.shape, a.n_theta_average, a.n_q, a.cpu_evals_per_core, defaults)
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            fpath = os.path.join(td, "filled.npz")
+            np.savez(fpath, Px_ZAM=filled["Px_ZAM"], cov_ZAM=filled["cov_ZAM"])
+            r = run_cpu("node", a.shape, a.n_theta_average, a.n_q, a.cpu_evals_per_core, defaults, filled_path=fpath)
         # the CPU leg's sample points scored by the GPU arm as well, inside a full production batch (same kernels,
         # same host-pointer C-ABI call as the e2e leg): oracle chi2 against device chi2 on the workload the number is quoted on
         pb = np.random.default_rng(99).uniform(lo, hi, size=(B, len(NAMES)))
@@ -430,6 +540,13 @@ def main():
                   "max_abs_dchi2_within_2ndata": float(dchi[near].max()) if near.any() else None,
                   "chi2_min": float(r["chi2"].min()), "chi2_max": float(r["chi2"].max()), "n_data": int(n_data),
                   "rule": "|dchi2| <= 1e-3 where chi2 <= 2 n_data, 1e-6 relative beyond (DESIGN.md section 5)"}
+        if grid_host is not None:
+            # the same sample points read out of the factorised whole-grid scan (its flattening puts q1, kp_Mpc first)
+            g_np, g_first, g_cnt, gn, perm = grid_host
+            flat = np.ravel_multi_index(tuple(r["grid_index"][:, j] for j in perm), gn)
+            dg = np.abs(g_np[flat - g_first] - r["chi2"])
+            grid["parity"] = {"n": int(len(dg)), "against": parity["against"], "max_abs_dchi2": float(dg.max()),
+                              "max_rel_dchi2": float((dg / np.abs(r["chi2"])).max()), "frac_within_1e-3": float(np.mean(dg <= 1e-3))}
         if r.get("chi2_truth") is not None:
             # the grid applies one (bias, beta, q1, kp) to all 12 z, so all of it is far from the best fit of this
             # data; the per-z truth (no columns: every z at its own defaults) is the point inside chi2 <= 2 n_data
@@ -444,7 +561,7 @@ def main():
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "setup_s": setup_s,
             "per_point_z_rate": value * len(likes)}
     emit(line)
     if world > 1:

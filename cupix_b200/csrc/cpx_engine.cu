@@ -16,6 +16,7 @@
 #include "cpx_kernels.cuh"
 #include "cpx_hankel_tc.cuh"
 #include "cpx_window_tc.cuh"
+#include "cpx_factor.cuh"
 
 namespace {
 
@@ -63,7 +64,8 @@ struct cpx_handle {
   int* d_nA_of_z = nullptr;
   int na_blk = 0;                    // a-block width shared by all z (template NA)
   int max_na = 0, max_nm = 0, max_nA = 0, max_nM = 0, max_nq = 0;
-  int chunk = 0;                     // points per chunk
+  int chunk = 0;                     // points the per-chunk scratch is currently sized for (grows on demand)
+  int chunk_max = 0;                 // upper limit: as many points as fit CPX_SCRATCH_MB of Px_Zam, at most 65536
   size_t device_bytes = 0;
   long long launches = 0;
   int wt_nb = 0;                     // > 0: k_window_tc (tcgen05 window contraction) for the chi2 stage
@@ -76,10 +78,29 @@ struct cpx_handle {
   double* d_model = nullptr;         // [chunk][n_z][max_nA][max_nM]  (lazy)
   double* d_pxout = nullptr;         // [chunk][n_z][max_na][max_nm]  (lazy)
   std::vector<void*> owned;
+  std::vector<void*> chunk_owned;    // the per-chunk scratch buffers (freed and re-allocated when the chunk grows)
+  size_t chunk_bytes = 0;
+  void* encode_tmap = nullptr;       // cuTensorMapEncodeTiled, when k_window_tc is available
+  void* d_tmaps = nullptr;           // CUtensorMap[n_z] of the Px_Zam scratch
+  // factorised path (cpx_factor.cuh): Gram matrices, tuple points, whole-batch staging in host-pointer mode
+  double* d_G = nullptr;
+  double* d_g = nullptr;
+  double* d_tpts = nullptr;
+  size_t cap_G = 0, cap_g = 0, cap_tpts = 0;
+  double* d_big_pts = nullptr;
+  double* d_big_chi2 = nullptr;
+  int* d_big_didx = nullptr;
+  size_t cap_big_pts = 0, cap_big_chi2 = 0, cap_big_didx = 0;
+  long long factored_calls = 0, factored_tuples = 0;
+  // calls on different streams share the scratch: each call records ev_done, the next one on another stream waits for it
+  cudaEvent_t ev_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
   // CPX_GUARD=1: every writable scratch buffer sits between two bands of kGuardBytes filled with kGuardByte;
   // cpx_get_info(CPX_INFO_GUARD_VIOLATIONS) counts the band bytes that changed (the GPU pool has no compute-sanitizer)
   bool guard = false;
-  std::vector<std::pair<unsigned char*, size_t>> guarded;   // (start of the front band, payload bytes)
+  struct Guarded { unsigned char* base; size_t bytes; bool per_chunk; };
+  std::vector<Guarded> guarded;      // (start of the front band, payload bytes)
 };
 
 namespace {
@@ -87,22 +108,44 @@ constexpr size_t kGuardBytes = 65536;
 constexpr int kGuardByte = 0xA5;
 
 // writable device buffer owned by the handle; with h->guard the payload is fenced by two guard bands
-int scratch_alloc(cpx_handle* h, void** p, size_t bytes) {
+int scratch_alloc(cpx_handle* h, void** p, size_t bytes, bool per_chunk = false) {
+  std::vector<void*>& owned = per_chunk ? h->chunk_owned : h->owned;
   if (!h->guard) {
     CPX_CUDA(cudaMalloc(p, bytes));
-    h->owned.push_back(*p);
+    owned.push_back(*p);
     h->device_bytes += bytes;
+    if (per_chunk) h->chunk_bytes += bytes;
     return CPX_OK;
   }
   const size_t payload = (bytes + 255) / 256 * 256;         // keeps the rear band (and the payload) 256-byte aligned
   unsigned char* base = nullptr;
   CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&base), payload + 2 * kGuardBytes));
-  h->owned.push_back(base);
+  owned.push_back(base);
   h->device_bytes += payload + 2 * kGuardBytes;
+  if (per_chunk) h->chunk_bytes += payload + 2 * kGuardBytes;
   CPX_CUDA(cudaMemset(base, kGuardByte, kGuardBytes));
   CPX_CUDA(cudaMemset(base + kGuardBytes + bytes, kGuardByte, payload - bytes + kGuardBytes));
-  h->guarded.emplace_back(base, bytes);
+  h->guarded.push_back({base, bytes, per_chunk});
   *p = base + kGuardBytes;
+  return CPX_OK;
+}
+
+// buffer of the factorised path that only ever grows (contents need not survive)
+template <typename T>
+int grow(cpx_handle* h, T** p, size_t* cap, size_t n) {
+  if (n <= *cap && *p) return CPX_OK;
+  if (*p) {
+    CPX_CUDA(cudaDeviceSynchronize());
+    CPX_CUDA(cudaFree(*p));
+    h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), static_cast<void*>(*p)), h->owned.end());
+    h->device_bytes -= *cap * sizeof(T);
+    *p = nullptr;
+  }
+  const size_t want = std::max(n, *cap + *cap / 2);
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
+  h->owned.push_back(*p);
+  h->device_bytes += want * sizeof(T);
+  *cap = want;
   return CPX_OK;
 }
 
@@ -461,7 +504,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
 int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
   cpx::ZDev& Z = zh.dev;
   const int nA = Z.n_A, nM = Z.n_M;
-  std::vector<double> yd(static_cast<size_t>(n_data) * nA * Z.n_M_pad, 0.0);
+  std::vector<double> yd(static_cast<size_t>(n_data) * nA * Z.n_M_pad, 0.0), ydd(n_data, 0.0);
   for (int dd = 0; dd < n_data; ++dd)
     for (int A = 0; A < nA; ++A) {
       const double* Li = &zh.Linv[static_cast<size_t>(A) * nM * nM];
@@ -471,18 +514,23 @@ int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
         double s = 0.0;
         for (int Mp = 0; Mp <= M; ++Mp) s += Li[M * nM + Mp] * x[Mp];
         y[M] = s;
+        ydd[dd] += s * s;
       }
     }
-  if (Z.yd) {
-    cudaFree(const_cast<double*>(Z.yd));
-    zh.owned.erase(std::remove(zh.owned.begin(), zh.owned.end(), (void*)Z.yd), zh.owned.end());
-  }
-  double* dptr;
+  for (const double* old : {Z.yd, Z.ydd})
+    if (old) {
+      cudaFree(const_cast<double*>(old));
+      zh.owned.erase(std::remove(zh.owned.begin(), zh.owned.end(), (void*)old), zh.owned.end());
+    }
+  double *dptr, *dptr2;
   int rc = upload(yd, &dptr, &h->device_bytes);
   if (rc) return rc;
-  Z.yd = dptr;
-  Z.n_data = n_data;
   zh.owned.push_back(dptr);
+  if ((rc = upload(ydd, &dptr2, &h->device_bytes))) return rc;
+  zh.owned.push_back(dptr2);
+  Z.yd = dptr;
+  Z.ydd = dptr2;
+  Z.n_data = n_data;
   return CPX_OK;
 }
 
@@ -560,6 +608,383 @@ int env_int(const char* name, int dflt) {
   return s ? std::atoi(s) : dflt;
 }
 
+// Per-chunk scratch (PtPar, RowPar, Px_Zam of every z; points, data indices, chi2, chi2_zA) for at least `need` points
+// (clamped to chunk_max).  Grows geometrically; growing synchronises the device, frees the old buffers and re-encodes the
+// tensor maps k_window_tc reads Px_Zam through.  The lazily allocated model / Px output buffers are dropped with it.
+int ensure_scratch(cpx_handle* h, long long need) {
+  need = std::max(1LL, std::min<long long>(need, h->chunk_max));
+  if (need <= h->chunk) return CPX_OK;
+  long long c = 256;
+  while (c < need) c *= 2;
+  c = std::min<long long>(c, h->chunk_max);
+  CPX_CUDA(cudaDeviceSynchronize());
+  for (void* p : h->chunk_owned) cudaFree(p);
+  h->chunk_owned.clear();
+  h->device_bytes -= h->chunk_bytes;
+  h->chunk_bytes = 0;
+  h->guarded.erase(std::remove_if(h->guarded.begin(), h->guarded.end(), [](const cpx_handle::Guarded& g) { return g.per_chunk; }),
+                   h->guarded.end());
+  h->d_model = h->d_pxout = nullptr;
+  h->chunk = 0;
+  const int n_z = static_cast<int>(h->z.size());
+  auto dmalloc = [&](void** p, size_t bytes) -> int { return scratch_alloc(h, p, bytes, true); };
+  int rc;
+  for (int i = 0; i < n_z; ++i) {
+    cpx::ZDev& Z = h->z[i].dev;
+    Z.ptpar = nullptr;
+    Z.rowpar = nullptr;
+    Z.pxzam = nullptr;
+    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.ptpar), sizeof(cpx::PtPar) * c))) return rc;
+    if (Z.flags & (CPX_INCLUDE_HCD | CPX_INCLUDE_CONTINUUM))
+      if ((rc = dmalloc(reinterpret_cast<void**>(&Z.rowpar), sizeof(cpx::RowPar) * static_cast<size_t>(c) * Z.n_m_pad))) return rc;
+    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.pxzam), static_cast<size_t>(c) * Z.n_a * Z.n_m_pad * 8 + 256))) return rc;
+  }
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_points), sizeof(double) * 16 * c))) return rc;
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_data_idx), sizeof(int) * c))) return rc;
+  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2), sizeof(double) * c))) return rc;
+  if (h->max_nA > 0)
+    if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2_zA), sizeof(double) * static_cast<size_t>(c) * n_z * h->max_nA))) return rc;
+  if (h->wt_nb > 0) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    std::vector<CUtensorMap> maps(n_z);
+    for (int i = 0; i < n_z; ++i) {
+      const cpx::ZDev& Z = h->z[i].dev;
+      if (Z.n_A <= 0) continue;
+      const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Z.n_m_pad), static_cast<cuuint64_t>(Z.n_a), static_cast<cuuint64_t>(c)};
+      const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Z.n_m_pad) * 8, static_cast<cuuint64_t>(Z.n_a) * Z.n_m_pad * 8};
+      const cuuint32_t box[3] = {16, 1, static_cast<cuuint32_t>(cpx::kWtPts)};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult r = reinterpret_cast<EncodeFn>(h->encode_tmap)(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Z.pxzam, dims, strides, box, estr,
+                                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(CPX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the Px_Zam scratch");
+    }
+    CPX_CUDA(cudaMemcpy(h->d_tmaps, maps.data(), sizeof(CUtensorMap) * n_z, cudaMemcpyHostToDevice));
+    for (int i = 0; i < n_z; ++i) h->z[i].dev.px_tmap = static_cast<CUtensorMap*>(h->d_tmaps) + i;
+  }
+  h->chunk = static_cast<int>(c);
+  return CPX_OK;
+}
+
+
+// ---- factorised path ---------------------------------------------------------------------------
+// slots whose parameter enters the model polynomially (cpx_factor.cuh); everything else defines the tuple
+bool is_amp_slot(int s) {
+  return s == CPX_BIAS || s == CPX_BETA || s == CPX_B_H || s == CPX_BETA_H || s == CPX_B_X || s == CPX_BETA_X || s == CPX_B_NOISE_MPC;
+}
+
+struct GridBox {
+  int start[16], len[16];
+  long long n_tup, n_amp;
+};
+
+// the flat index range [first, first + B) of a mixed-radix grid (last axis fastest) as at most 2 P hyper-rectangles
+void decompose_range(long long first, long long B, int P, const int32_t* n, const bool* amp, std::vector<GridBox>& boxes) {
+  long long stride[16];
+  stride[P - 1] = 1;
+  for (int j = P - 2; j >= 0; --j) stride[j] = stride[j + 1] * n[j + 1];
+  long long lo = first;
+  const long long hi = first + B;
+  while (lo < hi) {
+    int j = P - 1;
+    for (int jj = 0; jj < P; ++jj)
+      if (lo % stride[jj] == 0 && stride[jj] <= hi - lo) {
+        j = jj;
+        break;
+      }
+    const long long idx = (lo / stride[j]) % n[j];
+    const long long cnt = std::min<long long>((hi - lo) / stride[j], n[j] - idx);
+    GridBox b;
+    b.n_tup = b.n_amp = 1;
+    for (int i = 0; i < P; ++i) {
+      if (i < j) {
+        b.start[i] = static_cast<int>((lo / stride[i]) % n[i]);
+        b.len[i] = 1;
+      } else if (i == j) {
+        b.start[i] = static_cast<int>(idx);
+        b.len[i] = static_cast<int>(cnt);
+      } else {
+        b.start[i] = 0;
+        b.len[i] = n[i];
+      }
+      (amp[i] ? b.n_amp : b.n_tup) *= b.len[i];
+    }
+    boxes.push_back(b);
+    lo += cnt * stride[j];
+  }
+}
+
+typedef void (*KBasisFn)(const cpx::ZDev*, int, int, long long, int);
+KBasisFn kbasis_select(int nt) {
+  switch (nt) {
+    case 1: return cpx::k_basis_f64<1>;
+    case 2: return cpx::k_basis_f64<2>;
+    case 3: return cpx::k_basis_f64<3>;
+  }
+  return nullptr;
+}
+
+// Evaluates the call through the factorised path if it qualifies (*taken = true), else leaves it to the caller.
+int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const std::vector<int>& zl, bool* taken) {
+  using namespace cpx;
+  *taken = false;
+  if ((a->flags & CPX_NO_FACTOR) || env_int("CPX_FACTOR", 1) == 0) return CPX_OK;
+  if (!a->chi2 || a->chi2_zA || a->model_zAM || a->px_zam || a->P < 1) return CPX_OK;
+  const long long min_ratio = std::max(1, env_int("CPX_FACTOR_MIN", 24));
+  const int n_zl = static_cast<int>(zl.size());
+  const int P = a->P;
+  const bool dev_io = (a->flags & CPX_DEVICE_IO) != 0;
+  const int flags0 = h->z[zl[0]].dev.flags;
+  for (int zi : zl)
+    if (h->z[zi].dev.flags != flags0 || h->z[zi].dev.n_A <= 0) return CPX_OK;     // one basis layout for all evaluated z
+  bool amp[16];
+  int n_tcol = 0;
+  for (int j = 0; j < P; ++j) {
+    amp[j] = is_amp_slot(a->slot[j]);
+    n_tcol += !amp[j];
+  }
+  std::vector<GridBox> boxes;
+  if (a->grid_n) {
+    long long total = 1;
+    for (int j = 0; j < P; ++j) total *= a->grid_n[j];
+    if (a->grid_first + a->B > total) return fail(CPX_ERR_ARG, "cpx_eval: grid slice runs past the end of the grid");
+    decompose_range(a->grid_first, a->B, P, a->grid_n, amp, boxes);
+  } else {
+    if (n_tcol > 0) return CPX_OK;                   // explicit points sharing tuples are not searched for
+    GridBox b;
+    std::memset(&b, 0, sizeof b);
+    b.n_tup = 1;
+    b.n_amp = a->B;
+    boxes.push_back(b);
+  }
+  long long tuples = 0;
+  for (const GridBox& b : boxes) tuples += b.n_tup;
+  if (a->B < min_ratio * tuples) return CPX_OK;      // too few points per tuple for the (float64, 3-moment) tuple stage to pay
+  *taken = true;
+
+  const int nb = basis_count(flags0);
+  int nA_max = 0, nM_max = 0, nd_max = 0;
+  for (int zi : zl) {
+    nA_max = std::max(nA_max, h->z[zi].dev.n_A);
+    nM_max = std::max(nM_max, h->z[zi].dev.n_M);
+    nd_max = std::max(nd_max, h->z[zi].dev.n_data);
+  }
+  if (a->data_idx && !dev_io)
+    for (int64_t i = 0; i < a->B; ++i)
+      for (int zi : zl)
+        if (a->data_idx[i] < 0 || a->data_idx[i] >= h->z[zi].dev.n_data) return fail(CPX_ERR_ARG, "cpx_eval: data_idx out of range");
+
+  // tuples per batch: nb pseudo-points of the Px_Zam scratch each, Gram data within 256 MB
+  long long max_tup = 0;
+  for (const GridBox& b : boxes) max_tup = std::max(max_tup, b.n_tup);
+  int rc;
+  if ((rc = ensure_scratch(h, max_tup * nb))) return rc;
+  long long nt_cap = std::max(1, h->chunk / nb);
+  nt_cap = std::min<long long>(nt_cap, std::max<long long>(1, (256LL << 20) / (static_cast<long long>(n_zl) * nd_max * nb * 8)));
+  const size_t nz_all = h->z.size();
+  if (!h->d_model)
+    if ((rc = scratch_alloc(h, reinterpret_cast<void**>(&h->d_model), static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM * sizeof(double), true)))
+      return rc;
+  const long long nt_alloc = std::min(nt_cap, max_tup);
+  if ((rc = grow(h, &h->d_G, &h->cap_G, static_cast<size_t>(nt_alloc) * n_zl * nb * nb))) return rc;
+  if ((rc = grow(h, &h->d_g, &h->cap_g, static_cast<size_t>(nt_alloc) * n_zl * nd_max * nb))) return rc;
+  if ((rc = grow(h, &h->d_tpts, &h->cap_tpts, static_cast<size_t>(nt_alloc) * std::max(n_tcol, 1)))) return rc;
+
+  // whole-batch staging in host-pointer mode
+  const double* d_points = a->points;
+  const int* d_didx = a->data_idx;
+  double* d_chi2 = a->chi2;
+  if (!dev_io) {
+    if ((rc = grow(h, &h->d_big_chi2, &h->cap_big_chi2, static_cast<size_t>(a->B)))) return rc;
+    d_chi2 = h->d_big_chi2;
+    if (!a->grid_n) {
+      if ((rc = grow(h, &h->d_big_pts, &h->cap_big_pts, static_cast<size_t>(a->B) * P))) return rc;
+      CPX_CUDA(cudaMemcpyAsync(h->d_big_pts, a->points, sizeof(double) * a->B * P, cudaMemcpyHostToDevice, st));
+      d_points = h->d_big_pts;
+    }
+    if (a->data_idx) {
+      if ((rc = grow(h, &h->d_big_didx, &h->cap_big_didx, static_cast<size_t>(a->B)))) return rc;
+      CPX_CUDA(cudaMemcpyAsync(h->d_big_didx, a->data_idx, sizeof(int) * a->B, cudaMemcpyHostToDevice, st));
+      d_didx = h->d_big_didx;
+    }
+  }
+
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() -> int {
+    if (!a->stage_ms) return CPX_OK;
+    cudaEvent_t ev;
+    CPX_CUDA(cudaEventCreate(&ev));
+    CPX_CUDA(cudaEventRecord(ev, st));
+    evs.push_back(ev);
+    return CPX_OK;
+  };
+
+  CPX_CUDA(cudaMemcpyAsync(h->d_zlist, zl.data(), sizeof(int) * n_zl, cudaMemcpyHostToDevice, st));
+
+  // tuple columns only, for k_params
+  ParamsArgs pa;
+  std::memset(&pa, 0, sizeof(pa));
+  pa.P = n_tcol;
+  pa.n_z = n_zl;
+  pa.points = h->d_tpts;
+  QuadArgs q;
+  std::memset(&q, 0, sizeof(q));
+  q.P = P;
+  q.n_z = n_zl;
+  q.nb = nb;
+  q.grid_mode = a->grid_n ? 1 : 0;
+  q.nd_max = nd_max;
+  q.points = d_points;
+  q.data_idx = d_didx;
+  q.chi2 = d_chi2;
+  q.G = h->d_G;
+  q.g = h->d_g;
+  q.out_first = a->grid_first;
+  {
+    int jt = 0;
+    long long stride = 1;
+    for (int j = P - 1; j >= 0; --j) {
+      q.slot[j] = a->slot[j];
+      q.zsel[j] = a->zsel ? a->zsel[j] : -1;
+      q.is_amp[j] = amp[j] ? 1 : 0;
+      if (a->grid_n) {
+        q.grid_n[j] = a->grid_n[j];
+        q.grid_lo[j] = a->grid_lo[j];
+        q.grid_hi[j] = a->grid_hi[j];
+        q.grid_step[j] = a->grid_n[j] > 1 ? (a->grid_hi[j] - a->grid_lo[j]) / (a->grid_n[j] - 1) : 0.0;
+        q.ax_stride[j] = stride;
+        stride *= a->grid_n[j];
+      }
+    }
+    for (int j = 0; j < P; ++j)
+      if (!amp[j]) {
+        pa.slot[jt] = a->slot[j];
+        pa.zsel[jt] = a->zsel ? a->zsel[j] : -1;
+        ++jt;
+      }
+  }
+
+  std::vector<ZDev> tab(n_zl);
+  std::vector<double> tpts;
+  bool same_window_shape = true;
+  for (int i = 1; i < n_zl; ++i)
+    same_window_shape &= h->z[zl[i]].dev.n_M_pad == h->z[zl[0]].dev.n_M_pad && h->z[zl[i]].dev.n_mblk == h->z[zl[0]].dev.n_mblk;
+  int last_nt = -1;
+  for (const GridBox& b : boxes) {
+    for (int j = 0; j < P; ++j) {
+      q.ax_start[j] = b.start[j];
+      q.ax_len[j] = a->grid_n ? b.len[j] : 1;
+    }
+    q.n_amp = b.n_amp;
+    for (long long t0 = 0; t0 < b.n_tup; t0 += nt_cap) {
+      const int nt = static_cast<int>(std::min<long long>(nt_cap, b.n_tup - t0));
+      // ---- stage 0: tuple parameters ----
+      if ((rc = mark())) return rc;
+      if (n_tcol > 0) {
+        tpts.resize(static_cast<size_t>(nt) * n_tcol);
+        for (int tl = 0; tl < nt; ++tl) {
+          long long tr = t0 + tl;
+          int jt = n_tcol;
+          for (int j = P - 1; j >= 0; --j) {
+            if (amp[j]) continue;
+            const int ij = b.start[j] + static_cast<int>(tr % b.len[j]);
+            tr /= b.len[j];
+            const int n = a->grid_n[j];
+            // numpy.linspace, as k_params / k_quad form it (no FMA contraction on the host either)
+            volatile double prod = static_cast<double>(ij) * q.grid_step[j];
+            tpts[static_cast<size_t>(tl) * n_tcol + --jt] = (ij == n - 1 && n > 1) ? a->grid_hi[j] : prod + a->grid_lo[j];
+          }
+        }
+        CPX_CUDA(cudaMemcpyAsync(h->d_tpts, tpts.data(), sizeof(double) * tpts.size(), cudaMemcpyHostToDevice, st));
+      }
+      if (nt != last_nt) {
+        long long items = 0;
+        for (int i = 0; i < n_zl; ++i) {
+          tab[i] = h->z[zl[i]].dev;
+          tab[i].item_start = items;
+          items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * nt;
+        }
+        CPX_CUDA(cudaMemcpyAsync(h->d_ztab, tab.data(), sizeof(ZDev) * n_zl, cudaMemcpyHostToDevice, st));
+        last_nt = nt;
+      }
+      long long n_items = 0;
+      for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * nt;
+      pa.first = 0;
+      pa.count = nt;
+      k_params<<<dim3((nt + 127) / 128, n_zl), 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
+      ++h->launches;
+      // ---- stage 1: float64 cells, three mu-moment Hankel sums, basis tables ----
+      if ((rc = mark())) return rc;
+      {
+        KBasisFn fn = kbasis_select(h->na_blk / 8);
+        const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
+        fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, nt, n_items, nb);
+        ++h->launches;
+      }
+      // ---- stage 2: whitened window of every basis table, Gram matrices ----
+      if ((rc = mark())) return rc;
+      {
+        const int npseudo = nt * nb;
+        auto window_launch = [&](int i, int zslot, int gz, int nA_grid) {
+          const ZDev& Z = tab[i];
+          WindowArgs w;
+          w.count = npseudo;
+          w.zslot = zslot;
+          w.n_zl = n_zl;
+          w.nA_max = nA_max;
+          w.nM_max = nM_max;
+          w.data_idx = nullptr;
+          w.chi2_zA = nullptr;
+          w.model = h->d_model;
+          w.whiten = 1;
+          dim3 grid((npseudo + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
+          const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
+          k2_select<false>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
+          ++h->launches;
+        };
+        if (same_window_shape) {
+          window_launch(0, -1, n_zl, nA_max);
+        } else {
+          for (int i = 0; i < n_zl; ++i) window_launch(i, i, 1, tab[i].n_A);
+        }
+        k_gram<<<dim3(nt, n_zl), 256, sizeof(double) * nb * nM_max, st>>>(h->d_ztab, h->d_model, n_zl, nA_max, nM_max, nb, nd_max, h->d_G, h->d_g);
+        ++h->launches;
+      }
+      // ---- stage 3: quadratic form per point ----
+      if ((rc = mark())) return rc;
+      q.t0 = t0;
+      q.nt = nt;
+      {
+        const long long n_thr = q.n_amp * nt;
+        k_quad<<<static_cast<unsigned>((n_thr + 255) / 256), 256, 0, st>>>(q, h->d_ztab, h->d_zlist);
+        ++h->launches;
+      }
+      if ((rc = mark())) return rc;
+      h->factored_tuples += nt;
+    }
+  }
+  ++h->factored_calls;
+  CPX_CUDA(cudaGetLastError());
+  if (!dev_io) CPX_CUDA(cudaMemcpyAsync(a->chi2, d_chi2, sizeof(double) * a->B, cudaMemcpyDeviceToHost, st));
+  if (!dev_io || a->stage_ms) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(CPX_ERR_CUDA, std::string("cpx_eval (factorised): ") + cudaGetErrorString(e));
+  }
+  if (a->stage_ms) {
+    for (int s = 0; s < 4; ++s) a->stage_ms[s] = 0.f;
+    for (size_t i = 0; i + 4 < evs.size(); i += 5)
+      for (int s = 0; s < 4; ++s) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[i + s], evs[i + s + 1]);
+        a->stage_ms[s] += ms;
+      }
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  }
+  return CPX_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -576,6 +1001,8 @@ void cpx_destroy(cpx_handle* h) {
   for (auto& zh : h->z)
     for (void* p : zh.owned) cudaFree(p);
   for (void* p : h->owned) cudaFree(p);
+  for (void* p : h->chunk_owned) cudaFree(p);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -628,35 +1055,23 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     }
     per_point_bytes += static_cast<size_t>(h->z[i].dev.n_a) * h->z[i].dev.n_m_pad * 8 + sizeof(cpx::PtPar) + sizeof(cpx::RowPar) * h->z[i].dev.n_m_pad;
   }
-  // chunk: Px_Zam scratch of all z within the budget (default 4 GiB), multiple of 256 points
+  // chunk_max: Px_Zam scratch of all z within the budget (default 4 GiB), multiple of 256 points.  The scratch itself is
+  // allocated by ensure_scratch() for the largest batch seen so far, so that engines which only serve scalar calls
+  // (Theory.get_px_obs, Likelihood.get_chi2) do not pin gigabytes of HBM each.
   const size_t budget = static_cast<size_t>(env_int("CPX_SCRATCH_MB", 4096)) << 20;
   long long chunk = static_cast<long long>(budget / std::max<size_t>(per_point_bytes, 1));
   chunk = std::max(256LL, std::min(chunk, 65536LL)) / 256 * 256;
-  h->chunk = static_cast<int>(chunk);
+  h->chunk_max = static_cast<int>(chunk);
+  h->chunk = 0;
 
   h->guard = env_int("CPX_GUARD", 0) != 0;
   auto dmalloc = [&](void** p, size_t bytes) -> int { return scratch_alloc(h, p, bytes); };
   int rc;
-  for (int i = 0; i < n_zbins; ++i) {
-    cpx::ZDev& Z = h->z[i].dev;
-    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.ptpar), sizeof(cpx::PtPar) * h->chunk))) return bail(rc);
-    if (Z.flags & (CPX_INCLUDE_HCD | CPX_INCLUDE_CONTINUUM))
-      if ((rc = dmalloc(reinterpret_cast<void**>(&Z.rowpar), sizeof(cpx::RowPar) * static_cast<size_t>(h->chunk) * Z.n_m_pad)))
-        return bail(rc);
-    if ((rc = dmalloc(reinterpret_cast<void**>(&Z.pxzam),
-                      static_cast<size_t>(h->chunk) * Z.n_a * Z.n_m_pad * 8 + 256)))
-      return bail(rc);
-  }
   if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_ztab), sizeof(cpx::ZDev) * n_zbins))) return bail(rc);
   if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_zlist), sizeof(int) * n_zbins))) return bail(rc);
   if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_nA_of_z), sizeof(int) * n_zbins))) return bail(rc);
-  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_points), sizeof(double) * 16 * h->chunk))) return bail(rc);
-  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_data_idx), sizeof(int) * h->chunk))) return bail(rc);
-  if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2), sizeof(double) * h->chunk))) return bail(rc);
-  if (h->max_nA > 0)
-    if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_chi2_zA),
-                      sizeof(double) * static_cast<size_t>(h->chunk) * n_zbins * h->max_nA)))
-      return bail(rc);
+  if (cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(CPX_ERR_CUDA, "cudaEventCreate failed"));
 
   // opt in to the large dynamic shared memory for every k_p3d_hankel instantiation we may launch
   for (int pp = 1; pp <= 2; ++pp)
@@ -696,33 +1111,15 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     if (ok && nb > 0 && static_cast<size_t>(cpx::wt_smem_bytes(nb)) + 2048 <= static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
       if (cudaFuncSetAttribute(cpx::k_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, cpx::wt_smem_bytes(nb)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_window_tc"));
-      // tensor maps of the Px_Zam scratch of every z (k_window_tc streams it with tiled TMA loads)
-      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      // tensor maps of the Px_Zam scratch of every z (k_window_tc streams it with tiled TMA loads) are encoded by
+      // ensure_scratch() whenever the scratch is (re-)allocated
       void* fnp = nullptr;
       cudaDriverEntryPointQueryResult qres;
       if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres) != cudaSuccess || !fnp ||
           qres != cudaDriverEntryPointSuccess)
         return bail(fail(CPX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver"));
-      std::vector<CUtensorMap> maps(n_zbins);
-      for (int i = 0; i < n_zbins; ++i) {
-        const cpx::ZDev& Z = h->z[i].dev;
-        if (Z.n_A <= 0) continue;
-        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Z.n_m_pad), static_cast<cuuint64_t>(Z.n_a), static_cast<cuuint64_t>(h->chunk)};
-        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Z.n_m_pad) * 8, static_cast<cuuint64_t>(Z.n_a) * Z.n_m_pad * 8};
-        const cuuint32_t box[3] = {16, 1, static_cast<cuuint32_t>(cpx::kWtPts)};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = reinterpret_cast<EncodeFn>(fnp)(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Z.pxzam, dims, strides, box, estr,
-                                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return bail(fail(CPX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the Px_Zam scratch"));
-      }
-      CUtensorMap* dmaps = nullptr;
-      if ((rc = dmalloc(reinterpret_cast<void**>(&dmaps), sizeof(CUtensorMap) * n_zbins))) return bail(rc);
-      if (cudaMemcpy(dmaps, maps.data(), sizeof(CUtensorMap) * n_zbins, cudaMemcpyHostToDevice) != cudaSuccess)
-        return bail(fail(CPX_ERR_CUDA, "upload of the tensor maps failed"));
-      for (int i = 0; i < n_zbins; ++i) h->z[i].dev.px_tmap = dmaps + i;
+      h->encode_tmap = fnp;
+      if ((rc = dmalloc(&h->d_tmaps, sizeof(CUtensorMap) * n_zbins))) return bail(rc);
       h->wt_nb = nb;
     }
   }
@@ -735,7 +1132,7 @@ int cpx_set_data(cpx_handle* h, int32_t iz, const double* Px_AM, int32_t n_data)
     return fail(CPX_ERR_ARG, "cpx_set_data: bad arguments");
   if (h->z[iz].dev.n_A <= 0) return fail(CPX_ERR_ARG, "cpx_set_data: z bin has no measurement");
   CPX_CUDA(cudaSetDevice(h->device));
-  CPX_CUDA(cudaStreamSynchronize(h->stream));
+  CPX_CUDA(cudaDeviceSynchronize());     // evaluations may be in flight on any caller stream
   return upload_yd(h, h->z[iz], Px_AM, n_data);
 }
 
@@ -747,7 +1144,10 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
     case CPX_INFO_MAX_NM: *value = h->max_nm; break;
     case CPX_INFO_MAX_N_A: *value = h->max_nA; break;
     case CPX_INFO_MAX_N_M: *value = h->max_nM; break;
-    case CPX_INFO_CHUNK: *value = h->chunk; break;
+    case CPX_INFO_CHUNK: *value = h->chunk_max; break;
+    case CPX_INFO_CHUNK_ALLOCATED: *value = h->chunk; break;
+    case CPX_INFO_FACTORED_CALLS: *value = h->factored_calls; break;
+    case CPX_INFO_FACTORED_TUPLES: *value = h->factored_tuples; break;
     case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
     case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
     case CPX_INFO_SM_COUNT: *value = h->sm_count; break;
@@ -759,11 +1159,11 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
       std::vector<unsigned char> band(kGuardBytes + 256);
       int64_t bad = 0;
       for (const auto& g : h->guarded) {
-        const size_t payload = (g.second + 255) / 256 * 256;
-        const size_t rear = payload - g.second + kGuardBytes;
-        CPX_CUDA(cudaMemcpy(band.data(), g.first, kGuardBytes, cudaMemcpyDeviceToHost));
+        const size_t payload = (g.bytes + 255) / 256 * 256;
+        const size_t rear = payload - g.bytes + kGuardBytes;
+        CPX_CUDA(cudaMemcpy(band.data(), g.base, kGuardBytes, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < kGuardBytes; ++i) bad += band[i] != kGuardByte;
-        CPX_CUDA(cudaMemcpy(band.data(), g.first + kGuardBytes + g.second, rear, cudaMemcpyDeviceToHost));
+        CPX_CUDA(cudaMemcpy(band.data(), g.base + kGuardBytes + g.bytes, rear, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < rear; ++i) bad += band[i] != kGuardByte;
       }
       *value = bad;
@@ -780,6 +1180,8 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   if (a->B < 0 || a->P < 0 || a->P > 16) return fail(CPX_ERR_ARG, "cpx_eval: B < 0 or P outside 0..16");
   if (a->P > 0 && !a->slot) return fail(CPX_ERR_ARG, "cpx_eval: slot is NULL");
   if (a->P > 0 && !a->points && !a->grid_n) return fail(CPX_ERR_ARG, "cpx_eval: neither points nor a grid given");
+  if (a->grid_n && (!a->grid_lo || !a->grid_hi)) return fail(CPX_ERR_ARG, "cpx_eval: grid_n given without grid_lo / grid_hi");
+  if (a->grid_n && a->grid_first < 0) return fail(CPX_ERR_ARG, "cpx_eval: grid_first < 0");
   for (int j = 0; j < a->P; ++j) {
     if (a->slot[j] < 0 || a->slot[j] >= CPX_NSLOTS) return fail(CPX_ERR_ARG, "cpx_eval: slot out of range");
     if (a->grid_n && a->grid_n[j] < 1) return fail(CPX_ERR_ARG, "cpx_eval: grid_n < 1");
@@ -800,9 +1202,23 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     }
   if (a->B == 0) return CPX_OK;
   CPX_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : h->stream;
   const bool dev_io = (a->flags & CPX_DEVICE_IO) != 0;
   const bool precise = (a->flags & CPX_PRECISE_CELLS) != 0;
+  // Device I/O: the caller's buffers are ordered on a->stream, NULL meaning the CUDA default (legacy) stream -- what
+  // torch.cuda.current_stream().cuda_stream is for torch's default stream.  Host I/O: the handle's own stream unless given.
+  cudaStream_t st = (dev_io || a->stream) ? static_cast<cudaStream_t>(a->stream) : h->stream;
+  // all calls share the handle's scratch: order this call after the previous one if that ran on another stream
+  if (h->have_last && h->last_stream != st) CPX_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  struct Done {        // records the ordering event on every exit path once work may have been enqueued
+    cpx_handle* h;
+    cudaStream_t st;
+    ~Done() {
+      if (cudaEventRecord(h->ev_done, st) == cudaSuccess) {
+        h->last_stream = st;
+        h->have_last = true;
+      }
+    }
+  } done_guard{h, st};
 
   // ---- z selection ----
   std::vector<int> zl;
@@ -831,12 +1247,20 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
           return fail(CPX_ERR_ARG, "cpx_eval: data_idx out of range");
   }
 
-  // lazy scratch for the bulky optional outputs
+  int rc;
+  // ---- factorised path (cpx_factor.cuh): Hankel + window once per distinct tuple, chi2 per point a quadratic form ----
+  {
+    bool taken = false;
+    rc = eval_factored(h, a, st, zl, &taken);
+    if (taken || rc) return rc;
+  }
+  if ((rc = ensure_scratch(h, a->B))) return rc;
+
+  // lazy scratch for the bulky optional outputs (sized by the chunk, dropped when the chunk grows)
   auto lazy = [&](double** p, size_t n) -> int {
     if (*p) return CPX_OK;
-    return scratch_alloc(h, reinterpret_cast<void**>(p), n * sizeof(double));
+    return scratch_alloc(h, reinterpret_cast<void**>(p), n * sizeof(double), true);
   };
-  int rc;
   const size_t nz_all = h->z.size();
   if (want_model && !dev_io)
     if ((rc = lazy(&h->d_model, static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM))) return rc;
@@ -980,6 +1404,11 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     if ((rc = mark())) return rc;
     double* chi2_zA_dst = nullptr;
     if (want_chi2) chi2_zA_dst = (dev_io && a->chi2_zA) ? a->chi2_zA + first * n_zl * nA_max : h->d_chi2_zA;
+    if (a->chi2_zA) {   // slots A >= n_A of a z bin with fewer coarse theta bins than the widest one read as zero
+      bool ragged = false;
+      for (int i = 0; i < n_zl; ++i) ragged |= tab[i].n_A < nA_max;
+      if (ragged) CPX_CUDA(cudaMemsetAsync(chi2_zA_dst, 0, sizeof(double) * count * n_zl * nA_max, st));
+    }
     double* model_dst = nullptr;
     if (want_model) model_dst = dev_io ? a->model_zAM + first * n_zl * nA_max * nM_max : h->d_model;
     double* px_dst = nullptr;
@@ -998,6 +1427,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       w.data_idx = d_didx;
       w.chi2_zA = chi2_zA_dst;
       w.model = model_dst;
+      w.whiten = 0;
       dim3 grid((count + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {

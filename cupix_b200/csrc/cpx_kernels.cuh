@@ -87,6 +87,7 @@ struct ZDev {
   const double* T_chi;                  // [n_pairs][n_M_pad][n_m_pad]  L^-1 diag(V/Vsum) U
   const double* T_model;                // [n_pairs][n_M_pad][n_m_pad]  diag(V/Vsum) U
   const double* yd;                     // [n_data][n_A][n_M_pad]       L^-1 d
+  const double* ydd;                    // [n_data]                     |L^-1 d|^2 summed over (A, M): constant term of the factorised chi2
   // per-chunk buffers
   PtPar* ptpar;                         // [chunk]
   struct RowPar* rowpar;                // [chunk][n_m_pad], valid when flags & (HCD | CONTINUUM)
@@ -797,6 +798,7 @@ struct WindowArgs {
   const int* data_idx;   // [count] or null
   double* chi2_zA;    // [count][n_zl][nA_max]
   double* model;      // [count][n_zl][nA_max][nM_max] or null
+  int whiten;         // model mode with the whitened operator T_chi (basis vectors of the factorised path, cpx_factor.cuh)
 };
 
 template <int MT, bool CHI2>
@@ -817,7 +819,7 @@ __global__ void __launch_bounds__(128) k_window(const ZDev* __restrict__ ztab, i
   const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
   const int kchunks = Z.n_m_pad / kWinKC;
   const int n_steps = (p1 - p0) * kchunks;
-  const double* Tbase = CHI2 ? Z.T_chi : Z.T_model;
+  const double* Tbase = (CHI2 || w.whiten) ? Z.T_chi : Z.T_model;
   double chi2_part[2] = {0.0, 0.0};
 
   // coarse-k columns in blocks of 8*MT (one block unless n_M > 64)
@@ -879,7 +881,8 @@ __global__ void __launch_bounds__(128) k_window(const ZDev* __restrict__ ztab, i
     for (int i = 0; i < 2; ++i) {
       const int pt = pt_base + warp * 16 + 8 * i + g;
       if (CHI2) {
-        const int d = (w.data_idx != nullptr && pt < w.count) ? w.data_idx[pt] : 0;
+        // a data index outside the handle's data vectors (device-resident indices cannot be validated on the host) is clamped
+        const int d = (w.data_idx != nullptr && pt < w.count) ? min(max(w.data_idx[pt], 0), Z.n_data - 1) : 0;
         const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad + col0;
         double s = chi2_part[i];
 #pragma unroll

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
     unsigned char* const arow = sA + (h * 16 + (r >> 3)) * 128 + (r & 7) * 16;
     const int er = 32 * (warp & 3) + lane, hh = warp >> 2;   // epilogue: TMEM lane = point, column half
     const int ept = pt_base + er;
-    const int d = (w.data_idx != nullptr && ept < w.count) ? w.data_idx[ept] : 0;
+    const int d = (w.data_idx != nullptr && ept < w.count) ? min(max(w.data_idx[ept], 0), Z.n_data - 1) : 0;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
     uint32_t roff[8];                                        // byte offsets of this thread's 8 swizzled units within a ring slot
 #pragma unroll

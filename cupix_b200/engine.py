@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libc
 NSLOTS = 18
 DEVICE_IO = 1
 PRECISE_CELLS = 2
+NO_FACTOR = 4
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -99,7 +100,7 @@ class PxEngine(object):
 
     INFO = {"n_zbins": 0, "max_na": 1, "max_nm": 2, "max_nA": 3, "max_nM": 4, "chunk": 5,
             "device_bytes": 6, "kernel_launches": 7, "sm_count": 8, "guard_buffers": 9,
-            "guard_violations": 10}
+            "guard_violations": 10, "factored_calls": 11, "factored_tuples": 12, "chunk_allocated": 13}
 
     def __init__(self, plans, device=0, precise=False):
         """``precise=True`` evaluates the P3D cells in float64 as well (CPX_PRECISE_CELLS): the
@@ -164,11 +165,17 @@ class PxEngine(object):
         pl = [self.plans[i] for i in zs]
         return zs, max(p.n_a for p in pl), max(p.n_m for p in pl), max(p.n_A for p in pl), max(p.n_M for p in pl)
 
+    def _flags(self, factor, extra=0):
+        """cpx_eval flags.  ``factor``: None = the library decides (chi2-only calls whose points share tuples take the
+        factorised path, include/cupix_b200.h), False = every point through the full pipeline (CPX_NO_FACTOR)."""
+        return extra | (PRECISE_CELLS if self.precise else 0) | (NO_FACTOR if factor is False else 0)
+
     def eval(self, points=None, slots=(), zsel=None, grid=None, grid_first=0, B=None, data_idx=None,
-             z_list=None, want=("chi2",), stage_ms=False):
+             z_list=None, want=("chi2",), stage_ms=False, factor=None, chi2_out=None):
         """Host-buffer evaluation.  ``points`` [B, P] float64 (or ``grid=(lo, hi, n)`` for on-device
         meshgrid generation), ``slots`` [P] parameter slot per column.  Returns a dict of numpy
-        arrays for the requested outputs in ``want`` (chi2, chi2_zA, model, px_zam)."""
+        arrays for the requested outputs in ``want`` (chi2, chi2_zA, model, px_zam).  ``chi2_out``: caller's
+        float64 host array [B] (e.g. pinned memory) to receive chi2 instead of a fresh array."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         P = int(slots.size)
         args = EvalArgs()
@@ -192,7 +199,7 @@ class PxEngine(object):
             B = points.shape[0]
             args.points = points.ctypes.data_as(C.c_void_p) if P > 0 else None
             keep.append(points)
-        args.B, args.P, args.flags = int(B), P, (PRECISE_CELLS if self.precise else 0)
+        args.B, args.P, args.flags = int(B), P, self._flags(factor)
         args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
         if zsel is not None:
             zsel = np.ascontiguousarray(zsel, dtype=np.int32)
@@ -210,7 +217,11 @@ class PxEngine(object):
             keep.append(zl)
         out = {}
         if "chi2" in want:
-            out["chi2"] = np.empty(B)
+            if chi2_out is not None:
+                assert chi2_out.dtype == np.float64 and chi2_out.flags.c_contiguous and chi2_out.size >= B
+                out["chi2"] = chi2_out.reshape(-1)[:B]
+            else:
+                out["chi2"] = np.empty(B)
             args.chi2 = out["chi2"].ctypes.data_as(C.c_void_p)
         if "chi2_zA" in want:
             out["chi2_zA"] = np.zeros((B, len(zs), nA))
@@ -231,13 +242,13 @@ class PxEngine(object):
             out["stage_ms"] = np.array(list(ms))
         return out
 
-    def eval_host_into(self, points, slots, zsel, chi2_out, data_idx=None):
+    def eval_host_into(self, points, slots, zsel, chi2_out, data_idx=None, factor=None):
         """chi2 for host ``points`` [B, P] written into the caller's host array ``chi2_out`` [B]
         (e.g. pinned memory); H2D, kernels and D2H all happen inside this one cpx_eval call."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         assert points.flags.c_contiguous and points.dtype == np.float64 and chi2_out.flags.c_contiguous
         args = EvalArgs()
-        args.B, args.P, args.flags = points.shape[0], points.shape[1], (PRECISE_CELLS if self.precise else 0)
+        args.B, args.P, args.flags = points.shape[0], points.shape[1], self._flags(factor)
         args.points = points.ctypes.data_as(C.c_void_p)
         args.slot = slots.ctypes.data_as(c_ip)
         if zsel is not None:
@@ -254,12 +265,14 @@ class PxEngine(object):
 
     def eval_device(self, B, P, slots, points_ptr=None, grid=None, grid_first=0, zsel=None,
                     data_idx_ptr=None, z_list=None, chi2_ptr=None, chi2_zA_ptr=None, model_ptr=None,
-                    px_ptr=None, stream=None, stage_ms=False):
+                    px_ptr=None, stream=None, stage_ms=False, factor=None):
         """Device-pointer evaluation (asynchronous on ``stream``): pointers are raw device addresses
-        (e.g. ``torch.Tensor.data_ptr()``).  Returns stage times if requested (this synchronises)."""
+        (e.g. ``torch.Tensor.data_ptr()``).  ``stream`` is the raw ``cudaStream_t`` the buffers are ordered on; None or 0
+        is the CUDA default (legacy) stream -- what ``torch.cuda.current_stream().cuda_stream`` is for torch's default
+        stream.  Returns stage times if requested (this synchronises)."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         args = EvalArgs()
-        args.B, args.P, args.flags = int(B), int(P), DEVICE_IO | (PRECISE_CELLS if self.precise else 0)
+        args.B, args.P, args.flags = int(B), int(P), self._flags(factor, DEVICE_IO)
         args.slot = slots.ctypes.data_as(c_ip) if P > 0 else None
         args.points = points_ptr
         keep = [slots]

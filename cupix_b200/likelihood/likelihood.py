@@ -102,11 +102,12 @@ class Likelihood(object):
         return self.data.Px_ZAM[self.iz].size
 
     # ---- batched API (new) -------------------------------------------------------------------
-    def get_chi2_batch(self, points, names, return_info=False, data_idx=None):
-        """chi2 [B] for ``points`` [B, P] whose columns are the parameters ``names``."""
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None):
+        """chi2 [B] for ``points`` [B, P] whose columns are the parameters ``names``.  ``factor=False`` keeps every point
+        on the full pipeline (see PxEngine._flags)."""
         slots, _ = slots_from_names(names)
         want = ("chi2", "chi2_zA") if return_info else ("chi2",)
-        out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx)
+        out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx, factor=factor)
         if return_info:
             return out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"][:, 0]}
         return out["chi2"]
@@ -118,11 +119,11 @@ class Likelihood(object):
         slots, _ = slots_from_names(names)
         return self.engine().eval(points=points, slots=slots, want=("model",))["model"][:, 0]
 
-    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None):
+    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None, factor=None):
         """chi2 on the meshgrid(indexing='ij') of linspace(lo[j], hi[j], n[j]); points are generated
         on the device (scripts/chi2_scan_mock.py:107-111).  ``first``/``count`` select a flat slice."""
         slots, _ = slots_from_names(names)
-        return self.engine().eval(slots=slots, grid=(lo, hi, n), grid_first=first, B=count)["chi2"]
+        return self.engine().eval(slots=slots, grid=(lo, hi, n), grid_first=first, B=count, factor=factor)["chi2"]
 
     def get_chi2_from_arinyo_tensor(self, arinyo, names=("bias", "beta", "q1", "kvav", "av", "bv", "kp", "q2")):
         """Tensor hand-off from the ForestFlow emulator (model_lya.py:200-235): ``arinyo`` is a
@@ -179,10 +180,10 @@ class JointLikelihood(object):
     def get_ndata(self):
         return sum(lk.get_ndata() for lk in self.likes)
 
-    def get_chi2_batch(self, points, names, return_info=False, data_idx=None):
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None):
         slots, zsel = slots_from_names(names)
         want = ("chi2", "chi2_zA") if return_info else ("chi2",)
-        out = self.engine().eval(points=points, slots=slots, zsel=zsel, want=want, data_idx=data_idx)
+        out = self.engine().eval(points=points, slots=slots, zsel=zsel, want=want, data_idx=data_idx, factor=factor)
         return (out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"]}) if return_info else out["chi2"]
 
     def get_chi2(self, params={}, return_info=False):
@@ -191,9 +192,9 @@ class JointLikelihood(object):
         r = self.get_chi2_batch(pts, names, return_info=return_info)
         return (r[0][0], r[1]) if return_info else r[0]
 
-    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None):
+    def get_chi2_grid(self, names, lo, hi, n, first=0, count=None, factor=None):
         slots, zsel = slots_from_names(names)
-        return self.engine().eval(slots=slots, zsel=zsel, grid=(lo, hi, n), grid_first=first, B=count)["chi2"]
+        return self.engine().eval(slots=slots, zsel=zsel, grid=(lo, hi, n), grid_first=first, B=count, factor=factor)["chi2"]
 
     def get_convolved_px_batch(self, points, names):
         slots, zsel = slots_from_names(names)

@@ -28,7 +28,9 @@
  *   CPX_WTC=0       chi2 stage as the FP64 DMMA GEMM instead of the tcgen05 kernel (k_window_tc, the default for
  *                   calls with at least CPX_WTC_MIN = 49152 (point, z) pairs)
  *   CPX_TC=1        Hankel contraction on tcgen05 (k_p3d_hankel_tc) instead of FP64 DMMA
- *   CPX_SCRATCH_MB  size of the per-chunk Px_Zam scratch buffer (default 4096)
+ *   CPX_SCRATCH_MB  upper limit of the per-chunk Px_Zam scratch buffer (default 4096); the buffer is sized by the
+ *                   largest batch seen so far, so an engine that only serves scalar calls stays small
+ *   CPX_FACTOR=0    switch the factorised path (see CPX_NO_FACTOR below) off for the whole process
  *   CPX_GUARD=1     debugging: fence every writable scratch buffer with 64 KiB guard bands, checked by
  *                   cpx_get_info(CPX_INFO_GUARD_VIOLATIONS)
  *
@@ -112,9 +114,19 @@ typedef struct cpx_handle cpx_handle;
  * Any output pointer may be NULL. */
 enum {
   CPX_DEVICE_IO = 1,      /* points / outputs are device pointers, call is asynchronous on `stream`          */
-  CPX_PRECISE_CELLS = 2   /* evaluate the P3D cells in float64 too (reference-precision mode, ~4x slower):   */
+  CPX_PRECISE_CELLS = 2,  /* evaluate the P3D cells in float64 too (reference-precision mode, ~4x slower):   */
                           /* chi2 then agrees with the float64 oracle to ~1e-9 everywhere */
+  CPX_NO_FACTOR = 4       /* never take the factorised path (below): every point through the full pipeline   */
 };
+
+/* Factorised path (cpx_factor.cuh; taken automatically, CPX_FACTOR=0 or CPX_NO_FACTOR switch it off).  The model
+ * is a polynomial in the AMPLITUDE parameters bias, beta, b_H, beta_H, b_X, beta_X, b_noise_Mpc whose coefficient
+ * tables depend on the point only through the other ("tuple") parameters.  When a call asks for `chi2` alone and
+ * its points share tuples -- a grid whose points-per-distinct-tuple ratio is >= CPX_FACTOR_MIN (24), or explicit
+ * points whose columns are all amplitude parameters (one tuple) with B >= CPX_FACTOR_MIN -- the P3D / Hankel /
+ * window stages run once per distinct tuple (float64 cells) and chi2 per point is a quadratic form.  This is the
+ * shape of the reference's scans (scripts/chi2_scan_mock.py:107-140, chi2_scan_forecast.py:116-125).  Results agree
+ * with the float64 oracle to ~1e-9 relative; with the float32-cell pipeline to its own ~1e-7. */
 
 typedef struct cpx_eval_args {
   int64_t B;                 /* number of parameter points                                      */
@@ -138,7 +150,10 @@ typedef struct cpx_eval_args {
   double* chi2_zA;           /* [B][n_z_list][n_A_max]  per-(z, theta_A) chi2 (= -2 log_like_all) */
   double* model_zAM;         /* [B][n_z_list][n_A_max][n_M_max] convolved + rebinned model Px    */
   double* px_zam;            /* [B][n_z_list][n_a_max][n_m_max] unconvolved theory Px_Zam        */
-  void* stream;              /* cudaStream_t; NULL = the handle's own stream                     */
+  void* stream;              /* cudaStream_t.  Host I/O: NULL = the handle's own stream (the call synchronises).   */
+                             /* CPX_DEVICE_IO: the stream the caller's buffers are ordered on; NULL = the CUDA     */
+                             /* default (legacy) stream, as everywhere in CUDA.  Calls on different streams are    */
+                             /* ordered against each other by the library (they share the handle's scratch).       */
   float* stage_ms;           /* host [4] or NULL: device time of {params, p3d+hankel, window, reduce} */
                              /* summed over chunks, measured with CUDA events on the launching stream */
 } cpx_eval_args;
@@ -156,7 +171,11 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
        CPX_INFO_MAX_N_M = 4, CPX_INFO_CHUNK = 5, CPX_INFO_DEVICE_BYTES = 6, CPX_INFO_KERNEL_LAUNCHES = 7,
        CPX_INFO_SM_COUNT = 8,
        CPX_INFO_GUARD_BUFFERS = 9,      /* scratch buffers fenced by guard bands (handles created with CPX_GUARD=1) */
-       CPX_INFO_GUARD_VIOLATIONS = 10   /* guard-band bytes overwritten so far; synchronises the device            */ };
+       CPX_INFO_GUARD_VIOLATIONS = 10,  /* guard-band bytes overwritten so far; synchronises the device            */
+       CPX_INFO_FACTORED_CALLS = 11,    /* cpx_eval calls that took the factorised path                            */
+       CPX_INFO_FACTORED_TUPLES = 12,   /* distinct tuples those calls evaluated (Hankel stage runs once per tuple)*/
+       CPX_INFO_CHUNK_ALLOCATED = 13    /* points the per-chunk scratch is currently sized for (grows on demand    */
+                                        /* up to CPX_INFO_CHUNK)                                                    */ };
 
 /* Pipe-rate probes for the roofline denominators MEASURED_PEAKS.json does not hold: sustained
  * FP64 FMA (DFMA), FP32 FMA, MUFU.EX2 and FP64 tensor (DMMA m8n8k4, counted in FMAs) rates of this

@@ -71,7 +71,8 @@ def test_slot_enum_info_enum_and_field_offsets_match_header():
                "max_nA": "CPX_INFO_MAX_N_A", "max_nM": "CPX_INFO_MAX_N_M", "chunk": "CPX_INFO_CHUNK",
                "device_bytes": "CPX_INFO_DEVICE_BYTES", "kernel_launches": "CPX_INFO_KERNEL_LAUNCHES",
                "sm_count": "CPX_INFO_SM_COUNT", "guard_buffers": "CPX_INFO_GUARD_BUFFERS",
-               "guard_violations": "CPX_INFO_GUARD_VIOLATIONS"}
+               "guard_violations": "CPX_INFO_GUARD_VIOLATIONS", "factored_calls": "CPX_INFO_FACTORED_CALLS",
+               "factored_tuples": "CPX_INFO_FACTORED_TUPLES", "chunk_allocated": "CPX_INFO_CHUNK_ALLOCATED"}
     assert set(info_of) == set(engine.PxEngine.INFO)
     zfields = [f[0] for f in engine.ZbinDesc._fields_]
     efields = [f[0] for f in engine.EvalArgs._fields_]
@@ -81,7 +82,8 @@ def test_slot_enum_info_enum_and_field_offsets_match_header():
     lines += ['printf("z %s %%zu\\n", offsetof(cpx_zbin_desc, %s));' % (f, f) for f in zfields]
     lines += ['printf("e %s %%zu\\n", offsetof(cpx_eval_args, %s));' % (f, f) for f in efields]
     lines += ['printf("nslots x %d\\n", (int)CPX_NSLOTS);', 'printf("flag DEVICE_IO %d\\n", (int)CPX_DEVICE_IO);',
-              'printf("flag PRECISE_CELLS %d\\n", (int)CPX_PRECISE_CELLS);', "return 0;}"]
+              'printf("flag PRECISE_CELLS %d\\n", (int)CPX_PRECISE_CELLS);',
+              'printf("flag NO_FACTOR %d\\n", (int)CPX_NO_FACTOR);', "return 0;}"]
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "s.c"), "w").write("\n".join(lines) + "\n")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")])

@@ -115,18 +115,19 @@ def test_chi2_scan_16x16_vs_oracle():
     """16 x 16 (bias, beta) grid around truth on the S1 shape, |dchi2| <= 1e-3."""
     like, truth = _s1_like(N_t=2)
     lo, hi, n = [truth["bias"] - 0.02, truth["beta"] - 0.2], [truth["bias"] + 0.02, truth["beta"] + 0.2], [16, 16]
-    chi2 = like.get_chi2_grid(["bias", "beta"], lo, hi, n).reshape(16, 16)
+    # every point through the full pipeline (factor=False); the factorised path of such scans is tested in test_gpu_factor.py
+    chi2 = like.get_chi2_grid(["bias", "beta"], lo, hi, n, factor=False).reshape(16, 16)
     # the same points, explicitly, through the points path
     bb, ee = np.meshgrid(np.linspace(lo[0], hi[0], 16), np.linspace(lo[1], hi[1], 16), indexing="ij")
     pts = np.stack([bb.ravel(), ee.ravel()], axis=1)
-    np.testing.assert_array_equal(like.get_chi2_batch(pts, ["bias", "beta"]).reshape(16, 16), chi2)
+    np.testing.assert_array_equal(like.get_chi2_batch(pts, ["bias", "beta"], factor=False).reshape(16, 16), chi2)
     orc = H.oracle_likelihood(like)
     sel = [(0, 0), (3, 12), (8, 8), (15, 15), (15, 0), (7, 9), (11, 2)]
     for i, j in sel:
         ref = orc.get_chi2({"bias": bb[i, j], "beta": ee[i, j]})
         assert_chi2(chi2[i, j], ref, "grid point (%d,%d)" % (i, j), n_data=like.get_ndata())
     # a grid slice (how a rank takes its shard) equals the same slice of the full grid
-    part = like.get_chi2_grid(["bias", "beta"], lo, hi, n, first=100, count=57)
+    part = like.get_chi2_grid(["bias", "beta"], lo, hi, n, first=100, count=57, factor=False)
     np.testing.assert_array_equal(part, chi2.ravel()[100:157])
 
 
@@ -278,13 +279,14 @@ def test_large_batch_spans_chunks():
     like, truth = _s1_like(N_t=1, N_A=4, N_m=32, flags={"include_hcd": True})
     B = 70000
     pts = np.stack([np.linspace(-0.13, -0.10, B), np.linspace(1.3, 1.7, B)], axis=1)
-    chi2 = like.get_chi2_batch(pts, ["bias", "beta"])
+    chi2 = like.get_chi2_batch(pts, ["bias", "beta"], factor=False)          # the full pipeline is the subject here
     sel = np.array([0, 1, 65535, 65536, 65537, B - 1])
     # the big batch takes the tcgen05 window kernel, the 6-point one the FP64 DMMA kernel: equal to the ~2^-40 of
     # the integer split; within the big batch the chunk boundary must not show at all
     np.testing.assert_allclose(chi2[sel], like.get_chi2_batch(pts[sel], ["bias", "beta"]), rtol=1e-9)
-    np.testing.assert_array_equal(chi2[65530:65542], like.get_chi2_batch(pts[10000:], ["bias", "beta"])[55530:55542])
+    np.testing.assert_array_equal(chi2[65530:65542], like.get_chi2_batch(pts[10000:], ["bias", "beta"], factor=False)[55530:55542])
     assert np.isfinite(chi2).all()
+    assert like.engine().info("factored_calls") == 0
 
 
 def test_bao_refined_rule_on_device():
@@ -486,4 +488,4 @@ def test_device_outputs_stay_inside_their_buffers(B):
         assert bool(torch.isfinite(inner).all()) and not bool((inner == SENT).any()), "%s not fully written" % k
     chi2 = bufs["chi2"][0][G:-G].cpu().numpy()
     np.testing.assert_allclose(chi2, bufs["chi2_zA"][0][G:-G].cpu().numpy().reshape(B, -1).sum(axis=1), rtol=1e-12)
-    np.testing.assert_allclose(chi2[:50], joint.get_chi2_batch(pts[:50].cpu().numpy(), ["bias", "beta"]), rtol=1e-9)
+    np.testing.assert_allclose(chi2[:50], joint.get_chi2_batch(pts[:50].cpu().numpy(), ["bias", "beta"], factor=False), rtol=1e-9)

@@ -151,6 +151,7 @@ def test_scratch_guard_bands_stay_intact(monkeypatch, tc):
     base = np.array([plans[0].defaults[_plan.SLOT_INDEX[n]] for n in names])
     for precise in (False, True):
         eng = PxEngine(plans, precise=precise)
+        eng.eval(base[None, :], slots, zsel=zsel)                                  # the per-chunk scratch is allocated on demand
         assert eng.info("guard_buffers") >= 5 and eng.info("guard_violations") == 0
         for B in ((1, 77, 9000, 49152 // 4 + 13) if not precise else (1, 77)):
             pts = base[None, :] * rng.uniform(0.8, 1.2, size=(B, len(names)))
