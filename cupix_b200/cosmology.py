@@ -22,7 +22,9 @@ C_KMS = 299792.458
 
 class Cosmology(object):
     def __init__(self, cosmo_params_dict=None):
-        p = dict(H0=67.66, omch2=0.119, ombh2=0.0224, As=2.105e-9, ns=0.9665, Tcmb=2.7255)
+        # bao_amp > 0 superimposes a BAO-like oscillation (period 2 pi / 147 Mpc, Silk-damped) of that relative amplitude:
+        # what a CAMB / LaCE linear power looks like to the k_perp quadrature (0.05 is realistic); 0 = smooth
+        p = dict(H0=67.66, omch2=0.119, ombh2=0.0224, As=2.105e-9, ns=0.9665, Tcmb=2.7255, bao_amp=0.0)
         if cosmo_params_dict:
             for k, v in cosmo_params_dict.items():
                 if k in p:
@@ -98,6 +100,8 @@ class Cosmology(object):
             d2 = (4.0 / 25.0) * self.As * (k / self.k_pivot) ** (self.ns - 1.0) \
                 * (k * c_H0) ** 4 * T * T * D * D / self.Om ** 2
             P = np.where(k > 0, 2.0 * np.pi ** 2 * d2 / np.where(k > 0, k, 1.0) ** 3, 0.0)
+        if self.params["bao_amp"]:
+            P = P * (1.0 + self.params["bao_amp"] * np.sin(k * 147.0) * np.exp(-(k / 0.25) ** 1.4))
         return P
 
     def get_linP_Mpc_params(self, z, kp_Mpc=0.7):

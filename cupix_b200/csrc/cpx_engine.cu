@@ -351,7 +351,16 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     int rc = upload(kp, &dptr, &bytes);
     if (rc) return rc;
     Z.kpar = dptr;
+    Z.kpar_row = dptr;
     keep(dptr);
+    if (d.kpar_row_Mpc) {
+      std::copy(d.kpar_row_Mpc, d.kpar_row_Mpc + d.n_m, kp.begin());
+      double* drow;
+      rc = upload(kp, &drow, &bytes);
+      if (rc) return rc;
+      Z.kpar_row = drow;
+      keep(drow);
+    }
   }
   int rc;
   if (d.flags & CPX_INCLUDE_METAL) {
@@ -957,8 +966,17 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       q.t0 = t0;
       q.nt = nt;
       {
-        const long long n_thr = q.n_amp * nt;
-        k_quad<<<static_cast<unsigned>((n_thr + 255) / 256), 256, 0, st>>>(q, h->d_ztab, h->d_zlist);
+        const dim3 qgrid(static_cast<unsigned>((q.n_amp + 255) / 256), nt);
+        switch (flags0 & 7) {
+          case 0: k_quad<0><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 1: k_quad<1><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 2: k_quad<2><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 3: k_quad<3><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 4: k_quad<4><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 5: k_quad<5><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 6: k_quad<6><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+          case 7: k_quad<7><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
+        }
         ++h->launches;
       }
       if ((rc = mark())) return rc;

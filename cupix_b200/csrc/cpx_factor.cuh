@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab
       const bool row_ok = m < n_m;
       const double kpar = Z.kpar[m];
       const double F = (Z.flags & 1) ? exp(-kpar * pr.L_H) : 1.0;                // theory.py:267-282
-      double cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;       // theory.py:525-535
+      double cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;   // theory.py:525-535
       if (!row_ok) cont = 0.0;
       const double lya = cont * Z.dAA;
       const double sky = ((Z.flags & 4) && row_ok) ? cont * Z.sky_smooth[m] : 0.0;
@@ -203,39 +203,53 @@ struct QuadArgs {
   const double* g;              // [nt][n_z][nd_max][nb]
 };
 
+// FLAGS = CPX_INCLUDE_{HCD, METAL, SKY} of the evaluated z bins (one layout for all of them): the basis count is a
+// compile-time constant, the coefficient vector lives in registers.  grid = (amplitude points / 256, tuples of the batch):
+// a block's threads share their tuple, whose Gram matrix (and g, when there is one data vector) is staged in shared
+// memory z by z and read as broadcasts.
+template <int FLAGS>
 __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict__ ztab, const int* __restrict__ zlist) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= q.n_amp * q.nt) return;
-  const int tl = static_cast<int>(gid / q.n_amp);
-  long long r = gid % q.n_amp;
+  constexpr int NB = basis_count(FLAGS);
+  __shared__ double sG[NB * NB + NB];
+  const int tl = blockIdx.y;
+  long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = r < q.n_amp;
   double x[16];
-  long long out;
-  if (q.grid_mode) {
-    long long tr = q.t0 + tl, flat = 0;
-    for (int j = q.P - 1; j >= 0; --j) {
-      int ij;
-      if (q.is_amp[j]) {
-        ij = q.ax_start[j] + static_cast<int>(r % q.ax_len[j]);
-        r /= q.ax_len[j];
-      } else {
-        ij = q.ax_start[j] + static_cast<int>(tr % q.ax_len[j]);
-        tr /= q.ax_len[j];
+  long long out = 0;
+  if (live) {
+    if (q.grid_mode) {
+      long long tr = q.t0 + tl, flat = 0;
+      for (int j = q.P - 1; j >= 0; --j) {
+        int ij;
+        if (q.is_amp[j]) {
+          ij = q.ax_start[j] + static_cast<int>(r % q.ax_len[j]);
+          r /= q.ax_len[j];
+        } else {
+          ij = q.ax_start[j] + static_cast<int>(tr % q.ax_len[j]);
+          tr /= q.ax_len[j];
+        }
+        flat += ij * q.ax_stride[j];
+        const int n = q.grid_n[j];
+        // bit-identical to numpy.linspace (k_params)
+        x[j] = (ij == n - 1 && n > 1) ? q.grid_hi[j] : __dadd_rn(__dmul_rn(static_cast<double>(ij), q.grid_step[j]), q.grid_lo[j]);
       }
-      flat += ij * q.ax_stride[j];
-      const int n = q.grid_n[j];
-      // bit-identical to numpy.linspace (k_params)
-      x[j] = (ij == n - 1 && n > 1) ? q.grid_hi[j] : __dadd_rn(__dmul_rn(static_cast<double>(ij), q.grid_step[j]), q.grid_lo[j]);
+      out = flat - q.out_first;
+    } else {
+      out = r;
+      for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
     }
-    out = flat - q.out_first;
-  } else {
-    out = r;
-    for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
   }
-  const int d = q.data_idx ? q.data_idx[out] : 0;
-  const int nb = q.nb;
+  const int d = (live && q.data_idx) ? q.data_idx[out] : 0;
+  const bool one_data = q.nd_max == 1;
   double chi2 = 0.0;
   for (int zi = 0; zi < q.n_z; ++zi) {
     const ZDev& Z = ztab[zi];
+    const double* Gz = q.G + (static_cast<size_t>(tl) * q.n_z + zi) * NB * NB;
+    const double* gz = q.g + (static_cast<size_t>(tl) * q.n_z + zi) * q.nd_max * NB;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NB * NB + (one_data ? NB : 0); i += blockDim.x) sG[i] = i < NB * NB ? Gz[i] : gz[i - NB * NB];
+    __syncthreads();
+    if (!live) continue;
     const int zglobal = zlist[zi];
     double b = Z.defaults[0], be = Z.defaults[1], h = Z.defaults[8], eta = Z.defaults[9];
     double bx = Z.defaults[11], xi = Z.defaults[12], bn = Z.defaults[13];
@@ -252,12 +266,12 @@ __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict
         case 13: bn = v; break;
       }
     }
-    double c[kMaxBasis];
+    double c[NB];
     int k = 0;
     c[k++] = b * b;
     c[k++] = 2.0 * b * b * be;
     c[k++] = b * b * be * be;
-    if (Z.flags & 1) {
+    if (FLAGS & 1) {
       c[k++] = 2.0 * b * h;
       c[k++] = 2.0 * b * h * (be + eta);
       c[k++] = 2.0 * b * h * be * eta;
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict
       c[k++] = 2.0 * h * h * eta;
       c[k++] = h * h * eta * eta;
     }
-    if (Z.flags & 2) {
+    if (FLAGS & 2) {
       c[k++] = bx * bx;
       c[k++] = 2.0 * bx * bx * xi;
       c[k++] = bx * bx * xi * xi;
@@ -273,18 +287,19 @@ __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict
       c[k++] = b * bx * (be + xi);
       c[k++] = b * bx * be * xi;
     }
-    if (Z.flags & 4) c[k++] = bn;
-    const double* G = q.G + (static_cast<size_t>(tl) * q.n_z + zi) * nb * nb;
-    const double* g = q.g + ((static_cast<size_t>(tl) * q.n_z + zi) * q.nd_max + d) * nb;
+    if (FLAGS & 4) c[k++] = bn;
+    const double* g = one_data ? sG + NB * NB : gz + static_cast<size_t>(d) * NB;
     double s = Z.ydd[d];
-    for (int kk = 0; kk < nb; ++kk) {
+#pragma unroll
+    for (int kk = 0; kk < NB; ++kk) {
       double row = -2.0 * g[kk];
-      for (int l = 0; l < nb; ++l) row = fma(G[kk * nb + l], c[l], row);
+#pragma unroll
+      for (int l = 0; l < NB; ++l) row = fma(sG[kk * NB + l], c[l], row);
       s = fma(c[kk], row, s);
     }
     chi2 += s;
   }
-  q.chi2[out] = chi2;
+  if (live) q.chi2[out] = chi2;
 }
 
 }  // namespace cpx

@@ -72,7 +72,8 @@ struct ZDev {
   const float* cellc;                   // [n_tiles][n_q4][6][2][32][2] A-fragment order: lane = 4*g + t holds rows 8*(2*pr+e)+g, e = 0,1 (packed pair), node 4*ks+t
   const double* Wd;                     // [n_ablk][n_q4][NT][32]     B-fragment order: lane = 4*g + t holds W[theta 8*j+g][node 4*ks+t]
   const double* cell64;                 // [n_tiles][n_q4][6][4][32]  float64 cell constants (+K2, not -K2) for CPX_PRECISE_CELLS
-  const double* kpar;                   // [n_m_pad]
+  const double* kpar;                   // [n_m_pad]  k_par of the P3D models (cells, HCD)
+  const double* kpar_row;               // [n_m_pad]  k_par of the continuum distortion (differs only in kpar0 = 'reference' mode)
   const double* metal_auto;             // [3][n_a][n_m] or null
   const double* metal_cross;            // [3][n_a][n_m] or null
   const double* sky_xi;                 // [n_a] or null
@@ -286,7 +287,7 @@ __global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
   RowPar o;
   split_hi_lo(betaT, o.betaT_hi, o.betaT_lo);
   o.amp = bT * bT * Z.dAA;
-  o.cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;
+  o.cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;
   Z.rowpar[static_cast<size_t>(pt) * Z.n_m_pad + m] = o;
 }
 
@@ -745,7 +746,7 @@ __global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__
       double bT = pr.bias;
       if (Z.flags & 1) bT = pr.bias + pr.b_H * exp(-kpar * pr.L_H);
       const double amp = bT * bT * Z.dAA;
-      const double cont = (Z.flags & 8) ? tanh(pow(kpar / pr.kC, pr.pC)) : 1.0;
+      const double cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;
       double sky = 0.0;
       if ((Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];
 #pragma unroll

@@ -13,7 +13,8 @@ from cupix_b200.engine import PxEngine, slots_from_names
 from cupix_b200.likelihood.likelihood_parameter import dict_from_likeparam
 from cupix_b200.likelihood.model_contaminants import ContaminantsModel
 from cupix_b200.likelihood.model_lya import LyaModel
-from cupix_b200.quadrature import DEFAULT_K0, DEFAULT_KMAX, DEFAULT_NQ, PRESETS, KperpRule
+from cupix_b200 import quadrature as _quad
+from cupix_b200.quadrature import DEFAULT_K0, DEFAULT_KMAX, PRESETS, KperpRule
 
 COSMO_KEYS = ("H0", "omch2", "ombh2", "mnu", "omk", "As", "ns", "nrun", "w")
 
@@ -37,16 +38,36 @@ class Theory(object):
         self.include_metal = config.get('include_metal', False)
         self.include_sky = config.get('include_sky', False)
         self.include_continuum = config.get('include_continuum', False)
-        # k_perp quadrature: 'kperp_rule' picks a preset ('smooth': 88 log-uniform nodes, for a linear power
-        # without wiggles; 'bao': 112 nodes refined below ~0.3 1/Mpc, for a CAMB-like power with baryon
-        # acoustic oscillations); n_q / kperp_refine / kperp_k_refine override its fields
-        preset = dict(PRESETS[config.get('kperp_rule', 'smooth')])
+        # k_perp quadrature (cupix_b200.quadrature).  'kperp_rule': 'auto' (default) looks at the fiducial linear power --
+        # baryon wiggles need the refined 'bao' node family, a no-wiggle power the cheaper log-uniform 'smooth' one --
+        # and takes the cheapest node set whose measured error against the reference's algorithm is <= px_rtol / 3
+        # ('px_rtol', default 1e-5 = the north star's tolerance on model Px).  'smooth' / 'bao' force the family,
+        # 'smooth_fine' / 'bao_fine' name the finest sets; n_q / kperp_refine / kperp_k_refine override single fields.
+        kind = config.get('kperp_rule', 'auto')
+        self.px_rtol = float(config.get('px_rtol', _quad.DEFAULT_PX_RTOL))
+        self.wiggle_amplitude = None
+        if kind == 'auto':
+            self.wiggle_amplitude = _quad.wiggle_amplitude(self.fid_cosmo, z)
+            kind = 'bao' if self.wiggle_amplitude > _quad.WIGGLE_THRESHOLD else 'smooth'
+        if kind in _quad.RULES:
+            preset, self.rule_error, met = _quad.choose_rule(kind, self.px_rtol)
+            if not met and 'n_q' not in config:
+                import warnings
+                warnings.warn("cupix_b200: no '%s' k_perp node set is measured at px_rtol = %.1e / 3; using the finest "
+                              "one (error %.1e)" % (kind, self.px_rtol, self.rule_error))
+        else:
+            preset, self.rule_error = dict(PRESETS[kind]), None
+        self.kperp_family = kind
         self.rule = KperpRule(config.get('n_q', preset['n_q']), config.get('k0_Mpc', DEFAULT_K0),
                               config.get('kmax_Mpc', DEFAULT_KMAX),
                               refine=config.get('kperp_refine', preset.get('refine', 0.0)),
                               k_refine=config.get('kperp_k_refine', preset.get('k_refine', 0.3)))
         self.device = config.get('device', 0)
         self.precise_cells = config.get('precise_cells', False)
+        # k_par = 0 row: 'exact' = the mu = 0 limit; 'reference' = evaluated at 1e-4 1/Mpc like the reference's in-tree
+        # Px path (lyaP3D.py:35-39) -- for comparisons against outputs of that path (cupix_b200.plan.build_theory_plan)
+        self.kpar0 = config.get('kpar0', 'exact')
+        assert self.kpar0 in ('exact', 'reference'), "kpar0 must be 'exact' or 'reference'"
         self._engines = {}
 
     # -- cosmology (theory.py:49-64) ---------------------------------------------------------

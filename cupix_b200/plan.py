@@ -25,6 +25,7 @@ COSMO_SLOT_NAMES = ("As", "ns")
 INCLUDE_HCD, INCLUDE_METAL, INCLUDE_SKY, INCLUDE_CONTINUUM = 1, 2, 4, 8
 METAL_KP_MPC = 10.0      # theory.py:378,421
 PIXEL_AA = 0.8           # theory.py:495
+KPAR0_REFERENCE_MPC = 1e-4   # lyaP3D.py:35-39: what the reference's in-tree Px path substitutes for k_par = 0
 
 
 class ZbinPlan(object):
@@ -33,6 +34,7 @@ class ZbinPlan(object):
     n_M = 0
     n_data = 0
     metal_auto = metal_cross = sky_xi_a = sky_smooth_m = None
+    kpar_row_Mpc = None
     B_A_a = U_aMn = V_aM = Px_AM = cov_AMM = None
 
 
@@ -106,7 +108,16 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
     dAA = cosmo.get_dAA_dMpc(z, lambda_rest_AA=lr_lya)
     p.n_a, p.n_m, p.n_q = n_a, k_AA.size, rule.n_q
     p.dAA_dMpc = float(dAA)
-    p.kpar_Mpc = k_AA * dAA
+    # k_par = 0 (every DESI-like k_m grid starts there).  kpar0 = 'exact' (default): the mu = 0 limit of the integrand.
+    # kpar0 = 'reference': every P3D model sees k_par = 1e-4 1/Mpc instead, as the reference's in-tree Px path does
+    # (lyaP3D.py:35-39); the continuum distortion and the sky term, which the reference evaluates on k_AA directly
+    # (theory.py:476-535), keep the true value.
+    sub0 = getattr(theory, "kpar0", "exact") == "reference"
+
+    def p3d_kpar(kpar):
+        return np.where(kpar == 0, KPAR0_REFERENCE_MPC, kpar) if sub0 else kpar
+    p.kpar_Mpc = p3d_kpar(k_AA * dAA)
+    p.kpar_row_Mpc = k_AA * dAA if sub0 else None
     p.kperp_Mpc = rule.k.copy()
     p.hankel_w = rule.weights(theta_arc / darc, theta_group, theta_arc, n_a)
     k, _ = _cells(p.kpar_Mpc, p.kperp_Mpc)
@@ -125,7 +136,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
         for zz, lr, wiggle in ((z_auto, lr_metal, False), (z_cross, lr_cross, True)):
             darc_x = cosmo.get_darc_dMpc(zz)
             dAA_x = cosmo.get_dAA_dMpc(zz, lambda_rest_AA=lr)
-            kpar_x = k_AA * dAA_x
+            kpar_x = p3d_kpar(k_AA * dAA_x)
             W_x = rule.weights(theta_arc / darc_x, theta_group, theta_arc, n_a)       # [n_a, n_q]
             kx, mux = _cells(kpar_x, rule.k)
             base = _linP_on_cells(cosmo, zz, kx) * np.exp(-(kx / METAL_KP_MPC) ** 2)  # [n_m, n_q]
@@ -141,7 +152,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
         xi = theory.cont_model.get_xi_noise(theta_arc)
         wsum = np.bincount(theta_group, weights=theta_arc, minlength=n_a)
         p.sky_xi_a = np.bincount(theta_group, weights=theta_arc * xi, minlength=n_a) / wsum
-        x = (PIXEL_AA / dAA) * p.kpar_Mpc / 2.0
+        x = (PIXEL_AA / dAA) * (k_AA * dAA) / 2.0
         smooth = np.ones_like(x)
         pos = x > 0
         smooth[pos] = (np.sin(x[pos]) / x[pos]) ** 2

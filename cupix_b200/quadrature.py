@@ -16,19 +16,25 @@ is evaluated once per (z, binning) in float64 with Gauss-Legendre panels that re
 ``Px(k_par, r) = sum_q W[r, q] P3D(k_par, k_q)`` for every parameter point.  Because the rule is
 linear, the reference's theta sub-sampling average (cupix/likelihood/likelihood.py:99-130) is
 folded into the weights as well.  Measured error against a 2^20-point brute-force integral is
-< 2e-7 of the Px scale at the default n_q = 88 over the ForestFlow training box
-(tests/test_quadrature.py; 64 nodes: 4e-7, 96 nodes: 7e-8 -- `n_q` is a Theory config key).
+< 2.5e-7 of the Px scale at n_q = 88 over the ForestFlow training box down to theta = 0.5'
+(tests/test_quadrature.py; 56 nodes: 1.2e-6, 64 nodes: 8.7e-7 -- `n_q` / `px_rtol` are Theory config keys).
 
 That accuracy holds for a *smooth* linear power.  With baryon acoustic oscillations in P_L (period
-2 pi / r_s ~ 0.043 1/Mpc, what CAMB delivers) the log-uniform nodes are too sparse above k ~ 0.1:
-88 nodes give 7e-4, 192 nodes 1.4e-5 of the Px scale.  ``refine > 0`` therefore adds node density
+2 pi / r_s ~ 0.043 1/Mpc, what CAMB / LaCE deliver; they move Px by up to 4e-3 of its scale at low k_par) the
+log-uniform nodes are too sparse above k ~ 0.1: 88 nodes are off by 8e-4.  ``refine > 0`` therefore adds node density
 where the wiggles live: nodes are uniform in
 
     u(k) = ln(k + k0) + refine * k_refine * atan(k / k_refine),      du/dk = 1/(k + k0) + refine / (1 + (k/k_refine)^2)
 
-The preset ``PRESETS['bao']`` (112 nodes, refine = 50, k_refine = 0.3) reaches 5e-6 with a 5 %% wiggle
-and 1e-7 without (tests/test_quadrature.py), i.e. the 1e-5 tolerance of the north star at 1.27x the
-cost of the default rule instead of > 2.2x.
+(the extra density must stay gentle: refine = 50 starves the logarithmic part and costs 4e-5 at the smallest
+separations even on a smooth power -- the round-1 preset; refine = 15..25 with k_refine = 0.5..0.7 does not).
+
+``RULES`` lists the node sets on offer with their MEASURED worst-case error against the reference's own algorithm
+(oracle A: FFTLog on 2^11 nodes + splines, cupix/likelihood/lyaP3D.py:272-351, itself within 9e-8 of a 2^20-point
+brute-force integral for k_par > 0): max |dPx| / max |Px| over three Arinyo parameter sets (central and extreme rows of
+the ForestFlow training table, the CoLoRe fit), HCD on, theta = 0.5' .. 58' at z = 2.2, k_par = 0.0077 .. 1.19 1/A;
+for the 'bao' family with a 5 % BAO-like wiggle in P_L (tools/quadrature_scan.py, profiles/quadrature_scan_r02.txt).
+``choose_rule(kind, px_rtol)`` returns the cheapest entry whose error is at most px_rtol / 3.
 """
 from concurrent.futures import ThreadPoolExecutor
 import os
@@ -37,13 +43,47 @@ import numpy as np
 from scipy.interpolate import BSpline, make_interp_spline
 from scipy.special import j0
 
-PRESETS = {"smooth": dict(n_q=88, refine=0.0), "bao": dict(n_q=112, refine=50.0, k_refine=0.3)}
+# kind -> [(KperpRule keyword arguments, measured worst-case error)], cheapest first
+RULES = {
+    "smooth": [(dict(n_q=56), 1.5e-6), (dict(n_q=64), 8.7e-7), (dict(n_q=72), 3.0e-7), (dict(n_q=88), 3.0e-7)],
+    "bao": [(dict(n_q=112, refine=20.0, k_refine=0.5), 4.8e-6), (dict(n_q=128, refine=20.0, k_refine=0.5), 2.8e-6),
+            (dict(n_q=144, refine=20.0, k_refine=0.5), 1.3e-6), (dict(n_q=160, refine=15.0, k_refine=0.7), 5.8e-7),
+            (dict(n_q=176, refine=20.0, k_refine=0.5), 3.9e-7)],
+}
+RULE_MARGIN = 3.0
+DEFAULT_PX_RTOL = 1e-5          # BASELINE.json north_star: relative 1e-5 on model Px
+# named presets (Theory config 'kperp_rule'): the entries chosen for the default tolerance, and the finest ones
+PRESETS = {"smooth": RULES["smooth"][0][0], "bao": RULES["bao"][1][0],
+           "smooth_fine": RULES["smooth"][3][0], "bao_fine": RULES["bao"][3][0]}
+WIGGLE_THRESHOLD = 1.5e-3       # see wiggle_amplitude
 DEFAULT_NQ = 88
 DEFAULT_K0 = 0.01
 DEFAULT_KMAX = 200.0
 SPLINE_ORDER = 5
 _GL_N = 16
 _RAD_PER_PANEL = 4.0
+
+
+def choose_rule(kind, px_rtol=DEFAULT_PX_RTOL, margin=RULE_MARGIN):
+    """Keyword arguments of the cheapest rule of family ``kind`` ('smooth' | 'bao') whose measured error is at most
+    ``px_rtol / margin``; the finest one (with ``met = False``) if none is.  Returns (kwargs, error, met)."""
+    for kw, err in RULES[kind]:
+        if err * margin <= px_rtol:
+            return dict(kw), err, True
+    kw, err = min(RULES[kind], key=lambda e: e[1])
+    return dict(kw), err, False
+
+
+def wiggle_amplitude(cosmo, z):
+    """Largest deviation of ln P_L(k) from a degree-8 Chebyshev fit in ln k over 0.02 .. 0.6 1/Mpc: 5e-4 for a
+    no-wiggle (Eisenstein-Hu) power, ~ the relative BAO amplitude (0.05) for a CAMB-like one.  Decides between the
+    'smooth' and 'bao' node families when the Theory config does not (kperp_rule = 'auto')."""
+    k = np.geomspace(0.02, 0.6, 600)
+    x = np.log(k)
+    y = np.log(np.asarray(cosmo.get_linP_Mpc(z, k), dtype=np.float64))
+    xs = (x - x.mean()) / np.ptp(x) * 2.0
+    c = np.polynomial.chebyshev.chebfit(xs, y, 8)
+    return float(np.abs(y - np.polynomial.chebyshev.chebval(xs, c)).max())
 
 
 class KperpRule(object):

@@ -105,6 +105,9 @@ typedef struct cpx_zbin_desc {
   const double* cov_AMM;      /* [n_A][n_M][n_M] covariance blocks                               */
   double k_pivot_Mpc;         /* pivot of the primordial power law for CPX_AS / CPX_NS columns;  */
                               /* 0: the cosmology object does not expose one, such columns are refused */
+  const double* kpar_row_Mpc; /* [n_m] or NULL (= kpar_Mpc): k_par seen by the continuum distortion    */
+                              /* (theory.py:525-535) when kpar_Mpc carries the reference's k_par = 0 -> 1e-4 */
+                              /* substitution for the P3D models (lyaP3D.py:35-39; Theory config kpar0)      */
 } cpx_zbin_desc;
 
 typedef struct cpx_handle cpx_handle;

@@ -48,12 +48,15 @@ def _p3d_on_grid(p3d_func, k2d, mu2d, kmax=KT_MPC_MAX):
 
 
 class NodeHankel(object):
-    def __init__(self, k_nodes, weight_fn):
+    def __init__(self, k_nodes, weight_fn, kpar0=None):
         self.k_nodes = np.asarray(k_nodes, dtype=np.float64)
         self.weight_fn = weight_fn            # r[Nr] -> W[Nr, Nq]
+        self.kpar0 = kpar0                    # 1e-4: k_par = 0 replaced as the reference's in-tree path does (lyaP3D.py:35-39)
 
     def __call__(self, rt_Mpc, kp_Mpc, p3d_func):
         kp = np.atleast_1d(np.asarray(kp_Mpc, dtype=np.float64))
+        if self.kpar0 is not None:
+            kp = np.where(kp == 0, self.kpar0, kp)
         k2d, mu2d = _k_mu(kp, self.k_nodes)
         # the rule integrates over k_perp <= kmax; P3D is taken as is at every node
         ksafe = np.where(k2d > 0, k2d, 1.0)

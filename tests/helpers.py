@@ -40,7 +40,8 @@ def make_theory(z, model, flags, cosmo=None, n_q=96, extra=None):
 def oracle_for(theory, hankel=None):
     """OracleTheory with the same defaults / flags / cosmology as a product Theory."""
     r = theory.rule
-    hankel = hankel or NodeHankel(r.k, lambda rr: r.weights(rr, nthreads=1))
+    hankel = hankel or NodeHankel(r.k, lambda rr: r.weights(rr, nthreads=1),
+                                  kpar0=_plan.KPAR0_REFERENCE_MPC if getattr(theory, "kpar0", "exact") == "reference" else None)
     d = _plan.default_vector(theory, theory.fid_cosmo)
     lya = {k: d[_plan.SLOT_INDEX[k]] for k in LYA_KEYS}
     cont = {k: d[_plan.SLOT_INDEX[k]] for k in CONT_KEYS}
@@ -58,7 +59,9 @@ def emulate_plan_px(p, params):
             v[_plan.SLOT_INDEX[k]] = x
     bias, beta, q1, q2, kv, av, bv, kp = v[:8]
     b_H, beta_H, L_H, b_X, beta_X, b_noise, kC, pC = v[8:16]
-    kpar, kperp = p.kpar_Mpc, p.kperp_Mpc
+    kpar, kperp = p.kpar_Mpc, p.kperp_Mpc          # kpar: what the P3D sees (k_par = 0 replaced in kpar0 = 'reference' mode)
+    kpar_row = getattr(p, "kpar_row_Mpc", None)
+    kpar_row = kpar if kpar_row is None else kpar_row
     k2 = kpar[:, None] ** 2 + kperp[None, :] ** 2
     k = np.sqrt(k2)
     pos = k > 0
@@ -88,7 +91,7 @@ def emulate_plan_px(p, params):
     if p.flags & _plan.INCLUDE_SKY:
         px = px + b_noise * np.outer(p.sky_xi_a, p.sky_smooth_m)
     if p.flags & _plan.INCLUDE_CONTINUUM:
-        px = px * np.tanh((kpar / kC) ** pC)[None, :]
+        px = px * np.tanh((kpar_row / kC) ** pC)[None, :]
     return px
 
 

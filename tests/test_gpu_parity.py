@@ -290,11 +290,11 @@ def test_large_batch_spans_chunks():
 
 
 def test_bao_refined_rule_on_device():
-    """The 'bao' k_perp preset (112 non-log-uniform nodes = 28 DMMA k-steps) through the CUDA path against the
+    """A 'bao' k_perp node set (112 non-log-uniform nodes = 28 DMMA k-steps) through the CUDA path against the
     float64 emulation of the same plan and, for the model Px, against the oracle."""
     d = synthetic.make_measurement_dict("S1", N_A=7, N_m=40, Nz=1)
     th = H.make_theory(2.2, "best_fit_arinyo_from_gadget", {"include_hcd": True}, n_q=112, extra={"kperp_rule": "bao"})
-    assert th.rule.n_q == 112 and th.rule.refine == 50.0
+    assert th.rule.n_q == 112 and th.rule.refine == 20.0
     like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 2})
     names = ["bias", "beta", "q1", "kp_Mpc"]
     rng = np.random.default_rng(2)
