@@ -53,7 +53,9 @@ def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True
         with np.load(filled_path) as f:
             d["Px_ZAM"], d["cov_ZAM"] = f["Px_ZAM"], f["cov_ZAM"]
     cosmo = Cosmology()
-    cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": n_q}
+    cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True}
+    if n_q:
+        cfg["n_q"] = n_q
     theories = [Theory(float(z), fid_cosmo=cosmo, config=cfg) for z in d["z_centers"]]
     data = DESI_DR2(d)
     likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
@@ -245,7 +247,9 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 17, help="parameter points per GPU per step")
     ap.add_argument("--shape", default="S5")
     ap.add_argument("--n-theta-average", type=int, default=100)
-    ap.add_argument("--n-q", type=int, default=88)
+    ap.add_argument("--n-q", type=int, default=0,
+                    help="k_perp nodes; 0 = what Theory selects for px_rtol = 1e-5 and this linear power (56 log-uniform nodes)")
+    ap.add_argument("--alt-n-q", type=int, default=88, help="a second, short device-timed measurement at this node count (0 = skip)")
     ap.add_argument("--cpu-evals-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -269,6 +273,7 @@ def main():
             return
         import cupix_b200.plan as _plan
         d, data, likes, _ = build_workload(a.shape, a.n_theta_average, a.n_q, need_engine=False)
+        config.update(n_q=likes[0].theory.rule.n_q, kperp_family=likes[0].theory.kperp_family, px_rtol=likes[0].theory.px_rtol)
         defaults = _plan.default_vector(likes[0].theory, likes[0].theory.fid_cosmo)
         # W untimed and K timed steps like the B200 arm; a step is a bounded sample of the workload (one
         # evaluation per host core, a few seconds), and the counts are capped so that the run ends within minutes
@@ -303,6 +308,8 @@ def main():
     setup = {}
     filled, data, likes, joint = build_workload(a.shape, a.n_theta_average, a.n_q, precise=a.precise, timings=setup)
     eng = joint.engine()
+    n_q = likes[0].theory.rule.n_q          # the node set Theory selected (or --n-q)
+    config.update(n_q=n_q, kperp_family=likes[0].theory.kperp_family, px_rtol=likes[0].theory.px_rtol)
     # what a user pays once per measurement before the first chi2: host plans (cold Hankel-weight cache) + cpx_create
     setup_s = dict(setup, total_s=setup["plans_s"] + setup["cpx_create_s"])
     import cupix_b200.plan as _plan
@@ -394,6 +401,40 @@ def main():
         e2e = {"value": a.steps * B * world / dt, "unit": "evals/s", "h2d_bytes_per_step": B * len(NAMES) * 8,
                "d2h_bytes_per_step": B * 8, "api": "PxEngine.eval_host_into = C ABI cpx_eval with pinned host buffers (what JointLikelihood.get_chi2_batch calls)"}
 
+    # ---- the same device-timed step at a second node count (the accuracy / cost knob of the Hankel rule) ----
+    alt = None
+    if a.alt_n_q and a.alt_n_q != n_q and not a.precise:
+        from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
+        from cupix_b200.likelihood.theory import Theory
+        cfg2 = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": a.alt_n_q}
+        likes2 = [Likelihood(data, Theory(lk.theory.z, fid_cosmo=lk.theory.fid_cosmo, config=cfg2), lk.iz,
+                             config={"N_theta_average": a.n_theta_average}) for lk in likes]
+        eng2 = JointLikelihood(likes2, device=local_rank).engine()
+        n_alt = max(2, min(a.steps, 5))
+
+        def step_alt(i):
+            first = ((i * world + rank) * B) % max(total - B, 1)
+            eng2.eval_device(B, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=first, zsel=zsel,
+                             chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, factor=False)
+        for i in range(2):
+            step_alt(i)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for i in range(n_alt):
+            step_alt(2 + i)
+        a1.record(stream)
+        sync_all()
+        ams = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([ams], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ams = float(t.item())
+        alt = {"n_q": a.alt_n_q, "value": n_alt * B * world / (ams * 1e-3), "unit": "evals/s", "ms_per_step": ams / n_alt,
+               "steps": n_alt, "note": "same step, device-timed, with the round-1 node count; error of the node set vs the "
+                                       "reference algorithm: cupix_b200.quadrature.RULES"}
+        eng2.close()
+
     # ---- the whole 4-parameter grid as ONE scan through the factorised path (cpx_factor.cuh) ----
     # Same 10 485 760 points, flattened with the tuple axes (q1, kp_Mpc) slowest so that a rank's contiguous slice holds
     # whole tuples; each rank scans total / N points (strong scaling: the job is the grid), chi2 all-gathered.
@@ -461,7 +502,7 @@ def main():
                 "e2e": {"value": n_scan * total / gdt, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": cnt * 8,
                         "api": "PxEngine.eval(grid=...) = C ABI cpx_eval in grid mode with a pinned host output buffer"},
                 "algorithmic": None}
-        w_ = algorithmic_work(likes, a.n_q)       # per evaluation = summed over z
+        w_ = algorithmic_work(likes, n_q)         # per evaluation = summed over z
         nb_ = 9                                   # basis tables with HCD: F^i H_j, i, j = 0..2 (cpx_factor.cuh)
         grid["algorithmic"] = {"per": "tuple (all z) / point", "tuples": int(tuples_per_scan), "basis_tables": nb_,
                                "p3d_cells_f64_per_tuple": w_["p3d_cells"], "hankel_dfma_per_tuple": 3 * w_["hankel_dfma"],
@@ -476,7 +517,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ----
-    work = algorithmic_work(likes, a.n_q)
+    work = algorithmic_work(likes, n_q)
     peaks = probe_peaks(local_rank)
     k1_s = stage[1] * 1e-3
     k2_s = stage[2] * 1e-3
@@ -524,7 +565,7 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             fpath = os.path.join(td, "filled.npz")
             np.savez(fpath, Px_ZAM=filled["Px_ZAM"], cov_ZAM=filled["cov_ZAM"])
-            r = run_cpu("node", a.shape, a.n_theta_average, a.n_q, a.cpu_evals_per_core, defaults, filled_path=fpath)
+            r = run_cpu("node", a.shape, a.n_theta_average, n_q, a.cpu_evals_per_core, defaults, filled_path=fpath)
         # the CPU leg's sample points scored by the GPU arm as well, inside a full production batch (same kernels,
         # same host-pointer C-ABI call as the e2e leg): oracle chi2 against device chi2 on the workload the number is quoted on
         pb = np.random.default_rng(99).uniform(lo, hi, size=(B, len(NAMES)))
@@ -561,7 +602,7 @@ def main():
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "setup_s": setup_s,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "alt_n_q": alt, "setup_s": setup_s,
             "per_point_z_rate": value * len(likes)}
     emit(line)
     if world > 1:

@@ -1336,7 +1336,10 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
   int last_table_count = -1, last_pp = -1;
   for (int64_t first = 0; first < a->B; first += h->chunk) {
     const int count = static_cast<int>(std::min<int64_t>(h->chunk, a->B - first));
-    int pp = pp_env > 0 ? std::min(pp_env, 2) : 1;   // one point per warp, two CTAs per SM measured fastest
+    // one point per warp and two CTAs per SM measured fastest; node sets whose staged tile leaves room for one CTA only
+    // (n_q > 116: the 'bao' family from 128 nodes) take two points per warp instead
+    const size_t k1_smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
+    int pp = pp_env > 0 ? std::min(pp_env, 2) : (2 * (k1_smem + 2048) <= 227u * 1024u ? 1 : 2);
     const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
     const int n_pg = precise ? count : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
     auto items_of = [&](const ZDev& Z) {

@@ -36,9 +36,16 @@ PARAM_SETS = {
     "colore_like": dict(z=2.2, bias=-0.115, beta=1.55, q1=0.1, q2=0.0, kv=1.0, av=0.3, bv=1e-13, kp=0.6),
     "strong_nl": dict(z=3.0, bias=-0.23, beta=1.2, q1=0.9, q2=0.4, kv=0.8, av=0.6, bv=1.9, kp=20.0),
     "linear": dict(z=2.8, bias=-0.2, beta=1.0, q1=0.0, q2=0.0, kv=1.0, av=0.5, bv=1.5, kp=1e4),
+    # the same Arinyo parameters on a linear power with a 5 % BAO-like wiggle (Cosmology(bao_amp=0.05)): what the
+    # refined 'bao' node sets exist for
+    "gadget_z2.4_bao": dict(z=2.4, bias=-0.1483, beta=1.49, q1=0.297, q2=0.302, kv=0.527 ** (1 / 0.347), av=0.347, bv=1.68, kp=13.4,
+                            bao_amp=0.05),
+    "strong_nl_bao": dict(z=3.0, bias=-0.23, beta=1.2, q1=0.9, q2=0.4, kv=0.8, av=0.6, bv=1.9, kp=20.0, bao_amp=0.05),
 }
 RPERP = np.concatenate([[0.012, 0.05, 0.15, 0.3], np.geomspace(0.5, 80.0, 14)])
-KPAR = np.array([1e-3, 0.01, 0.05, 0.2, 0.5, 1.0, 2.0, 4.0])
+# 1e-4 is what the reference's model_Px substitutes for k_par = 0 (lyaP3D.py:35-39) before calling Px_Mpc_withSiIII,
+# which itself refuses a zero (:208-209): the first column IS the reference's k_par = 0 row
+KPAR = np.array([1e-4, 1e-3, 0.01, 0.05, 0.2, 0.5, 1.0, 2.0, 4.0])
 
 
 def load_reference_lyaP3D():
@@ -77,18 +84,29 @@ def arinyo_p3d(cosmo):
 
 def main():
     ref = load_reference_lyaP3D()
-    cosmo = Cosmology()
-    p3d = arinyo_p3d(cosmo)
+    # the substitution itself, executed by the reference: model_Px -> (patched) Px_Mpc_withSiIII sees 1e-4 where k_par was 0
+    seen = {}
+    orig = ref.Px_Mpc_withSiIII
+    ref.Px_Mpc_withSiIII = lambda z, kpar, *a, **k: seen.setdefault("kpar", np.array(kpar)) * 0.0
+    obj = ref.LyaP3D(np.array([2.4]), None, None, {"bias": np.array([-0.1])}, Si_contam=True, contam_coeffs={"x": 1})
+    obj.model_Px(np.array([[0.0, 0.5]]), np.array([[1.0, 2.0]]))
+    ref.Px_Mpc_withSiIII = orig
+    assert seen["kpar"][0, 0] == 1e-4 and seen["kpar"][0, 1] == 0.5, seen
 
-    class Model(object):
-        @staticmethod
-        def linP_Mpc(z, k):
-            return cosmo.get_linP_Mpc(z, k)
-
-    out = {"rperp_Mpc": RPERP, "kpar_Mpc": KPAR, "names": np.array(sorted(PARAM_SETS))}
+    out = {"rperp_Mpc": RPERP, "kpar_Mpc": KPAR, "names": np.array(sorted(PARAM_SETS)),
+           "kpar0_substitute": np.array(seen["kpar"][0, 0])}
     for name in sorted(PARAM_SETS):
         ps = dict(PARAM_SETS[name])
         z = ps.pop("z")
+        bao_amp = ps.pop("bao_amp", 0.0)
+        cosmo = Cosmology({"bao_amp": bao_amp}) if bao_amp else Cosmology()
+        p3d = arinyo_p3d(cosmo)
+
+        class Model(object):
+            @staticmethod
+            def linP_Mpc(z, k, cosmo=cosmo):
+                return cosmo.get_linP_Mpc(z, k)
+
         pp = {k: np.array([v]) for k, v in ps.items()}        # the reference indexes its coefficients by z bin
         zero = np.array([0.0])
         px = ref.Px_Mpc_withSiIII(np.array([z]), KPAR, RPERP, Model, lambda zz, k, mu, p: p3d(zz, k, mu, {kk: float(np.ravel(vv)[0]) for kk, vv in p.items()}),
@@ -96,7 +114,7 @@ def main():
                                   P3D_params=pp)
         px = np.asarray(px)[0]                                   # [Nr, Nk]
         out["px|" + name] = px
-        out["params|" + name] = np.array([z] + [PARAM_SETS[name][k] for k in ("bias", "beta", "q1", "q2", "kv", "av", "bv", "kp")])
+        out["params|" + name] = np.array([z] + [PARAM_SETS[name][k] for k in ("bias", "beta", "q1", "q2", "kv", "av", "bv", "kp")] + [bao_amp])
         print(name, px.shape, "Px range %.3e .. %.3e" % (px.min(), px.max()))
     np.savez_compressed(os.path.join(HERE, "ref_hankel_lyaP3D.npz"), **out)
     print("wrote ref_hankel_lyaP3D.npz")

@@ -489,3 +489,39 @@ def test_device_outputs_stay_inside_their_buffers(B):
     chi2 = bufs["chi2"][0][G:-G].cpu().numpy()
     np.testing.assert_allclose(chi2, bufs["chi2_zA"][0][G:-G].cpu().numpy().reshape(B, -1).sum(axis=1), rtol=1e-12)
     np.testing.assert_allclose(chi2[:50], joint.get_chi2_batch(pts[:50].cpu().numpy(), ["bias", "beta"], factor=False), rtol=1e-9)
+
+
+def test_kpar0_reference_mode_on_device():
+    """Theory(config={'kpar0': 'reference'}): every P3D model sees k_par = 1e-4 1/Mpc in the k_par = 0 row, as the
+    reference's in-tree Px path does (lyaP3D.py:35-39), while the continuum distortion and the sky term keep the true
+    k_par (theory.py:476-535).  Device against the oracle with the same substitution; all contaminants on."""
+    d = synthetic.make_measurement_dict("S1", N_A=6, N_m=40)
+    assert d["k_m"][0] == 0.0
+    res = {}
+    for mode in ("exact", "reference"):
+        th = H.make_theory(2.2, "best_fit_arinyo_from_gadget", FLAG_SETS["all"], extra={"kpar0": mode})
+        like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 2})
+        truth = {"bias": -0.115, "beta": 1.5}
+        filled = synthetic.fill_from_model(d, like.get_convolved_px(truth)[None], add_noise=True)
+        like = Likelihood(DESI_DR2(filled), th, 0, config={"N_theta_average": 2})
+        orc = H.oracle_likelihood(like)
+        assert (orc.theory.hankel.kpar0 is not None) == (mode == "reference")
+        for params in (truth, {"bias": -0.12, "beta": 1.6, "b_H": -0.03, "kC_Mpc": 0.02, "b_X": -0.004}):
+            px = like._compute_Px_Zam(params)
+            assert_px(px, orc.Px_Zam(params), msg="Px_Zam, kpar0 = %s" % mode)
+            assert_chi2(like.get_chi2(params), orc.get_chi2(params), "chi2, kpar0 = %s" % mode, n_data=like.get_ndata())
+        res[mode] = like._compute_Px_Zam(truth)
+        # the factorised path builds its tables from the same plan
+        pts = np.stack([np.linspace(-0.12, -0.11, 32), np.linspace(1.4, 1.6, 32)], axis=1)
+        np.testing.assert_allclose(like.get_chi2_batch(pts, ["bias", "beta"]), like.get_chi2_batch(pts, ["bias", "beta"], factor=False),
+                                   rtol=2e-6, atol=1e-3)
+    # continuum distortion on: tanh((k_par / kC)^pC) = 0 at the true k_par = 0 in both modes
+    assert np.all(res["exact"][:, 0] == 0.0) and np.all(res["reference"][:, 0] == 0.0)
+    np.testing.assert_array_equal(res["exact"][:, 1:], res["reference"][:, 1:])
+    th0 = H.make_theory(2.2, "best_fit_arinyo_from_gadget", {"include_hcd": True}, extra={"kpar0": "exact"})
+    th1 = H.make_theory(2.2, "best_fit_arinyo_from_gadget", {"include_hcd": True}, extra={"kpar0": "reference"})
+    theta, k_AA = np.array([1.0, 5.0, 30.0]), d["k_m"][:5]
+    p0, p1 = th0.get_px_obs(theta, k_AA), th1.get_px_obs(theta, k_AA)
+    np.testing.assert_array_equal(p0[:, 1:], p1[:, 1:])
+    rel = np.abs(p0[:, 0] - p1[:, 0]) / np.abs(p0).max()
+    assert 2e-5 < rel.max() < 1e-3                      # 1.7e-4 on the S1 shape (profiles/transform_choice_r02.txt)
