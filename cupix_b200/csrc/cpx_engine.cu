@@ -49,6 +49,7 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 struct ZHost {
   cpx::ZDev dev;                 // device pointers + dims (mirrored into the device table)
   std::vector<double> Linv;      // [n_A][n_M][n_M] inverse Cholesky factors (kept for cpx_set_data)
+  std::vector<double> Lfac;      // [n_A][n_M][n_M] Cholesky factors (cpx_generate_mocks returns mocks in data space)
   std::vector<void*> owned;      // device allocations of this z
 };
 
@@ -400,6 +401,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     const size_t tstride = static_cast<size_t>(Z.n_M_pad) * Z.n_m_pad;
     std::vector<double> Tm(Z.n_pairs * tstride, 0.0), Tc(Z.n_pairs * tstride, 0.0);
     zh.Linv.assign(static_cast<size_t>(nA) * nM * nM, 0.0);
+    zh.Lfac.assign(static_cast<size_t>(nA) * nM * nM, 0.0);
     std::vector<double> L, vsum(nM);
     for (int A = 0; A < nA; ++A) {
       if (!cholesky_lower(d.cov_AMM + static_cast<size_t>(A) * nM * nM, nM, L)) {
@@ -409,6 +411,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
       }
       double* Li = &zh.Linv[static_cast<size_t>(A) * nM * nM];
       invert_lower(L, nM, Li);
+      std::copy(L.begin(), L.end(), zh.Lfac.begin() + static_cast<size_t>(A) * nM * nM);
       std::fill(vsum.begin(), vsum.end(), 0.0);
       for (int p = pair_start[A]; p < pair_start[A + 1]; ++p)
         for (int M = 0; M < nM; ++M) vsum[M] += d.V_aM[static_cast<size_t>(pair_a[p]) * nM + M];
@@ -1011,7 +1014,11 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
 extern "C" {
 
 const char* cpx_last_error(void) { return g_err.c_str(); }
-int cpx_version(void) { return 100; }
+int cpx_version(void) { return 200; }
+int cpx_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 void cpx_destroy(cpx_handle* h) {
   if (!h) return;
@@ -1152,6 +1159,91 @@ int cpx_set_data(cpx_handle* h, int32_t iz, const double* Px_AM, int32_t n_data)
   CPX_CUDA(cudaSetDevice(h->device));
   CPX_CUDA(cudaDeviceSynchronize());     // evaluations may be in flight on any caller stream
   return upload_yd(h, h->z[iz], Px_AM, n_data);
+}
+
+int cpx_generate_mocks(cpx_handle* h, int32_t P, const int32_t* slot, const int32_t* zsel, const double* point,
+                       int32_t n_mocks, uint64_t seed, double* mocks_zdAM) {
+  if (!h || n_mocks <= 0 || P < 0 || P > 16 || (P > 0 && (!slot || !point)))
+    return fail(CPX_ERR_ARG, "cpx_generate_mocks: bad arguments");
+  const int n_z = static_cast<int>(h->z.size());
+  int nA_max = 0, nM_max = 0;
+  for (auto& zh : h->z) {
+    if (zh.dev.n_A <= 0) return fail(CPX_ERR_ARG, "cpx_generate_mocks: a z bin of the handle has no measurement");
+    nA_max = std::max(nA_max, zh.dev.n_A);
+    nM_max = std::max(nM_max, zh.dev.n_M);
+  }
+  // whitened model L^-1 m of every z at the truth: one point through the full pipeline
+  std::vector<double> ym(static_cast<size_t>(n_z) * nA_max * nM_max, 0.0);
+  cpx_eval_args ea;
+  std::memset(&ea, 0, sizeof ea);
+  ea.B = 1;
+  ea.P = P;
+  ea.flags = CPX_MODEL_WHITENED | CPX_NO_FACTOR;
+  ea.points = point;
+  ea.slot = slot;
+  ea.zsel = zsel;
+  ea.model_zAM = ym.data();
+  int rc = cpx_eval(h, &ea);
+  if (rc) return rc;
+  CPX_CUDA(cudaSetDevice(h->device));
+  CPX_CUDA(cudaDeviceSynchronize());         // evaluations may be in flight on any caller stream
+  double* d_ym = nullptr;
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_ym), sizeof(double) * std::max(1, nA_max * nM_max)));
+  std::vector<double> yd_host, tmp;
+  for (int iz = 0; iz < n_z; ++iz) {
+    ZHost& zh = h->z[iz];
+    cpx::ZDev& Z = zh.dev;
+    const int nA = Z.n_A, nM = Z.n_M;
+    tmp.assign(static_cast<size_t>(nA) * nM, 0.0);
+    for (int A = 0; A < nA; ++A)
+      std::copy(&ym[(static_cast<size_t>(iz) * nA_max + A) * nM_max], &ym[(static_cast<size_t>(iz) * nA_max + A) * nM_max] + nM, &tmp[static_cast<size_t>(A) * nM]);
+    cudaError_t e = cudaMemcpy(d_ym, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice);
+    double *d_yd = nullptr, *d_ydd = nullptr;
+    const size_t per_data = static_cast<size_t>(nA) * Z.n_M_pad;
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_yd), sizeof(double) * per_data * n_mocks);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_ydd), sizeof(double) * n_mocks);
+    if (e == cudaSuccess) e = cudaMemset(d_yd, 0, sizeof(double) * per_data * n_mocks);
+    if (e == cudaSuccess) {
+      const long long pairs = (static_cast<long long>(n_mocks) * nA * nM + 1) / 2;
+      cpx::k_mock_noise<<<static_cast<unsigned>((pairs + 255) / 256), 256>>>(d_ym, nA, nM, Z.n_M_pad, n_mocks, seed, iz, d_yd);
+      cpx::k_ydd<<<(n_mocks * 32 + 255) / 256, 256>>>(d_yd, static_cast<int>(per_data), n_mocks, d_ydd);
+      h->launches += 2;
+      e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+      cudaFree(d_yd);
+      cudaFree(d_ydd);
+      cudaFree(d_ym);
+      return fail(CPX_ERR_CUDA, std::string("cpx_generate_mocks: ") + cudaGetErrorString(e));
+    }
+    for (const double* old : {Z.yd, Z.ydd})
+      if (old) {
+        cudaFree(const_cast<double*>(old));
+        zh.owned.erase(std::remove(zh.owned.begin(), zh.owned.end(), (void*)old), zh.owned.end());
+      }
+    zh.owned.push_back(d_yd);
+    zh.owned.push_back(d_ydd);
+    Z.yd = d_yd;
+    Z.ydd = d_ydd;
+    Z.n_data = n_mocks;
+    if (mocks_zdAM) {     // data space: d = L yd
+      yd_host.resize(per_data * n_mocks);
+      CPX_CUDA(cudaMemcpy(yd_host.data(), d_yd, sizeof(double) * yd_host.size(), cudaMemcpyDeviceToHost));
+      for (int dd = 0; dd < n_mocks; ++dd)
+        for (int A = 0; A < nA; ++A) {
+          const double* L = &zh.Lfac[static_cast<size_t>(A) * nM * nM];
+          const double* y = &yd_host[(static_cast<size_t>(dd) * nA + A) * Z.n_M_pad];
+          double* out = mocks_zdAM + ((static_cast<size_t>(iz) * n_mocks + dd) * nA_max + A) * nM_max;
+          for (int M = 0; M < nM; ++M) {
+            double sacc = 0.0;
+            for (int Mp = 0; Mp <= M; ++Mp) sacc += L[M * nM + Mp] * y[Mp];
+            out[M] = sacc;
+          }
+        }
+    }
+  }
+  cudaFree(d_ym);
+  return CPX_OK;
 }
 
 int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
@@ -1448,7 +1540,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       w.data_idx = d_didx;
       w.chi2_zA = chi2_zA_dst;
       w.model = model_dst;
-      w.whiten = 0;
+      w.whiten = (a->flags & CPX_MODEL_WHITENED) ? 1 : 0;
       dim3 grid((count + kWinPts - 1) / kWinPts, std::max(nA_grid, 1), gz);
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
@@ -1514,6 +1606,44 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       }
     for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   }
+  return CPX_OK;
+}
+
+int cpx_hankel_jbar(int32_t device, int32_t n_groups, const int32_t* group_start, const double* r_Mpc, const double* weight,
+                    int64_t n_f, const double* kf, const double* meas, double* jbar) {
+  if (n_groups <= 0 || !group_start || !r_Mpc || !weight || n_f <= 0 || !kf || !meas || !jbar)
+    return fail(CPX_ERR_ARG, "cpx_hankel_jbar: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(CPX_ERR_CUDA, "cpx_hankel_jbar: no such CUDA device");
+  const int n_r = group_start[n_groups];
+  for (int g = 0; g < n_groups; ++g)
+    if (group_start[g + 1] <= group_start[g]) return fail(CPX_ERR_ARG, "cpx_hankel_jbar: empty or unsorted group");
+  CPX_CUDA(cudaSetDevice(device));
+  int* d_gs = nullptr;
+  double *d_r = nullptr, *d_w = nullptr, *d_kf = nullptr, *d_meas = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_gs); cudaFree(d_r); cudaFree(d_w); cudaFree(d_kf); cudaFree(d_meas); cudaFree(d_out);
+  };
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(dst, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up(reinterpret_cast<void**>(&d_gs), group_start, sizeof(int) * (n_groups + 1));
+  up(reinterpret_cast<void**>(&d_r), r_Mpc, sizeof(double) * n_r);
+  up(reinterpret_cast<void**>(&d_w), weight, sizeof(double) * n_r);
+  up(reinterpret_cast<void**>(&d_kf), kf, sizeof(double) * n_f);
+  up(reinterpret_cast<void**>(&d_meas), meas, sizeof(double) * n_f);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * n_groups * n_f);
+  if (e == cudaSuccess) {
+    cpx::k_jbar<<<dim3(static_cast<unsigned>((n_f + 255) / 256), n_groups), 256>>>(d_gs, d_r, d_w, d_kf, d_meas, n_f, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(jbar, d_out, sizeof(double) * n_groups * n_f, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(CPX_ERR_CUDA, std::string("cpx_hankel_jbar: ") + cudaGetErrorString(e));
   return CPX_OK;
 }
 

@@ -953,6 +953,88 @@ __global__ void k_unpad_pxzam(const ZDev* __restrict__ ztab, int zi, int zslot, 
 }
 
 // ------------------------------------------------------------------------------------------
+// k_mock_noise: many noisy realisations of a data vector, generated where they are scored (likelihood.py:37-50 draws
+// d = m + L n per mock on the host).  The device keeps data vectors whitened, yd = L^-1 d, so a mock is simply
+//   yd[d][A][M] = (L^-1 m)[A][M] + n,   n ~ N(0, 1)
+// with (L^-1 m) the whitened model from k_window (WindowArgs::whiten).  Counter-based generator (Philox4x32-10, key =
+// seed, counter = (pair index, z, 0): reproducible and independent of the launch geometry), Box-Muller on two 53-bit
+// uniforms per pair of elements.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c[4]) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mock_noise(const double* __restrict__ ymodel /*[n_A][n_M]*/, int n_A, int n_M, int n_M_pad,
+                                                    int n_mocks, unsigned long long seed, int zglobal, double* __restrict__ yd) {
+  const long long n_el = static_cast<long long>(n_mocks) * n_A * n_M;
+  const long long pair = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (2 * pair >= n_el) return;
+  uint32_t c[4] = {static_cast<uint32_t>(pair), static_cast<uint32_t>(pair >> 32), static_cast<uint32_t>(zglobal), 0u};
+  philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), c);
+  // two uniforms in (0, 1): 53 bits each, never exactly 0
+  const double u1 = (static_cast<double>((static_cast<unsigned long long>(c[0] >> 5) << 26) | (c[1] >> 6)) + 0.5) * 0x1.0p-53;
+  const double u2 = (static_cast<double>((static_cast<unsigned long long>(c[2] >> 5) << 26) | (c[3] >> 6)) + 0.5) * 0x1.0p-53;
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  const double z01[2] = {rad * cs, rad * sn};
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const long long el = 2 * pair + e;
+    if (el >= n_el) break;
+    const int M = static_cast<int>(el % n_M);
+    const long long dA = el / n_M;
+    const int A = static_cast<int>(dA % n_A);
+    yd[dA * n_M_pad + M] = ymodel[A * n_M + M] + z01[e];
+  }
+}
+
+// ydd[d] = sum_{A, M} yd^2 (the constant term of the factorised chi2); one warp per data vector
+__global__ void k_ydd(const double* __restrict__ yd, int per_data, int n_data, double* __restrict__ ydd) {
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (d >= n_data) return;
+  double s = 0.0;
+  for (int i = lane; i < per_data; i += 32) {
+    const double v = yd[static_cast<size_t>(d) * per_data + i];
+    s = fma(v, v, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) ydd[d] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_jbar: set-up helper for the Hankel weights (cupix_b200/quadrature.py): the theta-weighted average of J0 over the
+// separations of each fine theta bin (likelihood.py:99-130 folded into the weights) on the fine k_perp grid,
+//   jbar[g][f] = meas[f] / sum_{i in g} w_i  *  sum_{i in g} w_i J0(kf[f] r_i)
+// grid = (n_f / 256, n_groups).  2000 separations x 75 000 grid points per z bin at the S5 shape: seconds of NumPy, ms here.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_jbar(const int* __restrict__ gstart, const double* __restrict__ r, const double* __restrict__ w,
+                                              const double* __restrict__ kf, const double* __restrict__ meas, long long n_f,
+                                              double* __restrict__ jbar) {
+  const long long f = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (f >= n_f) return;
+  const int g = blockIdx.y;
+  const double k = kf[f];
+  double acc = 0.0, norm = 0.0;
+  for (int i = gstart[g]; i < gstart[g + 1]; ++i) {
+    acc = fma(w[i], j0(k * r[i]), acc);
+    norm += w[i];
+  }
+  jbar[static_cast<size_t>(g) * n_f + f] = acc * (meas[f] / norm);
+}
+
+// ------------------------------------------------------------------------------------------
 // pipe-rate probes (roofline denominators)
 // ------------------------------------------------------------------------------------------
 __global__ void k_probe_dfma(double* out, int iters, double x) {

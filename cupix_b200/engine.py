@@ -15,6 +15,7 @@ NSLOTS = 18
 DEVICE_IO = 1
 PRECISE_CELLS = 2
 NO_FACTOR = 4
+MODEL_WHITENED = 8
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -75,6 +76,12 @@ def load_library(path=None):
     lib.cpx_get_info.restype = C.c_int
     lib.cpx_probe_peaks.argtypes = [C.c_int32, c_dp, c_dp, c_dp, c_dp]
     lib.cpx_probe_peaks.restype = C.c_int
+    lib.cpx_generate_mocks.argtypes = [C.c_void_p, C.c_int32, c_ip, c_ip, c_dp, C.c_int32, C.c_uint64, c_dp]
+    lib.cpx_generate_mocks.restype = C.c_int
+    lib.cpx_device_count.argtypes = []
+    lib.cpx_device_count.restype = C.c_int
+    lib.cpx_hankel_jbar.argtypes = [C.c_int32, C.c_int32, c_ip, c_dp, c_dp, C.c_int64, c_dp, c_dp, c_dp]
+    lib.cpx_hankel_jbar.restype = C.c_int
     _LIB = lib
     return lib
 
@@ -94,6 +101,24 @@ def probe_peaks(device=0):
     if lib.cpx_probe_peaks(device, C.byref(d), C.byref(f), C.byref(m), C.byref(t)) != 0:
         raise CpxError(lib.cpx_last_error().decode())
     return {"dfma_per_s": d.value, "ffma_per_s": f.value, "mufu_per_s": m.value, "dmma_fma_per_s": t.value}
+
+
+def device_count():
+    """CUDA devices visible to the library (0 when there is none; raises CpxError if the library is not built)."""
+    return int(load_library().cpx_device_count())
+
+
+def hankel_jbar(device, group_start, r_Mpc, weight, kf, meas):
+    """jbar[g, f] = meas[f] sum_{i in g} w_i J0(kf[f] r_i) / sum_{i in g} w_i on the GPU (cpx_hankel_jbar): the J0 panel
+    sums of KperpRule.weights, the only expensive part of building a plan."""
+    lib = load_library()
+    gs = np.ascontiguousarray(group_start, dtype=np.int32)
+    r, w, kf, meas = (_f64(x) for x in (r_Mpc, weight, kf, meas))
+    out = np.empty((gs.size - 1, kf.size))
+    rc = lib.cpx_hankel_jbar(int(device), gs.size - 1, gs.ctypes.data_as(c_ip), _dp(r), _dp(w), kf.size, _dp(kf), _dp(meas), _dp(out))
+    if rc != 0:
+        raise CpxError("cpx_hankel_jbar failed (%d): %s" % (rc, lib.cpx_last_error().decode()))
+    return out
 
 
 class PxEngine(object):
@@ -159,6 +184,26 @@ class PxEngine(object):
         if rc != 0:
             raise CpxError("cpx_set_data failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
         self.plans[iz].n_data = Px_AM.shape[0]
+
+    def generate_mocks(self, n_mocks, seed, point=(), slots=(), zsel=None, return_mocks=True):
+        """``n_mocks`` realisations d = model(point) + L n of the data vector of every z bin, drawn on the device
+        (cpx_generate_mocks) and installed as data vectors 0 .. n_mocks-1.  Returns them in data space
+        [n_z, n_mocks, n_A_max, n_M_max] unless ``return_mocks`` is False."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        point = np.ascontiguousarray(point, dtype=np.float64).reshape(-1)
+        assert point.size == slots.size
+        zs = None if zsel is None else np.ascontiguousarray(zsel, dtype=np.int32)
+        out = None
+        if return_mocks:
+            out = np.zeros((self.n_z, int(n_mocks), max(p.n_A for p in self.plans), max(p.n_M for p in self.plans)))
+        rc = self.lib.cpx_generate_mocks(self._h, slots.size, slots.ctypes.data_as(c_ip) if slots.size else None,
+                                         None if zs is None else zs.ctypes.data_as(c_ip), _dp(point) if point.size else None,
+                                         int(n_mocks), int(seed) & 0xFFFFFFFFFFFFFFFF, _dp(out))
+        if rc != 0:
+            raise CpxError("cpx_generate_mocks failed (%d): %s" % (rc, self.lib.cpx_last_error().decode()))
+        for p in self.plans:
+            p.n_data = int(n_mocks)
+        return out
 
     # ----------------------------------------------------------------------------------------
     def _dims(self, z_list):

@@ -56,7 +56,12 @@ class BatchMinimizer(object):
     def _quadratic_model(self, x, data_idx):
         """chi2, gradient and Hessian of every fit from one batched stencil evaluation."""
         N, P, S = x.shape[0], self.P, self.offs.shape[0]
+        # no stencil point may leave [lower, upper] (the model can be undefined there, e.g. kp_Mpc <= 0): the stencil is
+        # centred one step inside the bounds and the quadratic model is translated back to x below
+        x_req = x
+        x = np.clip(x, np.minimum(self.lower + self.steps, self.upper), np.maximum(self.upper - self.steps, self.lower))
         pts = (x[:, None, :] + self.offs[None, :, :] * self.steps[None, None, :]).reshape(N * S, P)
+        pts = np.clip(pts, self.lower, self.upper)          # only bites when upper - lower < 2 steps
         didx = None if data_idx is None else np.repeat(data_idx, S)
         f = self._chi2(pts, didx).reshape(N, S)
         f0 = f[:, 0]
@@ -70,6 +75,11 @@ class BatchMinimizer(object):
         for n, (i, j) in enumerate(self.pairs):
             fij = f[:, 1 + 2 * P + n]
             H[:, i, j] = H[:, j, i] = (fij - f[:, 1 + 2 * i] - f[:, 1 + 2 * j] + f0) / (h[i] * h[j])
+        d = x_req - x
+        if np.any(d != 0.0):
+            Hd = np.einsum("nij,nj->ni", H, d)
+            f0 = f0 + np.einsum("ni,ni->n", g, d) + 0.5 * np.einsum("ni,ni->n", d, Hd)
+            g = g + Hd
         return f0, g, H
 
     def minimize(self, x0, data_idx=None, max_iter=20, tol=1e-4, lam0=1e-3):

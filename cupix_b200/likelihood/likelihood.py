@@ -31,6 +31,8 @@ class Likelihood(object):
         # float64 P3D cells as well (reference-precision mode, slower); default: float32 cells
         self.precise_cells = config.get('precise_cells', getattr(theory, 'precise_cells', False))
         self._engines = {}
+        self._mocks = None            # data vectors installed by set_mock_data / generate_mocks, re-applied to every engine
+        self._warned_mock0 = False
         if self.verbose:
             print("Likelihood will evaluate redshift bin", self.iz, "corresponds to z =", self.theory.z)
 
@@ -38,7 +40,7 @@ class Likelihood(object):
     def build_plan(self, cosmo=None):
         cosmo = self.theory.fid_cosmo if cosmo is None else cosmo
         return _plan.build_likelihood_plan(self.theory, cosmo, self.data, self.iz,
-                                           self.N_theta_average, self.theory.rule)
+                                           self.N_theta_average, self.theory.rule, device=_plan.weights_device(self.device))
 
     def engine(self, cosmo=None):
         """Device engine for the current N_theta_average (callers toggle that attribute, e.g.
@@ -48,13 +50,20 @@ class Likelihood(object):
             if len(self._engines) > 4:
                 self._engines.pop(next(iter(self._engines)))[0].close()
             # the cosmology object is kept with its engine (see cosmology.cache_key)
-            self._engines[key] = (PxEngine([self.build_plan(cosmo)], device=self.device, precise=self.precise_cells),
-                                  cosmo)
+            eng = PxEngine([self.build_plan(cosmo)], device=self.device, precise=self.precise_cells)
+            if self._mocks is not None:       # installed mocks are data: every engine of this likelihood scores against them
+                eng.set_data(0, self._mocks)
+            self._engines[key] = (eng, cosmo)
         return self._engines[key][0]
 
     def _scalar_eval(self, params, want):
+        if self._mocks is not None and not self._warned_mock0 and any(w.startswith("chi2") for w in want):
+            import warnings
+            warnings.warn("cupix_b200: mock data vectors are installed; scalar chi2 / log-likelihood calls score against "
+                          "mock 0, not the measurement (restore_data() re-installs it)")
+            self._warned_mock0 = True
         cosmo = self.theory.get_cosmology(params=params)
-        names, values = self.theory.split_params(params)
+        names, values = self.theory.resolve_params(cosmo, params)
         slots, _ = slots_from_names(names)
         return self.engine(cosmo).eval(points=values, slots=slots, want=want)
 
@@ -105,12 +114,42 @@ class Likelihood(object):
     def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None):
         """chi2 [B] for ``points`` [B, P] whose columns are the parameters ``names``.  ``factor=False`` keeps every point
         on the full pipeline (see PxEngine._flags)."""
+        if self.theory.lya_model.default_igm_params is not None:
+            assert not return_info, "return_info is not available in IGM (emulator) mode"
+            return self._chi2_batch_igm(points, names, data_idx)
         slots, _ = slots_from_names(names)
         want = ("chi2", "chi2_zA") if return_info else ("chi2",)
         out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx, factor=factor)
         if return_info:
             return out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"][:, 0]}
         return out["chi2"]
+
+    def _chi2_batch_igm(self, points, names, data_idx=None):
+        """IGM (emulator) mode for a batch (model_lya.py:200-235 once per point in the reference): the IGM columns go
+        through the emulator network in PyTorch on this likelihood's GPU, its [B, 8] Arinyo output and the remaining
+        columns are scored without leaving the device."""
+        import torch
+        from cupix_b200.likelihood.model_lya import FF_OUTPUT_NAMES, IGM_PARAM_NAMES, LYA_PARAM_NAMES
+        lm = self.theory.lya_model
+        bad = [n for n in names if n in LYA_PARAM_NAMES]
+        if bad:
+            raise KeyError("Arinyo parameters %s cannot be columns in IGM (emulator) mode: the emulator sets them" % bad)
+        dev = torch.device("cuda", self.device)
+        pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=dev)
+        igm_cols = [j for j, n in enumerate(names) if n in IGM_PARAM_NAMES]
+        other = [j for j, n in enumerate(names) if n not in IGM_PARAM_NAMES]
+        ff = lm.emulate_lya_params_tensor(self.theory.fid_cosmo, [names[j] for j in igm_cols], pts[:, igm_cols]).to(torch.float64)
+        col = {n: ff[:, i] for i, n in enumerate(FF_OUTPUT_NAMES)}
+        kv = torch.exp(torch.log(col["kvav"]) / col["av"])                                   # model_lya.py:13-18
+        cols = [col["bias"], col["beta"], col["q1"], col["q2"], kv, col["av"], col["bv"], col["kp"]] + [pts[:, j] for j in other]
+        full = torch.stack(cols, dim=1).contiguous()
+        slots, zsel = slots_from_names(list(LYA_PARAM_NAMES) + [names[j] for j in other])
+        out = torch.empty(full.shape[0], dtype=torch.float64, device=dev)
+        didx = None if data_idx is None else torch.as_tensor(np.ascontiguousarray(data_idx, dtype=np.int32), device=dev)
+        self.engine().eval_device(full.shape[0], full.shape[1], slots, points_ptr=full.data_ptr(), zsel=zsel,
+                                  data_idx_ptr=None if didx is None else didx.data_ptr(), chi2_ptr=out.data_ptr(),
+                                  stream=torch.cuda.current_stream(dev).cuda_stream)
+        return out.cpu().numpy()
 
     def get_log_like_batch(self, points, names, data_idx=None):
         return -0.5 * self.get_chi2_batch(points, names, data_idx=data_idx)
@@ -144,21 +183,45 @@ class Likelihood(object):
         return out
 
     def set_mock_data(self, Px_AM):
-        """Replace the data vector(s) [n_data, N_A, N_M] scored by ``data_idx`` (many-mock fits)."""
-        self.engine().set_data(0, Px_AM)
+        """Replace the data vector(s) [n_data, N_A, N_M] scored by ``data_idx`` (many-mock fits).  The vectors are kept
+        with the likelihood and installed in every engine it has or builds later (another N_theta_average, another
+        cosmology in ``params``); ``restore_data()`` goes back to the measurement."""
+        Px_AM = np.array(Px_AM, dtype=np.float64)
+        self._mocks = Px_AM[None] if Px_AM.ndim == 2 else Px_AM
+        self._warned_mock0 = False
+        for eng, _ in self._engines.values():
+            eng.set_data(0, self._mocks)
+        self.engine()
+
+    def restore_data(self):
+        """Score against the measurement ``data.Px_ZAM[iz]`` again."""
+        self._mocks = None
+        for eng, _ in self._engines.values():
+            eng.set_data(0, self.data.Px_ZAM[self.iz])
 
     def generate_mocks(self, n_mocks, params={}, seed=None, install=True):
         """``n_mocks`` noisy realisations ``model(params) + L n`` of the data vector, L L^T = cov per coarse theta
-        bin -- ``generate_px_forecast(add_noise=True)`` (likelihood.py:37-50) for many mocks at once, with the
-        Cholesky factors computed once and a seeded generator.  With ``install`` they become the data vectors
-        that ``data_idx = 0 .. n_mocks-1`` selects (scripts/fit_many_mocks.py:151-170 rebuilds data and
-        likelihood per mock instead).  Returns [n_mocks, N_A, N_M]."""
-        model = self.get_convolved_px(params=params)
-        L = np.linalg.cholesky(self.data.cov_ZAM[self.iz])                       # [N_A, N_M, N_M]
-        noise = np.random.default_rng(seed).normal(size=(int(n_mocks),) + model.shape)
-        mocks = model[None] + np.einsum("aij,naj->nai", L, noise)
-        if install:
-            self.set_mock_data(mocks)
+        bin -- ``generate_px_forecast(add_noise=True)`` (likelihood.py:37-50) for many mocks at once.  With ``install``
+        (default) they are drawn ON THE DEVICE (cpx_generate_mocks: the whitened model plus unit normals from a
+        counter-based Philox generator, written straight into the engine's data-vector table) and become the data
+        vectors that ``data_idx = 0 .. n_mocks-1`` selects (scripts/fit_many_mocks.py:151-170 rebuilds data and
+        likelihood per mock instead); without, they are drawn on the host with NumPy and only returned.  Seeded either
+        way (the two generators give different, equally distributed draws).  Returns [n_mocks, N_A, N_M]."""
+        if not install:
+            model = self.get_convolved_px(params=params)
+            L = np.linalg.cholesky(self.data.cov_ZAM[self.iz])                       # [N_A, N_M, N_M]
+            noise = np.random.default_rng(seed).normal(size=(int(n_mocks),) + model.shape)
+            return model[None] + np.einsum("aij,naj->nai", L, noise)
+        seed = int(np.random.SeedSequence().entropy % (1 << 63)) if seed is None else int(seed)
+        cosmo = self.theory.get_cosmology(params=params)
+        names, values = self.theory.split_params(params)
+        slots, _ = slots_from_names(names)
+        mocks = self.engine(cosmo).generate_mocks(n_mocks, seed, point=values, slots=slots)[0]
+        self._mocks = mocks
+        self._warned_mock0 = False
+        for eng, _ in self._engines.values():                 # engines for another binning / cosmology get the same vectors
+            if eng is not self.engine(cosmo):
+                eng.set_data(0, mocks)
         return mocks
 
 

@@ -13,6 +13,9 @@ import numpy as np
 from cupix_b200.utils.utils import data_path
 
 LYA_PARAM_NAMES = ("bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc")
+IGM_PARAM_NAMES = ("mF", "gamma", "sigT_Mpc", "kF_Mpc")                                 # model_lya.py:205-208
+EMU_INPUT_NAMES = ("Delta2_p", "n_p") + IGM_PARAM_NAMES                                  # model_lya.py:203-222
+FF_OUTPUT_NAMES = ("bias", "beta", "q1", "kvav", "av", "bv", "kp", "q2")                 # ForestFlow's Arinyo naming
 
 
 def lya_params_from_forestflow_params(ff_params):
@@ -43,8 +46,11 @@ class LyaModel(object):
         if 'igm' in self.default_lya_model:
             self.default_igm_params = self.get_default_igm_params(config)
             self.default_lya_params = None
-            self.emulator = self.get_emulator(config.get('emulator_label', 'forest_mpg'),
-                                              config.get('Nrealizations', 3000))
+            # config['emulator']: any object with ForestFlow's ``predict_Arinyos(emu_params=dict) -> dict`` (and, for
+            # batches, ``predict_Arinyos_tensor(x[B, 6]) -> [B, 8]`` in torch, columns EMU_INPUT_NAMES -> FF_OUTPUT_NAMES);
+            # default: ForestFlow's cINN, as in the reference
+            self.emulator = config['emulator'] if config.get('emulator') is not None else \
+                self.get_emulator(config.get('emulator_label', 'forest_mpg'), config.get('Nrealizations', 3000))
         else:
             self.default_lya_params = self.get_default_lya_params(config)
             self.default_igm_params = None
@@ -105,7 +111,7 @@ class LyaModel(object):
 
     def get_emulator(self, emulator_label, Nrealizations):
         """ForestFlow cINN (model_lya.py:159-171).  Runs in PyTorch; its [B, 8] Arinyo output is
-        handed to the device path as a tensor (``Likelihood.get_chi2_batch(arinyo=...)``)."""
+        handed to the device path as a tensor (``Likelihood.get_chi2_from_arinyo_tensor``)."""
         if emulator_label != "forest_mpg":
             raise ValueError("implement emulator_label", emulator_label)
         import forestflow                          # optional third-party dependency
@@ -128,6 +134,28 @@ class LyaModel(object):
             if key in params:
                 lya_params[key] = params[key]
         return lya_params
+
+    def emulate_lya_params_tensor(self, cosmo, igm_names, igm_values):
+        """Batched ``emulate_lya_params``: ``igm_values`` [B, len(igm_names)] (torch, any device) overrides the default IGM
+        parameters column by column; returns the emulator's Arinyo parameters [B, 8] in ForestFlow's naming
+        (FF_OUTPUT_NAMES) on the same device.  Uses ``emulator.predict_Arinyos_tensor`` when the emulator has it (one
+        network call for the batch); otherwise falls back to one ``predict_Arinyos`` call per row."""
+        import torch
+        assert self.default_igm_params is not None and self.emulator is not None, "need emulator for IGM params"
+        B = igm_values.shape[0]
+        lin = cosmo.get_linP_Mpc_params(z=self.z, kp_Mpc=0.7)
+        base = dict(self.default_igm_params, Delta2_p=lin['Delta2_p'], n_p=lin['n_p'])
+        x = torch.tensor([float(base[k]) for k in EMU_INPUT_NAMES], dtype=igm_values.dtype, device=igm_values.device).repeat(B, 1)
+        for j, name in enumerate(igm_names):
+            assert name in IGM_PARAM_NAMES, "not an IGM parameter: %r" % name
+            x[:, EMU_INPUT_NAMES.index(name)] = igm_values[:, j]
+        if hasattr(self.emulator, "predict_Arinyos_tensor"):
+            return self.emulator.predict_Arinyos_tensor(x)
+        rows = []
+        for row in x.cpu().numpy():
+            ff = self.emulator.predict_Arinyos(emu_params=dict(zip(EMU_INPUT_NAMES, row)))
+            rows.append([float(ff[k]) for k in FF_OUTPUT_NAMES])
+        return torch.tensor(rows, dtype=igm_values.dtype, device=igm_values.device)
 
     def emulate_lya_params(self, cosmo, igm_params):
         emu_params = {k: igm_params[k] for k in ('mF', 'gamma', 'sigT_Mpc', 'kF_Mpc')}

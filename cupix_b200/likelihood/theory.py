@@ -58,10 +58,10 @@ class Theory(object):
         else:
             preset, self.rule_error = dict(PRESETS[kind]), None
         self.kperp_family = kind
-        self.rule = KperpRule(config.get('n_q', preset['n_q']), config.get('k0_Mpc', DEFAULT_K0),
-                              config.get('kmax_Mpc', DEFAULT_KMAX),
-                              refine=config.get('kperp_refine', preset.get('refine', 0.0)),
-                              k_refine=config.get('kperp_k_refine', preset.get('k_refine', 0.3)))
+        self.rule = _quad.get_rule(config.get('n_q', preset['n_q']), config.get('k0_Mpc', DEFAULT_K0),
+                                   config.get('kmax_Mpc', DEFAULT_KMAX),
+                                   refine=config.get('kperp_refine', preset.get('refine', 0.0)),
+                                   k_refine=config.get('kperp_k_refine', preset.get('k_refine', 0.3)))
         self.device = config.get('device', 0)
         self.precise_cells = config.get('precise_cells', False)
         # k_par = 0 row: 'exact' = the mu = 0 limit; 'reference' = evaluated at 1e-4 1/Mpc like the reference's in-tree
@@ -103,15 +103,30 @@ class Theory(object):
         names = [k for k in params if k in _plan.SLOT_INDEX and k not in _plan.COSMO_SLOT_NAMES]
         return names, np.array([[float(params[k]) for k in names]], dtype=np.float64).reshape(1, len(names))
 
+    def resolve_params(self, cosmo, params):
+        """(names, values [1, P]) of the device columns for a scalar call.  Arinyo mode: the model keys of ``params``.
+        IGM (emulator) mode (model_lya.py:175-235): the emulator is evaluated at the IGM keys of ``params`` (mF, gamma,
+        sigT_Mpc, kF_Mpc; Delta2_p, n_p from ``cosmo``) and its eight Arinyo values become explicit columns -- the
+        reference re-emulates on every call; Arinyo keys in ``params`` are ignored in that mode, as there."""
+        if self.lya_model.default_igm_params is None:
+            return self.split_params(params)
+        lya = self.lya_model.get_lya_params(cosmo, params)
+        merged = {k: float(lya[k]) for k in _plan.SLOT_NAMES[:8]}
+        for k, v in params.items():
+            if k in _plan.SLOT_INDEX and k not in merged and k not in _plan.COSMO_SLOT_NAMES:
+                merged[k] = float(v)
+        return self.split_params(merged)
+
     # -- engine cache ---------------------------------------------------------------------------
-    def _theta_engine(self, theta_arc, k_AA, cosmo):
+    def _theta_engine(self, theta_arc, k_AA, cosmo, include=None):
         theta_arc = np.atleast_1d(np.asarray(theta_arc, dtype=np.float64))
         k_AA = np.atleast_1d(np.asarray(k_AA, dtype=np.float64))
-        key = (theta_arc.tobytes(), k_AA.tobytes(), _cosmology.cache_key(cosmo, self.fid_cosmo))
+        key = (theta_arc.tobytes(), k_AA.tobytes(), _cosmology.cache_key(cosmo, self.fid_cosmo), include)
         if key not in self._engines:
             if len(self._engines) > 8:
                 self._engines.pop(next(iter(self._engines)))[0].close()
-            p = _plan.build_theory_plan(self, cosmo, theta_arc, np.arange(theta_arc.size), k_AA, self.rule)
+            p = _plan.build_theory_plan(self, cosmo, theta_arc, np.arange(theta_arc.size), k_AA, self.rule,
+                                        device=_plan.weights_device(self.device), include=include)
             # the cosmology object is kept with its engine (see cosmology.cache_key)
             self._engines[key] = (PxEngine([p], device=self.device, precise=self.precise_cells), cosmo)
         return self._engines[key][0]
@@ -120,10 +135,51 @@ class Theory(object):
     def get_px_obs(self, theta_arc, k_AA, cosmo=None, params={}):
         """Px [N_theta, N_k] in Angstrom (theory.py:95-123)."""
         cosmo = self.get_cosmology(cosmo=cosmo, params=params)
-        names, values = self.split_params(params)
+        names, values = self.resolve_params(cosmo, params)
         eng = self._theta_engine(theta_arc, k_AA, cosmo)
         slots, zsel = slots_from_names(names)
         return eng.eval(points=values, slots=slots, want=("px_zam",))["px_zam"][0, 0]
+
+    # -- the components of get_px_obs, one by one (theory.py:126-247, 455-535): same device path with the other terms
+    #    switched off -- (hcd, metal, sky, continuum) flags of a separate plan -- or, for additive terms, zero bias
+    def _component(self, theta_arc, k_AA, cosmo, params, include, force=None):
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        names, values = self.resolve_params(cosmo, params)
+        for k, v in (force or {}).items():           # forced columns win over params (and over emulated values)
+            if k in names:
+                values[0, names.index(k)] = v
+            else:
+                names, values = names + [k], np.concatenate([values, [[v]]], axis=1)
+        slots, _ = slots_from_names(names)
+        return self._theta_engine(theta_arc, k_AA, cosmo, include=include).eval(points=values, slots=slots, want=("px_zam",))["px_zam"][0, 0]
+
+    def get_px_lya_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """Clean Lya term (theory.py:126-144)."""
+        return self._component(theta_arc, k_AA, cosmo, params, (False, False, False, False))
+
+    def get_px_lya_hcd_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """Lya with the HCD scale-dependent biases (theory.py:147-165)."""
+        return self._component(theta_arc, k_AA, cosmo, params, (True, False, False, False))
+
+    def get_px_metal_auto_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """SiIII auto term (theory.py:200-222): the metal plan evaluated at bias = 0, where the Lya and cross terms vanish."""
+        return self._component(theta_arc, k_AA, cosmo, params, (False, True, False, False), force={"bias": 0.0})
+
+    def get_px_metal_cross_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """Lya x SiIII cross term (theory.py:225-247): bilinear in (bias, b_X), so total - Lya-only - auto-only."""
+        tot = self._component(theta_arc, k_AA, cosmo, params, (False, True, False, False))
+        return tot - self.get_px_lya_obs(theta_arc, k_AA, cosmo, params) - self.get_px_metal_auto_obs(theta_arc, k_AA, cosmo, params)
+
+    def get_px_sky_obs(self, theta_arc, k_AA, cosmo=None, params={}):
+        """Correlated sky residuals (theory.py:455-473): the sky plan at bias = 0."""
+        return self._component(theta_arc, k_AA, cosmo, params, (False, False, True, False), force={"bias": 0.0})
+
+    def get_continuum_distortion_obs(self, k_AA, cosmo=None, params={}):
+        """tanh((k_par / kC)^pC) on the given wavenumbers (theory.py:509-535): a closed form of k alone."""
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        cp = self.cont_model.get_continuum_params(params)
+        kp_Mpc = np.asarray(k_AA, dtype=np.float64) * cosmo.get_dAA_dMpc(self.z, lambda_rest_AA=self.lya_model.lr_lya)
+        return np.tanh((kp_Mpc / cp["kC_Mpc"]) ** cp["pC"])
 
     def get_px_obs_batch(self, theta_arc, k_AA, points, names, cosmo=None):
         """Px [B, N_theta, N_k] for B parameter points (columns named by ``names``)."""

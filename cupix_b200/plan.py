@@ -21,6 +21,9 @@ SLOT_INDEX = {n: i for i, n in enumerate(SLOT_NAMES)}
 # rescales the linear power of the plan's cosmology by (As/As0) (k/k_pivot)^(ns-ns0) per point.  The
 # dict-based scalar API keeps the reference behaviour (a new cosmology object, hence a new plan).
 COSMO_SLOT_NAMES = ("As", "ns")
+# parameters the model is a polynomial in: the factorised path of cpx_eval (csrc/cpx_factor.cuh) takes them out of the
+# Hankel stage; all others define the "tuple" of a point
+AMP_SLOT_NAMES = ("bias", "beta", "b_H", "beta_H", "b_X", "beta_X", "b_noise_Mpc")
 
 INCLUDE_HCD, INCLUDE_METAL, INCLUDE_SKY, INCLUDE_CONTINUUM = 1, 2, 4, 8
 METAL_KP_MPC = 10.0      # theory.py:378,421
@@ -92,10 +95,31 @@ def k_pivot_of(cosmo):
     return 0.0
 
 
-def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
+def weights_device(device):
+    """The device on which the J0 sums of the Hankel weights are evaluated (cpx_hankel_jbar), or None where no CUDA
+    device is visible: plans are then built with the NumPy implementation -- host-side set-up logic that the CPU tests
+    exercise; evaluating a plan always needs the GPU (cpx_create raises without one)."""
+    from cupix_b200 import engine
+    try:
+        return device if engine.device_count() > 0 else None
+    except engine.CpxError:
+        return None
+
+
+def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None, device=None, include=None):
     """Theory part of a plan for separations ``theta_arc`` (arcmin) grouped into bins by
-    ``theta_group`` (theta-weighted average inside a group) and wavenumbers ``k_AA``."""
+    ``theta_group`` (theta-weighted average inside a group) and wavenumbers ``k_AA``.  ``device``: evaluate the J0 sums
+    of the Hankel weights on that GPU (cupix_b200.engine.hankel_jbar) instead of NumPy threads."""
     rule = rule or KperpRule()
+    # include = (hcd, metal, sky, continuum) overrides the theory's flags (component accessors of Theory)
+    inc_hcd, inc_metal, inc_sky, inc_cont = include if include is not None else (
+        theory.include_hcd, theory.include_metal, theory.include_sky, theory.include_continuum)
+    jbar_fn = None
+    if device is not None:
+        from cupix_b200 import engine
+
+        def jbar_fn(start, r, w, kf, meas, device=device):
+            return engine.hankel_jbar(device, start, r, w, kf, meas)
     p = ZbinPlan()
     z = theory.z
     theta_arc = np.asarray(theta_arc, dtype=np.float64)
@@ -119,15 +143,15 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
     p.kpar_Mpc = p3d_kpar(k_AA * dAA)
     p.kpar_row_Mpc = k_AA * dAA if sub0 else None
     p.kperp_Mpc = rule.k.copy()
-    p.hankel_w = rule.weights(theta_arc / darc, theta_group, theta_arc, n_a)
+    p.hankel_w = rule.weights(theta_arc / darc, theta_group, theta_arc, n_a, jbar_fn=jbar_fn)
     k, _ = _cells(p.kpar_Mpc, p.kperp_Mpc)
     p.linP_cell = _linP_on_cells(cosmo, z, k)
     p.defaults = default_vector(theory, cosmo)
     p.k_pivot_Mpc = k_pivot_of(cosmo)
-    p.flags = (INCLUDE_HCD * bool(theory.include_hcd) | INCLUDE_METAL * bool(theory.include_metal)
-               | INCLUDE_SKY * bool(theory.include_sky) | INCLUDE_CONTINUUM * bool(theory.include_continuum))
+    p.flags = (INCLUDE_HCD * bool(inc_hcd) | INCLUDE_METAL * bool(inc_metal)
+               | INCLUDE_SKY * bool(inc_sky) | INCLUDE_CONTINUUM * bool(inc_cont))
 
-    if theory.include_metal:
+    if inc_metal:
         # auto: z_X, lambda_X (theory.py:200-222, 361-381); cross: z_cross, sqrt(l_a l_X) (:225-247, 398-438)
         z_auto = theory.get_z_metal_auto()
         z_cross = theory.get_z_metal_cross()
@@ -137,7 +161,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
             darc_x = cosmo.get_darc_dMpc(zz)
             dAA_x = cosmo.get_dAA_dMpc(zz, lambda_rest_AA=lr)
             kpar_x = p3d_kpar(k_AA * dAA_x)
-            W_x = rule.weights(theta_arc / darc_x, theta_group, theta_arc, n_a)       # [n_a, n_q]
+            W_x = rule.weights(theta_arc / darc_x, theta_group, theta_arc, n_a, jbar_fn=jbar_fn)       # [n_a, n_q]
             kx, mux = _cells(kpar_x, rule.k)
             base = _linP_on_cells(cosmo, zz, kx) * np.exp(-(kx / METAL_KP_MPC) ** 2)  # [n_m, n_q]
             mom = np.stack([W_x @ (base * mux ** (2 * j)).T for j in range(3)]) * dAA_x   # [3, n_a, n_m]
@@ -148,7 +172,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None):
             tabs.append(np.ascontiguousarray(mom))
         p.metal_auto, p.metal_cross = tabs
 
-    if theory.include_sky:
+    if inc_sky:
         xi = theory.cont_model.get_xi_noise(theta_arc)
         wsum = np.bincount(theta_group, weights=theta_arc, minlength=n_a)
         p.sky_xi_a = np.bincount(theta_group, weights=theta_arc * xi, minlength=n_a) / wsum
@@ -174,7 +198,7 @@ def attach_measurement(p, data, iz):
     return p
 
 
-def build_likelihood_plan(theory, cosmo, data, iz, N_theta_average, rule=None):
+def build_likelihood_plan(theory, cosmo, data, iz, N_theta_average, rule=None, device=None):
     th, grp = fine_theta_grid(data.theta_min_a_arcmin, data.theta_max_a_arcmin, N_theta_average)
-    p = build_theory_plan(theory, cosmo, th, grp, data.k_m[iz], rule)
+    p = build_theory_plan(theory, cosmo, th, grp, data.k_m[iz], rule, device=device)
     return attach_measurement(p, data, iz)

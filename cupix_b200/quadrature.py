@@ -159,12 +159,14 @@ class KperpRule(object):
             self._fine_cache[key] = (kf, meas, design)
         return self._fine_cache[key]
 
-    def weights(self, r_Mpc, group_index=None, group_weight=None, n_groups=None, nthreads=None):
+    def weights(self, r_Mpc, group_index=None, group_weight=None, n_groups=None, nthreads=None, jbar_fn=None):
         """Hankel weights.
 
         r_Mpc [n_r]: transverse separations.  Without groups returns W[n_r, n_q].
         With ``group_index[n_r]`` / ``group_weight[n_r]`` returns the folded weights
         W[g, q] = sum_{i in g} w_i W_r[i, q] / sum_{i in g} w_i   (theta-weighted bin average).
+        ``jbar_fn(group_start, r_sorted, w_sorted, kf, meas) -> jbar[n_groups, n_f]``: the J0 panel sums done elsewhere
+        (cupix_b200.engine.hankel_jbar: on the GPU, where the product path builds its plans); default: NumPy threads.
         """
         r = np.atleast_1d(np.asarray(r_Mpc, dtype=np.float64))
         if group_index is None:
@@ -177,10 +179,15 @@ class KperpRule(object):
             ng = int(n_groups if n_groups is not None else gi.max() + 1)
         # the weights depend on the separations only: plans rebuilt for another primordial power (same
         # background, theory.py:54-56) or for another Likelihood on the same binning find them here
-        ckey = (r.tobytes(), np.asarray(gi, dtype=np.int64).tobytes(), gw.tobytes(), ng)
+        ckey = (r.tobytes(), np.asarray(gi, dtype=np.int64).tobytes(), gw.tobytes(), ng, jbar_fn is not None)
         if ckey in self._weights_cache:
             return self._weights_cache[ckey].copy()
         kf, meas, design = self._fine_grid(max(r.max(), 1e-3))
+        if jbar_fn is not None:
+            order = np.argsort(gi, kind="stable")
+            start = np.concatenate([[0], np.cumsum(np.bincount(gi, minlength=ng))])
+            jbar = jbar_fn(start, r[order], gw[order], kf, meas)
+            return self._project(jbar, design, ckey)
         norm = np.bincount(gi, weights=gw, minlength=ng)
         jbar = np.zeros((ng, kf.size))
         # one process per GPU: share the host cores between the ranks of this node
@@ -200,9 +207,25 @@ class KperpRule(object):
         else:
             for g in range(ng):
                 work(g)
+        return self._project(jbar, design, ckey)
+
+    def _project(self, jbar, design, ckey):
+        """jbar[g, f] -> W[g, q]: projection onto the cardinal splines of the nodes; result cached."""
         b = design.T.dot(jbar.T)                      # [n_coef, ng]
         W = np.ascontiguousarray((self._cardinal.T @ b).T)          # [ng, n_q]
         if len(self._weights_cache) >= 64:
             self._weights_cache.pop(next(iter(self._weights_cache)))
         self._weights_cache[ckey] = W
         return W.copy()
+
+
+_RULE_CACHE = {}
+
+
+def get_rule(n_q=DEFAULT_NQ, k0=DEFAULT_K0, kmax=DEFAULT_KMAX, order=SPLINE_ORDER, refine=0.0, k_refine=0.3):
+    """Shared KperpRule instance per parameter set: the Theory objects of all z bins of a measurement then share the
+    fine-grid panels, the spline design matrix and the weights cache instead of rebuilding them per z."""
+    key = (int(n_q), float(k0), float(kmax), int(order), float(refine), float(k_refine))
+    if key not in _RULE_CACHE:
+        _RULE_CACHE[key] = KperpRule(*key)
+    return _RULE_CACHE[key]

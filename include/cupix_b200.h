@@ -119,7 +119,9 @@ enum {
   CPX_DEVICE_IO = 1,      /* points / outputs are device pointers, call is asynchronous on `stream`          */
   CPX_PRECISE_CELLS = 2,  /* evaluate the P3D cells in float64 too (reference-precision mode, ~4x slower):   */
                           /* chi2 then agrees with the float64 oracle to ~1e-9 everywhere */
-  CPX_NO_FACTOR = 4       /* never take the factorised path (below): every point through the full pipeline   */
+  CPX_NO_FACTOR = 4,      /* never take the factorised path (below): every point through the full pipeline   */
+  CPX_MODEL_WHITENED = 8  /* model_zAM receives L_A^-1 model (the whitened model the chi2 is formed from) instead */
+                          /* of the model itself                                                               */
 };
 
 /* Factorised path (cpx_factor.cuh; taken automatically, CPX_FACTOR=0 or CPX_NO_FACTOR switch it off).  The model
@@ -164,11 +166,20 @@ typedef struct cpx_eval_args {
 int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_handle** out);
 int cpx_eval(cpx_handle* h, const cpx_eval_args* args);
 int cpx_set_data(cpx_handle* h, int32_t iz, const double* Px_AM, int32_t n_data);
+/* n_mocks noisy realisations d = m(point) + L n of the data vector of EVERY z bin of the handle, generated on the device
+ * and installed as its data vectors 0 .. n_mocks-1 (what data_idx selects) -- likelihood.py:37-50
+ * (generate_px_forecast(add_noise=True)) for many mocks at once; scripts/fit_many_mocks.py:151-170 draws and loads one mock
+ * at a time on the host.  `point` / `slot` / `zsel` name the truth like one row of cpx_eval (P may be 0: the defaults).
+ * Counter-based Philox generator: the same seed gives the same mocks on any GPU.  mocks_zdAM: host
+ * [n_z][n_mocks][n_A_max][n_M_max] to receive the mocks in data space, or NULL. */
+int cpx_generate_mocks(cpx_handle* h, int32_t P, const int32_t* slot, const int32_t* zsel, const double* point,
+                       int32_t n_mocks, uint64_t seed, double* mocks_zdAM);
 void cpx_destroy(cpx_handle* h);
 const char* cpx_last_error(void);
 
 /* introspection */
 int cpx_version(void);
+int cpx_device_count(void);          /* CUDA devices visible to the library, 0 if none (never fails) */
 int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value);
 enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_MAX_N_A = 3,
        CPX_INFO_MAX_N_M = 4, CPX_INFO_CHUNK = 5, CPX_INFO_DEVICE_BYTES = 6, CPX_INFO_KERNEL_LAUNCHES = 7,
@@ -179,6 +190,16 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
        CPX_INFO_FACTORED_TUPLES = 12,   /* distinct tuples those calls evaluated (Hankel stage runs once per tuple)*/
        CPX_INFO_CHUNK_ALLOCATED = 13    /* points the per-chunk scratch is currently sized for (grows on demand    */
                                         /* up to CPX_INFO_CHUNK)                                                    */ };
+
+/* Set-up helper (no handle needed): the J0 part of the Hankel weights that stand for forestflow.pcross.Px_Mpc_detailed
+ * (theory.py:250-264) with the theta sub-sampling average of likelihood.py:99-130 folded in.  For n_groups fine theta
+ * bins whose separations r_Mpc[group_start[g] .. group_start[g+1]) carry the weights weight[] (theta itself), and a fine
+ * k_perp grid kf[n_f] with measure meas[n_f]:
+ *     jbar[g][f] = meas[f] * sum_i weight_i J0(kf[f] r_i) / sum_i weight_i               (host arrays in, host array out)
+ * cupix_b200/quadrature.py projects jbar onto the cardinal splines of the node set; this call replaces its NumPy loop
+ * (2000 separations x 75 000 grid points per z bin at the stress shape: seconds per z on the host, milliseconds here). */
+int cpx_hankel_jbar(int32_t device, int32_t n_groups, const int32_t* group_start, const double* r_Mpc, const double* weight,
+                    int64_t n_f, const double* kf, const double* meas, double* jbar);
 
 /* Pipe-rate probes for the roofline denominators MEASURED_PEAKS.json does not hold: sustained
  * FP64 FMA (DFMA), FP32 FMA, MUFU.EX2 and FP64 tensor (DMMA m8n8k4, counted in FMAs) rates of this

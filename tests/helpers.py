@@ -114,3 +114,28 @@ def emulate_plan_chi2(p, params, data_index=0):
 def oracle_likelihood(like):
     """OracleLikelihood twin of a product Likelihood."""
     return OracleLikelihood.from_data(like.data, oracle_for(like.theory), like.iz, like.N_theta_average)
+
+
+class MockEmulator(object):
+    """Stand-in for ``forestflow.P3D_cINN.P3DEmulator`` (absent here): a smooth, deterministic map from the six emulator
+    inputs (Delta2_p, n_p, mF, gamma, sigT_Mpc, kF_Mpc) to the eight Arinyo parameters in ForestFlow's naming, written
+    in torch so that the batch runs on the GPU like the real network (model_lya.py:159-171, 200-235)."""
+
+    def predict_Arinyos_tensor(self, x):
+        import torch
+        d2p, n_p, mF, gamma, sigT, kF = [x[:, i] for i in range(6)]
+        bias = -0.12 - 0.25 * (0.75 - mF)
+        beta = 1.5 + 0.4 * (gamma - 1.5)
+        q1 = 0.3 + 0.4 * (d2p - 0.35)
+        kvav = 0.55 + 0.1 * (n_p + 2.3)
+        av = 0.35 + 0.5 * (sigT - 0.13)
+        bv = 1.6 + 0.0 * mF
+        kp = 12.0 + 0.8 * (kF - 10.0)
+        q2 = 0.25 + 0.1 * (mF - 0.75)
+        return torch.stack([bias, beta, q1, kvav, av, bv, kp, q2], dim=1)
+
+    def predict_Arinyos(self, emu_params):
+        import torch
+        from cupix_b200.likelihood.model_lya import EMU_INPUT_NAMES, FF_OUTPUT_NAMES
+        x = torch.tensor([[float(emu_params[k]) for k in EMU_INPUT_NAMES]], dtype=torch.float64)
+        return dict(zip(FF_OUTPUT_NAMES, [float(v) for v in self.predict_Arinyos_tensor(x)[0]]))

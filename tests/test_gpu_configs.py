@@ -79,11 +79,27 @@ def test_S4_fit_many_mocks_lockstep():
     like = likes[0]
     truth = like.build_plan().defaults[:2]
     n_mocks = 64
-    mocks = like.generate_mocks(n_mocks, seed=9)              # model(defaults) + L n, installed as data vectors 0..63
+    mocks = like.generate_mocks(n_mocks, seed=9)              # model(defaults) + L n, drawn on the device, installed as data vectors 0..63
     assert mocks.shape == (n_mocks,) + data.Px_ZAM[0].shape
-    white = np.linalg.solve(np.linalg.cholesky(data.cov_ZAM[0]), (mocks - data.Px_ZAM[0][None]).transpose(1, 2, 0))
+    Lc = np.linalg.cholesky(data.cov_ZAM[0])
+    white = np.linalg.solve(Lc, (mocks - data.Px_ZAM[0][None]).transpose(1, 2, 0))
     assert abs(white.std() - 1.0) < 0.02 and abs(white.mean()) < 0.02          # unit Gaussian after whitening
-    np.testing.assert_array_equal(like.generate_mocks(n_mocks, seed=9, install=False), mocks)     # seeded
+    np.testing.assert_array_equal(like.generate_mocks(n_mocks, seed=9), mocks)                   # seeded: Philox is counter-based
+    assert np.abs(like.generate_mocks(n_mocks, seed=10) - mocks).max() > 0
+    like.generate_mocks(n_mocks, seed=9)
+    # against the host generator (likelihood.py:37-50 with NumPy): same distribution, element by element
+    host = like.generate_mocks(4096, seed=3, install=False)
+    devm = like.generate_mocks(4096, seed=3)
+    sig = np.sqrt(np.einsum("aii->ai", data.cov_ZAM[0]))
+    assert np.all(np.abs(host.mean(0) - devm.mean(0)) < 6 * sig / np.sqrt(2048))
+    np.testing.assert_allclose(devm.std(0), host.std(0), rtol=0.12)
+    wd = np.linalg.solve(Lc, (devm - data.Px_ZAM[0][None]).transpose(1, 2, 0))                  # [A, M, n]
+    corr = np.einsum("amn,akn->amk", wd, wd) / wd.shape[-1]                                      # whitened covariance ~ identity
+    assert np.abs(corr - np.eye(corr.shape[-1])[None]).max() < 0.1
+    # what the device holds is what it returned: chi2 of the truth against mock j == |L^-1 (mock_j - model)|^2
+    chi2_dev = like.get_chi2_batch(np.tile(truth, (8, 1)), ["bias", "beta"], data_idx=np.arange(8), factor=False)
+    np.testing.assert_allclose(chi2_dev, (wd[:, :, :8] ** 2).sum(axis=(0, 1)), rtol=1e-6)
+    mocks = like.generate_mocks(n_mocks, seed=9)
     fitter = BatchMinimizer(like, ["bias", "beta"], steps=[2e-4, 5e-3])
     x0 = np.tile(truth * np.array([1.05, 0.93]), (n_mocks, 1))
     res = fitter.minimize(x0, data_idx=np.arange(n_mocks))
@@ -174,3 +190,39 @@ def test_emulator_tensor_handoff():
                                ["bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc"])
     torch.cuda.synchronize()
     np.testing.assert_allclose(chi2_t.cpu().numpy(), host, rtol=1e-9)
+
+
+def test_igm_emulator_mode_end_to_end():
+    """IGM-parameter mode (model_lya.py:200-235) with a mock emulator in ForestFlow's interface: the scalar calls
+    re-emulate per call (chi2 moves with mF), agree with the oracle evaluated at the emulated Arinyo parameters, and the
+    batched call (emulator network in torch on the GPU -> [B, 8] tensor -> cpx_eval with device pointers) equals them."""
+    from cupix_b200.cosmology import Cosmology
+    from cupix_b200.likelihood.theory import Theory
+    from oracle.px_oracle import OracleLikelihood
+    emu = H.MockEmulator()
+    d = synthetic.make_measurement_dict("S1", N_A=6, N_m=40, z0=2.4)
+    cosmo = Cosmology()
+    th = Theory(2.4, fid_cosmo=cosmo, config={"default_lya_model": "best_fit_igm_from_gadget", "emulator": emu, "n_q": 96,
+                                              "include_hcd": True})
+    like = Likelihood(DESI_DR2(d), th, 0, config={"N_theta_average": 2})
+    filled = synthetic.fill_from_model(d, like.get_convolved_px({})[None], add_noise=True)
+    like = Likelihood(DESI_DR2(filled), th, 0, config={"N_theta_average": 2})
+    igm0 = th.lya_model.default_igm_params
+    c0 = like.get_chi2({})
+    c1 = like.get_chi2({"mF": igm0["mF"] * 0.97})
+    assert abs(c1 - c0) > 1.0, "IGM keys must not be dropped"
+    # oracle: an Arinyo-mode theory with the emulated values as explicit parameters
+    th_a = H.make_theory(2.4, "best_fit_arinyo_from_gadget", {"include_hcd": True}, cosmo=cosmo)
+    orc = OracleLikelihood.from_data(like.data, H.oracle_for(th_a), 0, 2)
+    for params in ({}, {"mF": igm0["mF"] * 0.97}, {"gamma": igm0["gamma"] + 0.1, "kF_Mpc": igm0["kF_Mpc"] * 1.05, "b_H": -0.03}):
+        lya = th.lya_model.get_lya_params(cosmo, params)
+        ref = orc.get_chi2(dict(lya, **{k: v for k, v in params.items() if k == "b_H"}))
+        assert_chi2(like.get_chi2(params), ref, "IGM scalar %s" % params, n_data=like.get_ndata())
+    rng = np.random.default_rng(3)
+    names = ["mF", "gamma", "b_H"]
+    pts = np.stack([igm0["mF"] * rng.uniform(0.95, 1.05, 40), igm0["gamma"] + rng.uniform(-0.1, 0.1, 40), rng.uniform(-0.03, -0.01, 40)], axis=1)
+    batch = like.get_chi2_batch(pts, names)
+    one = np.array([like.get_chi2(dict(zip(names, p))) for p in pts[:6]])
+    np.testing.assert_allclose(batch[:6], one, rtol=1e-9)
+    with pytest.raises(KeyError):
+        like.get_chi2_batch(pts[:, :2], ["mF", "bias"])

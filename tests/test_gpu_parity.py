@@ -525,3 +525,28 @@ def test_kpar0_reference_mode_on_device():
     np.testing.assert_array_equal(p0[:, 1:], p1[:, 1:])
     rel = np.abs(p0[:, 0] - p1[:, 0]) / np.abs(p0).max()
     assert 2e-5 < rel.max() < 1e-3                      # 1.7e-4 on the S1 shape (profiles/transform_choice_r02.txt)
+
+
+def test_theory_component_accessors_vs_oracle():
+    """The per-component Px accessors notebooks call (theory.py:126-247, 455-535) on the device path, against the
+    oracle's terms; their sum reproduces get_px_obs."""
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS["all"])
+    orc = H.oracle_for(th)
+    theta, k_AA = G["theta_arc"], G["k_AA"]
+    params = {"bias": -0.13, "beta": 1.4, "b_H": -0.03, "b_X": -0.007, "beta_X": 0.6, "b_noise_Mpc": 0.002, "kC_Mpc": 0.03}
+    from oracle.px_oracle import LR_LYA, LR_METAL
+    lya = orc._px_obs(theta, k_AA, orc.z, LR_LYA, lambda k, mu: orc.p3d_lya(k, mu, params))
+    hcd = orc._px_obs(theta, k_AA, orc.z, LR_LYA, lambda k, mu: orc.p3d_lya_hcd(k, mu, params))
+    auto = orc._px_obs(theta, k_AA, orc.z_metal_auto(), LR_METAL, lambda k, mu: orc.p3d_metal_auto(k, mu, params))
+    cross = orc._px_obs(theta, k_AA, orc.z_metal_cross(), np.sqrt(LR_METAL * LR_LYA), lambda k, mu: orc.p3d_metal_cross(k, mu, params))
+    scale = np.abs(hcd).max()
+    assert_px(th.get_px_lya_obs(theta, k_AA, params=params), lya, msg="lya")
+    assert_px(th.get_px_lya_hcd_obs(theta, k_AA, params=params), hcd, msg="lya + hcd")
+    assert np.abs(th.get_px_metal_auto_obs(theta, k_AA, params=params) - auto).max() <= PX_RTOL * scale
+    assert np.abs(th.get_px_metal_cross_obs(theta, k_AA, params=params) - cross).max() <= PX_RTOL * scale
+    assert np.abs(th.get_px_sky_obs(theta, k_AA, params=params) - orc.px_sky_obs(theta, k_AA, params)).max() <= PX_RTOL * scale
+    cont = th.get_continuum_distortion_obs(k_AA, params=params)
+    np.testing.assert_allclose(cont, orc.continuum_distortion_obs(k_AA, params), rtol=1e-14)
+    total = (th.get_px_lya_hcd_obs(theta, k_AA, params=params) + th.get_px_metal_auto_obs(theta, k_AA, params=params)
+             + th.get_px_metal_cross_obs(theta, k_AA, params=params) + th.get_px_sky_obs(theta, k_AA, params=params)) * cont[None, :]
+    assert_px(total, th.get_px_obs(theta, k_AA, params=params), tol=1e-7, msg="sum of the components")

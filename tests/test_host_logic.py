@@ -242,3 +242,79 @@ def test_forecast_writer_roundtrip(tmp_path):
     white = np.linalg.solve(np.linalg.cholesky(data.cov_ZAM[0]), (n1[0] - 0.1)[..., None])
     assert 0.5 < white.std() < 1.5
     assert set(data_to_dict(data)) >= {"Px_ZAM", "cov_ZAM", "U_ZaMn", "V_ZaM", "B_A_a", "z_centers"}
+
+
+def test_igm_mode_reemulates_per_call_and_keeps_igm_keys():
+    """IGM (emulator) mode, model_lya.py:175-235: every call re-emulates the Arinyo parameters from the IGM keys of
+    ``params``; they are not dropped.  The ForestFlow network is absent here: a mock with its interface."""
+    from cupix_b200.cosmology import Cosmology
+    from cupix_b200.likelihood.model_lya import LYA_PARAM_NAMES, lya_params_from_forestflow_params
+    from cupix_b200.likelihood.theory import Theory
+    from tests import helpers as H
+    emu = H.MockEmulator()
+    cosmo = Cosmology()
+    th = Theory(2.4, fid_cosmo=cosmo, config={"default_lya_model": "best_fit_igm_from_gadget", "emulator": emu, "n_q": 56})
+    lm = th.lya_model
+    assert lm.default_lya_params is None and set(lm.default_igm_params) >= {"mF", "gamma", "sigT_Mpc", "kF_Mpc"}
+    base = lm.get_lya_params(cosmo, {})
+    moved = lm.get_lya_params(cosmo, {"mF": lm.default_igm_params["mF"] * 0.9, "bias": -5.0})   # Arinyo keys are ignored here
+    assert set(base) == set(LYA_PARAM_NAMES) and moved["bias"] != base["bias"] and moved["bias"] != -5.0
+    lin = cosmo.get_linP_Mpc_params(z=2.4, kp_Mpc=0.7)
+    emu_in = dict(lm.default_igm_params, Delta2_p=lin["Delta2_p"], n_p=lin["n_p"])
+    assert base == lya_params_from_forestflow_params(emu.predict_Arinyos(emu_params=emu_in))
+    names, values = th.resolve_params(cosmo, {"gamma": 1.7, "b_H": -0.03, "not_a_key": 1.0})
+    assert names[:8] == list(LYA_PARAM_NAMES) and names[8:] == ["b_H"] and values.shape == (1, 9)
+    assert values[0, 1] == lm.get_lya_params(cosmo, {"gamma": 1.7})["beta"]
+    # the plan's defaults are the emulated values at the default IGM point
+    from cupix_b200 import plan as _plan
+    np.testing.assert_allclose(_plan.default_vector(th, cosmo)[:8], [base[k] for k in LYA_PARAM_NAMES], rtol=0)
+    # the batched emulator call (one network evaluation) equals the per-row calls
+    import torch
+    x = torch.tensor([[0.70, 1.4], [0.80, 1.6], [0.75, 1.5]], dtype=torch.float64)
+    ff = lm.emulate_lya_params_tensor(cosmo, ["mF", "gamma"], x)
+    for i in range(3):
+        one = emu.predict_Arinyos(emu_params=dict(emu_in, mF=float(x[i, 0]), gamma=float(x[i, 1])))
+        np.testing.assert_allclose(ff[i].numpy(), [one[k] for k in ("bias", "beta", "q1", "kvav", "av", "bv", "kp", "q2")], rtol=1e-14)
+
+
+def test_likelihood_parameter_helpers_mirror_the_reference():
+    """The legacy parameter helpers of cupix/likelihood/likelihood_parameter.py:4-141 (unit-cube mapping, list <-> dict,
+    `_iz` key formatting, look-ups), value by value as the reference defines them."""
+    from cupix_b200.likelihood import likelihood_parameter as LP
+    p = LP.LikelihoodParameter("bias", min_value=-0.2, max_value=0.0, value=-0.05, Gauss_priors_width=0.3)
+    assert p.value_in_cube() == pytest.approx(0.75) and p.get_value_in_cube(-0.1) == pytest.approx(0.5)
+    assert p.value_from_cube(0.25) == pytest.approx(-0.15) and p.err_from_cube(0.1) == pytest.approx(0.02)
+    q = p.get_new_parameter(0.5)
+    assert (q.name, q.min_value, q.max_value, q.Gauss_priors_width) == ("bias", -0.2, 0.0, 0.3) and q.value == pytest.approx(-0.1)
+    p.set_without_cube(-0.12)
+    assert p.value == -0.12 and p.info_str() == "bias = -0.12" and p.info_str(all_info=True) == "bias = -0.12 , -0.2 , 0.0"
+    with pytest.raises(AssertionError):
+        p.set_without_cube(0.1)
+    assert LP.dict_from_likeparam(None) == {} and LP.likeparam_from_dict(None) == []
+    lst = LP.likeparam_from_dict({"bias": -0.1, "beta": 1.5})
+    assert [(x.name, x.min_value, x.max_value, x.value) for x in lst] == [("bias", -1000, 1000, -0.1), ("beta", -1000, 1000, 1.5)]
+    assert lst[1].value_in_cube() == pytest.approx((1.5 + 1000) / 2000) and LP.dict_from_likeparam(lst) == {"bias": -0.1, "beta": 1.5}
+    assert LP.index_by_name(lst, "beta") == 1 and LP.par_index(lst, "bias") == 0 and LP.like_parameter_by_name(lst, "beta") is lst[1]
+    with pytest.raises(ValueError):
+        LP.par_index(lst, "q1")
+    assert LP.format_like_params_dict(2, {"bias": -0.1, "beta_2": 1.5}) == {"bias_2": -0.1, "beta_2": 1.5}
+    assert LP.format_like_params_dict([0, 1], {"bias_0": -0.1, "beta_1": 1.5, "q1": 0.3}) == {"bias_0": -0.1, "beta_1": 1.5}
+
+
+def test_batch_minimizer_stencil_stays_inside_the_bounds():
+    """No finite-difference stencil point is evaluated outside [lower, upper] (kp_Mpc <= 0 would be), and a
+    fit whose optimum sits on a bound still converges onto it."""
+    from cupix_b200.likelihood.batch_minimizer import BatchMinimizer
+
+    class Like(object):
+        seen_lo, seen_hi = np.inf, -np.inf
+
+        def get_chi2_batch(self, pts, names, data_idx=None):
+            Like.seen_lo, Like.seen_hi = min(Like.seen_lo, pts[:, 1].min()), max(Like.seen_hi, pts[:, 1].max())
+            assert np.all(pts[:, 1] > 0.0), "kp evaluated at or below zero"
+            return 50.0 * (pts[:, 0] - 1.0) ** 2 + 3.0 * (np.log(pts[:, 1]) - np.log(0.02)) ** 2 + (pts[:, 0] - 1.0) * (pts[:, 1] - 0.02) * 5
+
+    fit = BatchMinimizer(Like(), ["a", "kp"], steps=[0.01, 0.05], lower=[-5.0, 0.04], upper=[5.0, 30.0])
+    res = fit.minimize(np.array([[1.3, 0.06], [0.8, 2.0]]))
+    assert Like.seen_lo >= 0.04 and Like.seen_hi <= 30.0
+    assert np.all(np.abs(res["x"][:, 1] - 0.04) < 0.02) and np.all(np.abs(res["x"][:, 0] - 1.0) < 0.05)

@@ -160,3 +160,27 @@ def test_weights_are_cached_by_separation():
     assert np.array_equal(rule.weights(r, grp, wgt, 2), w2)
     assert not np.array_equal(rule.weights(r * 1.01, grp, wgt, 2), w2) and len(rule._weights_cache) == 2
     assert rule.weights(r).shape == (4, 64) and len(rule._weights_cache) == 3
+
+
+def test_jbar_hook_and_shared_rules():
+    """The J0 panel sums can be supplied from outside (the product path evaluates them on the GPU, cpx_hankel_jbar): a
+    NumPy stand-in with the same contract gives the weights of the built-in path; rules are shared per parameter set."""
+    from scipy.special import j0
+    from cupix_b200 import quadrature as Q
+
+    def jbar_np(start, r, w, kf, meas):
+        out = np.empty((len(start) - 1, kf.size))
+        for g in range(len(start) - 1):
+            sl = slice(start[g], start[g + 1])
+            out[g] = (w[sl, None] * j0(kf[None, :] * r[sl, None])).sum(axis=0) * meas / w[sl].sum()
+        return out
+    rule = KperpRule(56)
+    th = np.array([5.0, 1.0, 1.2, 5.5, 1.4, 6.0])              # groups not contiguous: the hook receives them sorted
+    grp = np.array([1, 0, 0, 1, 0, 1])
+    r = th / 0.6
+    a = rule.weights(r, grp, th, 2, nthreads=1)
+    b = rule.weights(r, grp, th, 2, jbar_fn=jbar_np)
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-13 * np.abs(a).max())
+    assert len(rule._weights_cache) == 2                       # the two paths never answer for each other
+    assert Q.get_rule(56) is Q.get_rule(56) and Q.get_rule(56) is not Q.get_rule(64)
+    assert Q.get_rule(128, refine=20.0, k_refine=0.5).refine == 20.0
