@@ -45,21 +45,60 @@ __host__ __device__ constexpr int basis_count(int flags) {
 // k_p3d_hankel_f64; the four m-tiles are walked one after the other so that only 3 x NT accumulators are live.
 // Output: Z.pxzam viewed as [tuple * nb + k][a][m_pad].
 // ------------------------------------------------------------------------------------------
-template <int NT>
+// STAGE: the float64 cell constants of the (z, tile) and the weights of the theta block are staged in shared memory and
+// shared by the 8 warps of the CTA (8 consecutive tuples); a CTA walks a contiguous range of (z, tile, theta block,
+// tuple group) items, so the 86 KB tile (n_q = 56) is reloaded only at tile boundaries.  Without STAGE (node sets whose
+// tile does not fit) every warp reads its constants through L1/L2.
+constexpr int kBasisWarps = 8;
+__host__ __device__ constexpr size_t basis_smem_bytes(int n_q4, int nt) {
+  return static_cast<size_t>(n_q4) * (kCellConsts * 4 * 32 + nt * 32) * sizeof(double);
+}
+
+template <int NT, bool STAGE>
 __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items, int nb) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) double sm_basis[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long it = wid; it < n_items; it += nwarps) {
+  const int n_grp = (count + kBasisWarps - 1) / kBasisWarps;           // tuple groups per (z, tile, theta block)
+  const long long it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_z = -1, cur_tile = -1, cur_ablk = -1;
+  for (long long it = it0; it < it1; ++it) {
     int zi = 0;
     while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
     const ZDev& Z = ztab[zi];
     long long r = it - Z.item_start;
-    const int tp = static_cast<int>(r % count);
-    r /= count;
+    const int grp = static_cast<int>(r % n_grp);
+    r /= n_grp;
     const int ablk = static_cast<int>(r % Z.n_ablk);
     const int tile = static_cast<int>(r / Z.n_ablk);
+    const int n_ks = Z.n_q4;
+    const double* cg = Z.cell64 + static_cast<size_t>(tile) * n_ks * (kCellConsts * 4 * 32);
+    const double* wg = Z.Wd + static_cast<size_t>(ablk) * n_ks * (NT * 32);
+    if (STAGE) {
+      double* const s_w = sm_basis + static_cast<size_t>(n_ks) * (kCellConsts * 4 * 32);
+      const bool new_tile = zi != cur_z || tile != cur_tile, new_w = zi != cur_z || ablk != cur_ablk;
+      if (new_tile || new_w) {
+        __syncthreads();                                                   // every warp is done with the previous tile
+        if (new_tile) {
+          const double2* src = reinterpret_cast<const double2*>(cg);
+          double2* dst = reinterpret_cast<double2*>(sm_basis);
+          for (int i = threadIdx.x; i < n_ks * (kCellConsts * 4 * 32) / 2; i += blockDim.x) dst[i] = src[i];
+        }
+        if (new_w) {
+          const double2* src = reinterpret_cast<const double2*>(wg);
+          double2* dst = reinterpret_cast<double2*>(s_w);
+          for (int i = threadIdx.x; i < n_ks * (NT * 32) / 2; i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
+        cur_z = zi;
+        cur_tile = tile;
+        cur_ablk = ablk;
+      }
+      cg = sm_basis;
+      wg = s_w;
+    }
+    const int tp = grp * kBasisWarps + warp;
+    if (tp >= count) continue;
     const int m_base = tile * kTileRows;
     const PtPar& pr = Z.ptpar[tp];
     const double q1 = pr.q1_64, q2 = pr.q2_64, av = pr.av_64, bv = pr.bv_64, l2kv = pr.l2kv_64, ikp2 = pr.ikp2_64;
@@ -76,9 +115,10 @@ __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab
       for (int jm = 0; jm < 3; ++jm)
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[jm][j][0] = acc[jm][j][1] = 0.0;
-      const double* c = Z.cell64 + static_cast<size_t>(tile) * Z.n_q4 * (kCellConsts * 4 * 32) + lane;
-      const double* wb = Z.Wd + static_cast<size_t>(ablk) * Z.n_q4 * (NT * 32) + lane;
-      for (int ks = 0; ks < Z.n_q4; ++ks) {
+      const double* c = cg + lane;
+      const double* wb = wg + lane;
+#pragma unroll 2
+      for (int ks = 0; ks < n_ks; ++ks) {
         double bfrag[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) bfrag[j] = wb[j * 32];
@@ -145,35 +185,49 @@ __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab
 // ------------------------------------------------------------------------------------------
 // k_gram: block = (tuple, z).  Y[(tuple * nb + k)][z][A][M] (the model-output layout of k_window) ->
 //   G[tuple][z][k][l] = sum_{A, M} Y_k Y_l,   g[tuple][z][d][k] = sum_{A, M} yd[d][A][M] Y_k
+// kGramAT coarse theta bins are staged per barrier pair; rows are padded to an odd stride so that the threads of a warp,
+// which hold different (k, l), read distinct banks.
 // ------------------------------------------------------------------------------------------
+constexpr int kGramAT = 4;
+__host__ __device__ constexpr int gram_row_stride(int nM_max) { return (kGramAT * (nM_max | 1)) | 1; }
+
 __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, const double* __restrict__ Y, int n_zl, int nA_max,
                                               int nM_max, int nb, int nd_max, double* __restrict__ G, double* __restrict__ gv) {
-  extern __shared__ double sY[];                       // [nb][nM_max]
+  extern __shared__ double sY[];                       // [nb][row stride]: row k holds kGramAT x (nM_max | 1) values
   const int tp = blockIdx.x, zi = blockIdx.y;
   const ZDev& Z = ztab[zi];
   const int tid = threadIdx.x;
-  const int nM = Z.n_M, nd = Z.n_data;
+  const int nM = Z.n_M, nd = Z.n_data, nA = Z.n_A;
+  const int LD = nM_max | 1, RS = gram_row_stride(nM_max);
   const int k = tid / nb, l = tid % nb;
   double acc = 0.0;
   double* const gz = gv + (static_cast<size_t>(tp) * n_zl + zi) * nd_max * nb;
-  for (int A = 0; A < Z.n_A; ++A) {
+  const size_t ystride = static_cast<size_t>(n_zl) * nA_max * nM_max;          // between basis tables of a tuple
+  const double* const Y0 = Y + (static_cast<size_t>(tp) * nb * n_zl + zi) * nA_max * nM_max;
+  for (int A0 = 0; A0 < nA; A0 += kGramAT) {
+    const int na = min(kGramAT, nA - A0);
     __syncthreads();
-    for (int i = tid; i < nb * nM; i += blockDim.x) {
-      const int kk = i / nM, M = i % nM;
-      sY[kk * nM_max + M] = Y[((static_cast<size_t>(tp) * nb + kk) * n_zl + zi) * nA_max * nM_max + static_cast<size_t>(A) * nM_max + M];
+    for (int i = tid; i < nb * na * nM; i += blockDim.x) {
+      const int M = i % nM, rest = i / nM;
+      const int a = rest % na, kk = rest / na;
+      sY[kk * RS + a * LD + M] = Y0[kk * ystride + static_cast<size_t>(A0 + a) * nM_max + M];
     }
     __syncthreads();
     if (tid < nb * nb) {
-      const double* yk = sY + k * nM_max;
-      const double* yl = sY + l * nM_max;
-      for (int M = 0; M < nM; ++M) acc = fma(yk[M], yl[M], acc);
+      for (int a = 0; a < na; ++a) {
+        const double* yk = sY + k * RS + a * LD;
+        const double* yl = sY + l * RS + a * LD;
+        for (int M = 0; M < nM; ++M) acc = fma(yk[M], yl[M], acc);
+      }
     }
     for (int item = tid; item < nd * nb; item += blockDim.x) {
       const int d = item / nb, kk = item % nb;
-      const double* yd = Z.yd + (static_cast<size_t>(d) * Z.n_A + A) * Z.n_M_pad;
-      const double* yk = sY + kk * nM_max;
-      double s = (A == 0) ? 0.0 : gz[item];
-      for (int M = 0; M < nM; ++M) s = fma(yd[M], yk[M], s);
+      double s = (A0 == 0) ? 0.0 : gz[item];
+      for (int a = 0; a < na; ++a) {
+        const double* yd = Z.yd + (static_cast<size_t>(d) * nA + A0 + a) * Z.n_M_pad;
+        const double* yk = sY + kk * RS + a * LD;
+        for (int M = 0; M < nM; ++M) s = fma(yd[M], yk[M], s);
+      }
       gz[item] = s;
     }
   }

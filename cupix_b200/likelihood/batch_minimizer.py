@@ -103,7 +103,9 @@ class BatchMinimizer(object):
             edm = 0.5 * np.abs(np.einsum("ni,ni->n", g, dx))         # estimated distance to minimum
             x[better], f0[better], g[better], H[better] = xt[better], ft[better], gt[better], Ht[better]
             lam = np.where(better, np.maximum(lam * 0.3, 1e-9), np.minimum(lam * 10.0, 1e9))
-            done |= better & (edm < tol)
+            # converged once the step the quadratic model proposes promises less than `tol` in chi2 -- whether or not the
+            # trial point was numerically "better": at the minimum of an exactly polynomial chi2 (the factorised path) it is not
+            done |= edm < tol
             if done.all():
                 break
         cov = np.full((N, self.P, self.P), np.nan)
