@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-grid", action="store_true", help="skip the factorised whole-grid scan (`grid` key)")
+    ap.add_argument("--no-precise", action="store_true", help="skip the short float64-cell measurement (`precise` key)")
     ap.add_argument("--precise", action="store_true", help="float64 P3D cells (CPX_PRECISE_CELLS, reference-precision mode)")
     a = ap.parse_args()
 
@@ -383,9 +384,24 @@ def main():
         pts_np, out_np = pts_host.numpy(), out_host.numpy()
         pts_np[:] = rng.uniform(lo, hi, size=pts_np.shape)
 
+        gath_pin = torch.empty(B * world, dtype=torch.float64).pin_memory() if world > 1 else None
+
         def step_host(i):
-            # H2D of this step's points + all kernels + D2H of chi2, inside cpx_eval (host-pointer mode)
-            eng.eval_host_into(pts_np[i], slots, zsel, out_np[i])
+            if world == 1:
+                # the public batched call: H2D of this step's points + all kernels + D2H of chi2 inside cpx_eval
+                # (host-pointer mode), result written into the caller's (pinned) array
+                joint.get_chi2_batch(pts_np[i], NAMES, out=out_np[i])
+            else:
+                # N ranks: the step's points go up from pinned memory, cpx_eval runs on device pointers, the chi2 of all
+                # ranks are gathered on the device (NCCL) and the gathered array comes down to pinned host memory
+                with torch.cuda.stream(stream):
+                    p_dev = pts_host[i].to(dev, non_blocking=True)
+                    eng.eval_device(B, len(NAMES), slots, points_ptr=p_dev.data_ptr(), zsel=zsel, chi2_ptr=chi2_dev.data_ptr(),
+                                    stream=stream.cuda_stream)
+                    dist.all_gather_into_tensor(gathered, chi2_dev)
+                    gath_pin.copy_(gathered, non_blocking=True)
+                    p_dev.record_stream(stream)
+                stream.synchronize()
         for i in range(a.warmup):
             step_host(i)
         sync_all()
@@ -399,7 +415,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": a.steps * B * world / dt, "unit": "evals/s", "h2d_bytes_per_step": B * len(NAMES) * 8,
-               "d2h_bytes_per_step": B * 8, "api": "PxEngine.eval_host_into = C ABI cpx_eval with pinned host buffers (what JointLikelihood.get_chi2_batch calls)"}
+               "d2h_bytes_per_step": B * 8 * world,
+               "api": "JointLikelihood.get_chi2_batch(points, names, out=pinned array) -> C ABI cpx_eval with host pointers" if world == 1
+               else "pinned points -> device, cpx_eval with device pointers, NCCL all_gather of chi2, gathered chi2 -> pinned host"}
 
     # ---- the same device-timed step at a second node count (the accuracy / cost knob of the Hankel rule) ----
     alt = None
@@ -434,6 +452,36 @@ def main():
                "steps": n_alt, "note": "same step, device-timed, with the round-1 node count; error of the node set vs the "
                                        "reference algorithm: cupix_b200.quadrature.RULES"}
         eng2.close()
+
+    # ---- the reference-precision mode of the general-points pipeline (float64 P3D cells, CPX_PRECISE_CELLS) ----
+    precise_rec = None
+    if not a.precise and not a.no_precise:
+        Bp = min(B, 1 << 14)
+        eng.precise = True
+        try:
+            for i in range(2):
+                eng.eval_device(Bp, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=i * Bp, zsel=zsel,
+                                chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, factor=False)
+            sync_all()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_p = 3
+            p0.record(stream)
+            for i in range(n_p):
+                eng.eval_device(Bp, len(NAMES), slots, grid=(lo, hi, GRID_N), grid_first=(2 + i) * Bp, zsel=zsel,
+                                chi2_ptr=chi2_dev.data_ptr(), stream=stream.cuda_stream, factor=False)
+            p1.record(stream)
+            sync_all()
+            pms = p0.elapsed_time(p1)
+        finally:
+            eng.precise = False
+        if world > 1:
+            t = torch.tensor([pms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = float(t.item())
+        precise_rec = {"value": n_p * Bp * world / (pms * 1e-3), "unit": "evals/s", "points_per_gpu_per_step": Bp, "steps": n_p,
+                       "ms_per_step": pms / n_p,
+                       "what": "general-points pipeline with float64 P3D cells (Theory config precise_cells / CPX_PRECISE_CELLS): "
+                               "chi2 within 1e-3 absolute of the oracle at any chi2"}
 
     # ---- the whole 4-parameter grid as ONE scan through the factorised path (cpx_factor.cuh) ----
     # Same 10 485 760 points, flattened with the tuple axes (q1, kp_Mpc) slowest so that a rank's contiguous slice holds
@@ -588,6 +636,15 @@ def main():
             dg = np.abs(g_np[flat - g_first] - r["chi2"])
             grid["parity"] = {"n": int(len(dg)), "against": parity["against"], "max_abs_dchi2": float(dg.max()),
                               "max_rel_dchi2": float((dg / np.abs(r["chi2"])).max()), "frac_within_1e-3": float(np.mean(dg <= 1e-3))}
+        if precise_rec is not None:
+            eng.precise = True
+            try:
+                gotp = eng.eval_host_into(np.ascontiguousarray(r["points"]), slots, zsel, np.empty(len(r["points"])), factor=False)
+            finally:
+                eng.precise = False
+            dp = np.abs(gotp - r["chi2"])
+            precise_rec["parity"] = {"n": int(len(dp)), "against": parity["against"], "max_abs_dchi2": float(dp.max()),
+                                     "max_rel_dchi2": float((dp / np.abs(r["chi2"])).max()), "frac_within_1e-3": float(np.mean(dp <= 1e-3))}
         if r.get("chi2_truth") is not None:
             # the grid applies one (bias, beta, q1, kp) to all 12 z, so all of it is far from the best fit of this
             # data; the per-z truth (no columns: every z at its own defaults) is the point inside chi2 <= 2 n_data
@@ -602,7 +659,7 @@ def main():
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "alt_n_q": alt, "setup_s": setup_s,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "alt_n_q": alt, "precise": precise_rec, "setup_s": setup_s,
             "per_point_z_rate": value * len(likes)}
     emit(line)
     if world > 1:

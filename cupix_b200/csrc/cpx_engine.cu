@@ -729,13 +729,17 @@ void decompose_range(long long first, long long B, int P, const int32_t* n, cons
 }
 
 typedef void (*KBasisFn)(const cpx::ZDev*, int, int, long long, int);
-KBasisFn kbasis_select(int nt, bool stage) {
+template <int W>
+KBasisFn kbasis_select_w(int nt, bool stage) {
   switch (nt) {
-    case 1: return stage ? cpx::k_basis_f64<1, true> : cpx::k_basis_f64<1, false>;
-    case 2: return stage ? cpx::k_basis_f64<2, true> : cpx::k_basis_f64<2, false>;
-    case 3: return stage ? cpx::k_basis_f64<3, true> : cpx::k_basis_f64<3, false>;
+    case 1: return stage ? cpx::k_basis_f64<1, true, W> : cpx::k_basis_f64<1, false, W>;
+    case 2: return stage ? cpx::k_basis_f64<2, true, W> : cpx::k_basis_f64<2, false, W>;
+    case 3: return stage ? cpx::k_basis_f64<3, true, W> : cpx::k_basis_f64<3, false, W>;
   }
   return nullptr;
+}
+KBasisFn kbasis_select(int nt, bool stage, int warps) {
+  return warps == 8 ? kbasis_select_w<8>(nt, stage) : kbasis_select_w<16>(nt, stage);
 }
 
 // Evaluates the call through the factorised path if it qualifies (*taken = true), else leaves it to the caller.
@@ -878,6 +882,7 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       }
   }
 
+  const int bwarps = env_int("CPX_BASIS_WARPS", 16) == 8 ? 8 : 16;       // tuples per CTA of k_basis_f64
   std::vector<ZDev> tab(n_zl);
   std::vector<double> tpts;
   bool same_window_shape = true;
@@ -916,13 +921,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         for (int i = 0; i < n_zl; ++i) {
           tab[i] = h->z[zl[i]].dev;
           tab[i].item_start = items;
-          items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * ((nt + kBasisWarps - 1) / kBasisWarps);
+          items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * ((nt + bwarps - 1) / bwarps);
         }
         CPX_CUDA(cudaMemcpyAsync(h->d_ztab, tab.data(), sizeof(ZDev) * n_zl, cudaMemcpyHostToDevice, st));
         last_nt = nt;
       }
       long long n_items = 0;
-      for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * ((nt + kBasisWarps - 1) / kBasisWarps);
+      for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * ((nt + bwarps - 1) / bwarps);
       pa.first = 0;
       pa.count = nt;
       k_params<<<dim3((nt + 127) / 128, n_zl), 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
@@ -933,10 +938,10 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         // the float64 tile of cell constants staged in shared memory when it fits (n_q <= 132 at 24 theta columns)
         const size_t bsmem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
         const bool stage = bsmem + 1024 <= 227u * 1024u && env_int("CPX_BASIS_STAGE", 1) != 0;
-        KBasisFn fn = kbasis_select(h->na_blk / 8, stage);
+        KBasisFn fn = kbasis_select(h->na_blk / 8, stage, bwarps);
         if (stage) CPX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bsmem)));
         const int grid = static_cast<int>(std::min<long long>(n_items, static_cast<long long>(h->sm_count) * (stage ? 1 : 4)));
-        fn<<<grid, 256, stage ? bsmem : 0, st>>>(h->d_ztab, n_zl, nt, n_items, nb);
+        fn<<<grid, 32 * bwarps, stage ? bsmem : 0, st>>>(h->d_ztab, n_zl, nt, n_items, nb);
         ++h->launches;
       }
       // ---- stage 2: whitened window of every basis table, Gram matrices ----
@@ -965,9 +970,11 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         } else {
           for (int i = 0; i < n_zl; ++i) window_launch(i, i, 1, tab[i].n_A);
         }
-        const size_t gsmem = sizeof(double) * nb * gram_row_stride(nM_max);
+        int at = nA_max;                              // coarse theta bins staged at once: all, if they fit 200 KB
+        while (at > 1 && sizeof(double) * nb * gram_row_stride(nM_max, at) > 200u * 1024u) at = (at + 1) / 2;
+        const size_t gsmem = sizeof(double) * nb * gram_row_stride(nM_max, at);
         if (gsmem > 48u * 1024u) CPX_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
-        k_gram<<<dim3(nt, n_zl), 256, gsmem, st>>>(h->d_ztab, h->d_model, n_zl, nA_max, nM_max, nb, nd_max, h->d_G, h->d_g);
+        k_gram<<<dim3(nt, n_zl), 256, gsmem, st>>>(h->d_ztab, h->d_model, n_zl, nA_max, nM_max, nb, nd_max, at, h->d_G, h->d_g);
         ++h->launches;
       }
       // ---- stage 3: quadratic form per point ----

@@ -46,19 +46,21 @@ __host__ __device__ constexpr int basis_count(int flags) {
 // Output: Z.pxzam viewed as [tuple * nb + k][a][m_pad].
 // ------------------------------------------------------------------------------------------
 // STAGE: the float64 cell constants of the (z, tile) and the weights of the theta block are staged in shared memory and
-// shared by the 8 warps of the CTA (8 consecutive tuples); a CTA walks a contiguous range of (z, tile, theta block,
+// shared by the 16 warps of the CTA (16 consecutive tuples); a CTA walks a contiguous range of (z, tile, theta block,
 // tuple group) items, so the 86 KB tile (n_q = 56) is reloaded only at tile boundaries.  Without STAGE (node sets whose
 // tile does not fit) every warp reads its constants through L1/L2.
-constexpr int kBasisWarps = 8;
+// WARPS = 16 (default): 4 warps per scheduler -- the cell evaluation is a long dependent chain (exp2 -> exp -> DMMA) -- at
+// 128 registers; WARPS = 8 keeps 160 registers and no spills (CPX_BASIS_WARPS selects)
 __host__ __device__ constexpr size_t basis_smem_bytes(int n_q4, int nt) {
   return static_cast<size_t>(n_q4) * (kCellConsts * 4 * 32 + nt * 32) * sizeof(double);
 }
 
-template <int NT, bool STAGE>
-__global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items, int nb) {
+template <int NT, bool STAGE, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_basis_f64(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items, int nb) {
   extern __shared__ __align__(16) double sm_basis[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
+  constexpr int kBasisWarps = WARPS;
   const int n_grp = (count + kBasisWarps - 1) / kBasisWarps;           // tuple groups per (z, tile, theta block)
   const long long it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1) / gridDim.x;
   int cur_z = -1, cur_tile = -1, cur_ablk = -1;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab
         for (int j = 0; j < NT; ++j) acc[jm][j][0] = acc[jm][j][1] = 0.0;
       const double* c = cg + lane;
       const double* wb = wg + lane;
-#pragma unroll 2
+#pragma unroll 1
       for (int ks = 0; ks < n_ks; ++ks) {
         double bfrag[NT];
 #pragma unroll
@@ -185,27 +187,28 @@ __global__ void __launch_bounds__(256) k_basis_f64(const ZDev* __restrict__ ztab
 // ------------------------------------------------------------------------------------------
 // k_gram: block = (tuple, z).  Y[(tuple * nb + k)][z][A][M] (the model-output layout of k_window) ->
 //   G[tuple][z][k][l] = sum_{A, M} Y_k Y_l,   g[tuple][z][d][k] = sum_{A, M} yd[d][A][M] Y_k
-// kGramAT coarse theta bins are staged per barrier pair; rows are padded to an odd stride so that the threads of a warp,
+// rows are padded to an odd stride so that the threads of a warp,
 // which hold different (k, l), read distinct banks.
 // ------------------------------------------------------------------------------------------
-constexpr int kGramAT = 4;
-__host__ __device__ constexpr int gram_row_stride(int nM_max) { return (kGramAT * (nM_max | 1)) | 1; }
+// `at` coarse theta bins are staged per barrier pair -- all of them when they fit (93 KB for 9 tables of 20 x 64): every
+// thread then has ~45 independent loads in flight and the block synchronises once
+__host__ __device__ constexpr int gram_row_stride(int nM_max, int at) { return (at * (nM_max | 1)) | 1; }
 
 __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, const double* __restrict__ Y, int n_zl, int nA_max,
-                                              int nM_max, int nb, int nd_max, double* __restrict__ G, double* __restrict__ gv) {
+                                              int nM_max, int nb, int nd_max, int at, double* __restrict__ G, double* __restrict__ gv) {
   extern __shared__ double sY[];                       // [nb][row stride]: row k holds kGramAT x (nM_max | 1) values
   const int tp = blockIdx.x, zi = blockIdx.y;
   const ZDev& Z = ztab[zi];
   const int tid = threadIdx.x;
   const int nM = Z.n_M, nd = Z.n_data, nA = Z.n_A;
-  const int LD = nM_max | 1, RS = gram_row_stride(nM_max);
+  const int LD = nM_max | 1, RS = gram_row_stride(nM_max, at);
   const int k = tid / nb, l = tid % nb;
   double acc = 0.0;
   double* const gz = gv + (static_cast<size_t>(tp) * n_zl + zi) * nd_max * nb;
   const size_t ystride = static_cast<size_t>(n_zl) * nA_max * nM_max;          // between basis tables of a tuple
   const double* const Y0 = Y + (static_cast<size_t>(tp) * nb * n_zl + zi) * nA_max * nM_max;
-  for (int A0 = 0; A0 < nA; A0 += kGramAT) {
-    const int na = min(kGramAT, nA - A0);
+  for (int A0 = 0; A0 < nA; A0 += at) {
+    const int na = min(at, nA - A0);
     __syncthreads();
     for (int i = tid; i < nb * na * nM; i += blockDim.x) {
       const int M = i % nM, rest = i / nM;

@@ -111,15 +111,15 @@ class Likelihood(object):
         return self.data.Px_ZAM[self.iz].size
 
     # ---- batched API (new) -------------------------------------------------------------------
-    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None):
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None, out=None):
         """chi2 [B] for ``points`` [B, P] whose columns are the parameters ``names``.  ``factor=False`` keeps every point
-        on the full pipeline (see PxEngine._flags)."""
+        on the full pipeline (see PxEngine._flags); ``out``: float64 array [B] to receive the result."""
         if self.theory.lya_model.default_igm_params is not None:
             assert not return_info, "return_info is not available in IGM (emulator) mode"
             return self._chi2_batch_igm(points, names, data_idx)
         slots, _ = slots_from_names(names)
         want = ("chi2", "chi2_zA") if return_info else ("chi2",)
-        out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx, factor=factor)
+        out = self.engine().eval(points=points, slots=slots, want=want, data_idx=data_idx, factor=factor, chi2_out=out)
         if return_info:
             return out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"][:, 0]}
         return out["chi2"]
@@ -243,10 +243,12 @@ class JointLikelihood(object):
     def get_ndata(self):
         return sum(lk.get_ndata() for lk in self.likes)
 
-    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None):
+    def get_chi2_batch(self, points, names, return_info=False, data_idx=None, factor=None, out=None):
+        """chi2 [B] summed over all z bins for ``points`` [B, P].  ``out``: float64 array [B] (e.g. pinned memory) to
+        receive the result instead of a fresh one."""
         slots, zsel = slots_from_names(names)
         want = ("chi2", "chi2_zA") if return_info else ("chi2",)
-        out = self.engine().eval(points=points, slots=slots, zsel=zsel, want=want, data_idx=data_idx, factor=factor)
+        out = self.engine().eval(points=points, slots=slots, zsel=zsel, want=want, data_idx=data_idx, factor=factor, chi2_out=out)
         return (out["chi2"], {'log_like_all': -0.5 * out["chi2_zA"]}) if return_info else out["chi2"]
 
     def get_chi2(self, params={}, return_info=False):
