@@ -92,7 +92,12 @@ struct cpx_handle {
   double* d_big_chi2 = nullptr;
   int* d_big_didx = nullptr;
   size_t cap_big_pts = 0, cap_big_chi2 = 0, cap_big_didx = 0;
-  long long factored_calls = 0, factored_tuples = 0;
+  long long factored_calls = 0, factored_tuples = 0, factored_cache_hits = 0;
+  // single-tuple calls (amplitude-only batches of samplers and minimisers, bias x beta scans) repeat the same tuple call
+  // after call: the Gram data of the last one is kept and re-used while its signature (tuple values, columns, z list,
+  // data epoch) matches -- such a call is then one k_quad launch
+  std::vector<double> basis_sig;
+  long long data_epoch = 0;
   // calls on different streams share the scratch: each call records ev_done, the next one on another stream waits for it
   cudaEvent_t ev_done = nullptr;
   cudaStream_t last_stream = nullptr;
@@ -142,6 +147,7 @@ int grow(cpx_handle* h, T** p, size_t* cap, size_t n) {
     h->device_bytes -= *cap * sizeof(T);
     *p = nullptr;
   }
+  h->basis_sig.clear();                  // cached Gram data may live in the buffer being replaced
   const size_t want = std::max(n, *cap + *cap / 2);
   CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
   h->owned.push_back(*p);
@@ -543,6 +549,7 @@ int upload_yd(cpx_handle* h, ZHost& zh, const double* Px_AM, int n_data) {
   Z.yd = dptr;
   Z.ydd = dptr2;
   Z.n_data = n_data;
+  ++h->data_epoch;
   return CPX_OK;
 }
 
@@ -779,6 +786,7 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
   for (const GridBox& b : boxes) tuples += b.n_tup;
   if (a->B < min_ratio * tuples) return CPX_OK;      // too few points per tuple for the (float64, 3-moment) tuple stage to pay
   *taken = true;
+  if (!(boxes.size() == 1 && boxes[0].n_tup == 1)) h->basis_sig.clear();     // this call overwrites the cached Gram data
 
   const int nb = basis_count(flags0);
   int nA_max = 0, nM_max = 0, nd_max = 0;
@@ -885,6 +893,9 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
   const int bwarps = env_int("CPX_BASIS_WARPS", 16) == 8 ? 8 : 16;       // tuples per CTA of k_basis_f64
   std::vector<ZDev> tab(n_zl);
   std::vector<double> tpts;
+  // signature of a single-tuple call (see cpx_handle::basis_sig); filled below once the tuple values are known
+  const bool single_tuple = boxes.size() == 1 && boxes[0].n_tup == 1 && env_int("CPX_BASIS_CACHE", 1) != 0;
+  std::vector<double> sig;
   bool same_window_shape = true;
   for (int i = 1; i < n_zl; ++i)
     same_window_shape &= h->z[zl[i]].dev.n_M_pad == h->z[zl[0]].dev.n_M_pad && h->z[zl[i]].dev.n_mblk == h->z[zl[0]].dev.n_mblk;
@@ -916,6 +927,20 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         }
         CPX_CUDA(cudaMemcpyAsync(h->d_tpts, tpts.data(), sizeof(double) * tpts.size(), cudaMemcpyHostToDevice, st));
       }
+      bool cached = false;
+      if (single_tuple) {
+        sig.assign(tpts.begin(), tpts.begin() + n_tcol);
+        for (int j = 0; j < n_tcol; ++j) {
+          sig.push_back(pa.slot[j]);
+          sig.push_back(pa.zsel[j]);
+        }
+        for (int zi : zl) sig.push_back(zi);
+        sig.push_back(static_cast<double>(h->data_epoch));
+        sig.push_back(flags0);
+        sig.push_back(nd_max);
+        cached = sig == h->basis_sig;
+        h->basis_sig.clear();                // re-armed after the call has been enqueued completely
+      }
       if (nt != last_nt) {
         long long items = 0;
         for (int i = 0; i < n_zl; ++i) {
@@ -930,11 +955,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       for (int i = 0; i < n_zl; ++i) n_items += static_cast<long long>(tab[i].n_tiles) * tab[i].n_ablk * ((nt + bwarps - 1) / bwarps);
       pa.first = 0;
       pa.count = nt;
-      k_params<<<dim3((nt + 127) / 128, n_zl), 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
-      ++h->launches;
+      if (!cached) {
+        k_params<<<dim3((nt + 127) / 128, n_zl), 128, 0, st>>>(pa, h->d_ztab, h->d_zlist);
+        ++h->launches;
+      }
       // ---- stage 1: float64 cells, three mu-moment Hankel sums, basis tables ----
       if ((rc = mark())) return rc;
-      {
+      if (!cached) {
         // the float64 tile of cell constants staged in shared memory when it fits (n_q <= 132 at 24 theta columns)
         const size_t bsmem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
         const bool stage = bsmem + 1024 <= 227u * 1024u && env_int("CPX_BASIS_STAGE", 1) != 0;
@@ -946,7 +973,7 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       }
       // ---- stage 2: whitened window of every basis table, Gram matrices ----
       if ((rc = mark())) return rc;
-      {
+      if (!cached) {
         const int npseudo = nt * nb;
         auto window_launch = [&](int i, int zslot, int gz, int nA_grid) {
           const ZDev& Z = tab[i];
@@ -970,9 +997,9 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         } else {
           for (int i = 0; i < n_zl; ++i) window_launch(i, i, 1, tab[i].n_A);
         }
-        int at = nA_max;                              // coarse theta bins staged at once: all, if they fit 200 KB
-        while (at > 1 && sizeof(double) * nb * gram_row_stride(nM_max, at) > 200u * 1024u) at = (at + 1) / 2;
-        const size_t gsmem = sizeof(double) * nb * gram_row_stride(nM_max, at);
+        // coarse theta bins staged per barrier pair: ~24 KB of shared memory (8 CTAs per SM)
+        const int at = std::max(1, std::min(nA_max, static_cast<int>(24576 / (sizeof(double) * nb * (nM_max | 1)))));
+        const size_t gsmem = std::max(sizeof(double) * nb * gram_row_stride(nM_max, at), sizeof(double) * 256);
         if (gsmem > 48u * 1024u) CPX_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
         k_gram<<<dim3(nt, n_zl), 256, gsmem, st>>>(h->d_ztab, h->d_model, n_zl, nA_max, nM_max, nb, nd_max, at, h->d_G, h->d_g);
         ++h->launches;
@@ -996,11 +1023,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
         ++h->launches;
       }
       if ((rc = mark())) return rc;
-      h->factored_tuples += nt;
+      if (cached) ++h->factored_cache_hits;
+      else h->factored_tuples += nt;
     }
   }
   ++h->factored_calls;
   CPX_CUDA(cudaGetLastError());
+  if (single_tuple) h->basis_sig = sig;
   if (!dev_io) CPX_CUDA(cudaMemcpyAsync(a->chi2, d_chi2, sizeof(double) * a->B, cudaMemcpyDeviceToHost, st));
   if (!dev_io || a->stage_ms) {
     cudaError_t e = cudaStreamSynchronize(st);
@@ -1239,6 +1268,7 @@ int cpx_generate_mocks(cpx_handle* h, int32_t P, const int32_t* slot, const int3
     Z.yd = d_yd;
     Z.ydd = d_ydd;
     Z.n_data = n_mocks;
+    ++h->data_epoch;
     if (mocks_zdAM) {     // data space: d = L yd
       yd_host.resize(per_data * n_mocks);
       CPX_CUDA(cudaMemcpy(yd_host.data(), d_yd, sizeof(double) * yd_host.size(), cudaMemcpyDeviceToHost));
@@ -1271,6 +1301,7 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
     case CPX_INFO_CHUNK_ALLOCATED: *value = h->chunk; break;
     case CPX_INFO_FACTORED_CALLS: *value = h->factored_calls; break;
     case CPX_INFO_FACTORED_TUPLES: *value = h->factored_tuples; break;
+    case CPX_INFO_FACTORED_CACHE_HITS: *value = h->factored_cache_hits; break;
     case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
     case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
     case CPX_INFO_SM_COUNT: *value = h->sm_count; break;

@@ -190,20 +190,25 @@ __global__ void __launch_bounds__(32 * WARPS) k_basis_f64(const ZDev* __restrict
 // rows are padded to an odd stride so that the threads of a warp,
 // which hold different (k, l), read distinct banks.
 // ------------------------------------------------------------------------------------------
-// `at` coarse theta bins are staged per barrier pair -- all of them when they fit (93 KB for 9 tables of 20 x 64): every
-// thread then has ~45 independent loads in flight and the block synchronises once
+// `at` coarse theta bins are staged per barrier pair (host: ~24 KB of shared memory, so that 8 CTAs per SM overlap each
+// other's loads; staging everything at once -- 93 KB, 2 CTAs per SM -- measured slower)
 __host__ __device__ constexpr int gram_row_stride(int nM_max, int at) { return (at * (nM_max | 1)) | 1; }
 
 __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, const double* __restrict__ Y, int n_zl, int nA_max,
                                               int nM_max, int nb, int nd_max, int at, double* __restrict__ G, double* __restrict__ gv) {
-  extern __shared__ double sY[];                       // [nb][row stride]: row k holds kGramAT x (nM_max | 1) values
+  extern __shared__ double sY[];                       // [nb][row stride]: row k holds `at` x (nM_max | 1) values; then the partial sums
   const int tp = blockIdx.x, zi = blockIdx.y;
   const ZDev& Z = ztab[zi];
   const int tid = threadIdx.x;
   const int nM = Z.n_M, nd = Z.n_data, nA = Z.n_A;
   const int LD = nM_max | 1, RS = gram_row_stride(nM_max, at);
-  const int k = tid / nb, l = tid % nb;
-  double acc = 0.0;
+  // every (k, l) pair is shared by n_seg threads, each taking every n_seg-th coarse-k column with four independent
+  // accumulators: 243 of 256 threads busy for 9 tables, and no 1280-long dependent chain of FMAs behind two loads each
+  const int n_pairs = nb * nb, n_seg = max(1, static_cast<int>(blockDim.x) / n_pairs);
+  const int pair = tid % n_pairs, seg = tid / n_pairs;
+  const bool dot = seg < n_seg;
+  const int k = pair / nb, l = pair % nb;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   double* const gz = gv + (static_cast<size_t>(tp) * n_zl + zi) * nd_max * nb;
   const size_t ystride = static_cast<size_t>(n_zl) * nA_max * nM_max;          // between basis tables of a tuple
   const double* const Y0 = Y + (static_cast<size_t>(tp) * nb * n_zl + zi) * nA_max * nM_max;
@@ -216,11 +221,18 @@ __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, con
       sY[kk * RS + a * LD + M] = Y0[kk * ystride + static_cast<size_t>(A0 + a) * nM_max + M];
     }
     __syncthreads();
-    if (tid < nb * nb) {
+    if (dot) {
       for (int a = 0; a < na; ++a) {
         const double* yk = sY + k * RS + a * LD;
         const double* yl = sY + l * RS + a * LD;
-        for (int M = 0; M < nM; ++M) acc = fma(yk[M], yl[M], acc);
+        int M = seg;
+        for (; M + 3 * n_seg < nM; M += 4 * n_seg) {
+          acc[0] = fma(yk[M], yl[M], acc[0]);
+          acc[1] = fma(yk[M + n_seg], yl[M + n_seg], acc[1]);
+          acc[2] = fma(yk[M + 2 * n_seg], yl[M + 2 * n_seg], acc[2]);
+          acc[3] = fma(yk[M + 3 * n_seg], yl[M + 3 * n_seg], acc[3]);
+        }
+        for (; M < nM; M += n_seg) acc[0] = fma(yk[M], yl[M], acc[0]);
       }
     }
     for (int item = tid; item < nd * nb; item += blockDim.x) {
@@ -234,7 +246,14 @@ __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, con
       gz[item] = s;
     }
   }
-  if (tid < nb * nb) G[(static_cast<size_t>(tp) * n_zl + zi) * nb * nb + tid] = acc;
+  __syncthreads();                                     // the staging area becomes [n_seg][n_pairs] partial sums
+  if (dot) sY[seg * n_pairs + pair] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (tid < n_pairs) {
+    double s = 0.0;
+    for (int sg = 0; sg < n_seg; ++sg) s += sY[sg * n_pairs + tid];
+    G[(static_cast<size_t>(tp) * n_zl + zi) * n_pairs + tid] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -188,8 +188,10 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
        CPX_INFO_GUARD_VIOLATIONS = 10,  /* guard-band bytes overwritten so far; synchronises the device            */
        CPX_INFO_FACTORED_CALLS = 11,    /* cpx_eval calls that took the factorised path                            */
        CPX_INFO_FACTORED_TUPLES = 12,   /* distinct tuples those calls evaluated (Hankel stage runs once per tuple)*/
-       CPX_INFO_CHUNK_ALLOCATED = 13    /* points the per-chunk scratch is currently sized for (grows on demand    */
-                                        /* up to CPX_INFO_CHUNK)                                                    */ };
+       CPX_INFO_CHUNK_ALLOCATED = 13,   /* points the per-chunk scratch is currently sized for (grows on demand    */
+                                        /* up to CPX_INFO_CHUNK)                                                    */
+       CPX_INFO_FACTORED_CACHE_HITS = 14 /* single-tuple factorised calls that re-used the previous call's Gram data */
+                                        /* (same tuple values, columns, z list and data vectors): one kernel launch */ };
 
 /* Set-up helper (no handle needed): the J0 part of the Hankel weights that stand for forestflow.pcross.Px_Mpc_detailed
  * (theory.py:250-264) with the theta sub-sampling average of likelihood.py:99-130 folded in.  For n_groups fine theta

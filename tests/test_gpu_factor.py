@@ -50,7 +50,7 @@ def test_bias_beta_scan_is_one_tuple():
     lo, hi, n = [d0[0] - 0.02, d0[1] - 0.2], [d0[0] + 0.02, d0[1] + 0.2], [128, 128]
     eng = like.engine()
     chi2 = like.get_chi2_grid(["bias", "beta"], lo, hi, n)
-    assert eng.info("factored_calls") == 1 and eng.info("factored_tuples") == 1
+    assert eng.info("factored_calls") == 1 and eng.info("factored_tuples") == 1 and eng.info("factored_cache_hits") == 0
     pts = _grid_points(lo, hi, n)
     orc = H.oracle_likelihood(like)
     for i in (0, 127, 128 * 64 + 64, 128 * 128 - 1, 5000, 11111):
@@ -59,6 +59,17 @@ def test_bias_beta_scan_is_one_tuple():
     # explicit points whose columns are all amplitude parameters take the same path, with the same numbers
     np.testing.assert_array_equal(like.get_chi2_batch(pts[4000:4100], ["bias", "beta"]), chi2[4000:4100])
     assert eng.info("factored_calls") == 2
+    # ... and, the tuple being the one of the previous call, re-use its Gram data: that call was a single kernel launch
+    assert eng.info("factored_cache_hits") == 1 and eng.info("factored_tuples") == 1
+    l0 = eng.info("kernel_launches")
+    like.get_chi2_batch(pts[:64], ["bias", "beta"])
+    assert eng.info("kernel_launches") == l0 + 1 and eng.info("factored_cache_hits") == 2
+    # new data vectors invalidate it
+    like.set_mock_data(like.data.Px_ZAM[0] * 1.01)
+    moved = like.get_chi2_batch(pts[4000:4100], ["bias", "beta"])
+    assert eng.info("factored_cache_hits") == 2 and np.abs(moved - chi2[4000:4100]).max() > 1e-3
+    like.restore_data()
+    np.testing.assert_array_equal(like.get_chi2_batch(pts[4000:4100], ["bias", "beta"]), chi2[4000:4100])
     # a rank-style slice of the grid
     np.testing.assert_array_equal(like.get_chi2_grid(["bias", "beta"], lo, hi, n, first=777, count=3000), chi2[777:3777])
     # against the full pipeline: float32 cells within its own tolerance, and few points stay on the full pipeline
