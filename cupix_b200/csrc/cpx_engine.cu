@@ -138,7 +138,7 @@ int scratch_alloc(cpx_handle* h, void** p, size_t bytes, bool per_chunk = false)
 
 // buffer of the factorised path that only ever grows (contents need not survive)
 template <typename T>
-int grow(cpx_handle* h, T** p, size_t* cap, size_t n) {
+int grow(cpx_handle* h, T** p, size_t* cap, size_t n, bool holds_cache = false) {
   if (n <= *cap && *p) return CPX_OK;
   if (*p) {
     CPX_CUDA(cudaDeviceSynchronize());
@@ -147,7 +147,7 @@ int grow(cpx_handle* h, T** p, size_t* cap, size_t n) {
     h->device_bytes -= *cap * sizeof(T);
     *p = nullptr;
   }
-  h->basis_sig.clear();                  // cached Gram data may live in the buffer being replaced
+  if (holds_cache) h->basis_sig.clear();   // the cached Gram data lives in the buffer being replaced
   const size_t want = std::max(n, *cap + *cap / 2);
   CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
   h->owned.push_back(*p);
@@ -812,8 +812,8 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
     if ((rc = scratch_alloc(h, reinterpret_cast<void**>(&h->d_model), static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM * sizeof(double), true)))
       return rc;
   const long long nt_alloc = std::min(nt_cap, max_tup);
-  if ((rc = grow(h, &h->d_G, &h->cap_G, static_cast<size_t>(nt_alloc) * n_zl * nb * nb))) return rc;
-  if ((rc = grow(h, &h->d_g, &h->cap_g, static_cast<size_t>(nt_alloc) * n_zl * nd_max * nb))) return rc;
+  if ((rc = grow(h, &h->d_G, &h->cap_G, static_cast<size_t>(nt_alloc) * n_zl * nb * nb, true))) return rc;
+  if ((rc = grow(h, &h->d_g, &h->cap_g, static_cast<size_t>(nt_alloc) * n_zl * nd_max * nb, true))) return rc;
   if ((rc = grow(h, &h->d_tpts, &h->cap_tpts, static_cast<size_t>(nt_alloc) * std::max(n_tcol, 1)))) return rc;
 
   // whole-batch staging in host-pointer mode
