@@ -318,3 +318,69 @@ def test_batch_minimizer_stencil_stays_inside_the_bounds():
     res = fit.minimize(np.array([[1.3, 0.06], [0.8, 2.0]]))
     assert Like.seen_lo >= 0.04 and Like.seen_hi <= 30.0
     assert np.all(np.abs(res["x"][:, 1] - 0.04) < 0.02) and np.all(np.abs(res["x"][:, 0] - 1.0) < 0.05)
+
+
+def test_hdf5_layout_round_trip_and_reference_reader(monkeypatch):
+    """The HDF5 branches of the reader / writer / forecast writer (data_DESI_DR2.py:66-99 layout) executed against an
+    in-memory h5py stand-in (h5py is not installed here): our writer -> our reader, and -- where /root/reference is
+    present -- our writer -> the REFERENCE's own DESI_DR2 reader, array for array."""
+    import importlib
+    import os
+    import sys
+    import types
+    from tests import fake_h5py
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    from cupix_b200.px_data import synthetic
+    from cupix_b200.px_data.data_DESI_DR2 import DESI_DR2, write_px_file
+    d = synthetic.make_measurement_dict("tiny_rebin")
+    rng = np.random.default_rng(2)
+    d["Px_ZAM"] = rng.normal(size=d["Px_ZAM"].shape)
+    d["cov_ZAM"] = d["cov_ZAM"] * rng.uniform(1, 2, size=d["cov_ZAM"].shape[:2])[:, :, None, None]
+    write_px_file("/fake/px_measurement.hdf5", d, extra_attrs={"note": "unit test"})
+    a = DESI_DR2("/fake/px_measurement.hdf5")
+    b = DESI_DR2(d)
+    for name in ("Px_ZAM", "cov_ZAM", "U_ZaMn", "V_ZaM", "B_A_a", "k_m", "k_M_edges", "z", "theta_min_a_arcmin", "theta_max_A_arcmin"):
+        np.testing.assert_array_equal(np.asarray(getattr(a, name)), np.asarray(getattr(b, name)), err_msg=name)
+    cut = DESI_DR2("/fake/px_measurement.hdf5", theta_min_cut_arcmin=1.0, kM_max_cut_AA=0.2, km_max_cut_AA=0.22)
+    assert cut.U_ZaMn.shape == DESI_DR2(d, theta_min_cut_arcmin=1.0, kM_max_cut_AA=0.2, km_max_cut_AA=0.22).U_ZaMn.shape
+    # forecast writer, HDF5 flavour (generate_forecast_data.py:132-173): model parameters stored per z next to P_Z_AM
+    from cupix_b200.px_data.data_DESI_DR2 import write_forecast
+
+    class _Like(object):
+        def __init__(self, iz):
+            self.iz, self.data = iz, a
+            lm = type("L", (), {"default_lya_model": "best_fit_arinyo_from_colore", "default_lya_params": {"bias": -0.115, "beta": 1.5}})()
+            self.theory = type("T", (), {"lya_model": lm})()
+
+        def get_convolved_px(self, params={}):
+            return np.full(a.Px_ZAM[self.iz].shape, 0.25 * (self.iz + 1))
+    px = write_forecast([_Like(0), _Like(1)], "/fake/forecast.hdf5", params={"beta": 1.6})
+    back = DESI_DR2("/fake/forecast.hdf5")
+    np.testing.assert_array_equal(back.Px_ZAM, px)
+    np.testing.assert_array_equal(back.U_ZaMn, a.U_ZaMn)
+    with fake_h5py.File("/fake/forecast.hdf5", "r") as f:
+        assert f["P_Z_AM/z_1"].attrs["default_lya_model"] == "best_fit_arinyo_from_colore"
+        assert f["P_Z_AM/z_0/lya_params"].attrs["beta"] == 1.5 and bool(f["metadata"].attrs["forecast_add_noise"]) is False
+    ref_file = "/root/reference/cupix/px_data/data_DESI_DR2.py"
+    if not os.path.exists(ref_file):
+        return                                      # the GPU box has no /root/reference; the first half ran
+    pkg = types.ModuleType("cupix")
+    pkg.__path__ = ["/root/reference/cupix"]
+    mpl = types.ModuleType("matplotlib")
+    mpl.__path__ = []
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    mpl.colors = types.ModuleType("matplotlib.colors")
+    mpl.colors.ListedColormap = object
+    for name, mod in (("cupix", pkg), ("matplotlib", mpl), ("matplotlib.pyplot", mpl.pyplot), ("matplotlib.colors", mpl.colors)):
+        if name == "cupix" or name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mod)
+    for name in ("cupix.px_data", "cupix.px_data.base_px_data", "cupix.px_data.data_DESI_DR2"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    ref = importlib.import_module("cupix.px_data.data_DESI_DR2")
+    r = ref.DESI_DR2("/fake/px_measurement.hdf5")
+    for ours, theirs in (("Px_ZAM", "Px_ZAM"), ("cov_ZAM", "cov_ZAM"), ("U_ZaMn", "U_ZaMn"), ("V_ZaM", "V_ZaM"), ("B_A_a", "B_A_a"),
+                         ("k_m", "k_m"), ("k_M_edges", "k_M_edges"), ("z", "z")):
+        np.testing.assert_array_equal(np.asarray(getattr(a, ours)), np.asarray(getattr(r, theirs)), err_msg="reference reader: " + ours)
+    for name in list(sys.modules):
+        if name == "cupix" or name.startswith("cupix."):
+            monkeypatch.delitem(sys.modules, name, raising=False)
