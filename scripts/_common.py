@@ -22,6 +22,7 @@ def dist_setup():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()            # builds the NCCL communicator now, not inside the first timed gather
     return rank, world, local
 
 
