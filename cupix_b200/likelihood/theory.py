@@ -181,6 +181,46 @@ class Theory(object):
         kp_Mpc = np.asarray(k_AA, dtype=np.float64) * cosmo.get_dAA_dMpc(self.z, lambda_rest_AA=self.lya_model.lr_lya)
         return np.tanh((kp_Mpc / cp["kC_Mpc"]) ** cp["pC"])
 
+    # -- the P3D models as plain functions of (k, mu) (theory.py:285-344, 361-438), for plots and diagnostics: the device
+    #    evaluates the same expressions on its (k_par, k_perp) cell grid and never hands P3D itself out
+    def _lya_and_linP(self, k, cosmo, params, z=None):
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        return cosmo, self.lya_model.get_lya_params(cosmo, params), cosmo.get_linP_Mpc(self.z if z is None else z, k)
+
+    @staticmethod
+    def _dnl(k, mu, linP, lp):
+        d2 = k ** 3 * linP / (2.0 * np.pi ** 2)
+        growth = d2 * (lp["q1"] + lp["q2"] * d2)
+        damping = (k / lp["kv_Mpc"]) ** lp["av"] * mu ** lp["bv"]
+        return np.exp(growth * (1.0 - damping) - (k / lp["kp_Mpc"]) ** 2)
+
+    def get_p3d_lya_Mpc(self, k, mu, cosmo=None, params={}):
+        _, lp, linP = self._lya_and_linP(k, cosmo, params)
+        return (lp["bias"] * (1.0 + lp["beta"] * mu ** 2)) ** 2 * linP * self._dnl(k, mu, linP, lp)
+
+    def get_p3d_lya_hcd_Mpc(self, k, mu, cosmo=None, params={}):
+        _, lp, linP = self._lya_and_linP(k, cosmo, params)
+        hp = self.cont_model.get_hcd_params(params)
+        F = np.exp(-k * mu * hp["L_H_Mpc"])
+        b_T = lp["bias"] + hp["b_H"] * F
+        bbeta_T = lp["bias"] * lp["beta"] + hp["b_H"] * hp["beta_H"] * F
+        return (b_T + bbeta_T * mu ** 2) ** 2 * linP * self._dnl(k, mu, linP, lp)
+
+    def get_p3d_metal_auto_Mpc(self, k, mu, cosmo=None, params={}):
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        mp = self.cont_model.get_metal_params(params)
+        linP = cosmo.get_linP_Mpc(self.get_z_metal_auto(), k)
+        return (mp["b_X"] * (1.0 + mp["beta_X"] * mu ** 2)) ** 2 * linP * np.exp(-(k / _plan.METAL_KP_MPC) ** 2)
+
+    def get_p3d_metal_cross_Mpc(self, k, mu, cosmo=None, params={}):
+        cosmo, lp, _ = self._lya_and_linP(k, cosmo, params)
+        mp = self.cont_model.get_metal_params(params)
+        zc = self.get_z_metal_cross()
+        lr_x = np.sqrt(self.lya_model.lr_lya * self.cont_model.lr_metal)
+        dr_Mpc = np.log(self.lya_model.lr_lya / self.cont_model.lr_metal) * (1.0 + zc) * lr_x / cosmo.get_dAA_dMpc(zc, lambda_rest_AA=lr_x)
+        kaiser = lp["bias"] * mp["b_X"] * (1.0 + lp["beta"] * mu ** 2) * (1.0 + mp["beta_X"] * mu ** 2)
+        return kaiser * cosmo.get_linP_Mpc(zc, k) * np.exp(-(k / _plan.METAL_KP_MPC) ** 2) * 2.0 * np.cos(k * mu * dr_Mpc)
+
     def get_px_obs_batch(self, theta_arc, k_AA, points, names, cosmo=None):
         """Px [B, N_theta, N_k] for B parameter points (columns named by ``names``)."""
         cosmo = self.fid_cosmo if cosmo is None else cosmo

@@ -190,6 +190,19 @@ def test_emulator_tensor_handoff():
                                ["bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc"])
     torch.cuda.synchronize()
     np.testing.assert_allclose(chi2_t.cpu().numpy(), host, rtol=1e-9)
+    # a large batch produced and consumed on torch's default stream with no global synchronisation in between: the
+    # engine runs on the stream it is given (handle 0 = the legacy default stream) and torch's kernels on either side
+    # are ordered with it (the handle's private non-blocking stream was not)
+    Bb = 60000
+    big = torch.from_numpy(np.tile(ff, (Bb // B, 1))).cuda()
+    big = big * (1.0 + 1e-3 * torch.sin(torch.arange(Bb, device=big.device, dtype=torch.float64))[:, None])     # device-side producer
+    out = like.get_chi2_from_arinyo_tensor(big)
+    total = float(out.sum())                                       # device-side consumer, then the D2H of a scalar
+    bn = big.cpu().numpy()
+    kvb = np.exp(np.log(bn[:, 3]) / bn[:, 4])
+    ref = like.get_chi2_batch(np.stack([bn[:, 0], bn[:, 1], bn[:, 2], bn[:, 7], kvb, bn[:, 4], bn[:, 5], bn[:, 6]], axis=1),
+                              ["bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc"])
+    assert total == pytest.approx(ref.sum(), rel=1e-10)
 
 
 def test_igm_emulator_mode_end_to_end():

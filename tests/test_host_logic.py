@@ -384,3 +384,18 @@ def test_hdf5_layout_round_trip_and_reference_reader(monkeypatch):
     for name in list(sys.modules):
         if name == "cupix" or name.startswith("cupix."):
             monkeypatch.delitem(sys.modules, name, raising=False)
+
+
+def test_p3d_model_functions_equal_the_oracle():
+    """Theory.get_p3d_*_Mpc (theory.py:298-308, 325-344, 361-381, 398-438), the P3D models as functions of (k, mu) that
+    notebooks plot, against the oracle's restatement of the same reference lines."""
+    from tests import helpers as H
+    from tests.golden.ref_theory_param_sets import FLAG_SETS
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS["all"])
+    orc = H.oracle_for(th)
+    rng = np.random.default_rng(0)
+    k, mu = rng.uniform(0.01, 5.0, 64), rng.uniform(0.0, 1.0, 64)
+    params = {"bias": -0.13, "beta": 1.4, "q1": 0.5, "b_H": -0.03, "L_H_Mpc": 6.0, "b_X": -0.007, "beta_X": 0.6}
+    for ours, theirs in ((th.get_p3d_lya_Mpc, orc.p3d_lya), (th.get_p3d_lya_hcd_Mpc, orc.p3d_lya_hcd),
+                         (th.get_p3d_metal_auto_Mpc, orc.p3d_metal_auto), (th.get_p3d_metal_cross_Mpc, orc.p3d_metal_cross)):
+        np.testing.assert_allclose(ours(k, mu, params=params), theirs(k, mu, params), rtol=1e-13)
