@@ -374,6 +374,12 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     if (!d.metal_auto || !d.metal_cross) return fail(CPX_ERR_ARG, "include_metal set but metal tables are NULL");
     if ((rc = up_copy(d.metal_auto, 3ull * d.n_a * d.n_m, &Z.metal_auto))) return rc;
     if ((rc = up_copy(d.metal_cross, 3ull * d.n_a * d.n_m, &Z.metal_cross))) return rc;
+    if (d.metal_auto_dn && d.metal_cross_dn && d.metal_dn_order > 0) {
+      const size_t n = static_cast<size_t>(d.metal_dn_order + 1) * 3ull * d.n_a * d.n_m;
+      if ((rc = up_copy(d.metal_auto_dn, n, &Z.metal_auto_dn))) return rc;
+      if ((rc = up_copy(d.metal_cross_dn, n, &Z.metal_cross_dn))) return rc;
+      Z.metal_dn_order = d.metal_dn_order;
+    }
   }
   if (d.flags & CPX_INCLUDE_SKY) {
     if (!d.sky_xi_a || !d.sky_smooth_m) return fail(CPX_ERR_ARG, "include_sky set but sky tables are NULL");
@@ -1350,9 +1356,10 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     for (auto& zh : h->z) {
       if (!(zh.dev.k_pivot > 0.0))
         return fail(CPX_ERR_UNSUPPORTED, "cpx_eval: As / ns columns need k_pivot_Mpc and the default As of the plan's cosmology");
-      // the SiIII tables are Hankel moments of P_L at other redshifts: an amplitude factors out of them, a tilt does not
-      if (tilt && (zh.dev.flags & CPX_INCLUDE_METAL))
-        return fail(CPX_ERR_UNSUPPORTED, "cpx_eval: ns as a batch column is not available with include_metal (rebuild the plan per ns instead)");
+      // the SiIII tables are Hankel moments of P_L at other redshifts: an amplitude factors out of them, a tilt does not --
+      // it needs their Taylor tables in the tilt (cpx_zbin_desc::metal_auto_dn / metal_cross_dn)
+      if (tilt && (zh.dev.flags & CPX_INCLUDE_METAL) && !(zh.dev.metal_auto_dn && zh.dev.metal_cross_dn))
+        return fail(CPX_ERR_UNSUPPORTED, "cpx_eval: ns as a batch column with include_metal needs the tilt tables metal_auto_dn / metal_cross_dn in the descriptor");
     }
   if (a->B == 0) return CPX_OK;
   CPX_CUDA(cudaSetDevice(h->device));

@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_basis_f64(const ZDev* __restrict
             const double f = cont * pr.lin_amp;
 #pragma unroll
             for (int jm = 0; jm < 3; ++jm) {
-              o[static_cast<size_t>(k + jm) * tab] = row_ok ? f * Z.metal_auto[om + jm * st] : 0.0;
-              o[static_cast<size_t>(k + 3 + jm) * tab] = row_ok ? f * Z.metal_cross[om + jm * st] : 0.0;
+              o[static_cast<size_t>(k + jm) * tab] =
+                  row_ok ? f * metal_moment(Z.metal_auto, Z.metal_auto_dn, Z.metal_dn_order, om, st, jm, pr.dn_64) : 0.0;
+              o[static_cast<size_t>(k + 3 + jm) * tab] =
+                  row_ok ? f * metal_moment(Z.metal_cross, Z.metal_cross_dn, Z.metal_dn_order, om, st, jm, pr.dn_64) : 0.0;
             }
             k += 6;
           }

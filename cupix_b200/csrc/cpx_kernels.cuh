@@ -76,6 +76,9 @@ struct ZDev {
   const double* kpar_row;               // [n_m_pad]  k_par of the continuum distortion (differs only in kpar0 = 'reference' mode)
   const double* metal_auto;             // [3][n_a][n_m] or null
   const double* metal_cross;            // [3][n_a][n_m] or null
+  const double* metal_auto_dn;          // [metal_dn_order + 1][3][n_a][n_m] Taylor terms of metal_auto in the tilt dn, or null
+  const double* metal_cross_dn;         // same for metal_cross
+  int metal_dn_order, pad_dn;
   const double* sky_xi;                 // [n_a] or null
   const double* sky_smooth;             // [n_m] or null
   double defaults[18];
@@ -393,6 +396,17 @@ __device__ __forceinline__ float2 exp2_fl2(float2 x) {
   return make_float2(exp2_scale(ex2_approx(f.x), t.x), exp2_scale(ex2_approx(f.y), t.y));
 }
 
+// SiIII Hankel moment j of theta bin / row `o` (stride `st` between moments) for a point whose primordial tilt differs by dn
+// from the plan's cosmology: Horner in dn over the Taylor tables (plan.METAL_TILT_ORDER), the plain table when dn == 0
+__device__ __forceinline__ double metal_moment(const double* __restrict__ tab0, const double* __restrict__ tab_dn, int order,
+                                               size_t o, size_t st, int j, double dn) {
+  if (dn == 0.0 || tab_dn == nullptr) return tab0[o + j * st];
+  const double* t = tab_dn + j * st + o;
+  double s = t[static_cast<size_t>(order) * 3 * st];
+  for (int n = order - 1; n >= 0; --n) s = fma(s, dn, t[static_cast<size_t>(n) * 3 * st]);
+  return s;
+}
+
 // advance (zi, tile, ablk, pg) to the next work item without divisions
 __device__ __forceinline__ void next_item(const ZDev& Z, int n_pg, int& zi, int& tile, int& ablk, int& pg) {
   if (++pg == n_pg) {
@@ -652,9 +666,20 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
               if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
                 const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
                 const double bx = pr.b_X, btx = pr.beta_X;
-                add += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
-                add += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
-                                       pr.beta * btx * Z.metal_cross[o + 2 * st]);
+                if (COSMO && pr.dn_64 != 0.0) {      // tilted primordial power: metal moments from their Taylor tables in dn
+                  const double dn = pr.dn_64;
+                  const int ord = Z.metal_dn_order;
+                  add += bx * bx * (metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 0, dn) +
+                                    2.0 * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 1, dn) +
+                                    btx * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 2, dn));
+                  add += pr.bias * bx * (metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 0, dn) +
+                                         (pr.beta + btx) * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 1, dn) +
+                                         pr.beta * btx * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 2, dn));
+                } else {
+                  add += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+                  add += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
+                                         pr.beta * btx * Z.metal_cross[o + 2 * st]);
+                }
                 if (COSMO) add *= pr.lin_amp;
               }
               if (Z.flags & 4) add += sky * Z.sky_xi[a];
@@ -761,9 +786,14 @@ __global__ void __launch_bounds__(256) k_p3d_hankel_f64(const ZDev* __restrict__
             if (Z.flags & 2) {
               const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
               const double bx = pr.b_X, btx = pr.beta_X;
-              double ma = bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
-              double mc = pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] +
-                                          pr.beta * btx * Z.metal_cross[o + 2 * st]);
+              const double dn = pr.dn_64;
+              const int ord = Z.metal_dn_order;
+              double ma = bx * bx * (metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 0, dn) +
+                                     2.0 * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 1, dn) +
+                                     btx * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 2, dn));
+              double mc = pr.bias * bx * (metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 0, dn) +
+                                          (pr.beta + btx) * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 1, dn) +
+                                          pr.beta * btx * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 2, dn));
               if (cosmo) {
                 ma *= pr.lin_amp;
                 mc *= pr.lin_amp;

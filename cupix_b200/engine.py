@@ -32,6 +32,7 @@ class ZbinDesc(C.Structure):
         ("B_A_a", c_dp), ("U_aMn", c_dp), ("V_aM", c_dp), ("Px_AM", c_dp), ("cov_AMM", c_dp),
         ("k_pivot_Mpc", C.c_double),
         ("kpar_row_Mpc", c_dp),
+        ("metal_auto_dn", c_dp), ("metal_cross_dn", c_dp), ("metal_dn_order", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -141,13 +142,15 @@ class PxEngine(object):
         for d, p in zip(descs, self.plans):
             arrs = {k: _f64(getattr(p, k)) for k in
                     ("kpar_Mpc", "kperp_Mpc", "hankel_w", "linP_cell", "metal_auto", "metal_cross",
-                     "sky_xi_a", "sky_smooth_m", "B_A_a", "U_aMn", "V_aM", "Px_AM", "cov_AMM", "kpar_row_Mpc")}
+                     "sky_xi_a", "sky_smooth_m", "B_A_a", "U_aMn", "V_aM", "Px_AM", "cov_AMM", "kpar_row_Mpc",
+                     "metal_auto_dn", "metal_cross_dn")}
             self._keep.append(arrs)
             d.n_a, d.n_m, d.n_q = p.n_a, p.n_m, p.n_q
             d.n_A, d.n_M, d.n_data = p.n_A, p.n_M, p.n_data
             d.flags = p.flags
             d.dAA_dMpc = p.dAA_dMpc
             d.k_pivot_Mpc = float(getattr(p, "k_pivot_Mpc", 0.0))
+            d.metal_dn_order = int(getattr(p, "metal_dn_order", 0))
             for k, v in arrs.items():
                 setattr(d, k, _dp(v))
             for i in range(NSLOTS):

@@ -29,6 +29,10 @@ INCLUDE_HCD, INCLUDE_METAL, INCLUDE_SKY, INCLUDE_CONTINUUM = 1, 2, 4, 8
 METAL_KP_MPC = 10.0      # theory.py:378,421
 PIXEL_AA = 0.8           # theory.py:495
 KPAR0_REFERENCE_MPC = 1e-4   # lyaP3D.py:35-39: what the reference's in-tree Px path substitutes for k_par = 0
+# ns as a batch column with SiIII on: the tilt (k / k_pivot)^dn does not factor out of the metal Hankel moments, so they are
+# carried as a Taylor series in dn = ns - ns0: table_n = moments of P_L (ln k/k_pivot)^n / n!.  Order 8 keeps the series
+# within 1.4e-5 of the metal term (1e-6 of Px) for |dn ln(k/k_pivot)| <= 1.2, i.e. |ns - ns0| <= 0.2 over the k that matter.
+METAL_TILT_ORDER = 8
 
 
 class ZbinPlan(object):
@@ -37,6 +41,8 @@ class ZbinPlan(object):
     n_M = 0
     n_data = 0
     metal_auto = metal_cross = sky_xi_a = sky_smooth_m = None
+    metal_auto_dn = metal_cross_dn = None
+    metal_dn_order = 0
     kpar_row_Mpc = None
     B_A_a = U_aMn = V_aM = Px_AM = cov_AMM = None
 
@@ -156,7 +162,7 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None, de
         z_auto = theory.get_z_metal_auto()
         z_cross = theory.get_z_metal_cross()
         lr_cross = np.sqrt(lr_metal * lr_lya)
-        tabs = []
+        tabs, dn_tabs = [], []
         for zz, lr, wiggle in ((z_auto, lr_metal, False), (z_cross, lr_cross, True)):
             darc_x = cosmo.get_darc_dMpc(zz)
             dAA_x = cosmo.get_dAA_dMpc(zz, lambda_rest_AA=lr)
@@ -165,12 +171,26 @@ def build_theory_plan(theory, cosmo, theta_arc, theta_group, k_AA, rule=None, de
             kx, mux = _cells(kpar_x, rule.k)
             base = _linP_on_cells(cosmo, zz, kx) * np.exp(-(kx / METAL_KP_MPC) ** 2)  # [n_m, n_q]
             mom = np.stack([W_x @ (base * mux ** (2 * j)).T for j in range(3)]) * dAA_x   # [3, n_a, n_m]
+            phase = 1.0
             if wiggle:
                 dX_AA = np.log(lr_lya / lr_metal) * (1 + zz) * lr
                 drp_Mpc = dX_AA / dAA_x
-                mom = mom * (2.0 * np.cos(kpar_x * drp_Mpc))[None, None, :]
+                phase = (2.0 * np.cos(kpar_x * drp_Mpc))[None, None, :]
+                mom = mom * phase
             tabs.append(np.ascontiguousarray(mom))
+            if p.k_pivot_Mpc > 0:
+                # Taylor terms of the tilt: moments of P_L (ln k / k_pivot)^n / n!, n = 0 .. METAL_TILT_ORDER
+                with np.errstate(divide="ignore"):
+                    lnk = np.where(kx > 0, np.log(np.where(kx > 0, kx, 1.0) / p.k_pivot_Mpc), 0.0)
+                series, term = [], base
+                for n in range(METAL_TILT_ORDER + 1):
+                    series.append(np.stack([W_x @ (term * mux ** (2 * j)).T for j in range(3)]) * dAA_x * phase)
+                    term = term * lnk / (n + 1)
+                dn_tabs.append(np.ascontiguousarray(np.stack(series)))                     # [order + 1, 3, n_a, n_m]
         p.metal_auto, p.metal_cross = tabs
+        if dn_tabs:
+            p.metal_auto_dn, p.metal_cross_dn = dn_tabs
+            p.metal_dn_order = METAL_TILT_ORDER
 
     if inc_sky:
         xi = theory.cont_model.get_xi_noise(theta_arc)

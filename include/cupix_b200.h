@@ -108,6 +108,10 @@ typedef struct cpx_zbin_desc {
   const double* kpar_row_Mpc; /* [n_m] or NULL (= kpar_Mpc): k_par seen by the continuum distortion    */
                               /* (theory.py:525-535) when kpar_Mpc carries the reference's k_par = 0 -> 1e-4 */
                               /* substitution for the P3D models (lyaP3D.py:35-39; Theory config kpar0)      */
+  const double* metal_auto_dn;  /* [metal_dn_order + 1][3][n_a][n_m] or NULL: Taylor terms of metal_auto in the tilt, */
+  const double* metal_cross_dn; /* moments of P_L (ln k / k_pivot)^n / n! (term 0 = metal_auto / metal_cross); with    */
+  int32_t metal_dn_order;       /* them CPX_NS may be a batch column together with CPX_INCLUDE_METAL (theory.py:54-56, */
+  int32_t reserved2;            /* 361-438), without them that combination returns CPX_ERR_UNSUPPORTED                 */
 } cpx_zbin_desc;
 
 typedef struct cpx_handle cpx_handle;

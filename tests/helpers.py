@@ -86,6 +86,10 @@ def emulate_plan_px(p, params):
     px = (p.hankel_w @ cell.T) * (bT ** 2 * p.dAA_dMpc)[None, :]                        # [n_a, n_m]
     if p.flags & _plan.INCLUDE_METAL:
         ma, mc = p.metal_auto, p.metal_cross
+        dn = v[17] - p.defaults[17] if getattr(p, "k_pivot_Mpc", 0.0) > 0 else 0.0
+        if dn != 0.0:                 # tilt: Taylor tables of the metal moments in dn (k_p3d_hankel epilogue, metal_moment)
+            ma = sum(p.metal_auto_dn[n] * dn ** n for n in range(p.metal_dn_order + 1))
+            mc = sum(p.metal_cross_dn[n] * dn ** n for n in range(p.metal_dn_order + 1))
         px = px + amp * b_X ** 2 * (ma[0] + 2 * beta_X * ma[1] + beta_X ** 2 * ma[2])
         px = px + amp * bias * b_X * (mc[0] + (beta + beta_X) * mc[1] + beta * beta_X * mc[2])
     if p.flags & _plan.INCLUDE_SKY:

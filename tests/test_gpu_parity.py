@@ -433,8 +433,24 @@ def test_As_ns_batch_columns_vs_oracle():
     got = like_m.get_chi2_batch(np.array([[-0.12, 2.3e-9]]), ["bias", "As"])[0]
     orc_m.theory.cosmo = RescaledCosmology(fid, {"As": 2.3e-9})
     assert_chi2(got, orc_m.get_chi2({"bias": -0.12}), "As with SiIII", n_data=like_m.get_ndata())
-    with pytest.raises(CpxError, match="include_metal"):
-        like_m.get_chi2_batch(np.array([[-0.12, 0.95]]), ["bias", "ns"])
+    # ... it is carried by Taylor tables of the metal moments in dn = ns - ns0 (plan.METAL_TILT_ORDER): ns as a column
+    # together with SiIII, on the full pipeline (float32 and float64 cells) and on the factorised path, against the oracle
+    # with the rescaled cosmology (the reference: a new cosmology object per call, theory.py:54-56)
+    like_mp = Likelihood(like_m.data, like_m.theory, 0, config={"N_theta_average": 1, "precise_cells": True})
+    for ns_val, As_val in ((0.95, fid.As), (1.03, 2.0e-9), (fid.ns - 0.15, 2.3e-9)):
+        orc_m.theory.cosmo = RescaledCosmology(fid, {"As": As_val, "ns": ns_val})
+        par = {"bias": -0.12, "b_X": -0.008, "beta_X": 0.6}
+        ref = orc_m.get_chi2(par)
+        row = np.array([[par["bias"], par["b_X"], par["beta_X"], As_val, ns_val]])
+        cols = ["bias", "b_X", "beta_X", "As", "ns"]
+        assert_chi2(like_m.get_chi2_batch(row, cols)[0], ref, "ns = %.3f with SiIII" % ns_val, n_data=like_m.get_ndata())
+        assert like_mp.get_chi2_batch(row, cols)[0] == pytest.approx(ref, rel=3e-7)          # series truncation: 1e-5 of the metal term
+        assert_px(like_m.get_convolved_px_batch(row, cols)[0], orc_m.get_convolved_px(par), msg="model, ns = %.3f with SiIII" % ns_val)
+        lo, hi, n = [ns_val, -0.125, -0.009], [ns_val + 0.02, -0.115, -0.006], [2, 8, 5]
+        g = like_m.get_chi2_grid(["ns", "bias", "b_X"], lo, hi, n)                           # 2 tuples x 40 amplitude points
+        orc_m.theory.cosmo = RescaledCosmology(fid, {"ns": hi[0]})
+        assert g[-1] == pytest.approx(orc_m.get_chi2({"bias": hi[1], "b_X": hi[2]}), rel=3e-7)
+    assert like_m.engine().info("factored_calls") == 3
 
     # a cosmology object that does not expose As / ns / k_pivot: the columns are refused, everything else works
     class Opaque(object):

@@ -96,11 +96,14 @@ def test_data_cuts_match_reference():
     np.testing.assert_allclose(data.theta_min_a_arcmin, g["theta_min_a"])
 
 
-@pytest.mark.parametrize("fname,cosmo_cols", [
-    ("hcd", {"As": 2.4e-9, "ns": 0.93}), ("hcd", {"ns": 1.0}), ("lya", {"As": 1.7e-9}),
-    ("all", {"As": 2.4e-9}),                   # with SiIII only the amplitude may vary (a tilt does not factor out)
+@pytest.mark.parametrize("fname,cosmo_cols,tol", [
+    ("hcd", {"As": 2.4e-9, "ns": 0.93}, 1e-9), ("hcd", {"ns": 1.0}, 1e-9), ("lya", {"As": 1.7e-9}, 1e-9),
+    ("all", {"As": 2.4e-9}, 1e-9),             # with SiIII the amplitude factors out of the metal tables ...
+    # ... and the tilt is carried by their Taylor tables in dn = ns - ns0 (plan.METAL_TILT_ORDER = 8): exact to the
+    # truncation of exp(dn ln k/k_pivot), 1e-9 of the Px scale for everyday tilts, 2e-7 at dn = -0.17
+    ("all", {"As": 2.4e-9, "ns": 0.93}, 1e-9), ("metal", {"ns": 1.02}, 1e-9), ("all", {"ns": 0.80}, 2e-7),
 ])
-def test_plan_emulation_As_ns_columns_equal_rescaled_cosmology(fname, cosmo_cols):
+def test_plan_emulation_As_ns_columns_equal_rescaled_cosmology(fname, cosmo_cols, tol):
     """The per-point linear-power rescaling behind the As / ns batch columns (CPX_AS, CPX_NS) is what the
     reference gets by building a RescaledCosmology for the point (theory.py:54-56): same Px to 1e-9."""
     from cupix_b200.cosmology import RescaledCosmology
@@ -114,5 +117,6 @@ def test_plan_emulation_As_ns_columns_equal_rescaled_cosmology(fname, cosmo_cols
         params = PARAM_SETS[pname]
         ref = orc.get_px_obs(theta, G["k_AA"], params)
         got = H.emulate_plan_px(p, dict(params, **cosmo_cols))
-        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max(), err_msg=pname)
+        np.testing.assert_allclose(got, ref, rtol=tol, atol=max(tol * 1e-3, 1e-12) * np.abs(ref).max() if tol == 1e-9
+                                   else tol * np.abs(ref).max(), err_msg=pname)
         assert np.abs(H.emulate_plan_px(p, params) - ref).max() > 1e-4 * np.abs(ref).max()   # the columns did something
