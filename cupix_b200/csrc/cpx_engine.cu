@@ -741,6 +741,21 @@ void decompose_range(long long first, long long B, int P, const int32_t* n, cons
   }
 }
 
+typedef void (*KWgFn)(const cpx::ZDev*, int, int, int, int, double*, double*);
+KWgFn kwg_select(int mt) {
+  switch (mt) {
+    case 1: return cpx::k_window_gram<1>;
+    case 2: return cpx::k_window_gram<2>;
+    case 3: return cpx::k_window_gram<3>;
+    case 4: return cpx::k_window_gram<4>;
+    case 5: return cpx::k_window_gram<5>;
+    case 6: return cpx::k_window_gram<6>;
+    case 7: return cpx::k_window_gram<7>;
+    case 8: return cpx::k_window_gram<8>;
+  }
+  return nullptr;
+}
+
 typedef void (*KBasisFn)(const cpx::ZDev*, int, int, long long, int);
 template <int W>
 KBasisFn kbasis_select_w(int nt, bool stage) {
@@ -814,7 +829,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
   long long nt_cap = std::max(1, h->chunk / nb);
   nt_cap = std::min<long long>(nt_cap, std::max<long long>(1, (256LL << 20) / (static_cast<long long>(n_zl) * nd_max * nb * 8)));
   const size_t nz_all = h->z.size();
-  if (!h->d_model)
+  // fused window + Gram kernel (k_window_gram): one coarse-k block (n_M <= 64) and the same window shape for all z, few
+  // enough data vectors for its per-thread g accumulators; otherwise k_window writes the Y_k (model buffer) and k_gram
+  // reduces them
+  bool fused = env_int("CPX_FUSED_GRAM", 1) != 0 && (kWinPts / nb) * nd_max * nb <= 128 * kWgMaxG;
+  for (int zi : zl)
+    fused = fused && h->z[zi].dev.n_mblk == 1 && h->z[zi].dev.n_M_pad == h->z[zl[0]].dev.n_M_pad;
+  if (!fused && !h->d_model)
     if ((rc = scratch_alloc(h, reinterpret_cast<void**>(&h->d_model), static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM * sizeof(double), true)))
       return rc;
   const long long nt_alloc = std::min(nt_cap, max_tup);
@@ -979,7 +1000,12 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       }
       // ---- stage 2: whitened window of every basis table, Gram matrices ----
       if ((rc = mark())) return rc;
-      if (!cached) {
+      if (!cached && fused) {
+        const int npseudo = nt * nb, tp_cta = kWinPts / nb;
+        const int mt = tab[0].n_M_pad / 8;
+        kwg_select(mt)<<<dim3((nt + tp_cta - 1) / tp_cta, n_zl), 128, 0, st>>>(h->d_ztab, npseudo, n_zl, nb, nd_max, h->d_G, h->d_g);
+        ++h->launches;
+      } else if (!cached) {
         const int npseudo = nt * nb;
         auto window_launch = [&](int i, int zslot, int gz, int nA_grid) {
           const ZDev& Z = tab[i];

@@ -259,6 +259,151 @@ __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, con
 }
 
 // ------------------------------------------------------------------------------------------
+// k_window_gram: the whitened window of the basis tables and their Gram data in one kernel (n_M <= 64, few data vectors).
+// CTA = 4 warps = 64 pseudo-points = the basis tables of 64 / nb whole tuples, one z bin, ALL coarse theta bins in turn:
+// the FP64 DMMA contraction of k_window per theta bin, the 64 x n_M tile of Y written to shared memory (over the operand
+// stages, which are idle then), and every (tuple, k, l) dot product accumulated in the registers of one fixed thread --
+// deterministic, and the Y_k never travel to HBM (912 MB written and read back per tuple batch by k_window + k_gram).
+// ------------------------------------------------------------------------------------------
+constexpr int kWgMaxAcc = 8;     // (tuple, k, l) triples per thread: 64 / nb tuples x nb^2 pairs over 128 threads (nb = 16: 8)
+constexpr int kWgMaxG = 4;       // (tuple, data vector, k) items per thread: 64 / nb x nd x nb <= 512
+
+template <int MT>
+__global__ void __launch_bounds__(128) k_window_gram(const ZDev* __restrict__ ztab, int npseudo, int n_zl, int nb, int nd_max,
+                                                     double* __restrict__ G, double* __restrict__ gv) {
+  const int zi = blockIdx.y;
+  const ZDev& Z = ztab[zi];
+  const int tp_cta = kWinPts / nb;                       // whole tuples per CTA
+  const int tup0 = blockIdx.x * tp_cta;
+  const int pt_base = tup0 * nb;
+  constexpr int LDY = 8 * MT + 1;
+  __shared__ __align__(16) double smem[2 * kWinPts * kWinLd + 2 * 8 * MT * kWinLd];
+  double (*sA)[kWinPts][kWinLd] = reinterpret_cast<double (*)[kWinPts][kWinLd]>(smem);
+  double (*sB)[8 * MT][kWinLd] = reinterpret_cast<double (*)[8 * MT][kWinLd]>(smem + 2 * kWinPts * kWinLd);
+  double* const sY = smem;                               // [64][LDY], aliases the operand stages between theta bins
+  static_assert(kWinPts * LDY <= 2 * kWinPts * kWinLd + 2 * 8 * MT * kWinLd, "Y tile must fit the operand stages");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kchunks = Z.n_m_pad / kWinKC;
+  const int nM = Z.n_M, nd = Z.n_data, nA = Z.n_A;
+  const int n_trip = tp_cta * nb * nb, n_gi = tp_cta * nd * nb;
+  double gacc[kWgMaxAcc], hacc[kWgMaxG];
+#pragma unroll
+  for (int i = 0; i < kWgMaxAcc; ++i) gacc[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < kWgMaxG; ++i) hacc[i] = 0.0;
+
+  for (int A = 0; A < nA; ++A) {
+    const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
+    const int n_steps = (p1 - p0) * kchunks;
+    double acc[2][MT][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_stage = [&](int step, int buf) {
+      const int pair = p0 + step / kchunks;
+      const int k0 = (step % kchunks) * kWinKC;
+      const int a = Z.pair_a[pair];
+      for (int i = tid; i < kWinPts * (kWinKC / 2); i += 128) {
+        const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+        const int pt = min(pt_base + row, npseudo - 1);
+        cp_async16(&sA[buf][row][2 * c2], Z.pxzam + (static_cast<size_t>(pt) * Z.n_a + a) * Z.n_m_pad + k0 + 2 * c2);
+      }
+      for (int i = tid; i < 8 * MT * (kWinKC / 2); i += 128) {
+        const int row = i / (kWinKC / 2), c2 = i % (kWinKC / 2);
+        cp_async16(&sB[buf][row][2 * c2], Z.T_chi + (static_cast<size_t>(pair) * Z.n_M_pad + row) * Z.n_m_pad + k0 + 2 * c2);
+      }
+      cp_async_commit();
+    };
+
+    load_stage(0, 0);
+    for (int step = 0; step < n_steps; ++step) {
+      const int buf = step & 1;
+      if (step + 1 < n_steps) {
+        load_stage(step + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kWinKC; kk += 4) {
+        const double af0 = sA[buf][warp * 16 + g][kk + t], af1 = sA[buf][warp * 16 + 8 + g][kk + t];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const double bf = sB[buf][8 * j + g][kk + t];
+          dmma_884(acc[0][j][0], acc[0][j][1], af0, bf);
+          dmma_884(acc[1][j][0], acc[1][j][1], af1, bf);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- the Y tile of this theta bin into shared memory (C fragment: rows g (+8), columns 8j + 2t + {0, 1}) ----
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double* yr = sY + (warp * 16 + 8 * i + g) * LDY;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        yr[8 * j + 2 * t] = acc[i][j][0];
+        yr[8 * j + 2 * t + 1] = acc[i][j][1];
+      }
+    }
+    __syncthreads();
+    // ---- Gram contributions of this theta bin ----
+#pragma unroll
+    for (int i = 0; i < kWgMaxAcc; ++i) {
+      const int tr = tid + 128 * i;
+      if (tr < n_trip) {
+        const int tl = tr / (nb * nb), kl = tr % (nb * nb);
+        const double* yk = sY + (tl * nb + kl / nb) * LDY;
+        const double* yl = sY + (tl * nb + kl % nb) * LDY;
+        double s0 = 0.0, s1 = 0.0;
+        int M = 0;
+        for (; M + 1 < nM; M += 2) {
+          s0 = fma(yk[M], yl[M], s0);
+          s1 = fma(yk[M + 1], yl[M + 1], s1);
+        }
+        if (M < nM) s0 = fma(yk[M], yl[M], s0);
+        gacc[i] += s0 + s1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kWgMaxG; ++i) {
+      const int it = tid + 128 * i;
+      if (it < n_gi) {
+        const int kk = it % nb, d = (it / nb) % nd, tl = it / (nb * nd);
+        const double* yd = Z.yd + (static_cast<size_t>(d) * nA + A) * Z.n_M_pad;
+        const double* yk = sY + (tl * nb + kk) * LDY;
+        double s = 0.0;
+        for (int M = 0; M < nM; ++M) s = fma(yd[M], yk[M], s);
+        hacc[i] += s;
+      }
+    }
+    __syncthreads();                                     // the next theta bin's operand loads overwrite the Y tile
+  }
+  const int nt = (npseudo + nb - 1) / nb;
+#pragma unroll
+  for (int i = 0; i < kWgMaxAcc; ++i) {
+    const int tr = tid + 128 * i;
+    if (tr < n_trip) {
+      const int tl = tr / (nb * nb), kl = tr % (nb * nb);
+      if (tup0 + tl < nt) G[(static_cast<size_t>(tup0 + tl) * n_zl + zi) * nb * nb + kl] = gacc[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kWgMaxG; ++i) {
+    const int it = tid + 128 * i;
+    if (it < n_gi) {
+      const int kk = it % nb, d = (it / nb) % nd, tl = it / (nb * nd);
+      if (tup0 + tl < nt) gv[((static_cast<size_t>(tup0 + tl) * n_zl + zi) * nd_max + d) * nb + kk] = hacc[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_quad: one thread per (tuple of the batch, amplitude point).  Decodes the amplitude values (grid box or explicit
 // points), forms the coefficient vector per z and evaluates the quadratic form.
 // ------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ def _grid_points(lo, hi, n, first=0, count=None):
     return np.stack([axes[j][sub[:, j]] for j in range(len(n))], axis=1)
 
 
-def test_bias_beta_scan_is_one_tuple():
+def test_bias_beta_scan_is_one_tuple(monkeypatch):
     """chi2_scan_mock.py: a (bias, beta) grid shares one tuple -- the Hankel stage runs once for 128 x 128 points."""
     data, likes = _like(N_A=8, N_m=60, flags={"include_hcd": True})
     like = likes[0]
@@ -78,6 +78,11 @@ def test_bias_beta_scan_is_one_tuple():
     calls = eng.info("factored_calls")
     like.get_chi2_batch(pts[:5], ["bias", "beta"])
     assert eng.info("factored_calls") == calls
+    # the two-kernel form of the window / Gram stage (k_window + k_gram; taken for n_M > 64 or many data vectors) against the
+    # fused k_window_gram: the same sums in another order
+    monkeypatch.setenv("CPX_FUSED_GRAM", "0")
+    monkeypatch.setenv("CPX_BASIS_CACHE", "0")
+    np.testing.assert_allclose(like.get_chi2_grid(["bias", "beta"], lo, hi, n), chi2, rtol=1e-12)
 
 
 @pytest.mark.parametrize("names,n", [(["bias", "beta", "q1", "kp_Mpc"], [7, 6, 3, 4]),
