@@ -53,7 +53,8 @@ def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True
         with np.load(filled_path) as f:
             d["Px_ZAM"], d["cov_ZAM"] = f["Px_ZAM"], f["cov_ZAM"]
     cosmo = Cosmology()
-    cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True}
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "device": device}
     if n_q:
         cfg["n_q"] = n_q
     theories = [Theory(float(z), fid_cosmo=cosmo, config=cfg) for z in d["z_centers"]]
@@ -61,7 +62,6 @@ def build_workload(shape, n_theta_average, n_q, add_noise=True, need_engine=True
     likes = [Likelihood(data, th, iz, config={"N_theta_average": n_theta_average}) for iz, th in enumerate(theories)]
     if not need_engine:
         return d, data, likes, None
-    device = int(os.environ.get("LOCAL_RANK", "0"))
     t0 = time.time()
     plans = [lk.build_plan() for lk in likes]            # Hankel weights, linear power on the cells: the host side of set-up
     t1 = time.time()
@@ -424,7 +424,7 @@ def main():
     if a.alt_n_q and a.alt_n_q != n_q and not a.precise:
         from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
         from cupix_b200.likelihood.theory import Theory
-        cfg2 = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": a.alt_n_q}
+        cfg2 = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": a.alt_n_q, "device": local_rank}
         likes2 = [Likelihood(data, Theory(lk.theory.z, fid_cosmo=lk.theory.fid_cosmo, config=cfg2), lk.iz,
                              config={"N_theta_average": a.n_theta_average}) for lk in likes]
         eng2 = JointLikelihood(likes2, device=local_rank).engine()

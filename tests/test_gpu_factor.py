@@ -201,3 +201,42 @@ def test_As_amplitude_with_metals_and_device_io():
     host = like_p.get_chi2_batch(pts.cpu().numpy(), ["bias", "beta"], factor=False)
     np.testing.assert_allclose(out.cpu().numpy(), host, rtol=1e-9)
     assert best == host.min() or abs(best - host.min()) <= 1e-9 * host.min()
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_factorised_path_stays_inside_its_scratch(monkeypatch, fused):
+    """CPX_GUARD=1: guard bands around every per-chunk scratch buffer (tuple parameters, the Px_Zam scratch that holds the
+    basis tables, the model buffer that holds the Y_k in the two-kernel form).  Several tuple batches (small scratch), all
+    16 basis tables, padding in every dimension, many data vectors, partial last batch -- no band byte changes.  The Gram
+    buffers, which are plain allocations, are checked through the results: the same numbers as with one big batch."""
+    monkeypatch.setenv("CPX_GUARD", "1")
+    monkeypatch.setenv("CPX_SCRATCH_MB", "8")
+    monkeypatch.setenv("CPX_FUSED_GRAM", fused)
+    data, likes = _like(shape="S2", N_A=9, fine_per_coarse=2, N_m=70, Nz=2, flags=FLAG_SETS["all"], model="best_fit_arinyo_from_colore", N_t=2)
+    joint = JointLikelihood(likes)
+    eng = joint.engine()
+    rng = np.random.default_rng(5)
+    for iz in range(2):
+        eng.set_data(iz, data.Px_ZAM[iz][None] * (1 + 0.02 * rng.normal(size=(3,) + data.Px_ZAM[iz].shape)))
+    names = ["q1", "kC_Mpc", "bias", "b_X", "b_noise_Mpc"]
+    d0 = likes[0].build_plan().defaults
+    lo, hi, n = [0.3, 0.015, d0[0] - 0.01, -0.008, 0.001], [0.6, 0.025, d0[0] + 0.01, -0.003, 0.004], [13, 7, 6, 5, 4]
+    total = int(np.prod(n))
+    from cupix_b200.engine import slots_from_names
+    slots, zsel = slots_from_names(names)
+    didx = np.random.default_rng(6).integers(0, 3, total).astype(np.int32)
+    got = eng.eval(slots=slots, zsel=zsel, grid=(lo, hi, n), data_idx=didx)["chi2"]
+    assert eng.info("factored_calls") == 1 and eng.info("factored_tuples") == 91
+    assert eng.info("chunk_allocated") < 91 * 16, "the scratch must be small enough for several tuple batches"
+    assert eng.info("guard_buffers") >= 5 and eng.info("guard_violations") == 0
+    eng.close()
+    # the same evaluation in one tuple batch, guard off: bit for bit the same numbers (tuples are independent of the batching)
+    monkeypatch.setenv("CPX_SCRATCH_MB", "4096")
+    monkeypatch.setenv("CPX_GUARD", "0")
+    big = JointLikelihood(likes).engine()
+    rng = np.random.default_rng(5)
+    for iz in range(2):
+        big.set_data(iz, data.Px_ZAM[iz][None] * (1 + 0.02 * rng.normal(size=(3,) + data.Px_ZAM[iz].shape)))
+    ref = big.eval(slots=slots, zsel=zsel, grid=(lo, hi, n), data_idx=didx)["chi2"]
+    np.testing.assert_array_equal(got, ref)
+    assert np.isfinite(got).all() and np.ptp(got) > 1.0
