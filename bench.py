@@ -419,13 +419,13 @@ def main():
                "api": "JointLikelihood.get_chi2_batch(points, names, out=pinned array) -> C ABI cpx_eval with host pointers" if world == 1
                else "pinned points -> device, cpx_eval with device pointers, NCCL all_gather of chi2, gathered chi2 -> pinned host"}
 
-    # ---- the same device-timed step at a second node count (the accuracy / cost knob of the Hankel rule) ----
-    alt = None
-    if a.alt_n_q and a.alt_n_q != n_q and not a.precise:
+    # ---- the same device-timed step with other k_perp node sets (the accuracy / cost knob of the Hankel rule) ----
+    # alt_n_q: the round-1 node count on the same smooth power; alt_bao: a linear power with a 5 % BAO-like wiggle, i.e. what a
+    # CAMB / LaCE cosmology looks like -- Theory then selects the refined 'bao' node set by itself (128 nodes at px_rtol = 1e-5)
+    def timed_alt(cfg2, cosmo2):
         from cupix_b200.likelihood.likelihood import JointLikelihood, Likelihood
         from cupix_b200.likelihood.theory import Theory
-        cfg2 = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "n_q": a.alt_n_q, "device": local_rank}
-        likes2 = [Likelihood(data, Theory(lk.theory.z, fid_cosmo=lk.theory.fid_cosmo, config=cfg2), lk.iz,
+        likes2 = [Likelihood(data, Theory(lk.theory.z, fid_cosmo=cosmo2 or lk.theory.fid_cosmo, config=cfg2), lk.iz,
                              config={"N_theta_average": a.n_theta_average}) for lk in likes]
         eng2 = JointLikelihood(likes2, device=local_rank).engine()
         n_alt = max(2, min(a.steps, 5))
@@ -448,10 +448,20 @@ def main():
             t = torch.tensor([ams], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ams = float(t.item())
-        alt = {"n_q": a.alt_n_q, "value": n_alt * B * world / (ams * 1e-3), "unit": "evals/s", "ms_per_step": ams / n_alt,
-               "steps": n_alt, "note": "same step, device-timed, with the round-1 node count; error of the node set vs the "
-                                       "reference algorithm: cupix_b200.quadrature.RULES"}
+        th2 = likes2[0].theory
         eng2.close()
+        return {"n_q": th2.rule.n_q, "kperp_family": th2.kperp_family, "value": n_alt * B * world / (ams * 1e-3), "unit": "evals/s",
+                "ms_per_step": ams / n_alt, "steps": n_alt, "rule_error_vs_reference_algorithm": th2.rule_error}
+
+    alt = alt_bao = None
+    base_cfg = {"default_lya_model": "best_fit_arinyo_from_gadget", "include_hcd": True, "device": local_rank}
+    if a.alt_n_q and a.alt_n_q != n_q and not a.precise:
+        alt = timed_alt(dict(base_cfg, n_q=a.alt_n_q), None)
+        alt["note"] = "same step, device-timed, with the round-1 node count"
+        from cupix_b200.cosmology import Cosmology
+        alt_bao = timed_alt(dict(base_cfg), Cosmology({"bao_amp": 0.05}))
+        alt_bao["note"] = ("same step on a linear power with a 5 % BAO-like wiggle (what CAMB delivers): the node family and count "
+                           "were selected by Theory from that power (kperp_rule = 'auto', px_rtol = 1e-5)")
 
     # ---- the reference-precision mode of the general-points pipeline (float64 P3D cells, CPX_PRECISE_CELLS) ----
     precise_rec = None
@@ -659,7 +669,7 @@ def main():
     line = {"metric": "Px likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if a.precise else "f64 accumulate / f32 P3D cell", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "alt_n_q": alt, "precise": precise_rec, "setup_s": setup_s,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "grid": grid, "alt_n_q": alt, "alt_bao": alt_bao, "precise": precise_rec, "setup_s": setup_s,
             "per_point_z_rate": value * len(likes)}
     emit(line)
     if world > 1:
