@@ -1041,7 +1041,7 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       q.t0 = t0;
       q.nt = nt;
       {
-        const dim3 qgrid(static_cast<unsigned>((q.n_amp + 255) / 256), nt);
+        const dim3 qgrid(static_cast<unsigned>((q.n_amp + 256 * kQuadPts - 1) / (256 * kQuadPts)), nt);
         switch (flags0 & 7) {
           case 0: k_quad<0><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;
           case 1: k_quad<1><<<qgrid, 256, 0, st>>>(q, h->d_ztab, h->d_zlist); break;

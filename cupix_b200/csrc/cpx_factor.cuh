@@ -427,44 +427,95 @@ struct QuadArgs {
 };
 
 // FLAGS = CPX_INCLUDE_{HCD, METAL, SKY} of the evaluated z bins (one layout for all of them): the basis count is a
-// compile-time constant, the coefficient vector lives in registers.  grid = (amplitude points / 256, tuples of the batch):
+// compile-time constant, the coefficient vector lives in registers.  grid = (amplitude points / 512, tuples of the batch):
 // a block's threads share their tuple, whose Gram matrix (and g, when there is one data vector) is staged in shared
-// memory z by z and read as broadcasts.
+// memory z by z and read as broadcasts; every thread scores two points, and only the upper triangle of G is read -- the
+// kernel is bound by those shared-memory broadcasts (one per multiply-add), not by the FP64 pipe.
+constexpr int kQuadPts = 2;
+
+__device__ __forceinline__ long long quad_decode(const QuadArgs& q, int tl, long long r, double* x) {
+  if (!q.grid_mode) {
+    for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
+    return r;
+  }
+  long long tr = q.t0 + tl, flat = 0;
+  for (int j = q.P - 1; j >= 0; --j) {
+    int ij;
+    if (q.is_amp[j]) {
+      ij = q.ax_start[j] + static_cast<int>(r % q.ax_len[j]);
+      r /= q.ax_len[j];
+    } else {
+      ij = q.ax_start[j] + static_cast<int>(tr % q.ax_len[j]);
+      tr /= q.ax_len[j];
+    }
+    flat += ij * q.ax_stride[j];
+    const int n = q.grid_n[j];
+    // bit-identical to numpy.linspace (k_params)
+    x[j] = (ij == n - 1 && n > 1) ? q.grid_hi[j] : __dadd_rn(__dmul_rn(static_cast<double>(ij), q.grid_step[j]), q.grid_lo[j]);
+  }
+  return flat - q.out_first;
+}
+
+template <int FLAGS>
+__device__ __forceinline__ void quad_coefs(const QuadArgs& q, const ZDev& Z, int zglobal, const double* x, double* c) {
+  double b = Z.defaults[0], be = Z.defaults[1], h = Z.defaults[8], eta = Z.defaults[9];
+  double bx = Z.defaults[11], xi = Z.defaults[12], bn = Z.defaults[13];
+  for (int j = 0; j < q.P; ++j) {
+    if (!q.is_amp[j] || !(q.zsel[j] < 0 || q.zsel[j] == zglobal)) continue;
+    const double v = x[j];
+    switch (q.slot[j]) {
+      case 0: b = v; break;
+      case 1: be = v; break;
+      case 8: h = v; break;
+      case 9: eta = v; break;
+      case 11: bx = v; break;
+      case 12: xi = v; break;
+      case 13: bn = v; break;
+    }
+  }
+  int k = 0;
+  c[k++] = b * b;
+  c[k++] = 2.0 * b * b * be;
+  c[k++] = b * b * be * be;
+  if (FLAGS & 1) {
+    c[k++] = 2.0 * b * h;
+    c[k++] = 2.0 * b * h * (be + eta);
+    c[k++] = 2.0 * b * h * be * eta;
+    c[k++] = h * h;
+    c[k++] = 2.0 * h * h * eta;
+    c[k++] = h * h * eta * eta;
+  }
+  if (FLAGS & 2) {
+    c[k++] = bx * bx;
+    c[k++] = 2.0 * bx * bx * xi;
+    c[k++] = bx * bx * xi * xi;
+    c[k++] = b * bx;
+    c[k++] = b * bx * (be + xi);
+    c[k++] = b * bx * be * xi;
+  }
+  if (FLAGS & 4) c[k++] = bn;
+  (void)bn;
+}
+
 template <int FLAGS>
 __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict__ ztab, const int* __restrict__ zlist) {
   constexpr int NB = basis_count(FLAGS);
   __shared__ double sG[NB * NB + NB];
   const int tl = blockIdx.y;
-  long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool live = r < q.n_amp;
-  double x[16];
-  long long out = 0;
-  if (live) {
-    if (q.grid_mode) {
-      long long tr = q.t0 + tl, flat = 0;
-      for (int j = q.P - 1; j >= 0; --j) {
-        int ij;
-        if (q.is_amp[j]) {
-          ij = q.ax_start[j] + static_cast<int>(r % q.ax_len[j]);
-          r /= q.ax_len[j];
-        } else {
-          ij = q.ax_start[j] + static_cast<int>(tr % q.ax_len[j]);
-          tr /= q.ax_len[j];
-        }
-        flat += ij * q.ax_stride[j];
-        const int n = q.grid_n[j];
-        // bit-identical to numpy.linspace (k_params)
-        x[j] = (ij == n - 1 && n > 1) ? q.grid_hi[j] : __dadd_rn(__dmul_rn(static_cast<double>(ij), q.grid_step[j]), q.grid_lo[j]);
-      }
-      out = flat - q.out_first;
-    } else {
-      out = r;
-      for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
-    }
+  double x[kQuadPts][16];
+  long long out[kQuadPts];
+  bool live[kQuadPts];
+  int d[kQuadPts];
+  double chi2[kQuadPts];
+#pragma unroll
+  for (int p = 0; p < kQuadPts; ++p) {
+    const long long r = (static_cast<long long>(blockIdx.x) * kQuadPts + p) * blockDim.x + threadIdx.x;
+    live[p] = r < q.n_amp;
+    out[p] = live[p] ? quad_decode(q, tl, r, x[p]) : 0;
+    d[p] = (live[p] && q.data_idx) ? q.data_idx[out[p]] : 0;
+    chi2[p] = 0.0;
   }
-  const int d = (live && q.data_idx) ? q.data_idx[out] : 0;
   const bool one_data = q.nd_max == 1;
-  double chi2 = 0.0;
   for (int zi = 0; zi < q.n_z; ++zi) {
     const ZDev& Z = ztab[zi];
     const double* Gz = q.G + (static_cast<size_t>(tl) * q.n_z + zi) * NB * NB;
@@ -472,57 +523,37 @@ __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict
     __syncthreads();
     for (int i = threadIdx.x; i < NB * NB + (one_data ? NB : 0); i += blockDim.x) sG[i] = i < NB * NB ? Gz[i] : gz[i - NB * NB];
     __syncthreads();
-    if (!live) continue;
     const int zglobal = zlist[zi];
-    double b = Z.defaults[0], be = Z.defaults[1], h = Z.defaults[8], eta = Z.defaults[9];
-    double bx = Z.defaults[11], xi = Z.defaults[12], bn = Z.defaults[13];
-    for (int j = 0; j < q.P; ++j) {
-      if (!q.is_amp[j] || !(q.zsel[j] < 0 || q.zsel[j] == zglobal)) continue;
-      const double v = x[j];
-      switch (q.slot[j]) {
-        case 0: b = v; break;
-        case 1: be = v; break;
-        case 8: h = v; break;
-        case 9: eta = v; break;
-        case 11: bx = v; break;
-        case 12: xi = v; break;
-        case 13: bn = v; break;
-      }
-    }
-    double c[NB];
-    int k = 0;
-    c[k++] = b * b;
-    c[k++] = 2.0 * b * b * be;
-    c[k++] = b * b * be * be;
-    if (FLAGS & 1) {
-      c[k++] = 2.0 * b * h;
-      c[k++] = 2.0 * b * h * (be + eta);
-      c[k++] = 2.0 * b * h * be * eta;
-      c[k++] = h * h;
-      c[k++] = 2.0 * h * h * eta;
-      c[k++] = h * h * eta * eta;
-    }
-    if (FLAGS & 2) {
-      c[k++] = bx * bx;
-      c[k++] = 2.0 * bx * bx * xi;
-      c[k++] = bx * bx * xi * xi;
-      c[k++] = b * bx;
-      c[k++] = b * bx * (be + xi);
-      c[k++] = b * bx * be * xi;
-    }
-    if (FLAGS & 4) c[k++] = bn;
-    const double* g = one_data ? sG + NB * NB : gz + static_cast<size_t>(d) * NB;
-    double s = Z.ydd[d];
+    double c[kQuadPts][NB], row[kQuadPts];
+#pragma unroll
+    for (int p = 0; p < kQuadPts; ++p) quad_coefs<FLAGS>(q, Z, zglobal, x[p], c[p]);
+    double s[kQuadPts];
+#pragma unroll
+    for (int p = 0; p < kQuadPts; ++p) s[p] = Z.ydd[d[p]];
+    // chi2 = dd + sum_k c_k (-2 g_k + G_kk c_k + 2 sum_{l > k} G_kl c_l)
 #pragma unroll
     for (int kk = 0; kk < NB; ++kk) {
-      double row = -2.0 * g[kk];
+      const double gkk = sG[kk * NB + kk];
 #pragma unroll
-      for (int l = 0; l < NB; ++l) row = fma(sG[kk * NB + l], c[l], row);
-      s = fma(c[kk], row, s);
+      for (int p = 0; p < kQuadPts; ++p) {
+        const double gk = one_data ? sG[NB * NB + kk] : gz[static_cast<size_t>(d[p]) * NB + kk];
+        row[p] = fma(gkk, c[p][kk], -2.0 * gk);
+      }
+#pragma unroll
+      for (int l = kk + 1; l < NB; ++l) {
+        const double g2 = 2.0 * sG[kk * NB + l];
+#pragma unroll
+        for (int p = 0; p < kQuadPts; ++p) row[p] = fma(g2, c[p][l], row[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < kQuadPts; ++p) s[p] = fma(c[p][kk], row[p], s[p]);
     }
-    chi2 += s;
+#pragma unroll
+    for (int p = 0; p < kQuadPts; ++p) chi2[p] += s[p];
   }
-  if (live) q.chi2[out] = chi2;
+#pragma unroll
+  for (int p = 0; p < kQuadPts; ++p)
+    if (live[p]) q.chi2[out[p]] = chi2[p];
 }
 
 }  // namespace cpx

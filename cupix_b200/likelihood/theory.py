@@ -62,6 +62,12 @@ class Theory(object):
                                    config.get('kmax_Mpc', DEFAULT_KMAX),
                                    refine=config.get('kperp_refine', preset.get('refine', 0.0)),
                                    k_refine=config.get('kperp_k_refine', preset.get('k_refine', 0.3)))
+        if self.rule.n_q != preset['n_q'] or self.rule.refine != preset.get('refine', 0.0):
+            # a node set named by hand: its measured error if it is one of the listed sets, else unknown
+            listed = [e for fam in _quad.RULES.values() for kw, e in fam
+                      if kw['n_q'] == self.rule.n_q and kw.get('refine', 0.0) == self.rule.refine and
+                      (self.rule.refine == 0.0 or kw.get('k_refine') == self.rule.k_refine)]
+            self.rule_error = listed[0] if listed else None
         self.device = config.get('device', 0)
         self.precise_cells = config.get('precise_cells', False)
         # k_par = 0 row: 'exact' = the mu = 0 limit; 'reference' = evaluated at 1e-4 1/Mpc like the reference's in-tree
