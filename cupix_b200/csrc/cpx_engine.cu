@@ -597,6 +597,15 @@ K1Fn k1_select_tc(int np, bool add) {
   return nullptr;
 }
 
+K1Fn k1_select_f64s(int nt) {      // shared-memory staged variant, 16 points per CTA (cpx_factor.cuh)
+  switch (nt) {
+    case 1: return cpx::k_p3d_hankel_f64s<1, 16>;
+    case 2: return cpx::k_p3d_hankel_f64s<2, 16>;
+    case 3: return cpx::k_p3d_hankel_f64s<3, 16>;
+  }
+  return nullptr;
+}
+
 K1Fn k1_select_f64(int nt) {
   switch (nt) {
     case 1: return cpx::k_p3d_hankel_f64<1>;
@@ -1510,7 +1519,11 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     const size_t k1_smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
     int pp = pp_env > 0 ? std::min(pp_env, 2) : (2 * (k1_smem + 2048) <= 227u * 1024u ? 1 : 2);
     const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
-    const int n_pg = precise ? count : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
+    // float64 cells: the shared-memory staged kernel (16 points per CTA) when the float64 tile fits, else one warp per point
+    const size_t f64_smem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
+    const bool f64_staged = precise && f64_smem + 1024 <= 227u * 1024u && env_int("CPX_F64_STAGE", 1) != 0;
+    const int n_pg = precise ? (f64_staged ? (count + 15) / 16 : count)
+                             : (tc ? (count + kTcPts - 1) / kTcPts : (count + kK1Warps * pp - 1) / (kK1Warps * pp));
     auto items_of = [&](const ZDev& Z) {
       return tc ? static_cast<long long>(Z.tc_nt) * Z.tc_nablk * n_pg : static_cast<long long>(Z.n_tiles) * Z.n_ablk * n_pg;
     };
@@ -1574,7 +1587,12 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     {
       bool additive = false;
       for (int i = 0; i < n_zl; ++i) additive |= (tab[i].flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)) != 0;
-      if (precise) {
+      if (precise && f64_staged) {
+        K1Fn fn = k1_select_f64s(h->na_blk / 8);
+        CPX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(f64_smem)));
+        const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));
+        fn<<<grid, 512, f64_smem, st>>>(h->d_ztab, n_zl, count, n_items);
+      } else if (precise) {
         K1Fn fn = k1_select_f64(h->na_blk / 8);
         const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
         fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);

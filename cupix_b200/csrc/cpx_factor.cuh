@@ -187,6 +187,130 @@ __global__ void __launch_bounds__(32 * WARPS) k_basis_f64(const ZDev* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// k_p3d_hankel_f64s: the reference-precision cell evaluation of k_p3d_hankel_f64 (CPX_PRECISE_CELLS) on the skeleton of
+// k_basis_f64 -- float64 cell constants and weights staged in shared memory, WARPS points per CTA, contiguous item ranges.
+// Same arithmetic as k_p3d_hankel_f64 (theory.py:285-344 as written), one accumulator set; epilogue as in k_p3d_hankel.
+// ------------------------------------------------------------------------------------------
+template <int NT, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_p3d_hankel_f64s(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
+  extern __shared__ __align__(16) double sm_basis[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_grp = (count + WARPS - 1) / WARPS;
+  const long long it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_z = -1, cur_tile = -1, cur_ablk = -1;
+  for (long long it = it0; it < it1; ++it) {
+    int zi = 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it) ++zi;
+    const ZDev& Z = ztab[zi];
+    long long r = it - Z.item_start;
+    const int grp = static_cast<int>(r % n_grp);
+    r /= n_grp;
+    const int ablk = static_cast<int>(r % Z.n_ablk);
+    const int tile = static_cast<int>(r / Z.n_ablk);
+    const int n_ks = Z.n_q4;
+    double* const s_w = sm_basis + static_cast<size_t>(n_ks) * (kCellConsts * 4 * 32);
+    const bool new_tile = zi != cur_z || tile != cur_tile, new_w = zi != cur_z || ablk != cur_ablk;
+    if (new_tile || new_w) {
+      __syncthreads();
+      if (new_tile) {
+        const double2* src = reinterpret_cast<const double2*>(Z.cell64 + static_cast<size_t>(tile) * n_ks * (kCellConsts * 4 * 32));
+        double2* dst = reinterpret_cast<double2*>(sm_basis);
+        for (int i = threadIdx.x; i < n_ks * (kCellConsts * 4 * 32) / 2; i += blockDim.x) dst[i] = src[i];
+      }
+      if (new_w) {
+        const double2* src = reinterpret_cast<const double2*>(Z.Wd + static_cast<size_t>(ablk) * n_ks * (NT * 32));
+        double2* dst = reinterpret_cast<double2*>(s_w);
+        for (int i = threadIdx.x; i < n_ks * (NT * 32) / 2; i += blockDim.x) dst[i] = src[i];
+      }
+      __syncthreads();
+      cur_z = zi;
+      cur_tile = tile;
+      cur_ablk = ablk;
+    }
+    const int pt = grp * WARPS + warp;
+    if (pt >= count) continue;
+    const int m_base = tile * kTileRows;
+    const PtPar& pr = Z.ptpar[pt];
+    const double q1 = pr.q1_64, q2 = pr.q2_64, av = pr.av_64, bv = pr.bv_64, l2kv = pr.l2kv_64, ikp2 = pr.ikp2_64;
+    const bool cosmo = pr.dn_64 != 0.0 || pr.lr_64 != 0.0;
+    const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
+    const int a_lane0 = ablk * (8 * NT) + 2 * t;
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      const int m = m_base + 8 * mt + g;
+      const bool row_ok = m < n_m;
+      const double kpar = Z.kpar[m];
+      double bT = pr.bias, betaT = pr.beta;
+      if (Z.flags & 1) {                                                         // theory.py:267-282
+        const double F = exp(-kpar * pr.L_H);
+        bT = pr.bias + pr.b_H * F;
+        betaT = (pr.bias * pr.beta + pr.b_H * pr.beta_H * F) / bT;
+      }
+      double acc[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
+      const double* c = sm_basis + lane;
+      const double* wb = s_w + lane;
+#pragma unroll 1
+      for (int ks = 0; ks < n_ks; ++ks) {
+        const double L2K = c[(1 * 4 + mt) * 32], L2MU = c[(2 * 4 + mt) * 32];
+        const double MU2 = c[(3 * 4 + mt) * 32], K2 = c[(4 * 4 + mt) * 32];
+        double D = c[(0 * 4 + mt) * 32], PL = c[(5 * 4 + mt) * 32];
+        if (cosmo) {
+          const double f = exp2(fma(pr.dn_64, L2K, pr.lr_64));
+          D *= f;
+          PL *= f;
+        }
+        const double nl = D * (q1 + q2 * D);
+        const double v = exp2(av * (L2K - l2kv) + bv * L2MU);
+        const double e = exp(nl * (1.0 - v) - K2 * ikp2);
+        const double ka = 1.0 + betaT * MU2;
+        const double pd = PL * ka * ka * e;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_884(acc[j][0], acc[j][1], pd, wb[j * 32]);
+        c += kCellConsts * 4 * 32;
+        wb += NT * 32;
+      }
+      const double amp = bT * bT * Z.dAA;
+      const double cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;
+      const double sky = ((Z.flags & 4) && row_ok) ? pr.b_noise * Z.sky_smooth[m] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int a = a_lane0 + 8 * j + cc;
+          if (a >= n_a) continue;
+          double px = 0.0;
+          if (row_ok) {
+            px = amp * acc[j][cc];
+            if (Z.flags & 2) {
+              const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
+              const double bx = pr.b_X, btx = pr.beta_X, dn = pr.dn_64;
+              const int ord = Z.metal_dn_order;
+              double ma = bx * bx * (metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 0, dn) +
+                                     2.0 * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 1, dn) +
+                                     btx * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 2, dn));
+              double mc = pr.bias * bx * (metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 0, dn) +
+                                          (pr.beta + btx) * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 1, dn) +
+                                          pr.beta * btx * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 2, dn));
+              if (cosmo) {
+                ma *= pr.lin_amp;
+                mc *= pr.lin_amp;
+              }
+              px += ma;
+              px += mc;
+            }
+            if (Z.flags & 4) px += sky * Z.sky_xi[a];
+            px *= cont;
+          }
+          Z.pxzam[(static_cast<size_t>(pt) * n_a + a) * n_m_pad + m] = px;
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_gram: block = (tuple, z).  Y[(tuple * nb + k)][z][A][M] (the model-output layout of k_window) ->
 //   G[tuple][z][k][l] = sum_{A, M} Y_k Y_l,   g[tuple][z][d][k] = sum_{A, M} yd[d][A][M] Y_k
 // rows are padded to an odd stride so that the threads of a warp,

@@ -90,6 +90,23 @@ def test_S5_full_size_vs_oracle():
             worst_abs = max(worst_abs, np.abs(got - ref_tot)[near].max())
         if (~near).any():
             worst_rel = max(worst_rel, (np.abs(got - ref_tot) / ref_tot)[~near].max())
+    # the factorised path at the full size: an amplitude-only batch (bias, beta applied to all 12 z) is one tuple; float64
+    # cells, so the comparison with the oracle is relative 1e-8 at any chi2
+    amp = np.column_stack([rng.uniform(centre[0] - 0.02, centre[0] + 0.02, 64), rng.uniform(centre[1] - 0.2, centre[1] + 0.2, 64)])
+    f0 = joint.engine().info("factored_calls")
+    got_f = joint.get_chi2_batch(amp, ["bias", "beta"])
+    assert joint.engine().info("factored_calls") == f0 + 1
+    orcs = [_oracle(lk) for lk in likes]
+    for i in (0, 31, 63):
+        ref_f = sum(o.get_chi2({"bias": amp[i, 0], "beta": amp[i, 1]}) for o in orcs)
+        assert abs(got_f[i] - ref_f) <= 1e-8 * ref_f, "factorised path, point %d: %.10g vs oracle %.10g" % (i, got_f[i], ref_f)
+    # ... and the float64-cell mode of the full pipeline on the far corners: absolute tolerance at chi2 ~ 3e5
+    joint.engine().precise = True
+    try:
+        got_p = joint.engine().eval(points=pts[4:], slots=[_plan.SLOT_INDEX[n] for n in BENCH_NAMES], factor=False)["chi2"]
+    finally:
+        joint.engine().precise = False
+    assert np.abs(got_p - ref_tot[4:]).max() <= 1e-3, np.abs(got_p - ref_tot[4:]).max()
     print("S5 vs oracle: max |dPx|/max|Px| = %.2e, max |dchi2| (chi2 <= 2 n_data) = %.2e, max rel (beyond) = %.2e, chi2 = %s"
           % (worst_px, worst_abs, worst_rel, np.array2string(ref_tot, precision=1)))
 
