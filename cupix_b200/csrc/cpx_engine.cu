@@ -750,7 +750,7 @@ void decompose_range(long long first, long long B, int P, const int32_t* n, cons
   }
 }
 
-typedef void (*KWgFn)(const cpx::ZDev*, int, int, int, int, double*, double*);
+typedef void (*KWgFn)(const cpx::ZDev*, int, int, int, int, double*, double*, size_t, size_t);
 KWgFn kwg_select(int mt) {
   switch (mt) {
     case 1: return cpx::k_window_gram<1>;
@@ -848,8 +848,10 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
     if ((rc = scratch_alloc(h, reinterpret_cast<void**>(&h->d_model), static_cast<size_t>(h->chunk) * nz_all * h->max_nA * h->max_nM * sizeof(double), true)))
       return rc;
   const long long nt_alloc = std::min(nt_cap, max_tup);
-  if ((rc = grow(h, &h->d_G, &h->cap_G, static_cast<size_t>(nt_alloc) * n_zl * nb * nb, true))) return rc;
-  if ((rc = grow(h, &h->d_g, &h->cap_g, static_cast<size_t>(nt_alloc) * n_zl * nd_max * nb, true))) return rc;
+  const int n_split = fused ? kWgSplit : 1;           // partial sums of k_window_gram's theta-bin splits
+  const size_t G_stride = static_cast<size_t>(nt_alloc) * n_zl * nb * nb, g_stride = static_cast<size_t>(nt_alloc) * n_zl * nd_max * nb;
+  if ((rc = grow(h, &h->d_G, &h->cap_G, G_stride * n_split, true))) return rc;
+  if ((rc = grow(h, &h->d_g, &h->cap_g, g_stride * n_split, true))) return rc;
   if ((rc = grow(h, &h->d_tpts, &h->cap_tpts, static_cast<size_t>(nt_alloc) * std::max(n_tcol, 1)))) return rc;
 
   // whole-batch staging in host-pointer mode
@@ -1012,8 +1014,12 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       if (!cached && fused) {
         const int npseudo = nt * nb, tp_cta = kWinPts / nb;
         const int mt = tab[0].n_M_pad / 8;
-        kwg_select(mt)<<<dim3((nt + tp_cta - 1) / tp_cta, n_zl), 128, 0, st>>>(h->d_ztab, npseudo, n_zl, nb, nd_max, h->d_G, h->d_g);
-        ++h->launches;
+        kwg_select(mt)<<<dim3((nt + tp_cta - 1) / tp_cta, n_zl, n_split), 128, 0, st>>>(h->d_ztab, npseudo, n_zl, nb, nd_max, h->d_G,
+                                                                                          h->d_g, G_stride, g_stride);
+        const size_t nG = static_cast<size_t>(nt) * n_zl * nb * nb, ng = static_cast<size_t>(nt) * n_zl * nd_max * nb;
+        k_gsum<<<static_cast<unsigned>((nG + 255) / 256), 256, 0, st>>>(h->d_G, nG, G_stride, n_split);
+        k_gsum<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, st>>>(h->d_g, ng, g_stride, n_split);
+        h->launches += 3;
       } else if (!cached) {
         const int npseudo = nt * nb;
         auto window_launch = [&](int i, int zslot, int gz, int nA_grid) {

@@ -392,10 +392,16 @@ __global__ void __launch_bounds__(256) k_gram(const ZDev* __restrict__ ztab, con
 constexpr int kWgMaxAcc = 8;     // (tuple, k, l) triples per thread: 64 / nb tuples x nb^2 pairs over 128 threads (nb = 16: 8)
 constexpr int kWgMaxG = 4;       // (tuple, data vector, k) items per thread: 64 / nb x nd x nb <= 512
 
+// blockIdx.z splits the coarse theta bins between kWgSplit CTAs (partial sums, added by k_gsum in fixed order): the
+// 1416 CTAs of an S5 tuple batch are 2.4 waves of 4 CTAs per SM, 2832 half-length ones 4.8
+constexpr int kWgSplit = 2;
+
 template <int MT>
 __global__ void __launch_bounds__(128) k_window_gram(const ZDev* __restrict__ ztab, int npseudo, int n_zl, int nb, int nd_max,
-                                                     double* __restrict__ G, double* __restrict__ gv) {
+                                                     double* __restrict__ G, double* __restrict__ gv, size_t g_stride, size_t gv_stride) {
   const int zi = blockIdx.y;
+  G += blockIdx.z * g_stride;
+  gv += blockIdx.z * gv_stride;
   const ZDev& Z = ztab[zi];
   const int tp_cta = kWinPts / nb;                       // whole tuples per CTA
   const int tup0 = blockIdx.x * tp_cta;
@@ -418,7 +424,9 @@ __global__ void __launch_bounds__(128) k_window_gram(const ZDev* __restrict__ zt
 #pragma unroll
   for (int i = 0; i < kWgMaxG; ++i) hacc[i] = 0.0;
 
-  for (int A = 0; A < nA; ++A) {
+  const int a_per = (nA + gridDim.z - 1) / gridDim.z;
+  const int A_end = min(nA, static_cast<int>(blockIdx.z + 1) * a_per);
+  for (int A = blockIdx.z * a_per; A < A_end; ++A) {
     const int p0 = Z.pair_start[A], p1 = Z.pair_start[A + 1];
     const int n_steps = (p1 - p0) * kchunks;
     double acc[2][MT][2];
@@ -525,6 +533,15 @@ __global__ void __launch_bounds__(128) k_window_gram(const ZDev* __restrict__ zt
       if (tup0 + tl < nt) gv[((static_cast<size_t>(tup0 + tl) * n_zl + zi) * nd_max + d) * nb + kk] = hacc[i];
     }
   }
+}
+
+// partial Gram sums of the theta-bin splits of k_window_gram -> split 0, in fixed order
+__global__ void k_gsum(double* __restrict__ x, size_t n, size_t stride, int n_split) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = x[i];
+  for (int k = 1; k < n_split; ++k) s += x[i + k * stride];
+  x[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -33,6 +33,17 @@ def report(model, flags, N_t, label, npts=24, seed=1):
     dpx = np.abs(model_gpu - mref).max(axis=(1, 2)) / np.abs(mref).max(axis=(1, 2))
     print("%-28s chi2 range [%.1f, %.1f]  max|dchi2| %.2e  max|dchi2|/chi2 %.2e  rms dchi2 %.2e   max|dPx|/max|Px| %.2e"
           % (label, ref.min(), ref.max(), np.abs(dchi).max(), np.abs(dchi / ref).max(), np.sqrt(np.mean(dchi ** 2)), dpx.max()))
+    # the two float64-cell modes on the same measurement: the full pipeline with CPX_PRECISE_CELLS, and the factorised
+    # path (amplitude-only columns: bias, beta of the same points -> one tuple)
+    like_p = Likelihood(like.data, th, 0, config={"N_theta_average": N_t, "precise_cells": True})
+    dp = like_p.get_chi2_batch(pts, names, factor=False) - ref
+    amp = np.tile(pts[:, :2], (2, 1))                      # 48 points: above the 24-point threshold of the factorised path
+    ref_a = np.array([orc.get_chi2({"bias": p[0], "beta": p[1]}) for p in pts])
+    calls0 = like.engine().info("factored_calls")
+    da = like.get_chi2_batch(amp, ["bias", "beta"])[:npts] - ref_a
+    assert like.engine().info("factored_calls") == calls0 + 1
+    print("%-28s   float64 cells, full pipeline: max|dchi2| %.2e (%.2e relative);  factorised path: max|dchi2| %.2e (%.2e relative, chi2 up to %.0f)"
+          % ("", np.abs(dp).max(), np.abs(dp / ref).max(), np.abs(da).max(), np.abs(da / ref_a).max(), ref_a.max()))
     return dchi, ref
 
 
