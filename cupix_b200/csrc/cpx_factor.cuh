@@ -23,11 +23,13 @@
 // are evaluated in float64 (the formulas of theory.py:285-308 as written): chi2 from this path agrees with
 // the float64 oracle to ~1e-9 everywhere, not only near the best fit.
 //
-//   k_basis_f64  per (z, tuple): float64 P3D cells, three mu-moment Hankel sums on the FP64 tensor pipe (DMMA), epilogue
-//                writes the n_b basis tables B_k[a][m] as pseudo-points of the Px_Zam scratch
-//   k_window<MT, false> with WindowArgs::whiten: Y_k (the FP64 DMMA window kernel, whitened operator, no data)
-//   k_gram       per (z, tuple): G, g
-//   k_quad       per point: coefficients + quadratic form, summed over z
+//   k_basis_f64    per (z, tuple): float64 P3D cells, three mu-moment Hankel sums on the FP64 tensor pipe (DMMA), epilogue
+//                  writes the n_b basis tables B_k[a][m] as pseudo-points of the Px_Zam scratch
+//   k_window_gram  per (z, 64 / n_b tuples): the whitened window of the basis tables (FP64 DMMA) and G, g in one kernel;
+//                  the Y_k stay in shared memory.  For n_M > 64 or many data vectors: k_window<MT, false> with
+//                  WindowArgs::whiten (Y_k to HBM) followed by k_gram
+//   k_quad         per point: coefficients + quadratic form, summed over z
+//   k_p3d_hankel_f64s  (general points, CPX_PRECISE_CELLS) the float64-cell Hankel kernel on the same staged skeleton
 #pragma once
 #include "cpx_kernels.cuh"
 
@@ -44,13 +46,14 @@ __host__ __device__ constexpr int basis_count(int flags) {
 // k_basis_f64: one warp per (z, 32-row k_par tile, theta block, tuple).  Same DMMA fragment layout as
 // k_p3d_hankel_f64; the four m-tiles are walked one after the other so that only 3 x NT accumulators are live.
 // Output: Z.pxzam viewed as [tuple * nb + k][a][m_pad].
-// ------------------------------------------------------------------------------------------
 // STAGE: the float64 cell constants of the (z, tile) and the weights of the theta block are staged in shared memory and
 // shared by the 16 warps of the CTA (16 consecutive tuples); a CTA walks a contiguous range of (z, tile, theta block,
 // tuple group) items, so the 86 KB tile (n_q = 56) is reloaded only at tile boundaries.  Without STAGE (node sets whose
 // tile does not fit) every warp reads its constants through L1/L2.
 // WARPS = 16 (default): 4 warps per scheduler -- the cell evaluation is a long dependent chain (exp2 -> exp -> DMMA) -- at
-// 128 registers; WARPS = 8 keeps 160 registers and no spills (CPX_BASIS_WARPS selects)
+// 128 registers; WARPS = 8 keeps 160 registers and no spills (CPX_BASIS_WARPS selects).  Measured per S5 scan: 12.0 ms
+// unstaged, 7.2 ms staged with 8 warps, 5.0 ms staged with 16.
+// ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr size_t basis_smem_bytes(int n_q4, int nt) {
   return static_cast<size_t>(n_q4) * (kCellConsts * 4 * 32 + nt * 32) * sizeof(double);
 }

@@ -18,6 +18,10 @@
 //   k_p3d_hankel_tc  (cpx_hankel_tc.cuh) the Hankel contraction of k_p3d_hankel on tcgen05 with the same split;
 //                 opt-in (CPX_TC=1), currently slower than the DMMA kernel
 //   k_reduce      chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
+//   k_mock_noise  many noisy realisations of the data vector drawn on the device (likelihood.py:37-50), Philox4x32-10
+//   k_jbar        set-up: J0 sums of the Hankel weights (cupix_b200/quadrature.py)
+//   (cpx_factor.cuh) k_basis_f64, k_window_gram, k_gram, k_quad: the factorised path for scans and amplitude fits;
+//                 k_p3d_hankel_f64s: the staged float64-cell Hankel kernel
 //   k_probe_*     pipe-rate probes for the roofline denominators
 #pragma once
 #include <cuda_runtime.h>

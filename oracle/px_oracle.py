@@ -17,7 +17,12 @@ Parity status
   sets; tests/test_oracle_hankel_golden.py checks the FFTLog restatement in oracle/hankel.py against it
   (1e-10) and the fixed-node rule the device evaluates (<= 1e-5 of the Px scale for r >= 0.3 Mpc).  What
   stays unpinned is only the difference between that in-tree copy and today's ForestFlow HEAD (the
-  ``max_k_for_p3d`` argument of theory.py:264, which the in-tree copy does not have).
+  ``max_k_for_p3d`` argument of theory.py:264, which the in-tree copy does not have).  Round 2 added fixtures with a
+  BAO-like wiggle in the linear power and the reference's k_par = 0 -> 1e-4 row (lyaP3D.py:35-39, executed by the
+  generator), and profiles/transform_choice_r02.txt states what the choice of transform costs in chi2.
+* the posterior layer (posterior.py:39-84, free_parameter.py:34-50): PINNED -- tests/golden/make_golden_posterior.py runs
+  the unmodified reference classes on the reference Likelihood; tests/test_posterior_golden.py checks this oracle's
+  log-likelihood under cupix_b200's Posterior against them.
 """
 import numpy as np
 
