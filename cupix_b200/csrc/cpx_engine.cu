@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "cpx_kernels.cuh"
@@ -91,7 +92,9 @@ struct cpx_handle {
   double* d_big_pts = nullptr;
   double* d_big_chi2 = nullptr;
   int* d_big_didx = nullptr;
-  size_t cap_big_pts = 0, cap_big_chi2 = 0, cap_big_didx = 0;
+  int* d_perm = nullptr;
+  long long* d_tstart = nullptr;
+  size_t cap_big_pts = 0, cap_big_chi2 = 0, cap_big_didx = 0, cap_perm = 0, cap_tstart = 0;
   long long factored_calls = 0, factored_tuples = 0, factored_cache_hits = 0;
   // single-tuple calls (amplitude-only batches of samplers and minimisers, bias x beta scans) repeat the same tuple call
   // after call: the Gram data of the last one is kept and re-used while its signature (tuple values, columns, z list,
@@ -779,6 +782,85 @@ KBasisFn kbasis_select(int nt, bool stage, int warps) {
   return warps == 8 ? kbasis_select_w<8>(nt, stage) : kbasis_select_w<16>(nt, stage);
 }
 
+// Explicit host points whose tuple columns take few distinct values -- a meshgrid handed in as a point list, the way the
+// reference's scan scripts build theirs (scripts/chi2_scan_mock.py:107-111) -- grouped by tuple: tuple values, the points of
+// each tuple (perm, start) and the largest group.  Returns false when the points do not share tuples (decided on a strided
+// sample first, so that a batch of unrelated points costs a few milliseconds to rule out).
+struct TupleKey {
+  double v[11];
+  int n;
+  bool operator==(const TupleKey& o) const { return n == o.n && std::memcmp(v, o.v, sizeof(double) * n) == 0; }
+};
+struct TupleKeyHash {
+  size_t operator()(const TupleKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < k.n; ++i) {
+      uint64_t b;
+      std::memcpy(&b, &k.v[i], 8);
+      h = (h ^ b) * 1099511628211ull;
+      h ^= h >> 29;
+    }
+    return static_cast<size_t>(h);
+  }
+};
+struct PointGroups {
+  std::vector<double> tuple_vals;      // [T][n_tcol]
+  std::vector<long long> start;        // [T + 1]
+  std::vector<int> perm;               // [B]
+  long long max_count = 0;
+};
+
+bool group_points(const double* pts, int64_t B, int P, const bool* amp, int n_tcol, long long min_ratio, PointGroups& g) {
+  if (n_tcol > 11 || B >= (1LL << 31)) return false;
+  int tcol[16], nt = 0;
+  for (int j = 0; j < P; ++j)
+    if (!amp[j]) tcol[nt++] = j;
+  auto key_of = [&](int64_t i) {
+    TupleKey k;
+    k.n = n_tcol;
+    for (int j = 0; j < n_tcol; ++j) k.v[j] = pts[i * P + tcol[j]];
+    return k;
+  };
+  const int64_t S = std::min<int64_t>(B, 65536);
+  if (B > S) {             // sample: with T tuples shared by >= min_ratio points each, far fewer distinct keys than samples
+    std::unordered_map<TupleKey, int, TupleKeyHash> seen;
+    seen.reserve(static_cast<size_t>(S) * 2);
+    for (int64_t s = 0; s < S; ++s) seen.emplace(key_of(s * (B / S)), 0);
+    if (static_cast<double>(seen.size()) > 0.9 * static_cast<double>(S)) return false;
+  }
+  std::unordered_map<TupleKey, int, TupleKeyHash> ids;
+  ids.reserve(1 << 16);
+  std::vector<int> id_of(static_cast<size_t>(B));
+  std::vector<long long> count;
+  const long long max_tuples = B / min_ratio;
+  for (int64_t i = 0; i < B; ++i) {
+    auto it = ids.find(key_of(i));
+    int id;
+    if (it == ids.end()) {
+      id = static_cast<int>(count.size());
+      if (id >= max_tuples) return false;                 // too many tuples for the points there are
+      const TupleKey k = key_of(i);
+      ids.emplace(k, id);
+      g.tuple_vals.insert(g.tuple_vals.end(), k.v, k.v + n_tcol);
+      count.push_back(0);
+    } else {
+      id = it->second;
+    }
+    id_of[i] = id;
+    ++count[id];
+  }
+  const size_t T = count.size();
+  g.start.assign(T + 1, 0);
+  for (size_t t = 0; t < T; ++t) {
+    g.start[t + 1] = g.start[t] + count[t];
+    g.max_count = std::max(g.max_count, count[t]);
+  }
+  g.perm.resize(static_cast<size_t>(B));
+  std::vector<long long> fill(g.start.begin(), g.start.end() - 1);
+  for (int64_t i = 0; i < B; ++i) g.perm[fill[id_of[i]]++] = static_cast<int>(i);
+  return true;
+}
+
 // Evaluates the call through the factorised path if it qualifies (*taken = true), else leaves it to the caller.
 int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const std::vector<int>& zl, bool* taken) {
   using namespace cpx;
@@ -799,22 +881,32 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
     n_tcol += !amp[j];
   }
   std::vector<GridBox> boxes;
+  PointGroups groups;
+  bool grouped = false;
   if (a->grid_n) {
     long long total = 1;
     for (int j = 0; j < P; ++j) total *= a->grid_n[j];
     if (a->grid_first + a->B > total) return fail(CPX_ERR_ARG, "cpx_eval: grid slice runs past the end of the grid");
     decompose_range(a->grid_first, a->B, P, a->grid_n, amp, boxes);
   } else {
-    if (n_tcol > 0) return CPX_OK;                   // explicit points sharing tuples are not searched for
     GridBox b;
     std::memset(&b, 0, sizeof b);
     b.n_tup = 1;
     b.n_amp = a->B;
+    if (n_tcol > 0) {
+      // explicit points: grouped by tuple on the host when they share tuples (host pointers only)
+      if (dev_io || a->B < min_ratio || env_int("CPX_FACTOR_GROUP", 1) == 0) return CPX_OK;
+      if (!group_points(a->points, a->B, P, amp, n_tcol, min_ratio, groups)) return CPX_OK;
+      grouped = true;
+      b.n_tup = static_cast<long long>(groups.start.size()) - 1;
+      b.n_amp = groups.max_count;
+    }
     boxes.push_back(b);
   }
   long long tuples = 0;
   for (const GridBox& b : boxes) tuples += b.n_tup;
   if (a->B < min_ratio * tuples) return CPX_OK;      // too few points per tuple for the (float64, 3-moment) tuple stage to pay
+
   *taken = true;
   if (!(boxes.size() == 1 && boxes[0].n_tup == 1)) h->basis_sig.clear();     // this call overwrites the cached Gram data
 
@@ -873,6 +965,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
     }
   }
 
+  if (grouped) {
+    if ((rc = grow(h, &h->d_perm, &h->cap_perm, groups.perm.size()))) return rc;
+    if ((rc = grow(h, &h->d_tstart, &h->cap_tstart, groups.start.size()))) return rc;
+    CPX_CUDA(cudaMemcpyAsync(h->d_perm, groups.perm.data(), sizeof(int) * groups.perm.size(), cudaMemcpyHostToDevice, st));
+    CPX_CUDA(cudaMemcpyAsync(h->d_tstart, groups.start.data(), sizeof(long long) * groups.start.size(), cudaMemcpyHostToDevice, st));
+  }
+
   std::vector<cudaEvent_t> evs;
   auto mark = [&]() -> int {
     if (!a->stage_ms) return CPX_OK;
@@ -899,6 +998,8 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
   q.grid_mode = a->grid_n ? 1 : 0;
   q.nd_max = nd_max;
   q.points = d_points;
+  q.perm = grouped ? h->d_perm : nullptr;
+  q.t_start = grouped ? h->d_tstart : nullptr;
   q.data_idx = d_didx;
   q.chi2 = d_chi2;
   q.G = h->d_G;
@@ -948,7 +1049,13 @@ int eval_factored(cpx_handle* h, const cpx_eval_args* a, cudaStream_t st, const 
       const int nt = static_cast<int>(std::min<long long>(nt_cap, b.n_tup - t0));
       // ---- stage 0: tuple parameters ----
       if ((rc = mark())) return rc;
-      if (n_tcol > 0) {
+      if (grouped) {
+        tpts.assign(groups.tuple_vals.begin() + static_cast<size_t>(t0) * n_tcol, groups.tuple_vals.begin() + static_cast<size_t>(t0 + nt) * n_tcol);
+        CPX_CUDA(cudaMemcpyAsync(h->d_tpts, tpts.data(), sizeof(double) * tpts.size(), cudaMemcpyHostToDevice, st));
+        long long mx = 0;                                  // largest group of this batch: the k_quad grid
+        for (int tl = 0; tl < nt; ++tl) mx = std::max(mx, groups.start[t0 + tl + 1] - groups.start[t0 + tl]);
+        q.n_amp = mx;
+      } else if (n_tcol > 0) {
         tpts.resize(static_cast<size_t>(nt) * n_tcol);
         for (int tl = 0; tl < nt; ++tl) {
           long long tr = t0 + tl;

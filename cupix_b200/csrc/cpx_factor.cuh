@@ -564,6 +564,10 @@ struct QuadArgs {
   int nt;                       // tuples in this batch
   int nd_max;
   const double* points;         // points mode: [B][P]
+  // explicit points grouped by tuple on the host (a meshgrid handed in as a point list): tuple t of the call owns the
+  // points perm[t_start[t] .. t_start[t + 1]) of the caller's array
+  const int* perm;              // [B] or null
+  const long long* t_start;     // [tuples of the call + 1]
   const int* data_idx;          // [B] or null (indexed like chi2)
   double* chi2;
   const double* G;              // [nt][n_z][nb][nb]
@@ -579,6 +583,7 @@ constexpr int kQuadPts = 2;
 
 __device__ __forceinline__ long long quad_decode(const QuadArgs& q, int tl, long long r, double* x) {
   if (!q.grid_mode) {
+    if (q.perm) r = q.perm[q.t_start[q.t0 + tl] + r];
     for (int j = 0; j < q.P; ++j) x[j] = q.points[r * q.P + j];
     return r;
   }
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(256) k_quad(QuadArgs q, const ZDev* __restrict
 #pragma unroll
   for (int p = 0; p < kQuadPts; ++p) {
     const long long r = (static_cast<long long>(blockIdx.x) * kQuadPts + p) * blockDim.x + threadIdx.x;
-    live[p] = r < q.n_amp;
+    live[p] = r < (q.perm ? q.t_start[q.t0 + tl + 1] - q.t_start[q.t0 + tl] : q.n_amp);
     out[p] = live[p] ? quad_decode(q, tl, r, x[p]) : 0;
     d[p] = (live[p] && q.data_idx) ? q.data_idx[out[p]] : 0;
     chi2[p] = 0.0;

@@ -240,3 +240,45 @@ def test_factorised_path_stays_inside_its_scratch(monkeypatch, fused):
     ref = big.eval(slots=slots, zsel=zsel, grid=(lo, hi, n), data_idx=didx)["chi2"]
     np.testing.assert_array_equal(got, ref)
     assert np.isfinite(got).all() and np.ptp(got) > 1.0
+
+
+def test_explicit_meshgrid_points_are_grouped_by_tuple():
+    """A meshgrid handed in as an explicit point list -- how the reference's scan scripts build theirs
+    (scripts/chi2_scan_mock.py:107-111) -- in any order: the host groups the points by tuple and the call takes the
+    factorised path, with the numbers of the on-device grid; unrelated points stay on the full pipeline."""
+    data, likes = _like(N_A=6, N_m=48, flags={"include_hcd": True}, N_t=1)
+    like = likes[0]
+    d0 = like.build_plan().defaults
+    names = ["bias", "q1", "beta", "kp_Mpc"]
+    lo = [d0[0] - 0.02, d0[2] - 0.1, d0[1] - 0.2, d0[7] - 3.0]
+    hi = [d0[0] + 0.02, d0[2] + 0.1, d0[1] + 0.2, d0[7] + 3.0]
+    n = [12, 3, 10, 4]
+    eng = like.engine()
+    grid = like.get_chi2_grid(names, lo, hi, n)
+    assert eng.info("factored_calls") == 1 and eng.info("factored_tuples") == 12
+    pts = _grid_points(lo, hi, n)
+    perm = np.random.default_rng(0).permutation(len(pts))
+    got = like.get_chi2_batch(pts[perm], names)
+    assert eng.info("factored_calls") == 2 and eng.info("factored_tuples") == 24
+    np.testing.assert_array_equal(got, grid[perm])
+    # with per-point data vectors, and a subset in which the tuples own different numbers of points
+    rng = np.random.default_rng(1)
+    like.set_mock_data(like.data.Px_ZAM[0][None] * (1 + 0.02 * rng.normal(size=(3,) + like.data.Px_ZAM[0].shape)))
+    sub = perm[:900]
+    didx = rng.integers(0, 3, len(sub)).astype(np.int32)
+    got = like.get_chi2_batch(pts[sub], names, data_idx=didx)
+    ref = like.get_chi2_batch(pts[sub], names, data_idx=didx, factor=False)
+    assert eng.info("factored_calls") == 3
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-3)
+    like.restore_data()
+    # unrelated points: every tuple is its own -> the full pipeline
+    rnd = rng.uniform(lo, hi, size=(2000, 4))
+    like.get_chi2_batch(rnd, names)
+    assert eng.info("factored_calls") == 3
+    # a larger list (sampled first): 4 x 3 tuples x 9000 amplitude points, shuffled
+    n2 = [90, 4, 100, 3]
+    p2 = _grid_points(lo, hi, n2)
+    sh = rng.permutation(len(p2))
+    got2 = like.get_chi2_batch(p2[sh], names)
+    assert eng.info("factored_calls") == 4
+    np.testing.assert_array_equal(got2, like.get_chi2_grid(names, lo, hi, n2)[sh])
