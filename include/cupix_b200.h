@@ -131,8 +131,9 @@ enum {
 /* Factorised path (cpx_factor.cuh; taken automatically, CPX_FACTOR=0 or CPX_NO_FACTOR switch it off).  The model
  * is a polynomial in the AMPLITUDE parameters bias, beta, b_H, beta_H, b_X, beta_X, b_noise_Mpc whose coefficient
  * tables depend on the point only through the other ("tuple") parameters.  When a call asks for `chi2` alone and
- * its points share tuples -- a grid whose points-per-distinct-tuple ratio is >= CPX_FACTOR_MIN (24), or explicit
- * points whose columns are all amplitude parameters (one tuple) with B >= CPX_FACTOR_MIN -- the P3D / Hankel /
+ * its points share tuples -- a grid whose points-per-distinct-tuple ratio is >= CPX_FACTOR_MIN (24), explicit
+ * points whose columns are all amplitude parameters (one tuple) with B >= CPX_FACTOR_MIN, or explicit HOST points
+ * that share tuples at that ratio (a meshgrid handed in as a point list: grouped by tuple on the host) -- the P3D / Hankel /
  * window stages run once per distinct tuple (float64 cells) and chi2 per point is a quadratic form.  This is the
  * shape of the reference's scans (scripts/chi2_scan_mock.py:107-140, chi2_scan_forecast.py:116-125).  Results agree
  * with the float64 oracle to ~1e-9 relative; with the float32-cell pipeline to its own ~1e-7. */
