@@ -49,6 +49,7 @@ def test_sharded_scan_single_rank_equals_full():
 class _FakeLike(object):
     """quadratic log-likelihood with the batched interface of Likelihood"""
     verbose = False
+    theory = type("T", (), {"verbose": False})()
 
     def get_ndata(self):
         return 10
@@ -104,6 +105,19 @@ def test_ensemble_sampler_recovers_gaussian():
     assert 0.2 < smp.acceptance_fraction < 0.9
     assert np.all(np.abs(flat.mean(axis=0) - 1.0) < 0.1)      # _FakeLike: unit Gaussian centred on 1
     assert np.all(np.abs(flat.std(axis=0) - 1.0) < 0.15)
+    # the reference's interface (sampler.py:28-107): burn-in + max_nsteps iterations, emcee-style accessors, start points
+    es = smp.emcee_sampler
+    assert es.iteration == 750 and es.nwalkers == 32 and es.get_chain().shape == (750, 32, 2)
+    np.testing.assert_array_equal(es.get_chain(discard=150, flat=True), flat)
+    assert es.get_log_prob(discard=150, flat=True).shape == (600 * 32,)
+    fp2 = [FreeParameter("bias", -4, 6, ini_value=5.9, delta=0.5), FreeParameter("beta", -4, 6, ini_value=0.5, delta=0.2)]
+    s2 = Sampler(Posterior(_FakeLike(), fp2), {"seed": 1})
+    w = s2.get_initial_walkers()
+    assert w.shape == (10, 2) and s2.nburnin == 100 and s2.max_nsteps == 1000
+    assert np.all((w[:, 1] >= 0.5) & (w[:, 1] <= 0.7)) and np.all(w[:, 0] <= 6.0) and np.any(w[:, 0] == 6.0 - 0.005)
+    s2.verbose = True
+    s2.silence()
+    assert s2.verbose is False
 
 
 def test_cosmology_cache_key_and_branches():
