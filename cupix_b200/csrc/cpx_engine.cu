@@ -1855,6 +1855,30 @@ int cpx_hankel_jbar(int32_t device, int32_t n_groups, const int32_t* group_start
   return CPX_OK;
 }
 
+int cpx_hankel_apply(int32_t device, int32_t n_r, int32_t n_q, int32_t n_k, const double* W, const double* cells, double* px) {
+  if (n_r <= 0 || n_q <= 0 || n_k <= 0 || !W || !cells || !px) return fail(CPX_ERR_ARG, "cpx_hankel_apply: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(CPX_ERR_CUDA, "cpx_hankel_apply: no such CUDA device");
+  CPX_CUDA(cudaSetDevice(device));
+  double *d_W = nullptr, *d_c = nullptr, *d_px = nullptr;
+  const size_t bW = sizeof(double) * n_r * static_cast<size_t>(n_q), bc = sizeof(double) * n_k * static_cast<size_t>(n_q),
+               bp = sizeof(double) * n_r * static_cast<size_t>(n_k);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_W), bW);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_c), bc);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_px), bp);
+  if (e == cudaSuccess) e = cudaMemcpy(d_W, W, bW, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c, cells, bc, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cpx::k_hankel_apply<<<dim3((n_k + 63) / 64, (n_r + 31) / 32), 128>>>(d_W, d_c, n_r, n_q, n_k, d_px);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(px, d_px, bp, cudaMemcpyDeviceToHost);
+  cudaFree(d_W); cudaFree(d_c); cudaFree(d_px);
+  if (e != cudaSuccess) return fail(CPX_ERR_CUDA, std::string("cpx_hankel_apply: ") + cudaGetErrorString(e));
+  return CPX_OK;
+}
+
 int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s, double* dmma_fma_per_s) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)

@@ -20,6 +20,7 @@
 //   k_reduce      chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
 //   k_mock_noise  many noisy realisations of the data vector drawn on the device (likelihood.py:37-50), Philox4x32-10
 //   k_jbar        set-up: J0 sums of the Hankel weights (cupix_b200/quadrature.py)
+//   k_hankel_apply  the Hankel contraction alone, for caller-evaluated P3D cells (theory.py:250-264)
 //   (cpx_factor.cuh) k_basis_f64, k_window_gram, k_gram, k_quad: the factorised path for scans and amplitude fits;
 //                 k_p3d_hankel_f64s: the staged float64-cell Hankel kernel
 //   k_probe_*     pipe-rate probes for the roofline denominators
@@ -1066,6 +1067,42 @@ __global__ void __launch_bounds__(256) k_jbar(const int* __restrict__ gstart, co
     norm += w[i];
   }
   jbar[static_cast<size_t>(g) * n_f + f] = acc * (meas[f] / norm);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_hankel_apply: the Hankel contraction alone, for P3D cells the caller evaluated (Theory._compute_px_from_p3d with an
+// arbitrary P3D callable, theory.py:250-264):  px[r][k] = sum_q W[r][q] cells[k][q]  as an FP64 DMMA GEMM.
+// A warp owns 8 separations x 64 k_par values; both operands are row-major with q contiguous, which is the m8n8k4
+// fragment order of A (row.) and B (.col) as they lie in memory.  grid = (ceil(n_k / 64), ceil(n_r / 8 / 4)), 4 warps.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_hankel_apply(const double* __restrict__ W, const double* __restrict__ cells, int n_r, int n_q,
+                                                      int n_k, double* __restrict__ px) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = (blockIdx.y * 4 + warp) * 8, k0 = blockIdx.x * 64;
+  if (r0 >= n_r) return;
+  const int ra = min(r0 + g, n_r - 1);
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  for (int q0 = 0; q0 < n_q; q0 += 4) {
+    const bool in_q = q0 + t < n_q;
+    const double a = in_q ? W[static_cast<size_t>(ra) * n_q + q0 + t] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kb = min(k0 + 8 * j + g, n_k - 1);
+      const double b = in_q ? cells[static_cast<size_t>(kb) * n_q + q0 + t] : 0.0;
+      dmma_884(acc[j][0], acc[j][1], a, b);
+    }
+  }
+  if (r0 + g < n_r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kc = k0 + 8 * j + 2 * t;
+      if (kc < n_k) px[static_cast<size_t>(r0 + g) * n_k + kc] = acc[j][0];
+      if (kc + 1 < n_k) px[static_cast<size_t>(r0 + g) * n_k + kc + 1] = acc[j][1];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

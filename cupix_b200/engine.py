@@ -83,6 +83,8 @@ def load_library(path=None):
     lib.cpx_device_count.restype = C.c_int
     lib.cpx_hankel_jbar.argtypes = [C.c_int32, C.c_int32, c_ip, c_dp, c_dp, C.c_int64, c_dp, c_dp, c_dp]
     lib.cpx_hankel_jbar.restype = C.c_int
+    lib.cpx_hankel_apply.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp, c_dp]
+    lib.cpx_hankel_apply.restype = C.c_int
     _LIB = lib
     return lib
 
@@ -119,6 +121,19 @@ def hankel_jbar(device, group_start, r_Mpc, weight, kf, meas):
     rc = lib.cpx_hankel_jbar(int(device), gs.size - 1, gs.ctypes.data_as(c_ip), _dp(r), _dp(w), kf.size, _dp(kf), _dp(meas), _dp(out))
     if rc != 0:
         raise CpxError("cpx_hankel_jbar failed (%d): %s" % (rc, lib.cpx_last_error().decode()))
+    return out
+
+
+def hankel_apply(device, W, cells):
+    """px[r, k] = sum_q W[r, q] cells[k, q] on the GPU (cpx_hankel_apply): the Hankel contraction for P3D cells evaluated by
+    the caller (Theory._compute_px_from_p3d)."""
+    lib = load_library()
+    W, cells = _f64(W), _f64(cells)
+    assert W.ndim == 2 and cells.ndim == 2 and W.shape[1] == cells.shape[1], "W [n_r, n_q] and cells [n_k, n_q] expected"
+    out = np.empty((W.shape[0], cells.shape[0]))
+    rc = lib.cpx_hankel_apply(int(device), W.shape[0], W.shape[1], cells.shape[0], _dp(W), _dp(cells), _dp(out))
+    if rc != 0:
+        raise CpxError("cpx_hankel_apply failed (%d): %s" % (rc, lib.cpx_last_error().decode()))
     return out
 
 

@@ -17,17 +17,33 @@ class ContaminantsModel(object):
     def __init__(self, z, config={'verbose': False}):
         self.z_lya = z
         self.lr_metal = 1206.52   # SiIII
+        self.setup_from_config(config)
+
+    def setup_from_config(self, config):
+        """Defaults of all contaminant parameters and the xi_noise table (model_contaminants.py:17-31)."""
         self.verbose = config.get('verbose', False)
-        self.default_hcd_params = self._with_config({'b_H': -0.02, 'beta_H': 0.5, 'L_H_Mpc': 5.0 / 0.67}, config)
-        self.default_metal_params = self._with_config({'b_X': -0.005, 'beta_X': 0.5}, config)
-        self.default_sky_params = self._with_config(
-            {'b_noise_Mpc': 0.0035 if self.z_lya == 2.2 else 0.00125}, config)
-        if self.z_lya == 2.2:
-            cont = {'kC_Mpc': 0.019, 'pC': 0.63}
-        else:
-            cont = {'kC_Mpc': 0.012, 'pC': 0.45}
-        self.default_continuum_params = self._with_config(cont, config)
+        self.default_hcd_params = self.get_default_hcd_params(config)
+        self.default_metal_params = self.get_default_metal_params(config)
+        self.default_sky_params = self.get_default_sky_params(config)
+        self.default_continuum_params = self.get_default_continuum_params(config)
         self._xi_theta, self._xi_val = self.read_xi_noise(config)
+
+    def get_default_hcd_params(self, config):
+        """L_H in Mpc, not Mpc/h (model_contaminants.py:34-45)."""
+        return self._with_config({'b_H': -0.02, 'beta_H': 0.5, 'L_H_Mpc': 5.0 / 0.67}, config)
+
+    def get_default_metal_params(self, config):
+        """model_contaminants.py:48-57"""
+        return self._with_config({'b_X': -0.005, 'beta_X': 0.5}, config)
+
+    def get_default_sky_params(self, config):
+        """Preliminary DESI DR2 fits, by redshift (model_contaminants.py:60-79)."""
+        return self._with_config({'b_noise_Mpc': 0.0035 if self.z_lya == 2.2 else 0.00125}, config)
+
+    def get_default_continuum_params(self, config):
+        """Preliminary fits on mocks, by redshift (model_contaminants.py:82-100)."""
+        cont = {'kC_Mpc': 0.019, 'pC': 0.63} if self.z_lya == 2.2 else {'kC_Mpc': 0.012, 'pC': 0.45}
+        return self._with_config(cont, config)
 
     @staticmethod
     def _with_config(defaults, config):

@@ -41,6 +41,10 @@ class LyaModel(object):
     def __init__(self, z, config={'verbose': False}):
         self.z = z
         self.lr_lya = 1215.67
+        self._setup_from_config(config)
+
+    def _setup_from_config(self, config):
+        """Default parameter values, or IGM defaults plus an emulator (model_lya.py:35-57)."""
         self.verbose = config.get('verbose', False)
         self.default_lya_model = config.get('default_lya_model', 'best_fit_arinyo_from_p1d')
         if 'igm' in self.default_lya_model:

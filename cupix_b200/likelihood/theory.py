@@ -227,6 +227,69 @@ class Theory(object):
         kaiser = lp["bias"] * mp["b_X"] * (1.0 + lp["beta"] * mu ** 2) * (1.0 + mp["beta_X"] * mu ** 2)
         return kaiser * cosmo.get_linP_Mpc(zc, k) * np.exp(-(k / _plan.METAL_KP_MPC) ** 2) * 2.0 * np.cos(k * mu * dr_Mpc)
 
+    def _compute_lya_hcd_biases(self, kpar, lya_params, hcd_params):
+        """(b_T, beta_T) of Lya + HCD along k_par (theory.py:267-282); on the device: k_rowpars."""
+        F_H = np.exp(-kpar * hcd_params['L_H_Mpc'])
+        b_T = lya_params['bias'] + hcd_params['b_H'] * F_H
+        return b_T, (lya_params['bias'] * lya_params['beta'] + hcd_params['b_H'] * hcd_params['beta_H'] * F_H) / b_T
+
+    def _compute_DNL_Arinyo(self, k, mu, linP, lya_params):
+        """D_NL of Arinyo-i-Prats et al. 2015 (theory.py:285-295)."""
+        return self._dnl(k, mu, linP, lya_params)
+
+    # -- Px in Mpc units (theory.py:311-322, 347-358, 384-395, 441-452, 476-506, 525-535).  The built-in P3D models go
+    #    through the fused device path (cells evaluated inside k_p3d_hankel); an arbitrary P3D callable goes through
+    #    _compute_px_from_p3d: cells sampled on the host by the callable, contraction on the device.
+    def _compute_px_from_p3d(self, rt_Mpc, kp_Mpc, p3d_func_kmu, kt_Mpc_max=DEFAULT_KMAX):
+        """Px(k_par, r_perp) [N_r, N_k] in Mpc of an arbitrary ``p3d_func_kmu(k, mu)`` (theory.py:250-264, where ForestFlow's
+        ``Px_Mpc_detailed`` does the transform): the callable is sampled on this object's k_perp node set, the Hankel sum
+        runs on the GPU (``cpx_hankel_apply``) against weights whose J0 sums also come from the GPU.  P3D is taken as zero
+        at k = 0 and for k_perp > kt_Mpc_max; the k_par = 0 row follows ``kpar0`` like every other plan."""
+        rt = np.atleast_1d(np.asarray(rt_Mpc, dtype=np.float64))
+        kp = np.atleast_1d(np.asarray(kp_Mpc, dtype=np.float64))
+        if self.kpar0 == 'reference':
+            kp = np.where(kp == 0.0, _plan.KPAR0_REFERENCE_MPC, kp)
+        from cupix_b200 import engine as _engine
+        if _engine.device_count() <= 0:
+            raise _engine.CpxError("cupix_b200: _compute_px_from_p3d needs a CUDA device (no CPU evaluation path exists)")
+        dev = self.device
+        W = self.rule.weights(rt, jbar_fn=lambda gs, r, w, kf, meas: _engine.hankel_jbar(dev, gs, r, w, kf, meas))
+        k, mu = _plan._cells(kp, self.rule.k)
+        with np.errstate(all='ignore'):
+            cells = np.asarray(p3d_func_kmu(np.where(k > 0, k, 1.0), mu), dtype=np.float64)
+        cells = np.where((k > 0) & (self.rule.k[None, :] <= kt_Mpc_max * (1 + 1e-12)), cells, 0.0)
+        return _engine.hankel_apply(dev, W, cells)
+
+    def _px_Mpc(self, accessor, z, lambda_rest, rt_Mpc, kp_Mpc, cosmo, params):
+        cosmo = self.get_cosmology(cosmo=cosmo, params=params)
+        dAA_dMpc = cosmo.get_dAA_dMpc(z, lambda_rest_AA=lambda_rest)
+        theta_arc = np.atleast_1d(np.asarray(rt_Mpc, dtype=np.float64)) * cosmo.get_darc_dMpc(z)
+        k_AA = np.atleast_1d(np.asarray(kp_Mpc, dtype=np.float64)) / dAA_dMpc
+        return accessor(theta_arc, k_AA, cosmo, params) / dAA_dMpc
+
+    def get_px_lya_Mpc(self, rt_Mpc, kp_Mpc, cosmo=None, params={}):
+        return self._px_Mpc(self.get_px_lya_obs, self.z, self.lya_model.lr_lya, rt_Mpc, kp_Mpc, cosmo, params)
+
+    def get_px_lya_hcd_Mpc(self, rt_Mpc, kp_Mpc, cosmo=None, params={}):
+        return self._px_Mpc(self.get_px_lya_hcd_obs, self.z, self.lya_model.lr_lya, rt_Mpc, kp_Mpc, cosmo, params)
+
+    def get_px_metal_auto_Mpc(self, rt_Mpc, kp_Mpc, cosmo=None, params={}):
+        """In the units of the metal redshift (theory.py:200-222)."""
+        return self._px_Mpc(self.get_px_metal_auto_obs, self.get_z_metal_auto(), self.cont_model.lr_metal, rt_Mpc, kp_Mpc, cosmo, params)
+
+    def get_px_metal_cross_Mpc(self, rt_Mpc, kp_Mpc, cosmo=None, params={}):
+        """In the units of the cross redshift and wavelength (theory.py:225-247)."""
+        lr_cross = np.sqrt(self.cont_model.lr_metal * self.lya_model.lr_lya)
+        return self._px_Mpc(self.get_px_metal_cross_obs, self.get_z_metal_cross(), lr_cross, rt_Mpc, kp_Mpc, cosmo, params)
+
+    def get_px_sky_Mpc(self, rt_Mpc, kp_Mpc, cosmo=None, params={}):
+        return self._px_Mpc(self.get_px_sky_obs, self.z, self.lya_model.lr_lya, rt_Mpc, kp_Mpc, cosmo, params)
+
+    def get_continuum_distortion_Mpc(self, kp_Mpc, params={}):
+        """tanh((k_par / kC)^pC) (theory.py:525-535)."""
+        cp = self.cont_model.get_continuum_params(params)
+        return np.tanh((np.asarray(kp_Mpc, dtype=np.float64) / cp["kC_Mpc"]) ** cp["pC"])
+
     def get_px_obs_batch(self, theta_arc, k_AA, points, names, cosmo=None):
         """Px [B, N_theta, N_k] for B parameter points (columns named by ``names``)."""
         cosmo = self.fid_cosmo if cosmo is None else cosmo

@@ -121,6 +121,7 @@ class DESI_DR2(BaseDataPx):
             path = filepath
         else:
             d, path = _read_hdf5(filepath), filepath
+        self._file = d            # the file's content before any cut: what the reference's per-dataset getters return
         super().__init__(d["Px_ZAM"], d["cov_ZAM"], d["z_centers"], d["k_M_edges"],
                          d["theta_min_A"], d["theta_max_A"], d["N_fft"], d["L_fft"],
                          has_theta_rebinning=True, has_k_rebinning=True, k_m_AA=d["k_m"],
@@ -129,3 +130,21 @@ class DESI_DR2(BaseDataPx):
                          theta_min_cut_arcmin=theta_min_cut_arcmin, theta_max_cut_arcmin=theta_max_cut_arcmin,
                          kM_min_cut_AA=kM_min_cut_AA, kM_max_cut_AA=kM_max_cut_AA,
                          km_min_cut_AA=km_min_cut_AA, km_max_cut_AA=km_max_cut_AA)
+
+    # -- the reference's per-dataset getters (data_DESI_DR2.py:66-99; there each call re-opens the file) -------------
+    def read_from_file(self):
+        d = self._file
+        return (d["k_m"], d["k_M_edges"], d["theta_min_a"], d["theta_max_a"], d["theta_min_A"], d["theta_max_A"],
+                d["z_centers"], d["N_fft"], d["L_fft"], d["B_A_a"])
+
+    def get_Px_z_T(self, zbin_ind, theta_bin_ind):
+        return np.array(self._file["Px_ZAM"][zbin_ind][theta_bin_ind])
+
+    def get_cov_matrix_z_T(self, zbin_ind, theta_bin_ind):
+        return np.array(self._file["cov_ZAM"][zbin_ind][theta_bin_ind])
+
+    def get_window_matrix_z_t(self, zbin_ind, theta_bin_ind):
+        return np.array(self._file["U_ZaMn"][zbin_ind][theta_bin_ind])
+
+    def get_V_Z_aM(self, zbin_ind, theta_bin_ind):
+        return np.array(self._file["V_ZaM"][zbin_ind][theta_bin_ind])

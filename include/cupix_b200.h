@@ -208,6 +208,13 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
 int cpx_hankel_jbar(int32_t device, int32_t n_groups, const int32_t* group_start, const double* r_Mpc, const double* weight,
                     int64_t n_f, const double* kf, const double* meas, double* jbar);
 
+/* The Hankel contraction alone, for P3D cells the caller evaluated: px[r][k] = sum_q W[r][q] cells[k][q] in FP64 on the
+ * device (DMMA).  Replaces the transform inside Theory._compute_px_from_p3d (cupix/likelihood/theory.py:250-264 ->
+ * forestflow.pcross.Px_Mpc_detailed) when the P3D is an arbitrary host callable: the caller samples it on the rule's
+ * (k_par, k_perp node) grid, W are the rule's weights for the requested separations (cpx_hankel_jbar + spline
+ * projection).  Host pointers: W [n_r][n_q], cells [n_k][n_q], px [n_r][n_k]; synchronous. */
+int cpx_hankel_apply(int32_t device, int32_t n_r, int32_t n_q, int32_t n_k, const double* W, const double* cells, double* px);
+
 /* Pipe-rate probes for the roofline denominators MEASURED_PEAKS.json does not hold: sustained
  * FP64 FMA (DFMA), FP32 FMA, MUFU.EX2 and FP64 tensor (DMMA m8n8k4, counted in FMAs) rates of this
  * GPU (results in ops/s; an FMA counts as one op).  Any pointer may be NULL. */

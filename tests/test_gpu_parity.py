@@ -566,3 +566,66 @@ def test_theory_component_accessors_vs_oracle():
     total = (th.get_px_lya_hcd_obs(theta, k_AA, params=params) + th.get_px_metal_auto_obs(theta, k_AA, params=params)
              + th.get_px_metal_cross_obs(theta, k_AA, params=params) + th.get_px_sky_obs(theta, k_AA, params=params)) * cont[None, :]
     assert_px(total, th.get_px_obs(theta, k_AA, params=params), tol=1e-7, msg="sum of the components")
+
+
+def test_px_from_arbitrary_p3d_callable_and_Mpc_accessors():
+    """Theory._compute_px_from_p3d (theory.py:250-264) with an arbitrary P3D callable -- cells sampled by the callable on
+    the host, Hankel sum on the device (cpx_hankel_apply) -- and the reference's *_Mpc accessors (theory.py:311-322,
+    347-358, 384-395, 441-452, 476-506, 525-535)."""
+    th = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS["all"])
+    orc = H.oracle_for(th)
+    params = {"bias": -0.13, "beta": 1.4, "q1": 0.5, "b_H": -0.03, "b_X": -0.007, "beta_X": 0.6, "b_noise_Mpc": 0.002}
+    rt = np.array([0.05, 0.4, 2.0, 11.0, 37.0, 80.0])
+    kp = np.concatenate([[0.0], np.geomspace(0.02, 4.0, 70)])      # 71 values: ragged against the 64-wide warp tile
+    # (1) a model P3D through the generic path: float64 cells, so the oracle's node rule to rounding
+    got = th._compute_px_from_p3d(rt, kp, lambda k, mu: th.get_p3d_lya_hcd_Mpc(k, mu, params=params), 200.0)
+    want = orc.hankel(rt, kp, lambda k, mu: orc.p3d_lya_hcd(k, mu, params))
+    assert got.shape == (rt.size, kp.size)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()      # J0 on the device: 5e-12
+    # ... and the fused device path (float32 cells) for the same term, in Mpc units
+    fused = th.get_px_lya_hcd_Mpc(rt, kp, params=params)
+    assert np.abs(fused - want).max() <= PX_RTOL * np.abs(want).max()
+    # (2) a P3D that is no model of the package, with a closed-form transform:
+    #     P3D = exp(-s^2 k^2)  ->  Px = exp(-s^2 k_par^2) exp(-r^2 / 4 s^2) / (4 pi s^2)
+    s2 = 0.6 ** 2
+    got = th._compute_px_from_p3d(rt, kp, lambda k, mu: np.exp(-s2 * k ** 2), 200.0)
+    exact = np.exp(-s2 * kp[None, :] ** 2) * np.exp(-rt[:, None] ** 2 / (4 * s2)) / (4 * np.pi * s2)
+    assert np.abs(got - exact).max() <= 3e-5 * np.abs(exact).max()
+    # kt_Mpc_max cuts the integrand in k_perp: int_0^K = (1 - exp(-s^2 K^2)) / (4 pi s^2) at r = 0 (here r = 0.05: J0 ~ 1)
+    cut = th._compute_px_from_p3d(rt[:1], kp[:1], lambda k, mu: np.exp(-s2 * k ** 2), 1.0)
+    assert abs(cut[0, 0] / ((1 - np.exp(-s2)) / (4 * np.pi * s2)) - 1) < 0.15 and cut[0, 0] < 0.7 * got[0, 0]
+    # (3) the *_Mpc accessors against the oracle's terms in the units of their own redshift
+    from oracle.px_oracle import LR_LYA, LR_METAL
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(th.get_px_lya_Mpc(rt, kp, params=params), orc.hankel(rt, kp, lambda k, mu: orc.p3d_lya(k, mu, params)),
+                               rtol=0, atol=PX_RTOL * scale)
+    np.testing.assert_allclose(th.get_px_metal_auto_Mpc(rt, kp, params=params),
+                               orc.hankel(rt, kp, lambda k, mu: orc.p3d_metal_auto(k, mu, params)), rtol=0, atol=PX_RTOL * scale)
+    np.testing.assert_allclose(th.get_px_metal_cross_Mpc(rt, kp, params=params),
+                               orc.hankel(rt, kp, lambda k, mu: orc.p3d_metal_cross(k, mu, params)), rtol=0, atol=PX_RTOL * scale)
+    dAA = th.fid_cosmo.get_dAA_dMpc(th.z, lambda_rest_AA=LR_LYA)
+    theta = rt * th.fid_cosmo.get_darc_dMpc(th.z)
+    np.testing.assert_allclose(th.get_px_sky_Mpc(rt, kp, params=params), orc.px_sky_obs(theta, kp / dAA, params) / dAA,
+                               rtol=0, atol=PX_RTOL * scale)
+    np.testing.assert_allclose(th.get_continuum_distortion_Mpc(kp, params=params), orc.continuum_distortion_obs(kp / dAA, params), rtol=1e-13)
+    b_T, beta_T = th._compute_lya_hcd_biases(kp, th.lya_model.get_lya_params(th.fid_cosmo, params), th.cont_model.get_hcd_params(params))
+    F = np.exp(-kp * th.cont_model.get_hcd_params(params)["L_H_Mpc"])
+    np.testing.assert_allclose(b_T, -0.13 + -0.03 * F, rtol=1e-15)
+    np.testing.assert_allclose(beta_T * b_T, -0.13 * 1.4 + -0.03 * th.cont_model.get_hcd_params(params)["beta_H"] * F, rtol=1e-14)
+
+
+def test_window_and_rebin_helpers_on_device_px_zam():
+    """window_and_rebin.convolve_window / rebin_theta (window_and_rebin.py:59-76) applied on the host to the device's own
+    Px_Zam reproduce the device's window stage (likelihood.py:53-88)."""
+    from cupix_b200.likelihood.window_and_rebin import convolve_window, rebin_theta
+    d = synthetic.make_measurement_dict("S1", N_A=5, fine_per_coarse=3, N_m=45, rebin_k=3, Nz=1)
+    data = DESI_DR2(d)
+    th = H.make_theory(float(d["z_centers"][0]), "best_fit_arinyo_from_gadget", {"include_hcd": True})
+    like = Likelihood(data, th, 0, config={"N_theta_average": 2})
+    px_zam = like._compute_Px_Zam({"bias": -0.12})
+    out = like.get_convolved_px({"bias": -0.12})
+    for A in range(out.shape[0]):
+        members = np.where(data.B_A_a[A].astype(bool))[0]
+        conv = np.array([convolve_window(data.U_ZaMn[0, a], px_zam[a]) for a in members])
+        want = rebin_theta(data.V_ZaM[0, members], conv)
+        assert np.abs(out[A] - want).max() <= 1e-12 * np.abs(want).max()

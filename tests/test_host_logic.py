@@ -413,3 +413,33 @@ def test_p3d_model_functions_equal_the_oracle():
     for ours, theirs in ((th.get_p3d_lya_Mpc, orc.p3d_lya), (th.get_p3d_lya_hcd_Mpc, orc.p3d_lya_hcd),
                          (th.get_p3d_metal_auto_Mpc, orc.p3d_metal_auto), (th.get_p3d_metal_cross_Mpc, orc.p3d_metal_cross)):
         np.testing.assert_allclose(ours(k, mu, params=params), theirs(k, mu, params), rtol=1e-13)
+
+
+def test_reference_named_helpers_of_the_host_mirrors():
+    """Names the reference's scripts and notebooks reach for (data_DESI_DR2.py:66-99 per-dataset getters,
+    model_contaminants.py:17-100 default getters, window_and_rebin.py:59-76), on the host side of the boundary."""
+    from cupix_b200.likelihood.model_contaminants import ContaminantsModel
+    from cupix_b200.likelihood.window_and_rebin import convolve_window, rebin_theta
+    from oracle import px_oracle
+    d = synthetic.make_measurement_dict("S1", N_A=4, fine_per_coarse=2, N_m=30, rebin_k=3, Nz=2)
+    data = DESI_DR2(d, kM_max_cut_AA=0.12)         # cuts change the object, not what the file getters return
+    k_m, k_M_edges, tmin_a, tmax_a, tmin_A, tmax_A, zc, N_fft, L_fft, B_A_a = data.read_from_file()
+    np.testing.assert_array_equal(k_M_edges, d["k_M_edges"])
+    np.testing.assert_array_equal(B_A_a, d["B_A_a"])
+    np.testing.assert_array_equal(data.get_Px_z_T(1, 2), d["Px_ZAM"][1][2])
+    np.testing.assert_array_equal(data.get_cov_matrix_z_T(0, 3), d["cov_ZAM"][0][3])
+    np.testing.assert_array_equal(data.get_window_matrix_z_t(1, 5), d["U_ZaMn"][1][5])
+    np.testing.assert_array_equal(data.get_V_Z_aM(0, 7), d["V_ZaM"][0][7])
+    assert data.Px_ZAM.shape[-1] < d["Px_ZAM"].shape[-1]
+
+    c22, c30 = ContaminantsModel(2.2, {"b_H": -0.05}), ContaminantsModel(3.0, {"pC": 0.5})
+    assert c22.get_default_hcd_params({}) == {"b_H": -0.02, "beta_H": 0.5, "L_H_Mpc": 5.0 / 0.67}
+    assert c22.default_hcd_params["b_H"] == -0.05 and c22.get_default_metal_params({"beta_X": 1.0}) == {"b_X": -0.005, "beta_X": 1.0}
+    assert c22.get_default_sky_params({})["b_noise_Mpc"] == 0.0035 and c30.get_default_sky_params({})["b_noise_Mpc"] == 0.00125
+    assert c22.get_default_continuum_params({}) == {"kC_Mpc": 0.019, "pC": 0.63}
+    assert c30.default_continuum_params == {"kC_Mpc": 0.012, "pC": 0.5}
+
+    rng = np.random.default_rng(3)
+    U, model, V, P = rng.normal(size=(7, 30)), rng.normal(size=30), rng.uniform(0.5, 1.5, (3, 7)), rng.normal(size=(3, 7))
+    np.testing.assert_array_equal(convolve_window(U, model), px_oracle.convolve_window(U, model))
+    np.testing.assert_allclose(rebin_theta(V, P), px_oracle.rebin_theta(V, P), rtol=1e-15)
