@@ -16,6 +16,7 @@
 
 #include "cpx_kernels.cuh"
 #include "cpx_hankel_tc.cuh"
+#include "cpx_hankel_imma.cuh"
 #include "cpx_window_tc.cuh"
 #include "cpx_factor.cuh"
 
@@ -72,6 +73,7 @@ struct cpx_handle {
   long long launches = 0;
   int wt_nb = 0;                     // > 0: k_window_tc (tcgen05 window contraction) for the chi2 stage
   int tc_np = 0;                     // > 0: k_p3d_hankel_tc (tcgen05 Hankel contraction) with this many cell pairs per lane
+  int im_nkb = 0;                    // > 0: k_p3d_hankel_imma (mma.sync INT8 Hankel contraction) with this many 32-slot K blocks
   // per-chunk scratch
   double* d_points = nullptr;        // [chunk][16]
   int* d_data_idx = nullptr;         // [chunk]
@@ -343,6 +345,65 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     Z.tc_ta = dta;
     keep(dta);
   }
+  // ---- INT8 mma.sync Hankel path (cpx_hankel_imma.cuh): cell constants with P_L s_q, weight digits in B-fragment order ----
+  Z.im_cell = nullptr;
+  Z.im_wdig = nullptr;
+  Z.im_ta = nullptr;
+  if (h->im_nkb > 0 && Z.n_q4 <= 8 * h->im_nkb) {
+    const int NKB = h->im_nkb, nt = na_blk / 8;
+    std::vector<double> sq(d.n_q, 1.0);
+    for (int q = 0; q < d.n_q; ++q) {
+      double mx = 0.0;
+      for (int a = 0; a < d.n_a; ++a) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q]));
+      if (mx > 0.0) sq[q] = std::ldexp(1.0, std::max(-100, std::min(100, static_cast<int>(std::lround(std::log2(mx))))));
+    }
+    // cellc is still on the host side of this function only as `d`: rebuild the P_L entries scaled by s_q (exact)
+    std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * Z.n_q4 * kCellConsts * 4 * 32, 0.0f);
+    CPX_CUDA(cudaMemcpy(cell.data(), Z.cellc, cell.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int tile = 0; tile < Z.n_tiles; ++tile)
+      for (int ks = 0; ks < Z.n_q4; ++ks)
+        for (int i = 0; i < 2 * 32 * 2; ++i) {
+          const int lane = (i / 2) % 32, q = 4 * ks + (lane & 3);
+          if (q < d.n_q) cell[((static_cast<size_t>(tile) * Z.n_q4 + ks) * kCellConsts + 5) * 2 * 32 * 2 + i] *= static_cast<float>(sq[q]);
+        }
+    float* dcell;
+    int rc = upload(cell, &dcell, &bytes);
+    if (rc) return rc;
+    Z.im_cell = dcell;
+    keep(dcell);
+    std::vector<double> ta(static_cast<size_t>(Z.n_ablk) * na_blk, 1.0);
+    const size_t dig_bytes = static_cast<size_t>(imma_dig_bytes(NKB, nt));
+    std::vector<unsigned char> dig(static_cast<size_t>(Z.n_ablk) * dig_bytes, 0);
+    const double full = std::ldexp(1.0, 8 * kImNW);
+    for (int a = 0; a < d.n_a; ++a) {
+      double mx = 0.0;
+      for (int q = 0; q < d.n_q; ++q) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q] / sq[q]));
+      const double t = mx > 0.0 ? 2.05 * mx : 1.0;
+      ta[a] = t;
+      const int ablk = a / na_blk, jn = (a % na_blk) / 8, g = a % 8;
+      for (int q = 0; q < d.n_q; ++q) {
+        // K slot of node q: lane t = q % 4, ks = q / 4 = 8 b + 4 half + byte
+        const int tq = q % 4, ks = q / 4, b = ks / 8, half = (ks % 8) / 4, byte = ks % 4;
+        long long X = std::llrint(d.hankel_w[static_cast<size_t>(a) * d.n_q + q] / sq[q] / t * full);
+        for (int j = kImNW - 1; j >= 0; --j) {          // balanced base-256 digits, least significant first
+          long long dg = ((X + 128) % 256 + 256) % 256 - 128;
+          X = (X - dg) / 256;
+          dig[ablk * dig_bytes + ((((static_cast<size_t>(b) * kImNW + j) * nt + jn) * 32 + 4 * g + tq) * 2 + half) * 4 + byte] =
+              static_cast<unsigned char>(static_cast<signed char>(dg));
+        }
+      }
+    }
+    unsigned char* ddig;
+    rc = upload(dig, &ddig, &bytes);
+    if (rc) return rc;
+    Z.im_wdig = ddig;
+    keep(ddig);
+    double* dta;
+    rc = upload(ta, &dta, &bytes);
+    if (rc) return rc;
+    Z.im_ta = dta;
+    keep(dta);
+  }
   auto up_copy = [&](const double* src, size_t n, const double** dst) -> int {
     *dst = nullptr;
     if (!src) return CPX_OK;
@@ -598,6 +659,29 @@ K1Fn k1_select_tc(int np, bool add) {
     case 12: return add ? cpx::k_p3d_hankel_tc<12, true> : cpx::k_p3d_hankel_tc<12, false>;
   }
   return nullptr;
+}
+
+template <int NKB, bool ADD, bool COSMO>
+K1Fn k1_select_imma_nt(int nt) {
+  switch (nt) {
+    case 1: return cpx::k_p3d_hankel_imma<NKB, 1, ADD, COSMO>;
+    case 2: return cpx::k_p3d_hankel_imma<NKB, 2, ADD, COSMO>;
+    case 3: return cpx::k_p3d_hankel_imma<NKB, 3, ADD, COSMO>;
+  }
+  return nullptr;
+}
+template <int NKB>
+K1Fn k1_select_imma_nkb(int nt, bool add, bool cosmo) {
+  if (cosmo) return add ? k1_select_imma_nt<NKB, true, true>(nt) : k1_select_imma_nt<NKB, false, true>(nt);
+  return add ? k1_select_imma_nt<NKB, true, false>(nt) : k1_select_imma_nt<NKB, false, false>(nt);
+}
+K1Fn k1_select_imma(int nkb, int nt, bool add, bool cosmo) {
+  if (nkb == 2) return k1_select_imma_nkb<2>(nt, add, cosmo);
+  if (nkb == 3) return k1_select_imma_nkb<3>(nt, add, cosmo);
+  return nullptr;
+}
+size_t imma_smem_bytes(int max_nq, int nkb, int nt) {
+  return static_cast<size_t>((max_nq + 3) / 4) * (cpx::kCellConsts * 4 * 32 * 4) + cpx::imma_dig_bytes(nkb, nt) + 8 * nt * 8;
 }
 
 K1Fn k1_select_f64s(int nt) {      // shared-memory staged variant, 16 points per CTA (cpx_factor.cuh)
@@ -1265,6 +1349,10 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
   if (smem_need > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
     return bail(fail(CPX_ERR_UNSUPPORTED, "cpx_create: n_q too large for the shared-memory-resident grid"));
 
+  // INT8 mma.sync Hankel path (default): up to 96 k_perp nodes; CPX_IMMA=0 keeps the FP64 DMMA kernel
+  h->im_nkb = 0;
+  if (env_int("CPX_IMMA", 1) != 0 && h->max_nq <= 96) h->im_nkb = (h->max_nq + 3) / 4 <= 16 ? 2 : 3;
+
   h->z.resize(n_zbins);
   size_t per_point_bytes = 0;
   for (int i = 0; i < n_zbins; ++i) {
@@ -1302,6 +1390,17 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
     }
+  if (h->im_nkb > 0) {
+    bool ok = true;
+    for (auto& zh : h->z) ok &= zh.dev.im_cell != nullptr;
+    if (!ok) h->im_nkb = 0;
+    for (int add = 0; add < 4 && h->im_nkb > 0; ++add) {
+      K1Fn fn = k1_select_imma(h->im_nkb, h->na_blk / 8, (add & 1) != 0, (add & 2) != 0);
+      if (!fn || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(imma_smem_bytes(h->max_nq, h->im_nkb, h->na_blk / 8))) != cudaSuccess)
+        return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_p3d_hankel_imma"));
+    }
+  }
   // tensor-core Hankel path: every z must have its tables (n_q <= 96) and share the pairs-per-lane template value
   h->tc_np = 0;
   if (env_int("CPX_TC", 0) != 0) {   // opt-in: measured 43.7 ms against 38.7 ms of the FP64 DMMA kernel per 65536-point S5 step
@@ -1456,6 +1555,7 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
     case CPX_INFO_FACTORED_CALLS: *value = h->factored_calls; break;
     case CPX_INFO_FACTORED_TUPLES: *value = h->factored_tuples; break;
     case CPX_INFO_FACTORED_CACHE_HITS: *value = h->factored_cache_hits; break;
+    case CPX_INFO_HANKEL_KERNEL: *value = h->tc_np > 0 ? 1 : (h->im_nkb > 0 ? 2 : 0); break;
     case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
     case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
     case CPX_INFO_SM_COUNT: *value = h->sm_count; break;
@@ -1632,6 +1732,8 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     const size_t k1_smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
     int pp = pp_env > 0 ? std::min(pp_env, 2) : (2 * (k1_smem + 2048) <= 227u * 1024u ? 1 : 2);
     const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
+    const bool imma = h->im_nkb > 0 && !precise && !tc;   // INT8 mma.sync Hankel kernel: one point per warp (the default)
+    if (imma) pp = 1;
     // float64 cells: the shared-memory staged kernel (16 points per CTA) when the float64 tile fits, else one warp per point
     const size_t f64_smem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
     const bool f64_staged = precise && f64_smem + 1024 <= 227u * 1024u && env_int("CPX_F64_STAGE", 1) != 0;
@@ -1709,6 +1811,10 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         K1Fn fn = k1_select_f64(h->na_blk / 8);
         const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
         fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);
+      } else if (imma) {
+        K1Fn fn = k1_select_imma(h->im_nkb, h->na_blk / 8, additive, cosmo);
+        const int grid = static_cast<int>(std::min<long long>(n_items, 2LL * h->sm_count));
+        fn<<<grid, kK1Threads, imma_smem_bytes(h->max_nq, h->im_nkb, h->na_blk / 8), st>>>(h->d_ztab, n_zl, count, n_items);
       } else if (tc) {
         K1Fn fn = k1_select_tc(h->tc_np, additive);
         const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));

@@ -1,0 +1,335 @@
+// k_p3d_hankel_imma: the P3D -> Px Hankel contraction as an error-free integer split on the INT8 tensor path issued with
+// mma.sync (IMMA.16832), accumulators in registers.
+//
+// Same mathematics and the same FP32 cell evaluation as k_p3d_hankel (theory.py:250-344 + the theta average of
+// likelihood.py:99-130):   Px_Zam[pt][a][m] = amp(m) * sum_q W[a][q] * P3D'(m, q; pt).
+// Why: on B200 the FP64 DMMA occupies the datapath the FP32 cell evaluation needs, so the two add
+// (T = 16 N_DMMA + T_FP32).  mma.sync on s8/u8 runs on the tensor cores proper: 8 cycles per
+// m16n8k32 per sub-partition, 11.5 beside saturating FFMA2 traffic from other warps, which it does not slow down
+// (tools/imma_probe.cu, profiles/imma_probe_r02.txt).  Unlike the tcgen05 version of the same split (cpx_hankel_tc.cuh) this
+// one keeps the warp-level structure of k_p3d_hankel -- cells generated in the lanes that feed them to the MMA, no
+// shared-memory operand tiles, no tensor memory, no inter-warp hand-off -- which is what that version paid for.
+//
+//   * weights, constants of the batch:  W[a][q] = s_q t_a sum_j B_j[a][q] 256^-(j+1),  kImNW balanced base-256 digits (s8),
+//     s_q = 2^round(log2 max_a |W[a][q]|) folded into the P_L constant of the cell (exact), t_a applied in the epilogue;
+//   * a warp owns 16 k_par rows (rows g, g + 8 of the lane, as the packed FP32 pair) of one point at a time: lane (g, t)
+//     evaluates the cells of nodes 4 ks + t, ks = 0 .. n_q4 - 1, keeps them in registers, takes the exact row maximum
+//     (two shuffles), converts to 32-bit fixed point relative to it (U = rni(cell 2^(158 - e))) and transposes bytes:
+//     the four bytes of four consecutive cells are the A-fragment registers of the four u8 slices.  K slot (block b,
+//     half h, 4 t + j) of the MMA is node 4 (8 b + 4 h + j) + t: any permutation of K is allowed, the digit table uses
+//     the same one;
+//   * slice pairs (i, j) with i + j <= kImSmax go to accumulator i + j (INT32, exact: < 2^24 per accumulator); the
+//     rest (< 2^-32 of the row scale, unbiased: balanced digits, round-to-nearest cells) is not issued;
+//   * the epilogue combines the classes exactly (Horner, < 2^53) and applies 2^(e - 166) t_a amp cont.
+// Error against the float64 dot product of the same FP32 cells: <= 4e-9 of the Px scale per theta bin with 4 x 4 slices
+// and 10 pairs (tests/test_tc_split.py), a tenth of the float32 rounding of the cells themselves.
+//
+// CTA = 8 warps, 2 CTAs per SM, persistent over (z, 32-row tile, theta block, point group) items exactly like
+// k_p3d_hankel; cell constants of the tile (P_L scaled by s_q) and the digit table of the theta block are staged with
+// TMA bulk copies and stay resident.  n_q <= 32 NKB nodes (NKB = 2, 3); wider node sets keep the DMMA kernel.
+#pragma once
+#include "cpx_kernels.cuh"
+
+namespace cpx {
+
+constexpr int kImNA = 4;        // cell bytes (u8 slices)
+constexpr int kImNW = 4;        // weight digits (s8 slices)
+constexpr int kImSmax = 3;      // highest slice-pair class i + j issued
+constexpr int kImCls = kImSmax + 1;
+
+__host__ __device__ constexpr int imma_dig_bytes(int nkb, int nt) { return nkb * kImNW * nt * 32 * 8; }
+
+__device__ __forceinline__ void imma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ uint32_t im_f2u(float x) {
+  uint32_t u;
+  asm("cvt.rni.u32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ uint32_t im_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// exact int32 -> float64 on the ALU + FP64 pipes (I2F.F64 runs at the MUFU rate)
+__device__ __forceinline__ double im_i2d(int v) {
+  return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+template <int NKB, int NT, bool ADD, bool COSMO>
+__global__ void __launch_bounds__(kK1Threads, 2)
+    k_p3d_hankel_imma(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
+  constexpr int NKS = 8 * NKB;                         // cell slots per lane and row
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) ZDev s_Z;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_pg = (count + kK1Warps - 1) / kK1Warps;
+
+  const long long it0 = n_items * blockIdx.x / gridDim.x;
+  const long long it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+  if (it0 >= it1) return;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  int cur_z = -1, cur_tile = -1, cur_ablk = -1;
+
+  int zi, tile, ablk, pg;
+  {
+    zi = 0;
+    while (zi + 1 < n_z && ztab[zi + 1].item_start <= it0) ++zi;
+    long long r = it0 - ztab[zi].item_start;
+    pg = static_cast<int>(r % n_pg);
+    r /= n_pg;
+    ablk = static_cast<int>(r % ztab[zi].n_ablk);
+    tile = static_cast<int>(r / ztab[zi].n_ablk);
+  }
+
+  for (long long it = it0; it < it1; ++it) {
+    if (zi != cur_z) {
+      __syncthreads();
+      const int* src = reinterpret_cast<const int*>(&ztab[zi]);
+      int* dst = reinterpret_cast<int*>(&s_Z);
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(ZDev) / 4); i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+    }
+    const ZDev& Z = s_Z;
+    const int n_ks = Z.n_q4;
+    const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
+    constexpr uint32_t dig_bytes = imma_dig_bytes(NKB, NT);
+    constexpr uint32_t ta_bytes = 8 * NT * 8u;
+    const float2* s_cell = reinterpret_cast<const float2*>(smem_raw);
+    const uint2* s_dig = reinterpret_cast<const uint2*>(smem_raw + cell_bytes);
+    const double* s_ta = reinterpret_cast<const double*>(smem_raw + cell_bytes + dig_bytes);
+
+    const bool new_tile = (zi != cur_z) || (tile != cur_tile);
+    const bool new_w = (zi != cur_z) || (ablk != cur_ablk);
+    if (new_tile || new_w) {
+      __syncthreads();   // every warp is done reading the previous tile / digits
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (new_tile ? cell_bytes : 0u) + (new_w ? dig_bytes + ta_bytes : 0u));
+        if (new_tile) {
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(Z.im_cell) + static_cast<size_t>(tile) * cell_bytes;
+          for (uint32_t off = 0; off < cell_bytes; off += 32768u)
+            bulk_g2s(smem_raw + off, src + off, min(32768u, cell_bytes - off), &bar);
+        }
+        if (new_w) {
+          bulk_g2s(smem_raw + cell_bytes, reinterpret_cast<const unsigned char*>(Z.im_wdig) + static_cast<size_t>(ablk) * dig_bytes, dig_bytes, &bar);
+          bulk_g2s(smem_raw + cell_bytes + dig_bytes, reinterpret_cast<const unsigned char*>(Z.im_ta) + static_cast<size_t>(ablk) * ta_bytes,
+                   ta_bytes, &bar);
+        }
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+      cur_z = zi;
+      cur_tile = tile;
+      cur_ablk = ablk;
+    }
+
+    const int pt = pg * kK1Warps + warp;           // this warp's point
+    if (pt >= count) {
+      next_item(Z, n_pg, zi, tile, ablk, pg);
+      continue;
+    }
+    const int m_base = tile * kTileRows;
+    const bool rowwise = (Z.flags & 9) != 0;       // HCD or continuum: per-row scalars from k_rowpars
+    const PtPar& pr = Z.ptpar[pt];
+    const RowPar* const rp = Z.rowpar + static_cast<size_t>(pt) * Z.n_m_pad + m_base + g;
+
+    // warm L1 / L2 with the parameters of this warp's next item (same tile, next point group)
+    if (pg + 1 < n_pg) {
+      const int ptn = min(pt + kK1Warps, count - 1);
+      if (lane == 0) prefetch_l1(&Z.ptpar[ptn]);
+      if (rowwise && lane < 8) prefetch_l1(&Z.rowpar[static_cast<size_t>(ptn) * Z.n_m_pad + m_base + 4 * lane]);
+    }
+
+    const int a_lane0 = ablk * (8 * NT) + 2 * t;
+    const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
+    double* const outp = Z.pxzam + (static_cast<size_t>(pt) * n_a + a_lane0) * n_m_pad + m_base + g;
+
+    // the two 16-row halves of the tile, one after the other: rows 16 h2 + g (.x) and 16 h2 + 8 + g (.y)
+#pragma unroll 1
+    for (int h2 = 0; h2 < 2; ++h2) {
+      uint32_t A[NKB][kImNA][4];
+      int ebx, eby;
+      {
+        // ---- per-point scalars (duplicated into both halves of a packed register) and the Kaiser beta of the two rows ----
+        const float2 q1l = dup2(pr.q1l), q1lo = dup2(pr.q1l_lo), q2l = dup2(pr.q2l), q2lo = dup2(pr.q2l_lo);
+        const float2 av = dup2(pr.av), bv = dup2(pr.bv), nlkv = dup2(pr.nlkv), nlkvlo = dup2(pr.nlkv_lo);
+        const float2 ikp2l = dup2(pr.ikp2l), ikp2lo = dup2(pr.ikp2l_lo);
+        float2 cdn, clr, clrlo;
+        if (COSMO) {
+          cdn = dup2(pr.dn);
+          clr = dup2(pr.lr);
+          clrlo = dup2(pr.lr_lo);
+        }
+        float2 betaT, betaTlo;
+        if (rowwise) {
+          betaT = make_float2(rp[16 * h2].betaT_hi, rp[16 * h2 + 8].betaT_hi);
+          betaTlo = make_float2(kKaiserLoScale * rp[16 * h2].betaT_lo, kKaiserLoScale * rp[16 * h2 + 8].betaT_lo);
+        } else {
+          float hi, lo;
+          split_hi_lo(pr.beta, hi, lo);
+          betaT = dup2(hi);
+          betaTlo = dup2(kKaiserLoScale * lo);
+        }
+
+        // ---- the lane's cells of this half: nodes 4 ks + t, both rows packed ----
+        float2 x[NKS];
+        float mx = 0.0f, my = 0.0f;
+        const float2* c = s_cell + h2 * 32 + lane;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          x[ks] = make_float2(0.0f, 0.0f);
+          if (ks < n_ks) {
+            const float2 D0 = c[0 * 64], L2K = c[1 * 64], L2MU = c[2 * 64], MU2 = c[3 * 64], NK2 = c[4 * 64], PL0 = c[5 * 64];
+            float2 D = D0, PL = PL0;
+            if (COSMO) {   // P_L and Delta^2 of the rescaled cosmology (theory.py:54-56)
+              const float2 f = exp2_rr2(add2(fma2(cdn, L2K, clr), clrlo));
+              D = mul2(D0, f);
+              PL = mul2(PL0, f);
+            }
+            // identical arithmetic to k_p3d_hankel (see the comments there)
+            const float2 nl = mul2(D, add2(fma2(q2l, D, q1l), fma2(q2lo, D, q1lo)));
+            const float2 nv = exp2_rr2_neg(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
+            const float2 tt = fma2(NK2, ikp2lo, fma2(NK2, ikp2l, nl));
+            const float2 e = kExpDnl(fma2(nl, nv, tt));
+            float2 y = mul2(PL, e);
+#if CPX_KAISER == 0
+            y = fma2(mul2(y, betaT), MU2, y);
+            y = fma2(mul2(y, betaT), MU2, fma2(mul2(y, betaTlo), MU2, y));
+#else
+            const float2 bm = fma2(betaT, MU2, mul2(betaTlo, MU2));
+            y = fma2(y, bm, y);
+            y = fma2(y, bm, y);
+#endif
+            x[ks] = y;
+            mx = fmaxf(mx, y.x);
+            my = fmaxf(my, y.y);
+            c += kCellConsts * 2 * 32;
+          }
+        }
+        // exact row maxima over the four lanes that share the rows
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, 2));
+        // fixed point relative to the row maximum: rmax < 2^(e - 126)  =>  cell * 2^(158 - e) < 2^32
+        ebx = static_cast<int>(min(max(__float_as_uint(mx) >> 23, 31u), 254u));
+        eby = static_cast<int>(min(max(__float_as_uint(my) >> 23, 31u), 254u));
+        const float2 scale = make_float2(__uint_as_float(static_cast<uint32_t>(285 - ebx) << 23),
+                                         __uint_as_float(static_cast<uint32_t>(285 - eby) << 23));
+        // ---- 32-bit fixed point, 4 x 4 byte transposes: slice i takes byte 3 - i of four consecutive cells ----
+#pragma unroll
+        for (int q4 = 0; q4 < 2 * NKB; ++q4) {
+          uint32_t ux[4], uy[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 sc = mul2(x[4 * q4 + j], scale);
+            ux[j] = im_f2u(sc.x);
+            uy[j] = im_f2u(sc.y);
+          }
+          const int b = q4 >> 1, hh = q4 & 1;      // MMA K block and half: A registers 2 hh (row g) and 2 hh + 1 (row g + 8)
+          {
+            const uint32_t xa = im_prmt(ux[0], ux[1], 0x6273), ya = im_prmt(ux[0], ux[1], 0x4051);
+            const uint32_t xb = im_prmt(ux[2], ux[3], 0x6273), yb = im_prmt(ux[2], ux[3], 0x4051);
+            A[b][0][2 * hh] = im_prmt(xa, xb, 0x5410);
+            A[b][1][2 * hh] = im_prmt(xa, xb, 0x7632);
+            A[b][2][2 * hh] = im_prmt(ya, yb, 0x5410);
+            A[b][3][2 * hh] = im_prmt(ya, yb, 0x7632);
+          }
+          {
+            const uint32_t xa = im_prmt(uy[0], uy[1], 0x6273), ya = im_prmt(uy[0], uy[1], 0x4051);
+            const uint32_t xb = im_prmt(uy[2], uy[3], 0x6273), yb = im_prmt(uy[2], uy[3], 0x4051);
+            A[b][0][2 * hh + 1] = im_prmt(xa, xb, 0x5410);
+            A[b][1][2 * hh + 1] = im_prmt(xa, xb, 0x7632);
+            A[b][2][2 * hh + 1] = im_prmt(ya, yb, 0x5410);
+            A[b][3][2 * hh + 1] = im_prmt(ya, yb, 0x7632);
+          }
+        }
+      }
+
+      // ---- row factors of the epilogue: 2^(e - 166) amp cont; Px = (factor * t_a * H + additive) * cont ----
+      const int m0 = m_base + 16 * h2 + g, m1 = m0 + 8;
+      double amp_x, amp_y, cont_x = 1.0, cont_y = 1.0;
+      if (rowwise) {
+        amp_x = rp[16 * h2].amp;
+        amp_y = rp[16 * h2 + 8].amp;
+        cont_x = rp[16 * h2].cont;
+        cont_y = rp[16 * h2 + 8].cont;
+      } else {
+        amp_x = amp_y = pr.bias * pr.bias * Z.dAA;
+      }
+      constexpr int E0 = 158 - 8 * (kImNA - 2 - kImSmax);       // 166 for 4 bytes and classes 0..3
+      const double fx = (m0 < n_m) ? __hiloint2double((ebx - E0 + 1023) << 20, 0) * amp_x * cont_x : 0.0;
+      const double fy = (m1 < n_m) ? __hiloint2double((eby - E0 + 1023) << 20, 0) * amp_y * cont_y : 0.0;
+
+#pragma unroll
+      for (int jn = 0; jn < NT; ++jn) {
+        int acc[kImCls][4];
+#pragma unroll
+        for (int s = 0; s < kImCls; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0;
+#pragma unroll
+        for (int b = 0; b < NKB; ++b)
+#pragma unroll
+          for (int d = 0; d < kImNW; ++d) {
+            const uint2 B = s_dig[((b * kImNW + d) * NT + jn) * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < kImNA; ++i)
+              if (i + d <= kImSmax) imma_u8s8(acc[i + d], A[b][i], B);
+          }
+        // C fragment: (row g, cols 2t, 2t + 1), (row g + 8, cols 2t, 2t + 1)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int cc = r & 1, yrow = r >> 1;
+          const int a = a_lane0 + 8 * jn + cc;
+          if (a >= n_a) continue;
+          double H = im_i2d(acc[0][r]);
+#pragma unroll
+          for (int s = 1; s < kImCls; ++s) H = fma(H, 256.0, im_i2d(acc[s][r]));
+          double px = H * ((yrow ? fy : fx) * s_ta[8 * jn + 2 * t + cc]);
+          const int m = yrow ? m1 : m0;
+          if (ADD && m < n_m) {
+            const double cont = yrow ? cont_y : cont_x;
+            double add = 0.0;
+            if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
+              const size_t o = static_cast<size_t>(a) * n_m + m, st = static_cast<size_t>(n_a) * n_m;
+              const double bx = pr.b_X, btx = pr.beta_X;
+              if (COSMO && pr.dn_64 != 0.0) {
+                const double dn = pr.dn_64;
+                const int ord = Z.metal_dn_order;
+                add += bx * bx * (metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 0, dn) +
+                                  2.0 * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 1, dn) +
+                                  btx * btx * metal_moment(Z.metal_auto, Z.metal_auto_dn, ord, o, st, 2, dn));
+                add += pr.bias * bx * (metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 0, dn) +
+                                       (pr.beta + btx) * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 1, dn) +
+                                       pr.beta * btx * metal_moment(Z.metal_cross, Z.metal_cross_dn, ord, o, st, 2, dn));
+              } else {
+                add += bx * bx * (Z.metal_auto[o] + 2.0 * btx * Z.metal_auto[o + st] + btx * btx * Z.metal_auto[o + 2 * st]);
+                add += pr.bias * bx * (Z.metal_cross[o] + (pr.beta + btx) * Z.metal_cross[o + st] + pr.beta * btx * Z.metal_cross[o + 2 * st]);
+              }
+              if (COSMO) add *= pr.lin_amp;
+            }
+            if (Z.flags & 4) add += pr.b_noise * Z.sky_smooth[m] * Z.sky_xi[a];    // theory.py:476-506
+            px = fma(add, cont, px);
+          }
+          outp[static_cast<size_t>(8 * jn + cc) * n_m_pad + 16 * h2 + 8 * yrow] = px;
+        }
+      }
+    }
+    next_item(Z, n_pg, zi, tile, ablk, pg);
+  }
+}
+
+}  // namespace cpx

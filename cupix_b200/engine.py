@@ -143,7 +143,7 @@ class PxEngine(object):
     INFO = {"n_zbins": 0, "max_na": 1, "max_nm": 2, "max_nA": 3, "max_nM": 4, "chunk": 5,
             "device_bytes": 6, "kernel_launches": 7, "sm_count": 8, "guard_buffers": 9,
             "guard_violations": 10, "factored_calls": 11, "factored_tuples": 12, "chunk_allocated": 13,
-            "factored_cache_hits": 14}
+            "factored_cache_hits": 14, "hankel_kernel": 15}
 
     def __init__(self, plans, device=0, precise=False):
         """``precise=True`` evaluates the P3D cells in float64 as well (CPX_PRECISE_CELLS): the

@@ -73,7 +73,7 @@ def test_slot_enum_info_enum_and_field_offsets_match_header():
                "sm_count": "CPX_INFO_SM_COUNT", "guard_buffers": "CPX_INFO_GUARD_BUFFERS",
                "guard_violations": "CPX_INFO_GUARD_VIOLATIONS", "factored_calls": "CPX_INFO_FACTORED_CALLS",
                "factored_tuples": "CPX_INFO_FACTORED_TUPLES", "chunk_allocated": "CPX_INFO_CHUNK_ALLOCATED",
-               "factored_cache_hits": "CPX_INFO_FACTORED_CACHE_HITS"}
+               "factored_cache_hits": "CPX_INFO_FACTORED_CACHE_HITS", "hankel_kernel": "CPX_INFO_HANKEL_KERNEL"}
     assert set(info_of) == set(engine.PxEngine.INFO)
     zfields = [f[0] for f in engine.ZbinDesc._fields_]
     efields = [f[0] for f in engine.EvalArgs._fields_]

@@ -74,6 +74,59 @@ def test_tensor_path_extreme_parameters_stay_finite(monkeypatch):
     assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 1e-8
 
 
+def _imma_paths(monkeypatch, plans, pts, names, want=("chi2", "px_zam")):
+    """The default Hankel kernel (k_p3d_hankel_imma: INT8 mma.sync split) and the FP64 DMMA kernel (CPX_IMMA=0)."""
+    slots, zsel = slots_from_names(names)
+    out = {}
+    for im in ("0", "1"):
+        monkeypatch.setenv("CPX_IMMA", im)
+        eng = PxEngine(plans)
+        out[im] = eng.eval(pts, slots, zsel=zsel, want=want)
+        eng.close()
+    return out["0"], out["1"]
+
+
+@pytest.mark.parametrize("n_q,flags", [(56, {"include_hcd": True}), (64, {}), (96, ALL), (80, ALL), (72, {"include_continuum": True})])
+def test_imma_path_equals_dmma_path(monkeypatch, n_q, flags):
+    """Same FP32 cells on both paths, so they may differ only by the error of the integer split (tests/test_tc_split.py)."""
+    plans = _plans("S2", n_q, flags, N_m=70, N_A=9)          # ragged: 70 rows (3 tiles of 32, the last with 6 rows), 9 theta bins, 4 z
+    names = ["bias", "beta", "q1", "q2", "kv_Mpc", "av", "bv", "kp_Mpc", "b_H", "b_X", "b_noise_Mpc", "pC"]
+    base = np.array([plans[0].defaults[_plan.SLOT_INDEX[n]] for n in names])
+    rng = np.random.default_rng(12)
+    pts = base[None, :] * rng.uniform(0.7, 1.3, size=(37, len(names)))      # 37 points: four full groups of 8 + a tail of 5
+    ref, got = _imma_paths(monkeypatch, plans, pts, names)
+    scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
+    scale = np.where(scale > 0, scale, 1.0)
+    assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 2e-8
+    np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-6)
+    for i in (0, 36):
+        for iz, p in enumerate(plans):
+            px = H.emulate_plan_px(p, dict(zip(names, pts[i])))
+            assert np.abs(got["px_zam"][i, iz, :p.n_a, :p.n_m] - px).max() / np.abs(px).max() < 1e-6
+
+
+def test_imma_path_theta_blocks_cosmo_columns_and_extremes(monkeypatch):
+    plans = _plans("S1", 88, {"include_hcd": True}, N_t=1, N_A=40, N_m=40)   # 40 fine theta bins: two theta blocks of 24
+    ref, got = _imma_paths(monkeypatch, plans, np.array([[-0.12, 1.4]]), ["bias", "beta"])
+    scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
+    assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 2e-8
+    np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-6)
+    # primordial amplitude and tilt as columns (the COSMO instantiation), all contaminants on
+    plans = _plans("tiny", 56, ALL)
+    d0 = plans[0].defaults
+    pts = np.array([[d0[_plan.SLOT_INDEX["As"]] * f, d0[_plan.SLOT_INDEX["ns"]] + dn, -0.12] for f, dn in ((1.0, 0.0), (1.1, 0.02), (0.9, -0.03))])
+    ref, got = _imma_paths(monkeypatch, plans, pts, ["As", "ns", "bias"])
+    scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
+    assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 2e-8
+    # cells spanning hundreds of decades go through the per-row block exponent
+    plans = _plans("tiny", 88, {"include_hcd": True})
+    pts = np.array([[0.5, 3.0, 0.0], [300.0, 0.0, 0.0], [12.0, 0.0, 1.6], [3.0, 2.0, 1.0]])
+    ref, got = _imma_paths(monkeypatch, plans, pts, ["kp_Mpc", "q1", "q2"])
+    assert np.isfinite(got["px_zam"]).all()
+    scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
+    assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 2e-8
+
+
 def _window_paths(monkeypatch, plans, pts, names, data_idx=None):
     """chi2 per (z, theta_A) with the window stage on the tensor cores (default) and as the FP64 DMMA GEMM."""
     slots, zsel = slots_from_names(names)
