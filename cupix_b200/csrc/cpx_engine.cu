@@ -371,15 +371,16 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     if (rc) return rc;
     Z.im_cell = dcell;
     keep(dcell);
-    std::vector<double> ta(static_cast<size_t>(Z.n_ablk) * na_blk, 1.0);
+    std::vector<int> ta(static_cast<size_t>(Z.n_ablk) * na_blk, 0);          // k_a: column scale t_a = 2^k_a
     const size_t dig_bytes = static_cast<size_t>(imma_dig_bytes(NKB, nt));
     std::vector<unsigned char> dig(static_cast<size_t>(Z.n_ablk) * dig_bytes, 0);
     const double full = std::ldexp(1.0, 8 * kImNW);
     for (int a = 0; a < d.n_a; ++a) {
       double mx = 0.0;
       for (int q = 0; q < d.n_q; ++q) mx = std::max(mx, std::fabs(d.hankel_w[static_cast<size_t>(a) * d.n_q + q] / sq[q]));
-      const double t = mx > 0.0 ? 2.05 * mx : 1.0;
-      ta[a] = t;
+      const int ka = mx > 0.0 ? std::max(-200, std::min(200, static_cast<int>(std::ceil(std::log2(2.05 * mx))))) : 0;
+      const double t = std::ldexp(1.0, ka);
+      ta[a] = ka;
       const int ablk = a / na_blk, jn = (a % na_blk) / 8, g = a % 8;
       for (int q = 0; q < d.n_q; ++q) {
         // K slot of node q: lane t = q % 4, ks = q / 4 = 8 b + 4 half + byte
@@ -398,7 +399,7 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
     if (rc) return rc;
     Z.im_wdig = ddig;
     keep(ddig);
-    double* dta;
+    int* dta;
     rc = upload(ta, &dta, &bytes);
     if (rc) return rc;
     Z.im_ta = dta;
@@ -681,7 +682,7 @@ K1Fn k1_select_imma(int nkb, int nt, bool add, bool cosmo) {
   return nullptr;
 }
 size_t imma_smem_bytes(int max_nq, int nkb, int nt) {
-  return static_cast<size_t>((max_nq + 3) / 4) * (cpx::kCellConsts * 4 * 32 * 4) + cpx::imma_dig_bytes(nkb, nt) + 8 * nt * 8;
+  return static_cast<size_t>((max_nq + 3) / 4) * (cpx::kCellConsts * 4 * 32 * 4) + cpx::imma_dig_bytes(nkb, nt) + 8 * nt * 4;
 }
 
 K1Fn k1_select_f64s(int nt) {      // shared-memory staged variant, 16 points per CTA (cpx_factor.cuh)
@@ -2017,6 +2018,37 @@ int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, doub
     const double per_thread = which == 3 ? 8.0 * (iters / 8) * 8.0 : 8.0 * iters;
     if (outs[which]) *outs[which] = per_thread * static_cast<double>(blocks) * threads / (best * 1e-3);
   }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dbuf);
+  return CPX_OK;
+}
+
+int cpx_probe_imma(int32_t device, double* imma_ops_per_s) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(CPX_ERR_CUDA, "cpx_probe_imma: no such CUDA device");
+  CPX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CPX_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 13;
+  int* dbuf;
+  CPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 64));
+  cudaEvent_t e0, e1;
+  CPX_CUDA(cudaEventCreate(&e0));
+  CPX_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CPX_CUDA(cudaEventRecord(e0));
+    cpx::k_probe_imma<<<blocks, threads>>>(dbuf, iters, 0x01020304u);
+    CPX_CUDA(cudaEventRecord(e1));
+    CPX_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    CPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  // one m16n8k32 = 16 x 8 x 32 multiply-adds = 8192 integer operations per warp
+  if (imma_ops_per_s) *imma_ops_per_s = 8192.0 * 8.0 * iters * (static_cast<double>(blocks) * threads / 32.0) / (best * 1e-3);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(dbuf);

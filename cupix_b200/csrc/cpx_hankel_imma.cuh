@@ -11,7 +11,8 @@
 // shared-memory operand tiles, no tensor memory, no inter-warp hand-off -- which is what that version paid for.
 //
 //   * weights, constants of the batch:  W[a][q] = s_q t_a sum_j B_j[a][q] 256^-(j+1),  kImNW balanced base-256 digits (s8),
-//     s_q = 2^round(log2 max_a |W[a][q]|) folded into the P_L constant of the cell (exact), t_a applied in the epilogue;
+//     s_q = 2^round(log2 max_a |W[a][q]|) folded into the P_L constant of the cell (exact), t_a = 2^k_a (a power of two as
+//     well) applied in the epilogue;
 //   * a warp owns 16 k_par rows (rows g, g + 8 of the lane, as the packed FP32 pair) of one point at a time: lane (g, t)
 //     evaluates the cells of nodes 4 ks + t, ks = 0 .. n_q4 - 1, keeps them in registers, takes the exact row maximum
 //     (two shuffles), converts to 32-bit fixed point relative to it (U = rni(cell 2^(158 - e))) and transposes bytes:
@@ -20,7 +21,8 @@
 //     the same one;
 //   * slice pairs (i, j) with i + j <= kImSmax go to accumulator i + j (INT32, exact: < 2^24 per accumulator); the
 //     rest (< 2^-32 of the row scale, unbiased: balanced digits, round-to-nearest cells) is not issued;
-//   * the epilogue combines the classes exactly (Horner, < 2^53) and applies 2^(e - 166) t_a amp cont.
+//   * the epilogue combines the classes exactly in 64-bit integers and applies 2^(e - 166) t_a amp cont with one FP64
+//     instruction per output.
 // Error against the float64 dot product of the same FP32 cells: <= 4e-9 of the Px scale per theta bin with 4 x 4 slices
 // and 10 pairs (tests/test_tc_split.py), a tenth of the float32 rounding of the cells themselves.
 //
@@ -57,6 +59,23 @@ __device__ __forceinline__ uint32_t im_prmt(uint32_t a, uint32_t b, uint32_t sel
 // exact int32 -> float64 on the ALU + FP64 pipes (I2F.F64 runs at the MUFU rate)
 __device__ __forceinline__ double im_i2d(int v) {
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+// pipe-rate probe: 8 independent m16n8k32 chains per warp
+__global__ void k_probe_imma(int* out, int iters, uint32_t seed) {
+  int c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0;
+  const uint32_t a[4] = {seed, seed * 3u, seed * 5u, seed * 7u};
+  const uint2 b = make_uint2(seed * 11u, seed * 13u);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) imma_u8s8(c[i], a, b);
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (s == 123457) out[0] = s;
 }
 
 template <int NKB, int NT, bool ADD, bool COSMO>
@@ -107,10 +126,10 @@ __global__ void __launch_bounds__(kK1Threads, 2)
     const int n_ks = Z.n_q4;
     const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
     constexpr uint32_t dig_bytes = imma_dig_bytes(NKB, NT);
-    constexpr uint32_t ta_bytes = 8 * NT * 8u;
+    constexpr uint32_t ta_bytes = 8 * NT * 4u;
     const float2* s_cell = reinterpret_cast<const float2*>(smem_raw);
     const uint2* s_dig = reinterpret_cast<const uint2*>(smem_raw + cell_bytes);
-    const double* s_ta = reinterpret_cast<const double*>(smem_raw + cell_bytes + dig_bytes);
+    const int* s_tae = reinterpret_cast<const int*>(smem_raw + cell_bytes + dig_bytes);      // k_a: t_a = 2^k_a
 
     const bool new_tile = (zi != cur_z) || (tile != cur_tile);
     const bool new_w = (zi != cur_z) || (ablk != cur_ablk);
@@ -260,7 +279,31 @@ __global__ void __launch_bounds__(kK1Threads, 2)
         }
       }
 
-      // ---- row factors of the epilogue: 2^(e - 166) amp cont; Px = (factor * t_a * H + additive) * cont ----
+      int acc[NT][kImCls][4];
+#pragma unroll
+      for (int jn = 0; jn < NT; ++jn)
+#pragma unroll
+        for (int s = 0; s < kImCls; ++s) acc[jn][s][0] = acc[jn][s][1] = acc[jn][s][2] = acc[jn][s][3] = 0;
+      // consecutive MMAs go to different theta tiles: an accumulator is touched again NT MMAs later at the earliest
+#pragma unroll
+      for (int b = 0; b < NKB; ++b)
+#pragma unroll
+        for (int d = 0; d < kImNW; ++d) {
+          uint2 B[NT];
+#pragma unroll
+          for (int jn = 0; jn < NT; ++jn) B[jn] = s_dig[((b * kImNW + d) * NT + jn) * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < kImNA; ++i)
+            if (i + d <= kImSmax) {
+#pragma unroll
+              for (int jn = 0; jn < NT; ++jn) imma_u8s8(acc[jn][i + d], A[b][i], B[jn]);
+            }
+        }
+      // ---- row factors of the epilogue: s = 2^(e - 166) amp cont; Px = (s 2^k_a H + additive) * cont, t_a = 2^k_a ----
+      // FP64 instructions are starved by the FP32 traffic of the other warps (a DFMA takes 55 cycles
+      // beside three FFMA warps), so the epilogue spends one per output: the classes are combined in 64-bit integers, the
+      // integer becomes a double by the 2^52 trick (d = M + H, M = 2^52 + 2^51), and  Px = fma(d, s', -M s')  with the
+      // power-of-two column scale added to the exponent fields of s and -M s (integer adds).
       const int m0 = m_base + 16 * h2 + g, m1 = m0 + 8;
       double amp_x, amp_y, cont_x = 1.0, cont_y = 1.0;
       if (rowwise) {
@@ -272,33 +315,29 @@ __global__ void __launch_bounds__(kK1Threads, 2)
         amp_x = amp_y = pr.bias * pr.bias * Z.dAA;
       }
       constexpr int E0 = 158 - 8 * (kImNA - 2 - kImSmax);       // 166 for 4 bytes and classes 0..3
-      const double fx = (m0 < n_m) ? __hiloint2double((ebx - E0 + 1023) << 20, 0) * amp_x * cont_x : 0.0;
-      const double fy = (m1 < n_m) ? __hiloint2double((eby - E0 + 1023) << 20, 0) * amp_y * cont_y : 0.0;
+      constexpr double kMagic = 6755399441055744.0;             // 2^52 + 2^51
+      const double sx = (m0 < n_m) ? __hiloint2double((ebx - E0 + 1023) << 20, 0) * amp_x * cont_x : 0.0;
+      const double sy = (m1 < n_m) ? __hiloint2double((eby - E0 + 1023) << 20, 0) * amp_y * cont_y : 0.0;
+      const double cx = -kMagic * sx, cy = -kMagic * sy;
 
+      // C fragment: (row g, cols 2t, 2t + 1), (row g + 8, cols 2t, 2t + 1)
 #pragma unroll
-      for (int jn = 0; jn < NT; ++jn) {
-        int acc[kImCls][4];
-#pragma unroll
-        for (int s = 0; s < kImCls; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0;
-#pragma unroll
-        for (int b = 0; b < NKB; ++b)
-#pragma unroll
-          for (int d = 0; d < kImNW; ++d) {
-            const uint2 B = s_dig[((b * kImNW + d) * NT + jn) * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < kImNA; ++i)
-              if (i + d <= kImSmax) imma_u8s8(acc[i + d], A[b][i], B);
-          }
-        // C fragment: (row g, cols 2t, 2t + 1), (row g + 8, cols 2t, 2t + 1)
+      for (int jn = 0; jn < NT; ++jn)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int cc = r & 1, yrow = r >> 1;
           const int a = a_lane0 + 8 * jn + cc;
           if (a >= n_a) continue;
-          double H = im_i2d(acc[0][r]);
+          long long H = acc[jn][0][r];
 #pragma unroll
-          for (int s = 1; s < kImCls; ++s) H = fma(H, 256.0, im_i2d(acc[s][r]));
-          double px = H * ((yrow ? fy : fx) * s_ta[8 * jn + 2 * t + cc]);
+          for (int s = 1; s < kImCls; ++s) H = H * 256 + acc[jn][s][r];          // exact: |H| < 2^48
+          const double dH = __hiloint2double(static_cast<int>(H >> 32) + 0x43380000, static_cast<int>(H & 0xffffffffLL));   // M + H
+          const int kadd = s_tae[8 * jn + 2 * t + cc] << 20;
+          const double s_row = yrow ? sy : sx, c_row = yrow ? cy : cx;
+          double px = 0.0;
+          if (s_row != 0.0)
+            px = fma(dH, __hiloint2double(__double2hiint(s_row) + kadd, __double2loint(s_row)),
+                     __hiloint2double(__double2hiint(c_row) + kadd, __double2loint(c_row)));
           const int m = yrow ? m1 : m0;
           if (ADD && m < n_m) {
             const double cont = yrow ? cont_y : cont_x;
@@ -326,7 +365,6 @@ __global__ void __launch_bounds__(kK1Threads, 2)
           }
           outp[static_cast<size_t>(8 * jn + cc) * n_m_pad + 16 * h2 + 8 * yrow] = px;
         }
-      }
     }
     next_item(Z, n_pg, zi, tile, ablk, pg);
   }

@@ -123,7 +123,7 @@ struct ZDev {
   // INT8 mma.sync Hankel path, cpx_hankel_imma.cuh; im_cell == null: not available (n_q > 96)
   const float* im_cell;                 // cellc with P_L scaled by s_q (same layout)
   const unsigned char* im_wdig;         // [n_ablk][NKB][4 digits][NT][32 lanes][8] balanced base-256 digits of W / (s_q t_a), B-fragment order
-  const double* im_ta;                  // [n_ablk * na_blk] column scales t_a
+  const int* im_ta;                     // [n_ablk * na_blk] exponents k_a of the column scales t_a = 2^k_a
 };
 
 // ------------------------------------------------------------------------------------------

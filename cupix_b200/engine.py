@@ -85,6 +85,8 @@ def load_library(path=None):
     lib.cpx_hankel_jbar.restype = C.c_int
     lib.cpx_hankel_apply.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp, c_dp]
     lib.cpx_hankel_apply.restype = C.c_int
+    lib.cpx_probe_imma.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    lib.cpx_probe_imma.restype = C.c_int
     _LIB = lib
     return lib
 
@@ -95,6 +97,16 @@ def _dp(a):
 
 def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def probe_imma(device=0):
+    """INT8 mma.sync rate of this GPU in integer operations per second (cpx_probe_imma)."""
+    lib = load_library()
+    v = C.c_double(0.0)
+    rc = lib.cpx_probe_imma(int(device), C.byref(v))
+    if rc != 0:
+        raise CpxError("cpx_probe_imma failed (%d): %s" % (rc, lib.cpx_last_error().decode()))
+    return v.value
 
 
 def probe_peaks(device=0):

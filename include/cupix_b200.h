@@ -224,6 +224,10 @@ int cpx_hankel_apply(int32_t device, int32_t n_r, int32_t n_q, int32_t n_k, cons
 int cpx_probe_peaks(int32_t device, double* dfma_per_s, double* ffma_per_s, double* mufu_per_s,
                     double* dmma_fma_per_s);
 
+/* Rate of the INT8 tensor path as mma.sync issues it (m16n8k32, u8 x s8 -> s32; integer operations per second, a
+ * multiply-add counts as two): the pipe k_p3d_hankel_imma contracts on. */
+int cpx_probe_imma(int32_t device, double* imma_ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ def _plans(shape, n_q, flags, N_t=5, **over):
 
 
 def _both_paths(monkeypatch, plans, pts, names, want=("chi2", "px_zam")):
+    monkeypatch.setenv("CPX_IMMA", "0")          # the reference of these tests is the FP64 DMMA kernel
     slots, zsel = slots_from_names(names)
     out = {}
     for tc in ("0", "1"):

@@ -96,8 +96,8 @@ def imma_split_contract(W, cell32, na=4, nw=4, smax=3):
     mx = np.abs(W).max(axis=0)
     s_q = np.where(mx > 0, 2.0 ** np.clip(np.rint(np.log2(np.where(mx > 0, mx, 1.0))), -100, 100), 1.0)
     Ws = W / s_q[None, :]
-    t_a = 2.05 * np.abs(Ws).max(axis=1)
-    t_a = np.where(t_a > 0, t_a, 1.0)
+    mxa = np.abs(Ws).max(axis=1)
+    t_a = np.where(mxa > 0, 2.0 ** np.ceil(np.log2(2.05 * np.where(mxa > 0, mxa, 1.0))), 1.0)      # a power of two here
     X = np.rint(Ws / t_a[:, None] * 256.0 ** nw).astype(np.int64)
     B = []
     for _ in range(nw):
@@ -131,10 +131,12 @@ def test_imma_integer_split_matches_float64_contraction(n_q, params):
     got = imma_split_contract(p.hankel_w, cell32)
     err = np.abs(got - exact).max(axis=1) / np.abs(exact).max(axis=1)
     assert err.max() < 1e-8, err.max()
-    # no coherent offset worth the name: the mean signed error over all outputs (the rounding of the weight digits is the same
-    # for every point) stays below 1e-9 of the Px scale -- the MUFU bias the cell evaluation avoids is 5e-9 .. 5e-8
+    # no coherent offset worth the name: the mean signed error over all outputs stays below 3e-9 of the Px scale.  What
+    # there is comes from rounding the weights to 32 bits below the power-of-two column scale -- a fixed perturbation
+    # of the quadrature rule (whose own error is 1e-6), the same for every parameter point -- amplified where the Hankel
+    # sum cancels (the widest theta bins); the MUFU bias the cell evaluation avoids is 5e-9 .. 5e-8 and parameter dependent
     rel = (got - exact) / np.abs(exact).max(axis=1, keepdims=True)
-    assert abs(rel.mean()) < 1e-9
+    assert abs(rel.mean()) < 3e-9
 
 
 def test_weight_digits_reconstruct_the_weights():

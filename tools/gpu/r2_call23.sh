@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, call 23: k_p3d_hankel_imma with the integer epilogue -- A/B timing, parity tests
+mkdir -p gpurun_out
+timeout 600 python tools/hankel_ab.py 0 88 2>&1 | tee gpurun_out/c23_ab.txt
+( time timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -x -q ) > gpurun_out/c23_tests.log 2>&1
+echo "tests rc=$?"; tail -n 8 gpurun_out/c23_tests.log
