@@ -73,7 +73,7 @@ struct cpx_handle {
   long long launches = 0;
   int wt_nb = 0;                     // > 0: k_window_tc (tcgen05 window contraction) for the chi2 stage
   int tc_np = 0;                     // > 0: k_p3d_hankel_tc (tcgen05 Hankel contraction) with this many cell pairs per lane
-  int im_nkb = 0;                    // > 0: k_p3d_hankel_imma (mma.sync INT8 Hankel contraction) with this many 32-slot K blocks
+  int im_nks = 0;                    // > 0: k_p3d_hankel_imma (mma.sync INT8 Hankel contraction) instantiated for this n_q4 (all z alike)
   // per-chunk scratch
   double* d_points = nullptr;        // [chunk][16]
   int* d_data_idx = nullptr;         // [chunk]
@@ -349,8 +349,8 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
   Z.im_cell = nullptr;
   Z.im_wdig = nullptr;
   Z.im_ta = nullptr;
-  if (h->im_nkb > 0 && Z.n_q4 <= 8 * h->im_nkb) {
-    const int NKB = h->im_nkb, nt = na_blk / 8;
+  if (h->im_nks > 0 && Z.n_q4 == h->im_nks) {
+    const int NKB = (h->im_nks + 7) / 8, nt = na_blk / 8;
     std::vector<double> sq(d.n_q, 1.0);
     for (int q = 0; q < d.n_q; ++q) {
       double mx = 0.0;
@@ -358,14 +358,20 @@ int build_zbin(cpx_handle* h, const cpx_zbin_desc& d, int na_blk, ZHost& zh) {
       if (mx > 0.0) sq[q] = std::ldexp(1.0, std::max(-100, std::min(100, static_cast<int>(std::lround(std::log2(mx))))));
     }
     // cellc is still on the host side of this function only as `d`: rebuild the P_L entries scaled by s_q (exact)
-    std::vector<float> cell(static_cast<size_t>(Z.n_tiles) * Z.n_q4 * kCellConsts * 4 * 32, 0.0f);
-    CPX_CUDA(cudaMemcpy(cell.data(), Z.cellc, cell.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    // the P_L entries scaled by s_q (exact), constants interleaved in pairs: [tile][ks][3][half][lane][(c even).xy, (c odd).xy]
+    std::vector<float> src(static_cast<size_t>(Z.n_tiles) * Z.n_q4 * kCellConsts * 4 * 32, 0.0f), cell(src.size(), 0.0f);
+    CPX_CUDA(cudaMemcpy(src.data(), Z.cellc, src.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int tile = 0; tile < Z.n_tiles; ++tile)
       for (int ks = 0; ks < Z.n_q4; ++ks)
-        for (int i = 0; i < 2 * 32 * 2; ++i) {
-          const int lane = (i / 2) % 32, q = 4 * ks + (lane & 3);
-          if (q < d.n_q) cell[((static_cast<size_t>(tile) * Z.n_q4 + ks) * kCellConsts + 5) * 2 * 32 * 2 + i] *= static_cast<float>(sq[q]);
-        }
+        for (int cst = 0; cst < kCellConsts; ++cst)
+          for (int pr = 0; pr < 2; ++pr)
+            for (int lane = 0; lane < 32; ++lane)
+              for (int e = 0; e < 2; ++e) {
+                const int q = 4 * ks + (lane & 3);
+                float v = src[(((((static_cast<size_t>(tile) * Z.n_q4 + ks) * kCellConsts + cst) * 2 + pr) * 32 + lane) * 2) + e];
+                if (cst == 5 && q < d.n_q) v *= static_cast<float>(sq[q]);
+                cell[(((((static_cast<size_t>(tile) * Z.n_q4 + ks) * 3 + cst / 2) * 2 + pr) * 32 + lane) * 4) + (cst & 1) * 2 + e] = v;
+              }
     float* dcell;
     int rc = upload(cell, &dcell, &bytes);
     if (rc) return rc;
@@ -662,27 +668,32 @@ K1Fn k1_select_tc(int np, bool add) {
   return nullptr;
 }
 
-template <int NKB, bool ADD, bool COSMO>
+template <int NKS, bool ADD, bool COSMO>
 K1Fn k1_select_imma_nt(int nt) {
   switch (nt) {
-    case 1: return cpx::k_p3d_hankel_imma<NKB, 1, ADD, COSMO>;
-    case 2: return cpx::k_p3d_hankel_imma<NKB, 2, ADD, COSMO>;
-    case 3: return cpx::k_p3d_hankel_imma<NKB, 3, ADD, COSMO>;
+    case 1: return cpx::k_p3d_hankel_imma<NKS, 1, ADD, COSMO>;
+    case 2: return cpx::k_p3d_hankel_imma<NKS, 2, ADD, COSMO>;
+    case 3: return cpx::k_p3d_hankel_imma<NKS, 3, ADD, COSMO>;
   }
   return nullptr;
 }
-template <int NKB>
-K1Fn k1_select_imma_nkb(int nt, bool add, bool cosmo) {
-  if (cosmo) return add ? k1_select_imma_nt<NKB, true, true>(nt) : k1_select_imma_nt<NKB, false, true>(nt);
-  return add ? k1_select_imma_nt<NKB, true, false>(nt) : k1_select_imma_nt<NKB, false, false>(nt);
+template <int NKS>
+K1Fn k1_select_imma_nks(int nt, bool add, bool cosmo) {
+  if (cosmo) return add ? k1_select_imma_nt<NKS, true, true>(nt) : k1_select_imma_nt<NKS, false, true>(nt);
+  return add ? k1_select_imma_nt<NKS, true, false>(nt) : k1_select_imma_nt<NKS, false, false>(nt);
 }
-K1Fn k1_select_imma(int nkb, int nt, bool add, bool cosmo) {
-  if (nkb == 2) return k1_select_imma_nkb<2>(nt, add, cosmo);
-  if (nkb == 3) return k1_select_imma_nkb<3>(nt, add, cosmo);
+// n_q4 of the node sets the kernel is instantiated for: 56 (the default of the 'smooth' family), 64 and 88 nodes
+bool imma_supported(int nks) { return nks == 14 || nks == 16 || nks == 22; }
+K1Fn k1_select_imma(int nks, int nt, bool add, bool cosmo) {
+  switch (nks) {
+    case 14: return k1_select_imma_nks<14>(nt, add, cosmo);
+    case 16: return k1_select_imma_nks<16>(nt, add, cosmo);
+    case 22: return k1_select_imma_nks<22>(nt, add, cosmo);
+  }
   return nullptr;
 }
-size_t imma_smem_bytes(int max_nq, int nkb, int nt) {
-  return static_cast<size_t>((max_nq + 3) / 4) * (cpx::kCellConsts * 4 * 32 * 4) + cpx::imma_dig_bytes(nkb, nt) + 8 * nt * 4;
+size_t imma_smem_bytes(int nks, int nt) {
+  return static_cast<size_t>(nks) * (cpx::kCellConsts * 4 * 32 * 4) + cpx::imma_dig_bytes((nks + 7) / 8, nt) + 8 * nt * 4;
 }
 
 K1Fn k1_select_f64s(int nt) {      // shared-memory staged variant, 16 points per CTA (cpx_factor.cuh)
@@ -1350,9 +1361,10 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
   if (smem_need > static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024)
     return bail(fail(CPX_ERR_UNSUPPORTED, "cpx_create: n_q too large for the shared-memory-resident grid"));
 
-  // INT8 mma.sync Hankel path (default): up to 96 k_perp nodes; CPX_IMMA=0 keeps the FP64 DMMA kernel
-  h->im_nkb = 0;
-  if (env_int("CPX_IMMA", 1) != 0 && h->max_nq <= 96) h->im_nkb = (h->max_nq + 3) / 4 <= 16 ? 2 : 3;
+  // INT8 mma.sync Hankel path, opt-in (CPX_IMMA=1): parity-green, measured level with the FP64 DMMA kernel (50.7 against
+  // 49.3 ms per 131072-point S5 step at 56 nodes, 73.1 against 73.7 at 88; profiles/hankel_imma_r02.txt)
+  h->im_nks = 0;
+  if (env_int("CPX_IMMA", 0) != 0 && imma_supported((h->max_nq + 3) / 4)) h->im_nks = (h->max_nq + 3) / 4;
 
   h->z.resize(n_zbins);
   size_t per_point_bytes = 0;
@@ -1391,14 +1403,14 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_need)) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
     }
-  if (h->im_nkb > 0) {
+  if (h->im_nks > 0) {
     bool ok = true;
-    for (auto& zh : h->z) ok &= zh.dev.im_cell != nullptr;
-    if (!ok) h->im_nkb = 0;
-    for (int add = 0; add < 4 && h->im_nkb > 0; ++add) {
-      K1Fn fn = k1_select_imma(h->im_nkb, h->na_blk / 8, (add & 1) != 0, (add & 2) != 0);
+    for (auto& zh : h->z) ok &= zh.dev.im_cell != nullptr;        // every z on the same node count
+    if (!ok) h->im_nks = 0;
+    for (int add = 0; add < 4 && h->im_nks > 0; ++add) {
+      K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, (add & 1) != 0, (add & 2) != 0);
       if (!fn || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(imma_smem_bytes(h->max_nq, h->im_nkb, h->na_blk / 8))) != cudaSuccess)
+                                      static_cast<int>(imma_smem_bytes(h->im_nks, h->na_blk / 8))) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_p3d_hankel_imma"));
     }
   }
@@ -1556,7 +1568,7 @@ int cpx_get_info(const cpx_handle* h, int32_t what, int64_t* value) {
     case CPX_INFO_FACTORED_CALLS: *value = h->factored_calls; break;
     case CPX_INFO_FACTORED_TUPLES: *value = h->factored_tuples; break;
     case CPX_INFO_FACTORED_CACHE_HITS: *value = h->factored_cache_hits; break;
-    case CPX_INFO_HANKEL_KERNEL: *value = h->tc_np > 0 ? 1 : (h->im_nkb > 0 ? 2 : 0); break;
+    case CPX_INFO_HANKEL_KERNEL: *value = h->tc_np > 0 ? 1 : (h->im_nks > 0 ? 2 : 0); break;
     case CPX_INFO_DEVICE_BYTES: *value = static_cast<int64_t>(h->device_bytes); break;
     case CPX_INFO_KERNEL_LAUNCHES: *value = h->launches; break;
     case CPX_INFO_SM_COUNT: *value = h->sm_count; break;
@@ -1733,7 +1745,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     const size_t k1_smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
     int pp = pp_env > 0 ? std::min(pp_env, 2) : (2 * (k1_smem + 2048) <= 227u * 1024u ? 1 : 2);
     const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
-    const bool imma = h->im_nkb > 0 && !precise && !tc;   // INT8 mma.sync Hankel kernel: one point per warp (the default)
+    const bool imma = h->im_nks > 0 && !precise && !tc;   // INT8 mma.sync Hankel kernel: one point per warp (the default)
     if (imma) pp = 1;
     // float64 cells: the shared-memory staged kernel (16 points per CTA) when the float64 tile fits, else one warp per point
     const size_t f64_smem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
@@ -1813,9 +1825,9 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
         fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);
       } else if (imma) {
-        K1Fn fn = k1_select_imma(h->im_nkb, h->na_blk / 8, additive, cosmo);
+        K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, additive, cosmo);
         const int grid = static_cast<int>(std::min<long long>(n_items, 2LL * h->sm_count));
-        fn<<<grid, kK1Threads, imma_smem_bytes(h->max_nq, h->im_nkb, h->na_blk / 8), st>>>(h->d_ztab, n_zl, count, n_items);
+        fn<<<grid, kK1Threads, imma_smem_bytes(h->im_nks, h->na_blk / 8), st>>>(h->d_ztab, n_zl, count, n_items);
       } else if (tc) {
         K1Fn fn = k1_select_tc(h->tc_np, additive);
         const int grid = static_cast<int>(std::min<long long>(n_items, h->sm_count));

@@ -28,7 +28,13 @@
 //
 // CTA = 8 warps, 2 CTAs per SM, persistent over (z, 32-row tile, theta block, point group) items exactly like
 // k_p3d_hankel; cell constants of the tile (P_L scaled by s_q) and the digit table of the theta block are staged with
-// TMA bulk copies and stay resident.  n_q <= 32 NKB nodes (NKB = 2, 3); wider node sets keep the DMMA kernel.
+// TMA bulk copies and stay resident.  Instantiated for 56, 64 and 88 nodes (n_q4 = 14, 16, 22).
+//
+// Status: opt-in (CPX_IMMA=1).  Bit-for-bit the cells of k_p3d_hankel and chi2 within 1e-10 relative of it, but not
+// faster: 50.7 against 49.3 ms per 131 072-point S5 step at 56 nodes, 73.1 against 73.7 at 88.  The contraction does
+// leave the FP32 datapath (fmaheavy 47 % busy, tensor pipe 17 %), but conversion, byte transposes and the integer
+// epilogue make it 16 % more instructions per row than the DMMA kernel, and with 4 warps per sub-partition (128 registers)
+// the warp-serial phases leave issue at 54 % (profiles/k_p3d_hankel_imma_ncu_r02.txt, profiles/hankel_imma_r02.txt).
 #pragma once
 #include "cpx_kernels.cuh"
 
@@ -78,10 +84,12 @@ __global__ void k_probe_imma(int* out, int iters, uint32_t seed) {
   if (s == 123457) out[0] = s;
 }
 
-template <int NKB, int NT, bool ADD, bool COSMO>
+// NKS = n_q4 = ceil(n_q / 4): the lane's cells per row, a compile-time constant so that the cell loop carries neither
+// per-slot branches nor address arithmetic (a runtime count cost 18 % of the kernel in branch, move and LEA instructions)
+template <int NKS, int NT, bool ADD, bool COSMO>
 __global__ void __launch_bounds__(kK1Threads, 2)
     k_p3d_hankel_imma(const ZDev* __restrict__ ztab, int n_z, int count, long long n_items) {
-  constexpr int NKS = 8 * NKB;                         // cell slots per lane and row
+  constexpr int NKB = (NKS + 7) / 8;                   // 32-slot K blocks of the MMA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) ZDev s_Z;
@@ -123,11 +131,10 @@ __global__ void __launch_bounds__(kK1Threads, 2)
       __syncthreads();
     }
     const ZDev& Z = s_Z;
-    const int n_ks = Z.n_q4;
-    const uint32_t cell_bytes = static_cast<uint32_t>(n_ks) * (kCellConsts * kTileRows * 4 * 4u);
+    constexpr uint32_t cell_bytes = static_cast<uint32_t>(NKS) * (kCellConsts * kTileRows * 4 * 4u);      // Z.n_q4 == NKS (dispatch)
     constexpr uint32_t dig_bytes = imma_dig_bytes(NKB, NT);
     constexpr uint32_t ta_bytes = 8 * NT * 4u;
-    const float2* s_cell = reinterpret_cast<const float2*>(smem_raw);
+    const float4* s_cell = reinterpret_cast<const float4*>(smem_raw);
     const uint2* s_dig = reinterpret_cast<const uint2*>(smem_raw + cell_bytes);
     const int* s_tae = reinterpret_cast<const int*>(smem_raw + cell_bytes + dig_bytes);      // k_a: t_a = 2^k_a
 
@@ -177,67 +184,73 @@ __global__ void __launch_bounds__(kK1Threads, 2)
     const int n_a = Z.n_a, n_m = Z.n_m, n_m_pad = Z.n_m_pad;
     double* const outp = Z.pxzam + (static_cast<size_t>(pt) * n_a + a_lane0) * n_m_pad + m_base + g;
 
+    // per-point scalars, read once per item (packed FP32 instructions take a scalar operand for both halves: one register
+    // each).  Read inside the loop over halves they cost 5 % of the kernel in first-use stalls (ncu source view).
+    const float p_q1l = pr.q1l, p_q1lo = pr.q1l_lo, p_q2l = pr.q2l, p_q2lo = pr.q2l_lo, p_av = pr.av, p_bv = pr.bv;
+    const float p_nlkv = pr.nlkv, p_nlkvlo = pr.nlkv_lo, p_ikp2l = pr.ikp2l, p_ikp2lo = pr.ikp2l_lo;
+    float p_dn = 0.0f, p_lr = 0.0f, p_lrlo = 0.0f;
+    if (COSMO) {
+      p_dn = pr.dn;
+      p_lr = pr.lr;
+      p_lrlo = pr.lr_lo;
+    }
+    float b0_hi = 0.0f, b0_lo = 0.0f;
+    double amp0 = 0.0;
+    if (!rowwise) {
+      split_hi_lo(pr.beta, b0_hi, b0_lo);
+      amp0 = pr.bias * pr.bias * Z.dAA;
+    }
+
     // the two 16-row halves of the tile, one after the other: rows 16 h2 + g (.x) and 16 h2 + 8 + g (.y)
 #pragma unroll 1
     for (int h2 = 0; h2 < 2; ++h2) {
       uint32_t A[NKB][kImNA][4];
       int ebx, eby;
       {
-        // ---- per-point scalars (duplicated into both halves of a packed register) and the Kaiser beta of the two rows ----
-        const float2 q1l = dup2(pr.q1l), q1lo = dup2(pr.q1l_lo), q2l = dup2(pr.q2l), q2lo = dup2(pr.q2l_lo);
-        const float2 av = dup2(pr.av), bv = dup2(pr.bv), nlkv = dup2(pr.nlkv), nlkvlo = dup2(pr.nlkv_lo);
-        const float2 ikp2l = dup2(pr.ikp2l), ikp2lo = dup2(pr.ikp2l_lo);
-        float2 cdn, clr, clrlo;
-        if (COSMO) {
-          cdn = dup2(pr.dn);
-          clr = dup2(pr.lr);
-          clrlo = dup2(pr.lr_lo);
-        }
-        float2 betaT, betaTlo;
+        const float2 q1l = dup2(p_q1l), q1lo = dup2(p_q1lo), q2l = dup2(p_q2l), q2lo = dup2(p_q2lo);
+        const float2 av = dup2(p_av), bv = dup2(p_bv), nlkv = dup2(p_nlkv), nlkvlo = dup2(p_nlkvlo);
+        const float2 ikp2l = dup2(p_ikp2l), ikp2lo = dup2(p_ikp2lo);
+        const float2 cdn = dup2(p_dn), clr = dup2(p_lr), clrlo = dup2(p_lrlo);
+        // Kaiser beta of the two rows
+        float2 betaT = dup2(b0_hi), betaTlo = dup2(kKaiserLoScale * b0_lo);
         if (rowwise) {
           betaT = make_float2(rp[16 * h2].betaT_hi, rp[16 * h2 + 8].betaT_hi);
           betaTlo = make_float2(kKaiserLoScale * rp[16 * h2].betaT_lo, kKaiserLoScale * rp[16 * h2 + 8].betaT_lo);
-        } else {
-          float hi, lo;
-          split_hi_lo(pr.beta, hi, lo);
-          betaT = dup2(hi);
-          betaTlo = dup2(kKaiserLoScale * lo);
         }
 
         // ---- the lane's cells of this half: nodes 4 ks + t, both rows packed ----
         float2 x[NKS];
         float mx = 0.0f, my = 0.0f;
-        const float2* c = s_cell + h2 * 32 + lane;
+        const float4* const c = s_cell + h2 * 32 + lane;       // [ks][3 constant pairs][half][lane]: three LDS.128 per cell pair
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
-          x[ks] = make_float2(0.0f, 0.0f);
-          if (ks < n_ks) {
-            const float2 D0 = c[0 * 64], L2K = c[1 * 64], L2MU = c[2 * 64], MU2 = c[3 * 64], NK2 = c[4 * 64], PL0 = c[5 * 64];
-            float2 D = D0, PL = PL0;
-            if (COSMO) {   // P_L and Delta^2 of the rescaled cosmology (theory.py:54-56)
-              const float2 f = exp2_rr2(add2(fma2(cdn, L2K, clr), clrlo));
-              D = mul2(D0, f);
-              PL = mul2(PL0, f);
-            }
-            // identical arithmetic to k_p3d_hankel (see the comments there)
-            const float2 nl = mul2(D, add2(fma2(q2l, D, q1l), fma2(q2lo, D, q1lo)));
-            const float2 nv = exp2_rr2_neg(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
-            const float2 tt = fma2(NK2, ikp2lo, fma2(NK2, ikp2l, nl));
-            const float2 e = kExpDnl(fma2(nl, nv, tt));
-            float2 y = mul2(PL, e);
-#if CPX_KAISER == 0
-            y = fma2(mul2(y, betaT), MU2, y);
-            y = fma2(mul2(y, betaT), MU2, fma2(mul2(y, betaTlo), MU2, y));
-#else
-            const float2 bm = fma2(betaT, MU2, mul2(betaTlo, MU2));
-            y = fma2(y, bm, y);
-            y = fma2(y, bm, y);
-#endif
-            x[ks] = y;
-            mx = fmaxf(mx, y.x);
-            my = fmaxf(my, y.y);
-            c += kCellConsts * 2 * 32;
+          const float4* const ck = c + ks * (3 * 2 * 32);
+          const float4 v0 = ck[0 * 64], v1 = ck[1 * 64], v2 = ck[2 * 64];
+          const float2 D0 = make_float2(v0.x, v0.y), L2K = make_float2(v0.z, v0.w), L2MU = make_float2(v1.x, v1.y);
+          const float2 MU2 = make_float2(v1.z, v1.w), NK2 = make_float2(v2.x, v2.y), PL0 = make_float2(v2.z, v2.w);
+          float2 D = D0, PL = PL0;
+          if (COSMO) {   // P_L and Delta^2 of the rescaled cosmology (theory.py:54-56)
+            const float2 f = exp2_rr2(add2(fma2(cdn, L2K, clr), clrlo));
+            D = mul2(D0, f);
+            PL = mul2(PL0, f);
           }
+          // identical arithmetic to k_p3d_hankel (see the comments there)
+          const float2 nl = mul2(D, add2(fma2(q2l, D, q1l), fma2(q2lo, D, q1lo)));
+          const float2 nv = exp2_rr2_neg(add2(fma2(av, L2K, fma2(bv, L2MU, nlkv)), nlkvlo));
+          const float2 tt = fma2(NK2, ikp2lo, fma2(NK2, ikp2l, nl));
+          const float2 e = kExpDnl(fma2(nl, nv, tt));
+          float2 y = mul2(PL, e);
+#if CPX_KAISER == 0
+          y = fma2(mul2(y, betaT), MU2, y);
+          y = fma2(mul2(y, betaT), MU2, fma2(mul2(y, betaTlo), MU2, y));
+#else
+          const float2 bm = fma2(betaT, MU2, mul2(betaTlo, MU2));
+          y = fma2(y, bm, y);
+          y = fma2(y, bm, y);
+#endif
+          x[ks] = y;
+          mx = fmaxf(mx, y.x);
+          my = fmaxf(my, y.y);
         }
         // exact row maxima over the four lanes that share the rows
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -255,9 +268,12 @@ __global__ void __launch_bounds__(kK1Threads, 2)
           uint32_t ux[4], uy[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 sc = mul2(x[4 * q4 + j], scale);
-            ux[j] = im_f2u(sc.x);
-            uy[j] = im_f2u(sc.y);
+            ux[j] = uy[j] = 0u;
+            if (4 * q4 + j < NKS) {             // compile-time: the slots past the last node hold zeros
+              const float2 sc = mul2(x[4 * q4 + j], scale);
+              ux[j] = im_f2u(sc.x);
+              uy[j] = im_f2u(sc.y);
+            }
           }
           const int b = q4 >> 1, hh = q4 & 1;      // MMA K block and half: A registers 2 hh (row g) and 2 hh + 1 (row g + 8)
           {
@@ -305,21 +321,25 @@ __global__ void __launch_bounds__(kK1Threads, 2)
       // integer becomes a double by the 2^52 trick (d = M + H, M = 2^52 + 2^51), and  Px = fma(d, s', -M s')  with the
       // power-of-two column scale added to the exponent fields of s and -M s (integer adds).
       const int m0 = m_base + 16 * h2 + g, m1 = m0 + 8;
-      double amp_x, amp_y, cont_x = 1.0, cont_y = 1.0;
+      double acx = amp0, acy = amp0, cont_x = 1.0, cont_y = 1.0;
       if (rowwise) {
-        amp_x = rp[16 * h2].amp;
-        amp_y = rp[16 * h2 + 8].amp;
         cont_x = rp[16 * h2].cont;
         cont_y = rp[16 * h2 + 8].cont;
-      } else {
-        amp_x = amp_y = pr.bias * pr.bias * Z.dAA;
+        acx = rp[16 * h2].amp * cont_x;
+        acy = rp[16 * h2 + 8].amp * cont_y;
       }
       constexpr int E0 = 158 - 8 * (kImNA - 2 - kImSmax);       // 166 for 4 bytes and classes 0..3
       constexpr double kMagic = 6755399441055744.0;             // 2^52 + 2^51
-      const double sx = (m0 < n_m) ? __hiloint2double((ebx - E0 + 1023) << 20, 0) * amp_x * cont_x : 0.0;
-      const double sy = (m1 < n_m) ? __hiloint2double((eby - E0 + 1023) << 20, 0) * amp_y * cont_y : 0.0;
+      // s = 2^(e - 166) amp cont: the power of two goes into the exponent field (amp cont is far from the ends of the range)
+      const double sx = (m0 < n_m && acx != 0.0) ? __hiloint2double(__double2hiint(acx) + ((ebx - E0) << 20), __double2loint(acx)) : 0.0;
+      const double sy = (m1 < n_m && acy != 0.0) ? __hiloint2double(__double2hiint(acy) + ((eby - E0) << 20), __double2loint(acy)) : 0.0;
       const double cx = -kMagic * sx, cy = -kMagic * sy;
 
+      // a zero row factor (padded row, zero amplitude) must stay zero under the exponent add
+      const int mask_x = (sx != 0.0) ? -1 : 0, mask_y = (sy != 0.0) ? -1 : 0;
+      const int sxh = __double2hiint(sx), sxl = __double2loint(sx), syh = __double2hiint(sy), syl = __double2loint(sy);
+      const int cxh = __double2hiint(cx), cxl = __double2loint(cx), cyh = __double2hiint(cy), cyl = __double2loint(cy);
+      double* const prow = outp + 16 * h2;
       // C fragment: (row g, cols 2t, 2t + 1), (row g + 8, cols 2t, 2t + 1)
 #pragma unroll
       for (int jn = 0; jn < NT; ++jn)
@@ -327,19 +347,23 @@ __global__ void __launch_bounds__(kK1Threads, 2)
         for (int r = 0; r < 4; ++r) {
           const int cc = r & 1, yrow = r >> 1;
           const int a = a_lane0 + 8 * jn + cc;
-          if (a >= n_a) continue;
-          long long H = acc[jn][0][r];
+          long long H;
+          if (kImCls == 4) {       // two 32-bit halves, then one wide multiply-add (exact: |H| < 2^48)
+            const int hi32 = acc[jn][0][r] * 256 + acc[jn][1][r];
+            const long long lo = (NKB <= 2) ? static_cast<long long>(acc[jn][2][r] * 256 + acc[jn][3][r])
+                                            : static_cast<long long>(acc[jn][2][r]) * 256 + acc[jn][3][r];
+            H = static_cast<long long>(hi32) * 65536 + lo;
+          } else {
+            H = acc[jn][0][r];
 #pragma unroll
-          for (int s = 1; s < kImCls; ++s) H = H * 256 + acc[jn][s][r];          // exact: |H| < 2^48
+            for (int s = 1; s < kImCls; ++s) H = H * 256 + acc[jn][s][r];
+          }
           const double dH = __hiloint2double(static_cast<int>(H >> 32) + 0x43380000, static_cast<int>(H & 0xffffffffLL));   // M + H
-          const int kadd = s_tae[8 * jn + 2 * t + cc] << 20;
-          const double s_row = yrow ? sy : sx, c_row = yrow ? cy : cx;
-          double px = 0.0;
-          if (s_row != 0.0)
-            px = fma(dH, __hiloint2double(__double2hiint(s_row) + kadd, __double2loint(s_row)),
-                     __hiloint2double(__double2hiint(c_row) + kadd, __double2loint(c_row)));
+          const int kadd = (s_tae[8 * jn + 2 * t + cc] << 20) & (yrow ? mask_y : mask_x);
+          double px = fma(dH, __hiloint2double((yrow ? syh : sxh) + kadd, yrow ? syl : sxl),
+                          __hiloint2double((yrow ? cyh : cxh) + kadd, yrow ? cyl : cxl));
           const int m = yrow ? m1 : m0;
-          if (ADD && m < n_m) {
+          if (ADD && m < n_m && a < n_a) {
             const double cont = yrow ? cont_y : cont_x;
             double add = 0.0;
             if (Z.flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
@@ -363,7 +387,7 @@ __global__ void __launch_bounds__(kK1Threads, 2)
             if (Z.flags & 4) add += pr.b_noise * Z.sky_smooth[m] * Z.sky_xi[a];    // theory.py:476-506
             px = fma(add, cont, px);
           }
-          outp[static_cast<size_t>(8 * jn + cc) * n_m_pad + 16 * h2 + 8 * yrow] = px;
+          if (a < n_a) prow[static_cast<size_t>(8 * jn + cc) * n_m_pad + 8 * yrow] = px;
         }
     }
     next_item(Z, n_pg, zi, tile, ablk, pg);

@@ -15,8 +15,8 @@
 //                 FP64 tensor-core (DMMA) contraction (likelihood.py:53-88, 170-194)
 //   k_window_tc   (cpx_window_tc.cuh) the chi2 flavour of k_window on tcgen05: exact INT8 split of Px_Zam and of
 //                 the whitened window operator, INT32 accumulators in tensor memory, HBM-bound; the default
-//   k_p3d_hankel_imma  (cpx_hankel_imma.cuh) the same contraction as an exact integer split on mma.sync INT8 (default
-//                 for n_q <= 96)
+//   k_p3d_hankel_imma  (cpx_hankel_imma.cuh) the same contraction as an exact integer split on mma.sync INT8 (opt-in,
+//                 CPX_IMMA=1: level with the DMMA kernel)
 //   k_p3d_hankel_tc  (cpx_hankel_tc.cuh) the Hankel contraction of k_p3d_hankel on tcgen05 with the same split;
 //                 opt-in (CPX_TC=1), currently slower than the DMMA kernel
 //   k_reduce      chi2[pt] = sum_{z,A} chi2_zA in fixed order (likelihood.py:191)
@@ -121,7 +121,7 @@ struct ZDev {
   const double* wt_rs;                  // [n_A][wt_nb] row scales
   const void* px_tmap;                  // CUtensorMap of pxzam viewed as [chunk][n_a][n_m_pad] float64, box 128 x 1 x 16, 128-byte swizzle
   // INT8 mma.sync Hankel path, cpx_hankel_imma.cuh; im_cell == null: not available (n_q > 96)
-  const float* im_cell;                 // cellc with P_L scaled by s_q (same layout)
+  const float* im_cell;                 // [n_tiles][n_q4][3][2][32][4] cellc with P_L scaled by s_q, constants interleaved in pairs (LDS.128)
   const unsigned char* im_wdig;         // [n_ablk][NKB][4 digits][NT][32 lanes][8] balanced base-256 digits of W / (s_q t_a), B-fragment order
   const int* im_ta;                     // [n_ablk * na_blk] exponents k_a of the column scales t_a = 2^k_a
 };
