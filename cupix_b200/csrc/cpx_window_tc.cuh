@@ -39,9 +39,18 @@ namespace cpx {
 constexpr int kWtPts = 128;          // points per tile = UMMA M
 constexpr int kWtNA = 5;             // Px bytes
 constexpr int kWtNW = 5;             // T digits
-constexpr int kWtStages = 3;            // operand stages (u8 slices of Px + digit tile of T)
-constexpr int kWtRing = 2;              // ring slots (32 KB chunks of Px) of the converting workers (second read: L2)
-constexpr int kWtSRing = 2;             // ring slots of the scout warps (first read: HBM)
+#ifndef CPX_WT_STAGES
+#define CPX_WT_STAGES 3
+#endif
+#ifndef CPX_WT_RING
+#define CPX_WT_RING 2
+#endif
+#ifndef CPX_WT_SRING
+#define CPX_WT_SRING 2
+#endif
+constexpr int kWtStages = CPX_WT_STAGES;   // operand stages (u8 slices of Px + digit tile of T)
+constexpr int kWtRing = CPX_WT_RING;       // ring slots (32 KB chunks of Px) of the converting workers (second read: L2)
+constexpr int kWtSRing = CPX_WT_SRING;     // ring slots of the scout warps (first read: HBM)
 constexpr int kWtScouts = 4;            // scout warps
 constexpr int kWtKC = 32;            // K per stage (one UMMA K step)
 constexpr int kWtWorkers = 8;        // worker warps

@@ -56,7 +56,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or LIB_PATH
+    path = path or os.environ.get("CUPIX_B200_LIB") or LIB_PATH      # CUPIX_B200_LIB: another build of the same library (A/B runs)
     if not os.path.exists(path):
         raise CpxError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(cupix_b200 has no CPU fallback)" % path)
