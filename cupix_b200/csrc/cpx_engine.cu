@@ -668,27 +668,23 @@ K1Fn k1_select_tc(int np, bool add) {
   return nullptr;
 }
 
-template <int NKS, bool ADD, bool COSMO>
+template <int NKS, bool ADD>
 K1Fn k1_select_imma_nt(int nt) {
   switch (nt) {
-    case 1: return cpx::k_p3d_hankel_imma<NKS, 1, ADD, COSMO>;
-    case 2: return cpx::k_p3d_hankel_imma<NKS, 2, ADD, COSMO>;
-    case 3: return cpx::k_p3d_hankel_imma<NKS, 3, ADD, COSMO>;
+    case 1: return cpx::k_p3d_hankel_imma<NKS, 1, ADD, false>;
+    case 2: return cpx::k_p3d_hankel_imma<NKS, 2, ADD, false>;
+    case 3: return cpx::k_p3d_hankel_imma<NKS, 3, ADD, false>;
   }
   return nullptr;
 }
-template <int NKS>
-K1Fn k1_select_imma_nks(int nt, bool add, bool cosmo) {
-  if (cosmo) return add ? k1_select_imma_nt<NKS, true, true>(nt) : k1_select_imma_nt<NKS, false, true>(nt);
-  return add ? k1_select_imma_nt<NKS, true, false>(nt) : k1_select_imma_nt<NKS, false, false>(nt);
-}
-// n_q4 of the node sets the kernel is instantiated for: 56 (the default of the 'smooth' family), 64 and 88 nodes
-bool imma_supported(int nks) { return nks == 14 || nks == 16 || nks == 22; }
-K1Fn k1_select_imma(int nks, int nt, bool add, bool cosmo) {
+// n_q4 of the node sets the kernel is instantiated for: 56 (the default of the 'smooth' family) and 88 nodes; calls with
+// cosmology columns (CPX_AS / CPX_NS) keep the DMMA kernel (the COSMO instantiation exists in the template, it is left out
+// of the build to keep compile time down)
+bool imma_supported(int nks) { return nks == 14 || nks == 22; }
+K1Fn k1_select_imma(int nks, int nt, bool add) {
   switch (nks) {
-    case 14: return k1_select_imma_nks<14>(nt, add, cosmo);
-    case 16: return k1_select_imma_nks<16>(nt, add, cosmo);
-    case 22: return k1_select_imma_nks<22>(nt, add, cosmo);
+    case 14: return add ? k1_select_imma_nt<14, true>(nt) : k1_select_imma_nt<14, false>(nt);
+    case 22: return add ? k1_select_imma_nt<22, true>(nt) : k1_select_imma_nt<22, false>(nt);
   }
   return nullptr;
 }
@@ -1422,8 +1418,8 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     bool ok = true;
     for (auto& zh : h->z) ok &= zh.dev.im_cell != nullptr;        // every z on the same node count
     if (!ok) h->im_nks = 0;
-    for (int add = 0; add < 4 && h->im_nks > 0; ++add) {
-      K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, (add & 1) != 0, (add & 2) != 0);
+    for (int add = 0; add < 2 && h->im_nks > 0; ++add) {
+      K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, add != 0);
       if (!fn || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(imma_smem_bytes(h->im_nks, h->na_blk / 8))) != cudaSuccess)
         return bail(fail(CPX_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for k_p3d_hankel_imma"));
@@ -1760,7 +1756,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
     const size_t k1_smem = static_cast<size_t>((h->max_nq + 3) / 4) * (kCellConsts * 4 * 32 * 4 + h->na_blk * 32);
     int pp = pp_env > 0 ? std::min(pp_env, 2) : (2 * (k1_smem + 2048) <= 227u * 1024u ? 1 : 2);
     const bool tc = h->tc_np > 0 && !precise && !cosmo;   // k_p3d_hankel_tc has no rescaling variant
-    const bool imma = h->im_nks > 0 && !precise && !tc;   // INT8 mma.sync Hankel kernel: one point per warp (the default)
+    const bool imma = h->im_nks > 0 && !precise && !tc && !cosmo;   // INT8 mma.sync Hankel kernel: one point per warp (the default)
     if (imma) pp = 1;
     // float64 cells: the shared-memory staged kernel (16 points per CTA) when the float64 tile fits, else one warp per point
     const size_t f64_smem = basis_smem_bytes((h->max_nq + 3) / 4, h->na_blk / 8);
@@ -1840,7 +1836,7 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
         const int grid = static_cast<int>(std::min<long long>((n_items + 7) / 8, 8LL * h->sm_count));
         fn<<<grid, 256, 0, st>>>(h->d_ztab, n_zl, count, n_items);
       } else if (imma) {
-        K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, additive, cosmo);
+        K1Fn fn = k1_select_imma(h->im_nks, h->na_blk / 8, additive);
         const int grid = static_cast<int>(std::min<long long>(n_items, 2LL * h->sm_count));
         fn<<<grid, kK1Threads, imma_smem_bytes(h->im_nks, h->na_blk / 8), st>>>(h->d_ztab, n_zl, count, n_items);
       } else if (tc) {

@@ -89,7 +89,7 @@ def _imma_paths(monkeypatch, plans, pts, names, want=("chi2", "px_zam")):
     return out["0"], out["1"]
 
 
-@pytest.mark.parametrize("n_q,flags", [(56, {"include_hcd": True}), (64, {}), (88, ALL), (64, ALL), (56, {"include_continuum": True})])
+@pytest.mark.parametrize("n_q,flags", [(56, {"include_hcd": True}), (88, {}), (88, ALL), (56, ALL), (56, {"include_continuum": True})])
 def test_imma_path_equals_dmma_path(monkeypatch, n_q, flags):
     """Same FP32 cells on both paths, so they may differ only by the error of the integer split (tests/test_tc_split.py)."""
     plans = _plans("S2", n_q, flags, N_m=70, N_A=9)          # ragged: 70 rows (3 tiles of 32, the last with 6 rows), 9 theta bins, 4 z
@@ -114,7 +114,7 @@ def test_imma_path_theta_blocks_cosmo_columns_and_extremes(monkeypatch):
     scale = np.abs(ref["px_zam"]).max(axis=3, keepdims=True)
     assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 2e-8
     np.testing.assert_allclose(got["chi2"], ref["chi2"], rtol=2e-9, atol=1e-6)
-    # primordial amplitude and tilt as columns (the COSMO instantiation), all contaminants on
+    # primordial amplitude and tilt as columns: such calls keep the DMMA kernel (no COSMO instantiation in the build), all contaminants on
     plans = _plans("tiny", 56, ALL)
     d0 = plans[0].defaults
     pts = np.array([[d0[_plan.SLOT_INDEX["As"]] * f, d0[_plan.SLOT_INDEX["ns"]] + dn, -0.12] for f, dn in ((1.0, 0.0), (1.1, 0.02), (0.9, -0.03))])
