@@ -248,7 +248,7 @@ def main():
     ap.add_argument("--shape", default="S5")
     ap.add_argument("--n-theta-average", type=int, default=100)
     ap.add_argument("--n-q", type=int, default=0,
-                    help="k_perp nodes; 0 = what Theory selects for px_rtol = 1e-5 and this linear power (56 log-uniform nodes)")
+                    help="k_perp nodes; 0 = what Theory selects for px_rtol = 1e-5 and this linear power (52 log-uniform nodes)")
     ap.add_argument("--alt-n-q", type=int, default=88, help="a second, short device-timed measurement at this node count (0 = skip)")
     ap.add_argument("--cpu-evals-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

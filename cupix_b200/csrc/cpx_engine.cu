@@ -677,12 +677,13 @@ K1Fn k1_select_imma_nt(int nt) {
   }
   return nullptr;
 }
-// n_q4 of the node sets the kernel is instantiated for: 56 (the default of the 'smooth' family) and 88 nodes; calls with
+// n_q4 of the node sets the kernel is instantiated for: 52 (the default of the 'smooth' family), 56 and 88 nodes; calls with
 // cosmology columns (CPX_AS / CPX_NS) keep the DMMA kernel (the COSMO instantiation exists in the template, it is left out
 // of the build to keep compile time down)
-bool imma_supported(int nks) { return nks == 14 || nks == 22; }
+bool imma_supported(int nks) { return nks == 13 || nks == 14 || nks == 22; }
 K1Fn k1_select_imma(int nks, int nt, bool add) {
   switch (nks) {
+    case 13: return add ? k1_select_imma_nt<13, true>(nt) : k1_select_imma_nt<13, false>(nt);
     case 14: return add ? k1_select_imma_nt<14, true>(nt) : k1_select_imma_nt<14, false>(nt);
     case 22: return add ? k1_select_imma_nt<22, true>(nt) : k1_select_imma_nt<22, false>(nt);
   }

@@ -17,7 +17,7 @@ is evaluated once per (z, binning) in float64 with Gauss-Legendre panels that re
 linear, the reference's theta sub-sampling average (cupix/likelihood/likelihood.py:99-130) is
 folded into the weights as well.  Measured error against a 2^20-point brute-force integral is
 < 2.5e-7 of the Px scale at n_q = 88 over the ForestFlow training box down to theta = 0.5'
-(tests/test_quadrature.py; 56 nodes: 1.2e-6, 64 nodes: 8.7e-7 -- `n_q` / `px_rtol` are Theory config keys).
+(tests/test_quadrature.py; 52 nodes: 2.8e-6, 56 nodes: 1.5e-6, 64 nodes: 8.7e-7 -- `n_q` / `px_rtol` are Theory config keys).
 
 That accuracy holds for a *smooth* linear power.  With baryon acoustic oscillations in P_L (period
 2 pi / r_s ~ 0.043 1/Mpc, what CAMB / LaCE deliver; they move Px by up to 4e-3 of its scale at low k_par) the
@@ -45,7 +45,8 @@ from scipy.special import j0
 
 # kind -> [(KperpRule keyword arguments, measured worst-case error)], cheapest first
 RULES = {
-    "smooth": [(dict(n_q=56), 1.5e-6), (dict(n_q=64), 8.7e-7), (dict(n_q=72), 3.0e-7), (dict(n_q=88), 3.0e-7)],
+    "smooth": [(dict(n_q=52), 2.8e-6), (dict(n_q=56), 1.5e-6), (dict(n_q=64), 8.7e-7), (dict(n_q=72), 3.0e-7),
+               (dict(n_q=88), 3.0e-7)],
     "bao": [(dict(n_q=112, refine=20.0, k_refine=0.5), 4.8e-6), (dict(n_q=128, refine=20.0, k_refine=0.5), 2.8e-6),
             (dict(n_q=144, refine=20.0, k_refine=0.5), 1.3e-6), (dict(n_q=160, refine=15.0, k_refine=0.7), 5.8e-7),
             (dict(n_q=176, refine=20.0, k_refine=0.5), 3.9e-7)],
@@ -54,7 +55,7 @@ RULE_MARGIN = 3.0
 DEFAULT_PX_RTOL = 1e-5          # BASELINE.json north_star: relative 1e-5 on model Px
 # named presets (Theory config 'kperp_rule'): the entries chosen for the default tolerance, and the finest ones
 PRESETS = {"smooth": RULES["smooth"][0][0], "bao": RULES["bao"][1][0],
-           "smooth_fine": RULES["smooth"][3][0], "bao_fine": RULES["bao"][3][0]}
+           "smooth_fine": RULES["smooth"][4][0], "bao_fine": RULES["bao"][3][0]}
 WIGGLE_THRESHOLD = 1.5e-3       # see wiggle_amplitude
 DEFAULT_NQ = 88
 DEFAULT_K0 = 0.01

@@ -123,7 +123,7 @@ def test_rule_choice_follows_tolerance_and_linear_power():
     assert Q.wiggle_amplitude(smooth, 2.2) < Q.WIGGLE_THRESHOLD < Q.wiggle_amplitude(Cosmology({"bao_amp": 0.005}), 2.2)
     cfg = {"default_lya_model": "best_fit_arinyo_from_colore"}
     th = Theory(2.2, fid_cosmo=smooth, config=cfg)
-    assert th.kperp_family == "smooth" and th.rule.n_q == 56 and th.rule.refine == 0.0 and th.rule_error * 3 <= 1e-5
+    assert th.kperp_family == "smooth" and th.rule.n_q == 52 and th.rule.refine == 0.0 and th.rule_error * 3 <= 1e-5
     th = Theory(2.2, fid_cosmo=wiggly, config=cfg)
     assert th.kperp_family == "bao" and th.rule.n_q == 128 and th.rule.refine == 20.0 and th.rule_error * 3 <= 1e-5
     assert abs(th.wiggle_amplitude - 0.05) < 0.01

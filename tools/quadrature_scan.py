@@ -54,5 +54,46 @@ def main():
                                             ("%.1e" % listed[0]) if listed else "(not offered)"))
 
 
+def dense_scan():
+    """Second table: the log-uniform family on a denser grid over the range a measurement covers (26 theta from 0.5' to 59', 15
+    k_par from 0.0077 to 1.19 1/A), every other row (central / min / max) of the ForestFlow training table at z = 2 .. 4.5
+    plus the CoLoRe fit -- 17 parameter sets, each at its own redshift -- with where the worst error sits."""
+    import csv
+    from cupix_b200.utils.utils import data_path
+    theta = np.geomspace(0.5, 59.0, 26)
+    k_AA = np.concatenate([[0.0077], np.geomspace(0.013, 1.19, 14)])
+    sets = []
+    for r in csv.DictReader(open(data_path("ff_training_info.csv"))):
+        z = float(r["z"])
+        if not (2.0 <= z <= 4.6):
+            continue
+        for tag in ("central", "min", "max"):
+            av, kvav = float(r["av_" + tag]), float(r["kvav_" + tag])
+            sets.append((z, dict(bias=float(r["bias_" + tag]), beta=float(r["beta_" + tag]), q1=float(r["q1_" + tag]),
+                                 q2=float(r["q2_" + tag]), av=av, bv=float(r["bv_" + tag]), kp_Mpc=float(r["kp_" + tag]),
+                                 kv_Mpc=float(np.exp(np.log(kvav) / av)))))
+    sets.append((2.2, LYA_SETS["colore"]))
+    sets = sets[::2]
+    fft, cosmo = FFTLogHankel(), Cosmology()
+    refs = [OracleTheory(z, cosmo, p, CONT, XI, fft, include_hcd=True).get_px_obs(theta, k_AA, {}) for z, p in sets]
+    print()
+    print("dense scan, smooth P_L: %d parameter sets at z = %s" % (len(sets), sorted(set(round(z, 2) for z, _ in sets))))
+    cands = [kw for kw, _ in Q.RULES["smooth"]] + [dict(n_q=48), dict(n_q=48, k0=0.007), dict(n_q=44, k0=0.003), dict(n_q=44, k0=0.005)]
+    for kw in cands:
+        rule = Q.KperpRule(**kw)
+        worst, where = 0.0, ""
+        for (z, p), ref in zip(sets, refs):
+            th = OracleTheory(z, cosmo, p, CONT, XI, NodeHankel(rule.k, lambda r: rule.weights(r)), include_hcd=True)
+            d = np.abs(th.get_px_obs(theta, k_AA, {}) - ref) / np.abs(ref).max()
+            if d.max() > worst:
+                i, j = np.unravel_index(d.argmax(), d.shape)
+                worst, where = d.max(), "z = %.2f, theta = %.2f', k_par = %.4f 1/A" % (z, theta[i], k_AA[j])
+        listed = [e for k2, e in Q.RULES["smooth"] if k2 == kw]
+        print("%-32s %10.2e  worst at %-44s %s" % (kw, worst, where, ("listed %.1e" % listed[0]) if listed else "(not offered)"))
+    print("(48 nodes meet 1e-5 but not 1e-5 / 3 with the default map; node sets with k0 < 0.01 reach lower errors at isolated k0 values and\n"
+          " lose them at neighbouring ones -- 44 nodes: 1.2e-5 at k0 = 0.002, 6e-7 at 0.003, 2e-6 at 0.005 -- so they are not offered)")
+
+
 if __name__ == "__main__":
     main()
+    dense_scan()

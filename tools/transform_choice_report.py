@@ -4,7 +4,7 @@ chi2(oracle A) - chi2(oracle B) on the S1 shape (N_theta_average = 2, HCD on), w
   oracle A = the reference's algorithm (FFTLog + P1D splice + splines, cupix/likelihood/lyaP3D.py:272-351,
              including its k_par = 0 -> 1e-4 substitution, :35-39),
   oracle B = the fixed-node rule the device evaluates (float64 emulation of the device plan, tests/helpers.py),
-for the k_perp rules on offer (n_q = 56 / 64 / 88 log-uniform nodes, the refined 'bao' presets) and both treatments of
+for the k_perp rules on offer (n_q = 52 / 56 / 64 / 88 log-uniform nodes, the refined 'bao' presets) and both treatments of
 the k_par = 0 row (Theory config kpar0 = 'exact' | 'reference'), on a smooth linear power and on one with a 5 % BAO-like wiggle.  The data vector is oracle A at the truth plus noise,
 so the numbers are what a user comparing against the reference's own output would see: at the best fit and at
 delta chi2 = 2.30 / 6.17 / 11.8 along bias, and far from it.
@@ -64,7 +64,8 @@ def main(bao_amp=0.0):
     print()
     print("%-30s %-10s | %-22s | %s" % ("k_perp rule", "kpar0", "max|dPx_Zam|/max (all rows / k_par>0)",
                                          " | ".join("%-12s" % n[:12] for n, _ in pts)))
-    rules = [("smooth n_q=56", {"kperp_rule": "smooth"}, 56), ("smooth n_q=64", {"kperp_rule": "smooth"}, 64),
+    rules = [("smooth n_q=52 (default)", {"kperp_rule": "smooth"}, 52), ("smooth n_q=56", {"kperp_rule": "smooth"}, 56),
+             ("smooth n_q=64", {"kperp_rule": "smooth"}, 64),
              ("smooth n_q=88", {"kperp_rule": "smooth"}, 88), ("bao n_q=128 (20, 0.5)", {"kperp_rule": "bao"}, 128),
              ("bao_fine n_q=160 (15, 0.7)", {"kperp_rule": "bao_fine"}, 160)]
     for rname, extra, n_q in rules:
