@@ -28,7 +28,7 @@
 //
 // CTA = 8 warps, 2 CTAs per SM, persistent over (z, 32-row tile, theta block, point group) items exactly like
 // k_p3d_hankel; cell constants of the tile (P_L scaled by s_q) and the digit table of the theta block are staged with
-// TMA bulk copies and stay resident.  Instantiated for 56 and 88 nodes (n_q4 = 14, 22), without the COSMO variant.
+// TMA bulk copies and stay resident.  Instantiated for 52, 56 and 88 nodes (n_q4 = 13, 14, 22), without the COSMO variant.
 //
 // Status: opt-in (CPX_IMMA=1).  Bit-for-bit the cells of k_p3d_hankel and chi2 within 1e-10 relative of it, but not
 // faster: 50.7 against 49.3 ms per 131 072-point S5 step at 56 nodes, 73.1 against 73.7 at 88.  The contraction does

@@ -199,7 +199,7 @@ enum { CPX_INFO_N_ZBINS = 0, CPX_INFO_MAX_NA = 1, CPX_INFO_MAX_NM = 2, CPX_INFO_
                                         /* (same tuple values, columns, z list and data vectors): one kernel launch */
        CPX_INFO_HANKEL_KERNEL = 15      /* Hankel kernel of the general (float32-cell) pipeline: 0 = k_p3d_hankel (FP64 */
                                         /* DMMA, the default), 1 = k_p3d_hankel_tc (tcgen05 INT8, CPX_TC=1), 2 =         */
-                                        /* k_p3d_hankel_imma (mma.sync INT8, CPX_IMMA=1; 56 or 88 k_perp nodes)          */ };
+                                        /* k_p3d_hankel_imma (mma.sync INT8, CPX_IMMA=1; 52, 56 or 88 k_perp nodes)      */ };
 
 /* Set-up helper (no handle needed): the J0 part of the Hankel weights that stand for forestflow.pcross.Px_Mpc_detailed
  * (theory.py:250-264) with the theta sub-sampling average of likelihood.py:99-130 folded in.  For n_groups fine theta
