@@ -48,6 +48,27 @@ def test_no_cpu_fallback():
         th.get_px_obs(np.array([1.0, 2.0]), np.array([0.1, 0.2]))
 
 
+def test_device_helpers_fail_loudly_without_a_gpu():
+    """cpx_hankel_apply / cpx_hankel_jbar / cpx_probe_imma and Theory._compute_px_from_p3d have no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import numpy as np
+    from cupix_b200 import engine
+    from tests import helpers as H
+    with pytest.raises(engine.CpxError, match="cpx_hankel_apply failed"):
+        engine.hankel_apply(0, np.ones((3, 8)), np.ones((5, 8)))
+    with pytest.raises(engine.CpxError, match="cpx_probe_imma failed"):
+        engine.probe_imma(0)
+    with pytest.raises(engine.CpxError, match="cpx_hankel_jbar failed"):
+        engine.hankel_jbar(0, [0, 1], [1.0], [1.0], [0.1, 0.2], [1.0, 1.0])
+    th = H.make_theory(2.2, "best_fit_arinyo_from_colore", {})
+    with pytest.raises(engine.CpxError, match="needs a CUDA device"):
+        th._compute_px_from_p3d(np.array([1.0]), np.array([0.1]), lambda k, mu: np.exp(-k * k), 200.0)
+    with pytest.raises(AssertionError):
+        engine.hankel_apply(0, np.ones((3, 8)), np.ones((5, 7)))
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "cupix_b200")):
         for f in files:
