@@ -582,6 +582,12 @@ def test_px_from_arbitrary_p3d_callable_and_Mpc_accessors():
     want = orc.hankel(rt, kp, lambda k, mu: orc.p3d_lya_hcd(k, mu, params))
     assert got.shape == (rt.size, kp.size)
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()      # J0 on the device: 5e-12
+    # a node count that is no multiple of four, a single separation, a single k_par
+    th50 = H.make_theory(2.4, "best_fit_arinyo_from_gadget", FLAG_SETS["all"], n_q=50)
+    orc50 = H.oracle_for(th50)
+    got50 = th50._compute_px_from_p3d(rt[2:3], kp[5:6], lambda k, mu: th50.get_p3d_lya_Mpc(k, mu, params=params))
+    want50 = orc50.hankel(rt[2:3], kp[5:6], lambda k, mu: orc50.p3d_lya(k, mu, params))
+    assert got50.shape == (1, 1) and abs(got50[0, 0] / want50[0, 0] - 1) <= 1e-10
     # ... and the fused device path (float32 cells) for the same term, in Mpc units
     fused = th.get_px_lya_hcd_Mpc(rt, kp, params=params)
     assert np.abs(fused - want).max() <= PX_RTOL * np.abs(want).max()
