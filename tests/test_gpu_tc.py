@@ -130,6 +130,28 @@ def test_imma_path_theta_blocks_cosmo_columns_and_extremes(monkeypatch):
     assert (np.abs(got["px_zam"] - ref["px_zam"]) / scale).max() < 5e-8      # 2.6e-8 at these far-out points
 
 
+def test_imma_path_under_guard_bands(monkeypatch):
+    """CPX_GUARD=1 around the per-chunk scratch buffers while k_p3d_hankel_imma writes ragged tiles (70 rows, 9 theta bins,
+    37 points): no guard word touched, same numbers as without the guards."""
+    plans = _plans("S2", 52, ALL, N_m=70, N_A=9)
+    names = ["bias", "beta", "q1", "kp_Mpc", "b_H"]
+    base = np.array([plans[0].defaults[_plan.SLOT_INDEX[n]] for n in names])
+    pts = base[None, :] * np.random.default_rng(5).uniform(0.8, 1.2, size=(37, len(names)))
+    slots, zsel = slots_from_names(names)
+    monkeypatch.setenv("CPX_IMMA", "1")
+    eng = PxEngine(plans)
+    ref = eng.eval(pts, slots, zsel=zsel, want=("chi2", "px_zam"))
+    eng.close()
+    monkeypatch.setenv("CPX_GUARD", "1")
+    eng = PxEngine(plans)
+    assert eng.info("hankel_kernel") == 2
+    got = eng.eval(pts, slots, zsel=zsel, want=("chi2", "px_zam"))
+    assert eng.info("guard_buffers") >= 5 and eng.info("guard_violations") == 0
+    eng.close()
+    np.testing.assert_array_equal(got["chi2"], ref["chi2"])
+    np.testing.assert_array_equal(got["px_zam"], ref["px_zam"])
+
+
 def test_imma_path_falls_back_for_other_node_counts(monkeypatch):
     monkeypatch.setenv("CPX_IMMA", "1")
     eng = PxEngine(_plans("tiny", 80, {}))
