@@ -1884,7 +1884,12 @@ int cpx_eval(cpx_handle* h, const cpx_eval_args* a) {
       const int mt = Z.n_M_pad / 8 / std::max(Z.n_mblk, 1);
       if (want_chi2) {
         if (wtc) {
-          dim3 tgrid((count + kWtPts - 1) / kWtPts, std::min(std::max(nA_grid, 1), env_int("CPX_WTC_AGROUPS", 4)), gz);
+          // theta_A groups per 128-point tile: one CTA walking all theta_A re-uses its pipeline fill best (19.4 against 20.2 ms
+          // per 131 072-point S5 step, profiles/window_tc_depths_r02.txt); more groups only while the grid is below four waves
+          const long long tiles = static_cast<long long>((count + kWtPts - 1) / kWtPts) * gz;
+          const int auto_groups = static_cast<int>(std::min<long long>(4, std::max<long long>(1, (4LL * h->sm_count + tiles - 1) / tiles)));
+          const int agroups = env_int("CPX_WTC_AGROUPS", 0) > 0 ? env_int("CPX_WTC_AGROUPS", 0) : auto_groups;
+          dim3 tgrid((count + kWtPts - 1) / kWtPts, std::min(std::max(nA_grid, 1), agroups), gz);
           k_window_tc<<<tgrid, kWtThreads, wt_smem_bytes(h->wt_nb), st>>>(h->d_ztab, i, w);
         } else {
           k2_select<true>(mt)<<<grid, 128, 0, st>>>(h->d_ztab, i, w);
