@@ -1389,12 +1389,28 @@ int cpx_create(const cpx_zbin_desc* zbins, int32_t n_zbins, int32_t device, cpx_
     }
     per_point_bytes += static_cast<size_t>(h->z[i].dev.n_a) * h->z[i].dev.n_m_pad * 8 + sizeof(cpx::PtPar) + sizeof(cpx::RowPar) * h->z[i].dev.n_m_pad;
   }
-  // chunk_max: Px_Zam scratch of all z within the budget (default 4 GiB), multiple of 256 points.  The scratch itself is
+  // chunk_max: Px_Zam scratch of all z within the budget (default 6 GiB), multiple of 256 points.  The scratch itself is
   // allocated by ensure_scratch() for the largest batch seen so far, so that engines which only serve scalar calls
   // (Theory.get_px_obs, Likelihood.get_chi2) do not pin gigabytes of HBM each.
-  const size_t budget = static_cast<size_t>(env_int("CPX_SCRATCH_MB", 4096)) << 20;
+  const size_t budget = static_cast<size_t>(env_int("CPX_SCRATCH_MB", 6144)) << 20;
   long long chunk = static_cast<long long>(budget / std::max<size_t>(per_point_bytes, 1));
   chunk = std::max(256LL, std::min(chunk, 65536LL)) / 256 * 256;
+  // The window kernels run one CTA per (128-point tile, z) and SM: within the upper half of what the budget allows, take the
+  // chunk whose grid fills its last wave best (S5: 9472 points = 74 tiles x 12 z = 6.00 waves of 148 SMs instead of 4.70 with
+  // 7424 points: 18.7 against 19.4 ms per 131 072-point step, profiles/window_tc_depths_r02.txt)
+  if (chunk >= 2048) {
+    long long best = chunk;
+    double best_eff = 0.0;
+    for (long long c = chunk; c >= chunk / 2; c -= 256) {
+      const double T = static_cast<double>(c / 128) * n_zbins;
+      const double eff = T / (std::ceil(T / h->sm_count) * h->sm_count);
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        best = c;
+      }
+    }
+    chunk = best;
+  }
   h->chunk_max = static_cast<int>(chunk);
   h->chunk = 0;
 

@@ -28,7 +28,7 @@
  *   CPX_WTC=0       chi2 stage as the FP64 DMMA GEMM instead of the tcgen05 kernel (k_window_tc, the default for
  *                   calls with at least CPX_WTC_MIN = 49152 (point, z) pairs)
  *   CPX_TC=1        Hankel contraction on tcgen05 (k_p3d_hankel_tc) instead of FP64 DMMA
- *   CPX_SCRATCH_MB  upper limit of the per-chunk Px_Zam scratch buffer (default 4096); the buffer is sized by the
+ *   CPX_SCRATCH_MB  upper limit of the per-chunk Px_Zam scratch buffer (default 6144); the buffer is sized by the
  *                   largest batch seen so far, so an engine that only serves scalar calls stays small
  *   CPX_FACTOR=0    switch the factorised path (see CPX_NO_FACTOR below) off for the whole process
  *   CPX_GUARD=1     debugging: fence every writable scratch buffer with 64 KiB guard bands, checked by
