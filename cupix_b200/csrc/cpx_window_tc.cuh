@@ -78,6 +78,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap,
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+// the same with an L2 cache policy: the scouts' read (from HBM) is marked evict_last so that the line is still there when the
+// workers read it again a tile later, the workers' read evict_first because nobody reads it a third time (CPX_WT_L2HINT)
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#ifndef CPX_WT_L2HINT
+#define CPX_WT_L2HINT 1
+#endif
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 2, %0;" ::"n"(kWtWorkers * 32) : "memory"); }
 
 __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restrict__ ztab, int zi, WindowArgs w) {
@@ -209,6 +230,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       uint64_t* const full = scout ? bar_sfull : bar_rfull;
       uint64_t* const free_ = scout ? bar_sfree : bar_rfree;
       const uint32_t ring = smem_u32(scout ? sS : sR);
+#if CPX_WT_L2HINT
+      const uint64_t l2pol = scout ? l2_policy_evict_last() : l2_policy_evict_first();
+#endif
       int rc = 0;
       for (int A = blockIdx.y; A < n_A; A += a_step)
         for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) {
@@ -217,8 +241,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
             const int slot = rc % nslots;
             if (rc >= nslots) mbar_wait_parked(&free_[slot], static_cast<uint32_t>(rc / nslots - 1) & 1u);
             mbar_expect_tx(&full[slot], static_cast<uint32_t>(kWtRingBytes));
+#if CPX_WT_L2HINT
+            tma_load_3d_hint(ring + slot * kWtRingBytes, Z.px_tmap, mc * kWtKC, a, pt_base, &full[slot], l2pol);
+            tma_load_3d_hint(ring + slot * kWtRingBytes + kWtRingBytes / 2, Z.px_tmap, mc * kWtKC + 16, a, pt_base, &full[slot], l2pol);
+#else
             tma_load_3d(ring + slot * kWtRingBytes, Z.px_tmap, mc * kWtKC, a, pt_base, &full[slot]);
             tma_load_3d(ring + slot * kWtRingBytes + kWtRingBytes / 2, Z.px_tmap, mc * kWtKC + 16, a, pt_base, &full[slot]);
+#endif
           }
         }
     }
