@@ -96,6 +96,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// CPX_WT_REVERSE: the workers walk the chunks of a tile in the opposite order to the scouts, so that their (second) read
+// starts with the lines the scouts touched last -- the ones most likely still in L2 (integer accumulation: same result)
+#ifndef CPX_WT_REVERSE
+#define CPX_WT_REVERSE 0
+#endif
 #ifndef CPX_WT_L2HINT
 #define CPX_WT_L2HINT 1
 #endif
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
             mbar_wait_parked(&bar_free[s], ph);
           }
           mbar_expect_tx(&bar_fullB[s], static_cast<uint32_t>(B_STAGE));
-          bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(c) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
+          const int cw = CPX_WT_REVERSE ? n_chunks - 1 - c : c;      // the workers' chunk order
+          bulk_g2s(sB + s * B_STAGE, src + static_cast<size_t>(cw) * B_STAGE, static_cast<uint32_t>(B_STAGE), &bar_fullB[s]);
         }
       }
     }
@@ -234,10 +240,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       const uint64_t l2pol = scout ? l2_policy_evict_last() : l2_policy_evict_first();
 #endif
       int rc = 0;
+      const bool rev = CPX_WT_REVERSE && !scout;
       for (int A = blockIdx.y; A < n_A; A += a_step)
-        for (int p = Z.pair_start[A]; p < Z.pair_start[A + 1]; ++p) {
+        for (int pi = Z.pair_start[A]; pi < Z.pair_start[A + 1]; ++pi) {
+          const int p = rev ? Z.pair_start[A] + Z.pair_start[A + 1] - 1 - pi : pi;
           const int a = Z.pair_a[p];
-          for (int mc = 0; mc < cpp; ++mc, ++rc) {
+          for (int mi = 0; mi < cpp; ++mi, ++rc) {
+            const int mc = rev ? cpp - 1 - mi : mi;
             const int slot = rc % nslots;
             if (rc >= nslots) mbar_wait_parked(&free_[slot], static_cast<uint32_t>(rc / nslots - 1) & 1u);
             mbar_expect_tx(&full[slot], static_cast<uint32_t>(kWtRingBytes));
@@ -311,11 +320,11 @@ __global__ void __launch_bounds__(kWtThreads, 1) k_window_tc(const ZDev* __restr
       __threadfence_block();
       const int emax = sE[(tile & 1) * kWtPts + r];
       // ---- convert, slice, store ----
-      int cs_next = cs[0];                                     // column-scale exponent, loaded one chunk ahead
+      int cs_next = cs[CPX_WT_REVERSE ? 2 * (n_chunks - 1) : 0];      // column-scale exponent, loaded one chunk ahead
       for (int c = 0; c < n_chunks; ++c, ++gc, ++rc) {
         const int s = gc % kWtStages;
         const int cs_cur = cs_next;
-        if (c + 1 < n_chunks) cs_next = cs[2 * (c + 1)];
+        if (c + 1 < n_chunks) cs_next = cs[2 * (CPX_WT_REVERSE ? n_chunks - 2 - c : c + 1)];
         mbar_wait(&bar_rfull[rc % kWtRing], static_cast<uint32_t>(rc / kWtRing) & 1u);
         // |x 2^c| < 2^(emax - 1022)  =>  |x 2^(c + 1061 - emax)| < 2^39
         const int sh = min(max(cs_cur + 1061 - emax, -1000), 1000);
