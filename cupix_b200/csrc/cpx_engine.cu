@@ -763,10 +763,14 @@ int ensure_scratch(cpx_handle* h, long long need) {
     cpx::ZDev& Z = h->z[i].dev;
     Z.ptpar = nullptr;
     Z.rowpar = nullptr;
+    Z.rowcont = nullptr;
     Z.pxzam = nullptr;
     if ((rc = dmalloc(reinterpret_cast<void**>(&Z.ptpar), sizeof(cpx::PtPar) * c))) return rc;
     if (Z.flags & (CPX_INCLUDE_HCD | CPX_INCLUDE_CONTINUUM))
       if ((rc = dmalloc(reinterpret_cast<void**>(&Z.rowpar), sizeof(cpx::RowPar) * static_cast<size_t>(c) * Z.n_m_pad))) return rc;
+    // the continuum factor on its own: only the additive terms (SiIII, sky) need it beside RowPar::ampcont
+    if ((Z.flags & CPX_INCLUDE_CONTINUUM) && (Z.flags & (CPX_INCLUDE_METAL | CPX_INCLUDE_SKY)))
+      if ((rc = dmalloc(reinterpret_cast<void**>(&Z.rowcont), sizeof(double) * static_cast<size_t>(c) * Z.n_m_pad))) return rc;
     if ((rc = dmalloc(reinterpret_cast<void**>(&Z.pxzam), static_cast<size_t>(c) * Z.n_a * Z.n_m_pad * 8 + 256))) return rc;
   }
   if ((rc = dmalloc(reinterpret_cast<void**>(&h->d_points), sizeof(double) * 16 * c))) return rc;

@@ -323,10 +323,12 @@ __global__ void __launch_bounds__(kK1Threads, 2)
       const int m0 = m_base + 16 * h2 + g, m1 = m0 + 8;
       double acx = amp0, acy = amp0, cont_x = 1.0, cont_y = 1.0;
       if (rowwise) {
-        cont_x = rp[16 * h2].cont;
-        cont_y = rp[16 * h2 + 8].cont;
-        acx = rp[16 * h2].amp * cont_x;
-        acy = rp[16 * h2 + 8].amp * cont_y;
+        acx = rp[16 * h2].ampcont;
+        acy = rp[16 * h2 + 8].ampcont;
+        if (ADD && Z.rowcont != nullptr) {
+          cont_x = Z.rowcont[static_cast<size_t>(pt) * n_m_pad + m0];
+          cont_y = Z.rowcont[static_cast<size_t>(pt) * n_m_pad + m1];
+        }
       }
       constexpr int E0 = 158 - 8 * (kImNA - 2 - kImSmax);       // 166 for 4 bytes and classes 0..3
       constexpr double kMagic = 6755399441055744.0;             // 2^52 + 2^51

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               const int a = a0 + c + j, n_m = Zg.n_m, flags = Zg.flags;
               if (mrow < n_m) {
                 const PtPar& pr = Zg.ptpar[ptc];
-                const double cont = (flags & 9) ? Zg.rowpar[static_cast<size_t>(ptc) * n_m_pad + mrow].cont : 1.0;
+                const double cont = Zg.rowcont != nullptr ? Zg.rowcont[static_cast<size_t>(ptc) * n_m_pad + mrow] : 1.0;
                 double add = 0.0;
                 if (flags & 2) {   // SiIII auto + cross from precomputed Hankel moments, theory.py:361-438
                   const size_t o = static_cast<size_t>(a) * n_m + mrow, st = static_cast<size_t>(n_a) * n_m;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       unsigned char* dst = sP + (st * kTcPts + warp) * kTcStageBytes;
       if (lane < 4) {
         cp_async16(dst + 16 * lane, reinterpret_cast<const unsigned char*>(&Z.ptpar[pt_]) + 16 * lane);
-      } else if (lane < 16 && (Z.flags & 9)) {
+      } else if (lane < 12 && (Z.flags & 9)) {      // 8 rows x 16 bytes
         const unsigned char* src = reinterpret_cast<const unsigned char*>(&Z.rowpar[static_cast<size_t>(pt_) * Z.n_m_pad + tile_ * kTcRows]);
         cp_async16(dst + 64 + 16 * (lane - 4), src + 16 * (lane - 4));
       }
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const RowPar& rp = reinterpret_cast<const RowPar*>(pst + 64)[row];
         bhi = rp.betaT_hi;
         blo = rp.betaT_lo;
-        ampcont = rp.amp * rp.cont;
+        ampcont = rp.ampcont;
       } else {
         const double bias = *reinterpret_cast<const double*>(pst + 48), beta = *reinterpret_cast<const double*>(pst + 56);
         split_hi_lo(beta, bhi, blo);

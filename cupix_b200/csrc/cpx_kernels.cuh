@@ -102,6 +102,7 @@ struct ZDev {
   // per-chunk buffers
   PtPar* ptpar;                         // [chunk]
   struct RowPar* rowpar;                // [chunk][n_m_pad], valid when flags & (HCD | CONTINUUM)
+  double* rowcont;                      // [chunk][n_m_pad] continuum factor alone, or null (only with CONTINUUM and additive terms)
   double* pxzam;                        // [chunk][n_a][n_m_pad]
   long long item_start;                 // first k_p3d_hankel work item of this z in the launch
   // tensor-core (tcgen05) Hankel path, cpx_hankel_tc.cuh; tc_np == 0: not available for this z (n_q > 96)
@@ -278,10 +279,11 @@ __global__ void k_params(ParamsArgs a, const ZDev* __restrict__ ztab, const int*
 // ------------------------------------------------------------------------------------------
 struct RowPar {
   float betaT_hi, betaT_lo;   // Kaiser beta of the row (hi + lo float pair)
-  double amp;                 // b_T(k_par)^2 * dAA_dMpc
-  double cont;                // tanh((k_par / kC)^pC), 1 without continuum distortion
+  double ampcont;             // b_T(k_par)^2 * dAA_dMpc * tanh((k_par / kC)^pC)  (the last factor is 1 without continuum distortion)
 };
-static_assert(sizeof(RowPar) == 24, "RowPar layout");
+static_assert(sizeof(RowPar) == 16, "RowPar layout");
+// The continuum factor on its own (ZDev::rowcont) is needed only by the additive terms (SiIII, sky), which it multiplies too:
+// it is written when the z bin has both.  16 instead of 24 bytes per (point, z, row): k_rowpars is bound by its writes.
 
 __global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
   const ZDev& Z = ztab[blockIdx.y];
@@ -300,9 +302,10 @@ __global__ void k_rowpars(const ZDev* __restrict__ ztab, int count) {
   }
   RowPar o;
   split_hi_lo(betaT, o.betaT_hi, o.betaT_lo);
-  o.amp = bT * bT * Z.dAA;
-  o.cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;
+  const double cont = (Z.flags & 8) ? tanh(pow(Z.kpar_row[m] / pr.kC, pr.pC)) : 1.0;
+  o.ampcont = bT * bT * Z.dAA * cont;
   Z.rowpar[static_cast<size_t>(pt) * Z.n_m_pad + m] = o;
+  if (Z.rowcont != nullptr) Z.rowcont[static_cast<size_t>(pt) * Z.n_m_pad + m] = cont;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -657,12 +660,12 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
       for (int mt = 0; mt < 4; ++mt) {
         const int m = m_base + 8 * mt + g;
         const bool row_ok = m < n_m;
-        double amp = amp0, cont = 1.0;
+        double ampcont = amp0, cont = 1.0;
         if (rowwise) {
-          amp = rp[8 * mt].amp;
-          cont = rp[8 * mt].cont;
+          ampcont = rp[8 * mt].ampcont;
+          if (ADD && Z.rowcont != nullptr) cont = Z.rowcont[static_cast<size_t>(pt) * n_m_pad + m];
         }
-        const double scale = row_ok ? amp * cont : 0.0;
+        const double scale = row_ok ? ampcont : 0.0;
         double sky = 0.0;
         if (ADD && (Z.flags & 4) && row_ok) sky = pr.b_noise * Z.sky_smooth[m];    // theory.py:476-506
 #pragma unroll
